@@ -1,0 +1,252 @@
+// fused bias + activation (+ gradient modes), HBM-bound elementwise kernel for sm_100a.
+//
+// Replaces op/fused_bias_act_kernel.cu:18-49 of the reference: same arithmetic
+//   y = act(x + b[c]) * scale          (grad 0)
+//   y = (ref > 0 ? x : alpha * x) * scale   (grad 1, x may carry a bias: double-backward)
+//   y = 0                                (grad 2)
+// but with 16-byte vector accesses, several independent loads in flight per thread,
+// 64-bit-safe indexing and one integer divide per vector instead of div+mod per element.
+//
+// Algorithmic bytes per element: 2*sizeof(T) forward, 3*sizeof(T) in gradient mode
+// (SURVEY.md 8d); roofline = HBM.
+#include "common.cuh"
+
+namespace fm {
+
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T, int N>
+struct alignas(16) Pack { T v[N]; };
+
+template <typename T>
+__device__ __forceinline__ Pack<T, Vec16<T>::N> ld16(const T* p) {
+  Pack<T, Vec16<T>::N> r;
+  *reinterpret_cast<uint4*>(&r) = __ldg(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ void st16(T* p, const Pack<T, Vec16<T>::N>& v) {
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
+}
+
+__device__ __forceinline__ float act_apply(float x, float ref, int mode, float alpha) {
+  // mode = act*10+grad, op/fused_bias_act_kernel.cu:36-45
+  switch (mode) {
+    case 30: return x > 0.f ? x : x * alpha;
+    case 31: return ref > 0.f ? x : x * alpha;
+    case 12:
+    case 32: return 0.f;
+    default: return x;  // 10, 11 and the reference's "default:" label
+  }
+}
+
+// Vector kernel: `inner` is a multiple of the vector width, so a 16-byte vector never
+// straddles a channel.  IdxT is uint32_t when the vector count fits, else uint64_t.
+template <typename T, typename IdxT, int MODE, bool HAS_BIAS, bool HAS_REF, int UNROLL>
+__global__ void __launch_bounds__(256) bias_act_vec_kernel(T* __restrict__ out, const T* __restrict__ x,
+                                                           const T* __restrict__ bias, const T* __restrict__ ref,
+                                                           IdxT n_vec, IdxT vec_per_row, uint32_t channels,
+                                                           float alpha, float scale) {
+  constexpr int N = Vec16<T>::N;
+  const IdxT stride = static_cast<IdxT>(gridDim.x) * blockDim.x;
+  IdxT v0 = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; v0 < n_vec; v0 += stride * UNROLL) {
+    Pack<T, N> xv[UNROLL], rv[UNROLL];
+    float bv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const IdxT v = v0 + stride * u;
+      if (v < n_vec) {
+        xv[u] = ld16<T>(x + static_cast<size_t>(v) * N);
+        if (HAS_REF) rv[u] = ld16<T>(ref + static_cast<size_t>(v) * N);
+        if (HAS_BIAS) bv[u] = to_f32<T>(__ldg(bias + static_cast<uint32_t>((v / vec_per_row) % channels)));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const IdxT v = v0 + stride * u;
+      if (v < n_vec) {
+        Pack<T, N> o;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          float xf = to_f32<T>(xv[u].v[j]);
+          if (HAS_BIAS) xf += bv[u];
+          const float rf = HAS_REF ? to_f32<T>(rv[u].v[j]) : 0.f;
+          o.v[j] = from_f32<T>(act_apply(xf, rf, MODE, alpha) * scale);
+        }
+        st16<T>(out + static_cast<size_t>(v) * N, o);
+      }
+    }
+  }
+}
+
+// Scalar fallback (inner not a multiple of the vector width, or unaligned pointers).
+template <typename T, int MODE, bool HAS_BIAS, bool HAS_REF>
+__global__ void __launch_bounds__(256) bias_act_scalar_kernel(T* __restrict__ out, const T* __restrict__ x,
+                                                              const T* __restrict__ bias, const T* __restrict__ ref,
+                                                              uint64_t n, uint64_t inner, uint32_t channels, float alpha,
+                                                              float scale) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float xf = to_f32<T>(x[i]);
+    if (HAS_BIAS) xf += to_f32<T>(__ldg(bias + static_cast<uint32_t>((i / inner) % channels)));
+    const float rf = HAS_REF ? to_f32<T>(ref[i]) : 0.f;
+    out[i] = from_f32<T>(act_apply(xf, rf, MODE, alpha) * scale);
+  }
+}
+
+template <typename T, int MODE, bool HAS_BIAS, bool HAS_REF>
+static int launch_bias_act(void* out, const void* x, const void* bias, const void* ref, int64_t n_outer,
+                           int64_t channels, int64_t inner, float alpha, float scale, cudaStream_t st) {
+  constexpr int N = Vec16<T>::N;
+  const uint64_t n = static_cast<uint64_t>(n_outer) * channels * inner;
+  if (n == 0) return FM_OK;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x) |
+                         (HAS_REF ? reinterpret_cast<uintptr_t>(ref) : 0)) & 15) == 0;
+  const int sms = sm_count();
+  if (aligned && inner % N == 0) {
+    constexpr int UNROLL = 4;
+    const uint64_t n_vec = n / N;
+    const uint64_t want = (n_vec + 256ull * UNROLL - 1) / (256ull * UNROLL);
+    const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sms) * 16 ? (want ? want : 1) : sms * 16);
+    if (n_vec < 0xFFFFFFFFull - 256ull * UNROLL * grid) {
+      bias_act_vec_kernel<T, uint32_t, MODE, HAS_BIAS, HAS_REF, UNROLL><<<grid, 256, 0, st>>>(
+          static_cast<T*>(out), static_cast<const T*>(x), static_cast<const T*>(bias), static_cast<const T*>(ref),
+          static_cast<uint32_t>(n_vec), static_cast<uint32_t>(inner / N), static_cast<uint32_t>(channels), alpha, scale);
+    } else {
+      bias_act_vec_kernel<T, uint64_t, MODE, HAS_BIAS, HAS_REF, UNROLL><<<grid, 256, 0, st>>>(
+          static_cast<T*>(out), static_cast<const T*>(x), static_cast<const T*>(bias), static_cast<const T*>(ref), n_vec,
+          static_cast<uint64_t>(inner / N), static_cast<uint32_t>(channels), alpha, scale);
+    }
+  } else {
+    const uint64_t want = (n + 255) / 256;
+    const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sms) * 32 ? want : sms * 32);
+    bias_act_scalar_kernel<T, MODE, HAS_BIAS, HAS_REF><<<grid, 256, 0, st>>>(
+        static_cast<T*>(out), static_cast<const T*>(x), static_cast<const T*>(bias), static_cast<const T*>(ref), n,
+        static_cast<uint64_t>(inner), static_cast<uint32_t>(channels), alpha, scale);
+  }
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+template <typename T, int MODE>
+static int dispatch_flags(void* out, const void* x, const void* bias, const void* ref, int64_t n_outer, int64_t channels,
+                          int64_t inner, float alpha, float scale, cudaStream_t st) {
+  const bool hb = bias != nullptr, hr = ref != nullptr;
+  if (hb && hr) return launch_bias_act<T, MODE, true, true>(out, x, bias, ref, n_outer, channels, inner, alpha, scale, st);
+  if (hb) return launch_bias_act<T, MODE, true, false>(out, x, bias, ref, n_outer, channels, inner, alpha, scale, st);
+  if (hr) return launch_bias_act<T, MODE, false, true>(out, x, bias, ref, n_outer, channels, inner, alpha, scale, st);
+  return launch_bias_act<T, MODE, false, false>(out, x, bias, ref, n_outer, channels, inner, alpha, scale, st);
+}
+
+template <typename T>
+static int dispatch_mode(int mode, void* out, const void* x, const void* bias, const void* ref, int64_t n_outer,
+                         int64_t channels, int64_t inner, float alpha, float scale, cudaStream_t st) {
+  switch (mode) {
+    case 30: return dispatch_flags<T, 30>(out, x, bias, ref, n_outer, channels, inner, alpha, scale, st);
+    case 31: return dispatch_flags<T, 31>(out, x, bias, ref, n_outer, channels, inner, alpha, scale, st);
+    case 12:
+    case 32: return dispatch_flags<T, 32>(out, x, bias, ref, n_outer, channels, inner, alpha, scale, st);
+    default: return dispatch_flags<T, 10>(out, x, bias, ref, n_outer, channels, inner, alpha, scale, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// gradient + fused bias-gradient reduction.
+// One block handles a slab of one (n, c) row; block-reduces gx in fp32 and issues a single
+// atomicAdd per block into grad_bias[c]  (the reference runs a separate torch sum over the
+// whole tensor, op/fused_act.py:42-48: one extra full read).
+// ------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) bias_act_grad_bias_kernel(T* __restrict__ gin, float* __restrict__ gbias,
+                                                                 const T* __restrict__ gout, const T* __restrict__ ref,
+                                                                 uint64_t inner, uint32_t channels, uint32_t slabs_per_row,
+                                                                 uint64_t slab, float alpha, float scale) {
+  const uint64_t row = blockIdx.x / slabs_per_row;
+  const uint32_t sl = blockIdx.x % slabs_per_row;
+  const uint32_t c = static_cast<uint32_t>(row % channels);
+  const uint64_t lo = static_cast<uint64_t>(sl) * slab;
+  const uint64_t hi = lo + slab < inner ? lo + slab : inner;
+  const T* g = gout + row * inner;
+  const T* r = ref + row * inner;
+  T* o = gin + row * inner;
+  float acc = 0.f;
+  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float y = act_apply(to_f32<T>(g[i]), to_f32<T>(r[i]), MODE, alpha) * scale;
+    const T yq = from_f32<T>(y);
+    o[i] = yq;
+    acc += to_f32<T>(yq);   // the reference sums the rounded grad_input tensor
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  __shared__ float wsum[8];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = wsum[threadIdx.x];
+#pragma unroll
+    for (int s = 4; s > 0; s >>= 1) v += __shfl_xor_sync(0xffu, v, s);
+    if (threadIdx.x == 0) atomicAdd(gbias + c, v);
+  }
+}
+
+template <typename T>
+static int launch_grad_bias(void* gin, float* gbias, const void* gout, const void* ref, int64_t n_outer, int64_t channels,
+                            int64_t inner, int act, float alpha, float scale, cudaStream_t st) {
+  const uint64_t rows = static_cast<uint64_t>(n_outer) * channels;
+  if (rows == 0 || inner == 0) return FM_OK;
+  // Aim for >= 4 waves of blocks; slab >= 2048 elements when the row is long.
+  uint64_t slab = static_cast<uint64_t>(inner);
+  const uint64_t target_blocks = static_cast<uint64_t>(sm_count()) * 32;
+  while (slab > 2048 && rows * ((inner + slab - 1) / slab) < target_blocks) slab = (slab + 1) / 2;
+  const uint64_t slabs = (inner + slab - 1) / slab;
+  const uint64_t blocks = rows * slabs;
+  FM_CHECK_ARG(blocks < 0x7FFFFFFFull, "bias_act_grad_bias: too many blocks (%llu)", (unsigned long long)blocks);
+  if (act == 3)
+    bias_act_grad_bias_kernel<T, 31><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        static_cast<T*>(gin), gbias, static_cast<const T*>(gout), static_cast<const T*>(ref), static_cast<uint64_t>(inner),
+        static_cast<uint32_t>(channels), static_cast<uint32_t>(slabs), slab, alpha, scale);
+  else
+    bias_act_grad_bias_kernel<T, 11><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        static_cast<T*>(gin), gbias, static_cast<const T*>(gout), static_cast<const T*>(ref), static_cast<uint64_t>(inner),
+        static_cast<uint32_t>(channels), static_cast<uint32_t>(slabs), slab, alpha, scale);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+}  // namespace fm
+
+extern "C" int fm_bias_act(void* out, const void* x, const void* bias, const void* ref, int64_t n_outer, int64_t channels,
+                           int64_t inner, int act, int grad, float alpha, float scale, int dtype, void* stream) {
+  FM_CHECK_ARG(n_outer >= 0 && channels >= 0 && inner >= 0, "fm_bias_act: negative size");
+  FM_CHECK_ARG(out && x, "fm_bias_act: null tensor");
+  FM_CHECK_ARG(act == 1 || act == 3, "fm_bias_act: act must be 1 (linear) or 3 (lrelu), got %d", act);
+  FM_CHECK_ARG(grad >= 0 && grad <= 2, "fm_bias_act: grad must be 0..2, got %d", grad);
+  FM_CHECK_ARG(grad != 1 || act != 3 || ref != nullptr, "fm_bias_act: grad=1 with lrelu needs ref");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int mode = act * 10 + grad;
+  if (mode != 31) ref = nullptr;  // ref is only read by mode 31 (.cu:42)
+  switch (dtype) {
+    case FM_F32: return fm::dispatch_mode<float>(mode, out, x, bias, ref, n_outer, channels, inner, alpha, scale, st);
+    case FM_F16: return fm::dispatch_mode<__half>(mode, out, x, bias, ref, n_outer, channels, inner, alpha, scale, st);
+    case FM_BF16: return fm::dispatch_mode<__nv_bfloat16>(mode, out, x, bias, ref, n_outer, channels, inner, alpha, scale, st);
+    default: fm::set_error("fm_bias_act: bad dtype %d", dtype); return FM_ERR_INVALID;
+  }
+}
+
+extern "C" int fm_bias_act_grad_bias(void* grad_in, float* grad_bias_f32, const void* grad_out, const void* ref,
+                                     int64_t n_outer, int64_t channels, int64_t inner, int act, float alpha, float scale,
+                                     int dtype, void* stream) {
+  FM_CHECK_ARG(n_outer >= 0 && channels >= 0 && inner >= 0, "fm_bias_act_grad_bias: negative size");
+  FM_CHECK_ARG(grad_in && grad_bias_f32 && grad_out && ref, "fm_bias_act_grad_bias: null tensor");
+  FM_CHECK_ARG(act == 1 || act == 3, "fm_bias_act_grad_bias: act must be 1 or 3, got %d", act);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case FM_F32: return fm::launch_grad_bias<float>(grad_in, grad_bias_f32, grad_out, ref, n_outer, channels, inner, act, alpha, scale, st);
+    case FM_F16: return fm::launch_grad_bias<__half>(grad_in, grad_bias_f32, grad_out, ref, n_outer, channels, inner, act, alpha, scale, st);
+    case FM_BF16: return fm::launch_grad_bias<__nv_bfloat16>(grad_in, grad_bias_f32, grad_out, ref, n_outer, channels, inner, act, alpha, scale, st);
+    default: fm::set_error("fm_bias_act_grad_bias: bad dtype %d", dtype); return FM_ERR_INVALID;
+  }
+}

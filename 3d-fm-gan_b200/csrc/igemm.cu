@@ -1,0 +1,423 @@
+// Implicit-GEMM convolution on tcgen05 / TMEM, fed by TMA (sm_100a).
+//
+// GEMM view:  D[M = B*OH*OW pixels, N = Cout] = sum_{tap, c} A[pixel shifted by tap, c] * W[tap][n][c]
+//   A: NHWC bf16 activations.  One 4-D TMA box (64 channels x tile_w x tile_h x tile_b) per
+//      (tap, channel chunk) lands as a K-major SWIZZLE_128B [128 x 64] operand tile; the conv's
+//      zero padding is TMA out-of-bounds fill, the conv stride is the TMA element stride.
+//   W: bf16 [ntaps][rows][cin], one 2-D TMA box (64 x BLOCK_N) per (tap, chunk), shared by the batch.
+//   D: fp32 in TMEM, double buffered (2 x BLOCK_N columns) so the epilogue of tile i overlaps
+//      the MMAs of tile i+1.
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5
+// epilogue (TMEM lane quarter = warp_idx % 4).  Persistent CTAs, static round-robin tiles.
+//
+// Epilogue (per element; tables staged in smem per tile):
+//   v = acc*T0 + T1 + noise*noise_w (+ residual);  v = v>0 ? v : v*T2;  rgb += v*T[4..6];  out = v*T3
+// which covers demodulation, noise injection, bias, leaky-ReLU*sqrt2, the next layer's style
+// modulation and the fused ToRGB 1x1 conv (stylegan2.py:258-262, 312, 371, 393), and for the
+// encoders folded BatchNorm + ReLU/PReLU/LeakyReLU + residual add.
+//
+// Algorithmic FLOPs per launch: 2 * B*OH*OW * Cin * Cout * ntaps   (SURVEY.md 8d).
+#include "common.cuh"
+
+namespace fm {
+
+constexpr int IG_BM = 128;     // pixels per tile (UMMA M)
+constexpr int IG_BK = 64;      // channels per k-step (128 B rows, SWIZZLE_128B)
+constexpr int IG_THREADS = 192;
+constexpr int IG_TAB_ROWS = 512;  // staged table rows per tile (tile_b_eff * BLOCK_N <= 512)
+
+struct IgemmParams {
+  int OH, OW, B;
+  int tw, th, tb;                  // tile dims, tw*th*tb == 128
+  int tiles_x, tiles_y, tiles_b, tiles_n, num_tiles;
+  int kchunks, ntaps, stride, w_rows, Cout;
+  void* out;
+  int out_H, out_W, out_cstride, out_y0, out_x0, out_ys, out_xs, out_nchw_f32;
+  const float* tab;
+  int tab_bstride;
+  const float* noise;
+  int noise_bstride;
+  const float* noise_w;
+  const __nv_bfloat16* residual;
+  float* rgb;
+  int8_t tap_dy[FM_MAX_TAPS];
+  int8_t tap_dx[FM_MAX_TAPS];
+  int8_t tap_widx[FM_MAX_TAPS];
+};
+
+template <int BN> struct IgemmCfg {
+  static constexpr int A_BYTES = IG_BM * IG_BK * 2;        // 16 KB
+  static constexpr int B_BYTES = BN * IG_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TAB_BYTES = IG_TAB_ROWS * 32;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + TAB_BYTES + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(IG_THREADS, 1)
+igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
+  using Cfg = IgemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_stage = smem;
+  float4* s_tab = reinterpret_cast<float4*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAB_BYTES);
+  uint64_t* full_bar = bars;                        // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + Cfg::STAGES;         // [STAGES]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;     // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]     epilogue -> MMA
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(s_tmem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int kiters = p.ntaps * p.kchunks;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.tiles_n;
+      int m = tile / p.tiles_n;
+      const int bx = m % p.tiles_x; m /= p.tiles_x;
+      const int by = m % p.tiles_y;
+      const int bb = m / p.tiles_y;
+      const int x0 = bx * p.tw * p.stride, y0 = by * p.th * p.stride, b0 = bb * p.tb, n0 = nt * BN;
+      for (int it = 0; it < kiters; ++it) {
+        const int tap = it / p.kchunks;
+        const int kc = it - tap * p.kchunks;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = s_stage + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(sa, &tmA, &full_bar[stage], kc * IG_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kc * IG_BK, p.tap_widx[tap] * p.w_rows + n0);
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    constexpr uint32_t idesc = umma_idesc_bf16(IG_BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int titer = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++titer) {
+      const int buf = titer & 1;
+      const uint32_t aphase = (titer >> 1) & 1;
+      mbar_wait(&tempty_bar[buf], aphase ^ 1);     // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * BN;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(&full_bar[stage], phase);        // TMA bytes have landed
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(s_stage + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_smem_desc_sw128(sa);
+          const uint64_t bdesc = umma_smem_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < IG_BK / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs finish
+          if (it == kiters - 1) umma_commit(&tfull_bar[buf]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // pixel index inside the tile
+    const int etid = threadIdx.x - 64;      // 0..127
+    const int tbe = p.tab_bstride ? p.tb : 1;
+    const float nw = p.noise ? (p.noise_w ? __ldg(p.noise_w) : 1.f) : 0.f;
+    int titer = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++titer) {
+      const int buf = titer & 1;
+      const uint32_t aphase = (titer >> 1) & 1;
+      const int nt = tile % p.tiles_n;
+      int m = tile / p.tiles_n;
+      const int bx = m % p.tiles_x; m /= p.tiles_x;
+      const int by = m % p.tiles_y;
+      const int bb = m / p.tiles_y;
+      const int n0 = nt * BN;
+      const int lx = row % p.tw;
+      const int ly = (row / p.tw) % p.th;
+      const int lb = row / (p.tw * p.th);
+      const int ox = bx * p.tw + lx, oy = by * p.th + ly, b = bb * p.tb + lb;
+      const bool valid = ox < p.OW && oy < p.OH && b < p.B;
+
+      // ---- stage this tile's epilogue tables (overlaps the tile's MMAs)
+      for (int i = etid; i < tbe * BN; i += 128) {
+        const int sb = i / BN, j = i - sb * BN;
+        const int o = n0 + j;
+        const int bsrc = p.tab_bstride ? (bb * p.tb + sb) : 0;
+        float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+        if (o < p.Cout && bsrc < p.B) {
+          const float4* src = reinterpret_cast<const float4*>(p.tab + (static_cast<size_t>(bsrc) * p.Cout + o) * 8);
+          t0 = __ldg(src);
+          t1 = __ldg(src + 1);
+        }
+        s_tab[2 * i] = t0;
+        s_tab[2 * i + 1] = t1;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      const int Y = oy * p.out_ys + p.out_y0, X = ox * p.out_xs + p.out_x0;
+      float nz = 0.f;
+      if (valid && p.noise)
+        nz = nw * __ldg(p.noise + (static_cast<size_t>(p.noise_bstride ? b : 0) * p.out_H + Y) * p.out_W + X);
+      const size_t pix = (static_cast<size_t>(b) * p.out_H + Y) * p.out_W + X;
+      const float4* trow = s_tab + static_cast<size_t>(p.tab_bstride ? lb : 0) * BN * 2;
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+
+      mbar_wait(&tfull_bar[buf], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c * 32, acc);
+        tmem_ld_wait();
+        const int o0 = n0 + c * 32;
+        if (o0 >= p.out_cstride && !(p.out_nchw_f32 && o0 < p.Cout)) continue;   // nothing to write (warp-uniform)
+        float v[32];
+        uint4 resv[4];
+        if (p.residual && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.out_cstride + o0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) resv[g] = (o0 + 8 * g < p.out_cstride) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 t0 = trow[2 * (c * 32 + j)];
+          float x = fmaf(__uint_as_float(acc[j]), t0.x, t0.y + nz);
+          if (p.residual) {
+            const uint32_t w = reinterpret_cast<const uint32_t*>(resv)[j >> 1];
+            const float2 f = unpack_bf16x2(w);
+            x += (j & 1) ? f.y : f.x;
+          }
+          x = x > 0.f ? x : x * t0.z;
+          if (p.rgb) {
+            const float4 t1 = trow[2 * (c * 32 + j) + 1];
+            r0 = fmaf(x, t1.x, r0);
+            r1 = fmaf(x, t1.y, r1);
+            r2 = fmaf(x, t1.z, r2);
+          }
+          v[j] = x * t0.w;
+        }
+        if (valid) {
+          if (p.out_nchw_f32) {
+            float* op = static_cast<float*>(p.out);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (o0 + j < p.Cout)
+                op[((static_cast<size_t>(b) * p.Cout + o0 + j) * p.out_H + Y) * p.out_W + X] = v[j];
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.out_cstride + o0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (o0 + 8 * g < p.out_cstride) {
+                uint4 w;
+                w.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+                w.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+                w.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+                w.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+                op[g] = w;
+              }
+            }
+          }
+        }
+      }
+      // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (p.rgb && valid) {
+        float* rp = p.rgb + pix * 4;
+        if (p.tiles_n == 1) {
+          *reinterpret_cast<float4*>(rp) = make_float4(r0, r1, r2, 0.f);
+        } else {
+          atomicAdd(rp + 0, r0);
+          atomicAdd(rp + 1, r1);
+          atomicAdd(rp + 2, r2);
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");   // tables are free to be overwritten
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+template <int BN>
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
+  using Cfg = IgemmCfg<BN>;
+  static bool attr_set = false;   // per-process, per-instantiation; benign race
+  if (!attr_set) {
+    FM_CUDA_OK(cudaFuncSetAttribute(igemm_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  igemm_conv_kernel<BN><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+}  // namespace fm
+
+extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
+  using namespace fm;
+  FM_CHECK_ARG(d != nullptr, "fm_conv_igemm: null desc");
+  FM_CHECK_ARG(d->x && d->w && d->out && d->tab, "fm_conv_igemm: null tensor");
+  FM_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "fm_conv_igemm: bad sizes");
+  FM_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= FM_MAX_TAPS, "fm_conv_igemm: ntaps %d out of range", d->ntaps);
+  FM_CHECK_ARG(d->stride == 1 || d->stride == 2, "fm_conv_igemm: stride must be 1 or 2");
+  FM_CHECK_ARG(d->x_cstride % 8 == 0 && d->x_cstride >= d->Cin, "fm_conv_igemm: x_cstride must be a multiple of 8 and >= Cin");
+  FM_CHECK_ARG(d->w_cstride % 8 == 0 && d->w_cstride >= d->Cin, "fm_conv_igemm: w_cstride must be a multiple of 8 and >= Cin");
+  FM_CHECK_ARG(d->w_rows >= d->Cout, "fm_conv_igemm: w_rows < Cout");
+  FM_CHECK_ARG((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "fm_conv_igemm: tensors must be 16-byte aligned");
+  FM_CHECK_ARG(d->out_nchw_f32 || (d->out_cstride % 8 == 0 && d->out_cstride >= d->Cout),
+               "fm_conv_igemm: out_cstride must be a multiple of 8 and >= Cout");
+  FM_CHECK_ARG(d->OH > 0 && d->OW > 0 && d->out_ys >= 1 && d->out_xs >= 1, "fm_conv_igemm: bad output grid");
+  FM_CHECK_ARG((d->OH - 1) * d->out_ys + d->out_y0 < d->out_H && (d->OW - 1) * d->out_xs + d->out_x0 < d->out_W,
+               "fm_conv_igemm: output grid does not fit the output tensor");
+  FM_CHECK_ARG(!(d->residual && d->out_nchw_f32), "fm_conv_igemm: residual needs NHWC output");
+
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) { set_error("fm_conv_igemm: cuTensorMapEncodeTiled driver entry point unavailable"); return FM_ERR_NO_DEVICE; }
+
+  IgemmParams p{};
+  p.OH = d->OH; p.OW = d->OW; p.B = d->B;
+  // ---- tile shape: tw*th*tb = 128 pixels
+  int tw = d->tile_w, th = d->tile_h;
+  if (tw <= 0 || th <= 0) {
+    tw = 1; while (tw < d->OW && tw < 128) tw <<= 1;
+    th = 1; while (th < d->OH && tw * th < 128) th <<= 1;
+  }
+  FM_CHECK_ARG(tw >= 1 && th >= 1 && 128 % (tw * th) == 0, "fm_conv_igemm: tile %dx%d does not divide 128", tw, th);
+  p.tw = tw; p.th = th; p.tb = 128 / (tw * th);
+  FM_CHECK_ARG(tw * d->stride <= 256 && th * d->stride <= 256 && p.tb <= 256, "fm_conv_igemm: TMA box too large");
+  p.tiles_x = (d->OW + tw - 1) / tw;
+  p.tiles_y = (d->OH + th - 1) / th;
+  p.tiles_b = (d->B + p.tb - 1) / p.tb;
+  // ---- block_n
+  const int tbe = d->tab_bstride ? p.tb : 1;
+  int bn = d->block_n;
+  if (bn <= 0) {
+    bn = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
+    // small problems: more, narrower tiles fill more SMs
+    const int sms = sm_count();
+    while (bn > 64 && static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.tiles_b * ((d->Cout + bn - 1) / bn) < sms) bn >>= 1;
+  }
+  while (bn > 64 && tbe * bn > IG_TAB_ROWS) bn >>= 1;
+  FM_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "fm_conv_igemm: block_n must be 64/128/256");
+  FM_CHECK_ARG(tbe * bn <= IG_TAB_ROWS, "fm_conv_igemm: per-sample tables do not fit (tile_b %d x block_n %d)", tbe, bn);
+  p.tiles_n = (d->Cout + bn - 1) / bn;
+  const int64_t nt = static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.tiles_b * p.tiles_n;
+  FM_CHECK_ARG(nt < 0x7FFFFFFF, "fm_conv_igemm: too many tiles");
+  p.num_tiles = static_cast<int>(nt);
+  p.kchunks = (d->Cin + IG_BK - 1) / IG_BK;
+  p.ntaps = d->ntaps; p.stride = d->stride; p.w_rows = d->w_rows; p.Cout = d->Cout;
+  p.out = d->out; p.out_H = d->out_H; p.out_W = d->out_W; p.out_cstride = d->out_cstride;
+  p.out_y0 = d->out_y0; p.out_x0 = d->out_x0; p.out_ys = d->out_ys; p.out_xs = d->out_xs;
+  p.out_nchw_f32 = d->out_nchw_f32;
+  p.tab = d->tab; p.tab_bstride = d->tab_bstride ? 1 : 0;
+  p.noise = d->noise; p.noise_bstride = d->noise_bstride ? 1 : 0; p.noise_w = d->noise_w;
+  p.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  p.rgb = d->rgb;
+  int max_widx = 0;
+  for (int i = 0; i < d->ntaps; ++i) {
+    p.tap_dy[i] = d->tap_dy[i]; p.tap_dx[i] = d->tap_dx[i]; p.tap_widx[i] = d->tap_widx[i];
+    FM_CHECK_ARG(d->tap_widx[i] >= 0, "fm_conv_igemm: negative tap_widx");
+    if (d->tap_widx[i] > max_widx) max_widx = d->tap_widx[i];
+  }
+
+  // ---- tensor maps
+  CUtensorMap tmA, tmB;
+  {
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->Cin), static_cast<cuuint64_t>(d->W), static_cast<cuuint64_t>(d->H),
+                                static_cast<cuuint64_t>(d->B)};
+    const cuuint64_t cs = static_cast<cuuint64_t>(d->x_cstride) * 2;
+    const cuuint64_t strides[3] = {cs, cs * d->W, cs * d->W * d->H};
+    // with an element stride s TMA loads ceil(box/s) elements: box = n*s loads n
+    const cuuint32_t box[4] = {IG_BK, static_cast<cuuint32_t>(tw * d->stride), static_cast<cuuint32_t>(th * d->stride),
+                               static_cast<cuuint32_t>(p.tb)};
+    const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d->stride), static_cast<cuuint32_t>(d->stride), 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("fm_conv_igemm: cuTensorMapEncodeTiled(A) failed with CUresult %d", (int)r); return FM_ERR_CUDA; }
+  }
+  {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d->Cin), static_cast<cuuint64_t>(max_widx + 1) * d->w_rows};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d->w_cstride) * 2};
+    const cuuint32_t box[2] = {IG_BK, static_cast<cuuint32_t>(bn)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("fm_conv_igemm: cuTensorMapEncodeTiled(B) failed with CUresult %d", (int)r); return FM_ERR_CUDA; }
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 64: return launch_igemm<64>(tmA, tmB, p, st);
+    case 128: return launch_igemm<128>(tmA, tmB, p, st);
+    default: return launch_igemm<256>(tmA, tmB, p, st);
+  }
+}

@@ -1,0 +1,395 @@
+// Bandwidth-bound helper kernels of the synthesis path (sm_100a): style affine, epilogue
+// tables (demodulation), layout converts, the fused blur+noise+bias+lrelu pass after the
+// stride-2 transposed conv, the ToRGB tail and weight preparation.
+#include "common.cuh"
+
+namespace fm {
+
+// ------------------------------------------------------------------------------------
+// s[b,i] = latent[b, idx, :] . (wmod[i,:] * 1/sqrt(D)) + bmod[i]
+// EqualLinear(style_dim, cin, bias_init=1), stylegan2.py:165-175, 240, 257.
+// grid (ceil(max_cin/8), n_layers); one warp per output channel, all samples.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) style_affine_kernel(const fm_style_layer* __restrict__ layers,
+                                                           const float* __restrict__ latent, int B, int n_latent,
+                                                           int D, float scale) {
+  const fm_style_layer L = layers[blockIdx.y];
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= L.cin) return;
+  const float* w = L.wmod + static_cast<size_t>(i) * D;
+  const float bias = __ldg(L.bmod + i);
+  for (int b = 0; b < B; ++b) {
+    const float* x = latent + (static_cast<size_t>(b) * n_latent + L.latent_idx) * D;
+    float acc = 0.f;
+    for (int k = lane; k < D; k += 32) acc = fmaf(__ldg(w + k) * scale, __ldg(x + k), acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) L.s[static_cast<size_t>(b) * L.cin + i] = acc + bias;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Epilogue tables, one warp per (layer, out channel), all samples.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_tables_kernel(const fm_table_layer* __restrict__ layers, int B) {
+  const fm_table_layer L = layers[blockIdx.y];
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= L.cout) return;
+  const float rgb_scale = rsqrtf(static_cast<float>(L.cout));   // ToRGB fan_in = cout*1*1 (stylegan2.py:232-233)
+  for (int b = 0; b < B; ++b) {
+    float d = 1.f;
+    if (L.wsq) {
+      const float* s = L.s + static_cast<size_t>(b) * L.cin;
+      const float* q = L.wsq + static_cast<size_t>(o) * L.cin;
+      float acc = 0.f;
+      for (int i = lane; i < L.cin; i += 32) {
+        const float sv = __ldg(s + i);
+        acc = fmaf(sv * sv, __ldg(q + i), acc);
+      }
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+      d = rsqrtf(acc + 1e-8f);                                   // stylegan2.py:261 (literal 1e-8)
+    }
+    if (lane == 0) {
+      float* t = L.tab + (static_cast<size_t>(b) * L.cout + o) * 8;
+      float4 t0, t1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      t0.x = d;
+      t0.y = L.act_bias ? __ldg(L.act_bias + o) : 0.f;
+      t0.z = L.slope;
+      t0.w = L.gain * (L.s_next ? __ldg(L.s_next + static_cast<size_t>(b) * L.cout + o) : 1.f);
+      if (L.wrgb) {
+        const float sr = __ldg(L.s_rgb + static_cast<size_t>(b) * L.cout + o) * L.gain;
+        t1.x = rgb_scale * __ldg(L.wrgb + o) * sr;
+        t1.y = rgb_scale * __ldg(L.wrgb + L.cout + o) * sr;
+        t1.z = rgb_scale * __ldg(L.wrgb + 2 * L.cout + o) * sr;
+      }
+      *reinterpret_cast<float4*>(t) = t0;
+      *reinterpret_cast<float4*>(t + 4) = t1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// layout converts
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x,
+                                                           const float* __restrict__ scale, int C, int HW, int cs,
+                                                           int64_t total) {
+  const int groups = cs / 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int pix = static_cast<int>(idx % HW);
+    const int64_t t = idx / HW;
+    const int g = static_cast<int>(t % groups);
+    const int64_t b = t / groups;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      float f = 0.f;
+      if (c < C) {
+        f = x[(b * C + c) * HW + pix];
+        if (scale) f *= __ldg(scale + b * C + c);
+      }
+      v[j] = f;
+    }
+    uint4 w;
+    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + (b * HW + pix) * cs + g * 8) = w;
+  }
+}
+
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(float* __restrict__ out, const __nv_bfloat16* __restrict__ x,
+                                                           const float* __restrict__ inv_scale, int C, int HW, int cs,
+                                                           int64_t total) {
+  const int groups = (C + 7) / 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int pix = static_cast<int>(idx % HW);
+    const int64_t t = idx / HW;
+    const int g = static_cast<int>(t % groups);
+    const int64_t b = t / groups;
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(x + (b * HW + pix) * cs + g * 8));
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      if (c < C) {
+        const float2 f = unpack_bf16x2(ws[j >> 1]);
+        float v = (j & 1) ? f.y : f.x;
+        if (inv_scale) v /= __ldg(inv_scale + b * C + c);
+        out[(b * C + c) * HW + pix] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// blur (4x4 FIR, pad (1,1)) + demod + noise + bias + lrelu + next style, NHWC bf16.
+// t [B, OH+1, OW+1, cs] -> out [B, OH, OW, cs].  Replaces Blur (stylegan2.py:279 ->
+// upfirdn2d mode 1), NoiseInjection (:312) and FusedLeakyReLU (:371) after the stride-2
+// transposed conv.  Each thread owns 8 channels of a 2x2 output block: 25 16-byte loads
+// feed 4 outputs (6.25 loads/output instead of 16).
+// Algorithmic bytes per output pixel-channel: 2 B read ((OH+1)(OW+1)/(OH*OW) ~ 1) + 2 B write.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) blur_act_nhwc_kernel(__nv_bfloat16* __restrict__ out,
+                                                            const __nv_bfloat16* __restrict__ t,
+                                                            const float* __restrict__ kernel, const float* __restrict__ tab,
+                                                            const float* __restrict__ noise, int noise_bstride,
+                                                            const float* __restrict__ noise_w, int B, int OH, int OW, int C,
+                                                            int cs, int64_t total) {
+  __shared__ float s_k[16];
+  if (threadIdx.x < 16) {
+    const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
+    s_k[threadIdx.x] = kernel[(3 - a) * 4 + (3 - b)];   // flipped taps (true convolution)
+  }
+  __syncthreads();
+  const int groups = cs / 8;
+  const int bw = (OW + 1) / 2, bh = (OH + 1) / 2;
+  const int IH = OH + 1, IW = OW + 1;
+  const float nw = noise ? (noise_w ? __ldg(noise_w) : 1.f) : 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int g = static_cast<int>(idx % groups);
+    int64_t r = idx / groups;
+    const int bxp = static_cast<int>(r % bw); r /= bw;
+    const int byp = static_cast<int>(r % bh);
+    const int b = static_cast<int>(r / bh);
+    const int X0 = bxp * 2, Y0 = byp * 2;
+    float acc[2][2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][j][c] = 0.f;
+    const __nv_bfloat16* tb = t + static_cast<size_t>(b) * IH * IW * cs + g * 8;
+#pragma unroll
+    for (int ry = 0; ry < 5; ++ry) {
+      const int iy = Y0 - 1 + ry;
+      if (iy < 0 || iy >= IH) continue;
+#pragma unroll
+      for (int rx = 0; rx < 5; ++rx) {
+        const int ix = X0 - 1 + rx;
+        if (ix < 0 || ix >= IW) continue;
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(tb + (static_cast<size_t>(iy) * IW + ix) * cs));
+        float v[8];
+        float2 f;
+        f = unpack_bf16x2(w.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(w.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(w.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(w.w); v[6] = f.x; v[7] = f.y;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int a = ry - i;           // tap row for output row Y0+i
+          if (a < 0 || a > 3) continue;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int bb = rx - j;
+            if (bb < 0 || bb > 3) continue;
+            const float kv = s_k[a * 4 + bb];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[i][j][c] = fmaf(v[c], kv, acc[i][j][c]);
+          }
+        }
+      }
+    }
+    float4 tabv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int o = g * 8 + c;
+      tabv[c] = o < C ? __ldg(reinterpret_cast<const float4*>(tab + (static_cast<size_t>(b) * C + o) * 8))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int Y = Y0 + i;
+      if (Y >= OH) continue;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int X = X0 + j;
+        if (X >= OW) continue;
+        float nz = 0.f;
+        if (noise) nz = nw * __ldg(noise + (static_cast<size_t>(noise_bstride ? b : 0) * OH + Y) * OW + X);
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float x = fmaf(acc[i][j][c], tabv[c].x, tabv[c].y + nz);
+          x = x > 0.f ? x : x * tabv[c].z;
+          v[c] = x * tabv[c].w;
+        }
+        uint4 w;
+        w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+        w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * OH + Y) * OW + X) * cs + g * 8) = w;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// ToRGB tail: rgb_out = acc + bias + Upsample(skip)   (stylegan2.py:394-399; Upsample =
+// upfirdn2d(up=2, pad=(2,1)) with kernel*4, stylegan2.py:52-63).  One thread per pixel.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rgb_finalize_kernel(float* __restrict__ rgb_out, float* __restrict__ acc,
+                                                           const float* __restrict__ bias3, const float* __restrict__ skip,
+                                                           const float* __restrict__ kernel, int H, int W, int64_t total) {
+  __shared__ float s_k[16];
+  if (threadIdx.x < 16) {
+    const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
+    s_k[threadIdx.x] = kernel ? kernel[(3 - a) * 4 + (3 - b)] : 0.f;
+  }
+  __syncthreads();
+  const int h2 = H / 2, w2 = W / 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int x = static_cast<int>(idx % W);
+    const int y = static_cast<int>((idx / W) % H);
+    const int64_t b = idx / (static_cast<int64_t>(W) * H);
+    float4* ap = reinterpret_cast<float4*>(acc + idx * 4);
+    const float4 a = *ap;
+    *ap = make_float4(0.f, 0.f, 0.f, 0.f);
+    float v[3] = {a.x + __ldg(bias3 + 0), a.y + __ldg(bias3 + 1), a.z + __ldg(bias3 + 2)};
+    if (skip) {
+      float up[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ta = 0; ta < 4; ++ta) {
+        const int u = y + ta - 2;             // row in the zero-stuffed image
+        if (u < 0 || (u & 1) || (u >> 1) >= h2) continue;
+#pragma unroll
+        for (int tb = 0; tb < 4; ++tb) {
+          const int w = x + tb - 2;
+          if (w < 0 || (w & 1) || (w >> 1) >= w2) continue;
+          const float kv = s_k[ta * 4 + tb];
+          const size_t off = (static_cast<size_t>(u >> 1)) * w2 + (w >> 1);
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            up[c] = fmaf(__ldg(skip + (b * 3 + c) * static_cast<size_t>(h2) * w2 + off), kv, up[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] += up[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb_out[((b * 3 + c) * H + y) * static_cast<size_t>(W) + x] = v[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// weight prep: [cout][cin][kh][kw] fp32 -> bf16 [tap][cout_rows][cin_stride] (scaled), and
+// wsq[cout][cin] = sum_taps (scale*W)^2 for the demodulation table.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_weight_kernel(__nv_bfloat16* __restrict__ wq, float* __restrict__ wsq,
+                                                          const float* __restrict__ w, int cout, int cin, int taps,
+                                                          float scale, int cout_rows, int cin_stride, int64_t total) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int i = static_cast<int>(idx % cin_stride);
+    const int o = static_cast<int>(idx / cin_stride);   // 0..cout_rows-1
+    float sq = 0.f;
+    for (int t = 0; t < taps; ++t) {
+      float v = 0.f;
+      if (o < cout && i < cin) v = w[(static_cast<size_t>(o) * cin + i) * taps + t] * scale;
+      sq = fmaf(v, v, sq);
+      wq[(static_cast<size_t>(t) * cout_rows + o) * cin_stride + i] = __float2bfloat16_rn(v);
+    }
+    if (wsq && o < cout && i < cin) wsq[static_cast<size_t>(o) * cin + i] = sq;
+  }
+}
+
+static inline unsigned grid_for(int64_t total, int per_block = 256, int waves = 16) {
+  int64_t want = (total + per_block - 1) / per_block;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * waves;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<unsigned>(want);
+}
+
+}  // namespace fm
+
+using namespace fm;
+
+extern "C" int fm_style_affine(const fm_style_layer* layers_dev, int n_layers, int max_cin, const float* latent, int B,
+                               int n_latent, int style_dim, void* stream) {
+  FM_CHECK_ARG(layers_dev && latent && n_layers > 0 && max_cin > 0 && B > 0 && style_dim > 0, "fm_style_affine: bad args");
+  dim3 grid((max_cin + 7) / 8, n_layers);
+  style_affine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(layers_dev, latent, B, n_latent, style_dim,
+                                                                           1.0f / sqrtf(static_cast<float>(style_dim)));
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_build_tables(const fm_table_layer* layers_dev, int n_layers, int max_cout, int B, void* stream) {
+  FM_CHECK_ARG(layers_dev && n_layers > 0 && max_cout > 0 && B > 0, "fm_build_tables: bad args");
+  dim3 grid((max_cout + 7) / 8, n_layers);
+  build_tables_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(layers_dev, B);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_nchw_to_nhwc_bf16(void* out, const float* x, const float* scale_bc, int B, int C, int H, int W,
+                                    int out_cstride, void* stream) {
+  FM_CHECK_ARG(out && x && B > 0 && C > 0 && H > 0 && W > 0, "fm_nchw_to_nhwc_bf16: bad args");
+  FM_CHECK_ARG(out_cstride % 8 == 0 && out_cstride >= C, "fm_nchw_to_nhwc_bf16: cstride must be a multiple of 8 >= C");
+  const int64_t total = static_cast<int64_t>(B) * (out_cstride / 8) * H * W;
+  nchw_to_nhwc_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(out), x, scale_bc, C, H * W, out_cstride, total);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_nhwc_bf16_to_nchw(float* out, const void* x, const float* inv_scale_bc, int B, int C, int H, int W,
+                                    int x_cstride, void* stream) {
+  FM_CHECK_ARG(out && x && B > 0 && C > 0 && H > 0 && W > 0, "fm_nhwc_bf16_to_nchw: bad args");
+  FM_CHECK_ARG(x_cstride % 8 == 0 && x_cstride >= C, "fm_nhwc_bf16_to_nchw: cstride must be a multiple of 8 >= C");
+  const int64_t total = static_cast<int64_t>(B) * ((C + 7) / 8) * H * W;
+  nhwc_to_nchw_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out, static_cast<const __nv_bfloat16*>(x), inv_scale_bc, C, H * W, x_cstride, total);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4, const float* tab, const float* noise,
+                                int noise_bstride, const float* noise_w, int B, int OH, int OW, int C, int cstride,
+                                void* stream) {
+  FM_CHECK_ARG(out && t && kernel4x4 && tab && B > 0 && OH > 0 && OW > 0 && C > 0, "fm_blur_act_nhwc: bad args");
+  FM_CHECK_ARG(cstride % 8 == 0 && cstride >= C, "fm_blur_act_nhwc: cstride must be a multiple of 8 >= C");
+  const int64_t total = static_cast<int64_t>(B) * ((OH + 1) / 2) * ((OW + 1) / 2) * (cstride / 8);
+  blur_act_nhwc_kernel<<<grid_for(total, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(t), kernel4x4, tab, noise, noise_bstride, noise_w,
+      B, OH, OW, C, cstride, total);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_rgb_finalize(float* rgb_out, float* acc, const float* bias3, const float* skip, const float* kernel4x4,
+                               int B, int H, int W, void* stream) {
+  FM_CHECK_ARG(rgb_out && acc && bias3 && B > 0 && H > 0 && W > 0, "fm_rgb_finalize: bad args");
+  FM_CHECK_ARG(!skip || (kernel4x4 && H % 2 == 0 && W % 2 == 0), "fm_rgb_finalize: skip needs a kernel and even H, W");
+  const int64_t total = static_cast<int64_t>(B) * H * W;
+  rgb_finalize_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(rgb_out, acc, bias3, skip, kernel4x4,
+                                                                                     H, W, total);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_prep_weight(void* wq, float* wsq, const float* w_oikk, int cout, int cin, int kh, int kw, float scale,
+                              int cout_rows, int cin_stride, void* stream) {
+  FM_CHECK_ARG(wq && w_oikk && cout > 0 && cin > 0 && kh > 0 && kw > 0, "fm_prep_weight: bad args");
+  FM_CHECK_ARG(cout_rows >= cout && cin_stride >= cin && cin_stride % 8 == 0, "fm_prep_weight: bad padded sizes");
+  const int64_t total = static_cast<int64_t>(cout_rows) * cin_stride;
+  prep_weight_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(wq), wsq, w_oikk, cout, cin, kh * kw, scale, cout_rows, cin_stride, total);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}

@@ -1,0 +1,98 @@
+"""ctypes binding of libfm3d.so (the C ABI declared in include/fm3d.h).
+
+The library is built in-tree by ``csrc/build.sh`` (``__graft_entry__.build()``).  There is
+no fallback: if the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfm3d.so")
+
+FM_F32, FM_F16, FM_BF16 = 0, 1, 2
+FM_MAX_TAPS = 49
+
+
+class ConvDesc(C.Structure):
+    """fm_conv_desc (include/fm3d.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
+        ("x_cstride", C.c_int32),
+        ("w", C.c_void_p), ("ntaps", C.c_int32), ("Cout", C.c_int32), ("w_rows", C.c_int32), ("w_cstride", C.c_int32),
+        ("tap_dy", C.c_int8 * FM_MAX_TAPS), ("tap_dx", C.c_int8 * FM_MAX_TAPS), ("tap_widx", C.c_int8 * FM_MAX_TAPS),
+        ("stride", C.c_int32),
+        ("OH", C.c_int32), ("OW", C.c_int32),
+        ("out", C.c_void_p),
+        ("out_H", C.c_int32), ("out_W", C.c_int32), ("out_cstride", C.c_int32), ("out_y0", C.c_int32),
+        ("out_x0", C.c_int32), ("out_ys", C.c_int32), ("out_xs", C.c_int32), ("out_nchw_f32", C.c_int32),
+        ("tab", C.c_void_p), ("tab_bstride", C.c_int32),
+        ("noise", C.c_void_p), ("noise_bstride", C.c_int32), ("noise_w", C.c_void_p),
+        ("residual", C.c_void_p), ("rgb", C.c_void_p),
+        ("block_n", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32),
+    ]
+
+
+class StyleLayer(C.Structure):
+    """fm_style_layer."""
+    _fields_ = [("wmod", C.c_void_p), ("bmod", C.c_void_p), ("s", C.c_void_p),
+                ("cin", C.c_int32), ("latent_idx", C.c_int32)]
+
+
+class TableLayer(C.Structure):
+    """fm_table_layer."""
+    _fields_ = [("s", C.c_void_p), ("wsq", C.c_void_p), ("act_bias", C.c_void_p), ("s_next", C.c_void_p),
+                ("wrgb", C.c_void_p), ("s_rgb", C.c_void_p), ("tab", C.c_void_p),
+                ("cin", C.c_int32), ("cout", C.c_int32), ("slope", C.c_float), ("gain", C.c_float)]
+
+
+_SIGNATURES = {
+    "fm_version": (C.c_int, []),
+    "fm_last_error": (C.c_char_p, []),
+    "fm_launch_count": (C.c_int64, []),
+    "fm_bias_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                              C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "fm_bias_act_grad_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                        C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "fm_upfirdn2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int] * 12 + [C.c_int, C.c_void_p]),
+    "fm_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "fm_style_affine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fm_build_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fm_nchw_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    "fm_nhwc_bf16_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    "fm_blur_act_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+                         + [C.c_int] * 5 + [C.c_void_p]),
+    "fm_rgb_finalize": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p]),
+    "fm_prep_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                 C.c_int, C.c_int, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
+
+_lib = None
+
+
+def lib():
+    """Load libfm3d.so (once).  Fails loudly: the product has no CPU / PyTorch fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"libfm3d.so not found at {LIB_PATH}: build it with 3d-fm-gan_b200/csrc/build.sh "
+                "(or __graft_entry__.build()); there is no fallback path")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().fm_last_error()
+        raise RuntimeError(f"{what} failed (fm_status {status}): {msg.decode() if msg else ''}")
+
+
+def launch_count():
+    return int(lib().fm_launch_count())

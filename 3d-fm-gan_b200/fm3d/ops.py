@@ -1,0 +1,215 @@
+"""Tensor-level wrappers over the C ABI: unpack torch tensors (device pointer, sizes,
+current stream), allocate outputs, call libfm3d.  Mirrors what the reference's pybind
+shims do (op/fused_bias_act.cpp:11-17, op/upfirdn2d.cpp:12-19): CUDA checks, contiguity,
+``torch.empty`` outputs, current-stream semantics.  No CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, FM_BF16, FM_F16, FM_F32
+
+_DTYPES = {torch.float32: FM_F32, torch.float16: FM_F16, torch.bfloat16: FM_BF16}
+
+
+def _dtype_code(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"libfm3d: unsupported dtype {t.dtype} (float32, float16, bfloat16 only)")
+
+
+def _check_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (libfm3d has no CPU path)")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------ bias + activation
+def bias_act(x, bias=None, ref=None, act=3, grad=0, alpha=0.2, scale=2 ** 0.5):
+    """fused_bias_act(input, bias, refer, act, grad, alpha, scale) of the reference
+    (op/fused_bias_act.cpp:11-17); ``None`` / empty tensors mean "absent" (.cu:62-63)."""
+    _check_cuda(x, "input")
+    x = x.contiguous()
+    if bias is not None and bias.numel() == 0:
+        bias = None
+    if ref is not None and ref.numel() == 0:
+        ref = None
+    if bias is not None:
+        _check_cuda(bias, "bias")
+        bias = bias.contiguous().to(x.dtype)
+    if ref is not None:
+        ref = ref.contiguous().to(x.dtype)
+        if ref.numel() != x.numel():
+            raise RuntimeError("refer must have as many elements as input")
+    out = torch.empty_like(x)
+    if x.numel() == 0:
+        return out
+    if x.ndim >= 2:
+        n_outer, channels = x.shape[0], x.shape[1]
+        inner = x.numel() // (n_outer * channels)
+    else:                       # 1-D: the reference's step_b = 1, bias indexed by xi % size_b
+        n_outer, channels, inner = 1, x.shape[0], 1
+    if bias is not None and bias.numel() != channels:
+        raise RuntimeError(f"bias has {bias.numel()} elements, expected {channels}")
+    with torch.cuda.device(x.device):
+        st = _lib.lib().fm_bias_act(_ptr(out), _ptr(x), _ptr(bias), _ptr(ref), n_outer, channels, inner,
+                                    int(act), int(grad), float(alpha), float(scale), _dtype_code(x), _stream())
+    _lib.check(st, "fm_bias_act")
+    return out
+
+
+def bias_act_grad_bias(grad_out, ref, act=3, alpha=0.2, scale=2 ** 0.5):
+    """Gradient w.r.t. the input plus the per-channel bias gradient in one pass."""
+    _check_cuda(grad_out, "grad_output")
+    g = grad_out.contiguous()
+    ref = ref.contiguous().to(g.dtype)
+    gin = torch.empty_like(g)
+    if g.ndim >= 2:
+        n_outer, channels = g.shape[0], g.shape[1]
+        inner = g.numel() // max(n_outer * channels, 1)
+    else:
+        n_outer, channels, inner = 1, g.shape[0], 1
+    gb = torch.zeros(channels, device=g.device, dtype=torch.float32)
+    if g.numel():
+        with torch.cuda.device(g.device):
+            st = _lib.lib().fm_bias_act_grad_bias(_ptr(gin), _ptr(gb), _ptr(g), _ptr(ref), n_outer, channels, inner,
+                                                  int(act), float(alpha), float(scale), _dtype_code(g), _stream())
+        _lib.check(st, "fm_bias_act_grad_bias")
+    return gin, gb.to(g.dtype)
+
+
+# ------------------------------------------------------------------ upfirdn2d
+def upfirdn2d_planes(x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
+    """x [..., H, W] -> [..., out_h, out_w] (the reference's [major,H,W,1] layout,
+    op/upfirdn2d.py:108)."""
+    _check_cuda(x, "input")
+    _check_cuda(kernel, "kernel")
+    x = x.contiguous()
+    k = kernel.contiguous().to(torch.float32)
+    in_h, in_w = x.shape[-2], x.shape[-1]
+    kh, kw = k.shape
+    out_h = (in_h * up_y + pad_y0 + pad_y1 - kh + down_y) // down_y     # op/upfirdn2d_kernel.cu:237
+    out_w = (in_w * up_x + pad_x0 + pad_x1 - kw + down_x) // down_x
+    out_h, out_w = max(out_h, 0), max(out_w, 0)
+    planes = x.numel() // max(in_h * in_w, 1) if in_h * in_w else 0
+    out = torch.empty(*x.shape[:-2], out_h, out_w, device=x.device, dtype=x.dtype)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(x.device):
+        st = _lib.lib().fm_upfirdn2d(_ptr(out), _ptr(x), _ptr(k), planes, in_h, in_w, kh, kw,
+                                     up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1,
+                                     _dtype_code(x), _stream())
+    _lib.check(st, "fm_upfirdn2d")
+    return out
+
+
+# ------------------------------------------------------------------ implicit-GEMM conv
+def conv_taps(kh, kw, pad):
+    """Tap list (dy, dx, weight slab) of a plain correlation (F.conv2d semantics)."""
+    return [(ky - pad, kx - pad, ky * kw + kx) for ky in range(kh) for kx in range(kw)]
+
+
+def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_rows=None,
+               out_H=None, out_W=None, out_y0=0, out_x0=0, out_ys=1, out_xs=1, out_nchw_f32=False,
+               tab_per_sample=False, noise=None, noise_per_sample=True, noise_w=None, residual=None,
+               rgb=None, block_n=0, tile_w=0, tile_h=0):
+    """Launch fm_conv_igemm.  x: bf16 NHWC [B,H,W,cs]; w: bf16 [slabs, w_rows, cin_stride];
+    out: bf16 NHWC [B,out_H,out_W,cs_out] or fp32 NCHW; tab: fp32 [B|1, Cout, 8]."""
+    d = ConvDesc()
+    d.x = x.data_ptr(); d.B, d.H, d.W, d.Cin = B, H, W, Cin
+    d.x_cstride = x.shape[-1]
+    d.w = w.data_ptr(); d.ntaps = len(taps); d.Cout = Cout
+    d.w_rows = w.shape[1] if w_rows is None else w_rows
+    d.w_cstride = w.shape[2]
+    for i, (dy, dx, wi) in enumerate(taps):
+        d.tap_dy[i] = dy; d.tap_dx[i] = dx; d.tap_widx[i] = wi
+    d.stride = stride
+    d.OH, d.OW = OH, OW
+    d.out = out.data_ptr()
+    d.out_H = OH if out_H is None else out_H
+    d.out_W = OW if out_W is None else out_W
+    d.out_cstride = Cout if out_nchw_f32 else out.shape[-1]
+    d.out_y0, d.out_x0, d.out_ys, d.out_xs = out_y0, out_x0, out_ys, out_xs
+    d.out_nchw_f32 = 1 if out_nchw_f32 else 0
+    d.tab = tab.data_ptr(); d.tab_bstride = 1 if tab_per_sample else 0
+    d.noise = _ptr(noise); d.noise_bstride = 1 if noise_per_sample else 0
+    d.noise_w = _ptr(noise_w)
+    d.residual = _ptr(residual)
+    d.rgb = _ptr(rgb)
+    d.block_n, d.tile_w, d.tile_h = block_n, tile_w, tile_h
+    with torch.cuda.device(x.device):
+        st = _lib.lib().fm_conv_igemm(C.byref(d), _stream())
+    _lib.check(st, "fm_conv_igemm")
+    return out
+
+
+def prep_weight(w_oikk, scale, cout_rows=None, cin_stride=None, want_wsq=True):
+    """fp32 [O,I,kh,kw] -> (bf16 [kh*kw, rows, cin_stride], fp32 wsq [O,I] or None)."""
+    _check_cuda(w_oikk, "weight")
+    w = w_oikk.contiguous().to(torch.float32)
+    O, I, kh, kw = w.shape
+    rows = O if cout_rows is None else cout_rows
+    cs = (I + 7) // 8 * 8 if cin_stride is None else cin_stride
+    wq = torch.empty(kh * kw, rows, cs, device=w.device, dtype=torch.bfloat16)
+    wsq = torch.empty(O, I, device=w.device, dtype=torch.float32) if want_wsq else None
+    with torch.cuda.device(w.device):
+        st = _lib.lib().fm_prep_weight(_ptr(wq), _ptr(wsq), _ptr(w), O, I, kh, kw, float(scale), rows, cs, _stream())
+    _lib.check(st, "fm_prep_weight")
+    return wq, wsq
+
+
+def nchw_to_nhwc_bf16(x, scale_bc=None, cstride=None):
+    _check_cuda(x, "input")
+    x = x.contiguous().to(torch.float32)
+    B, Cc, H, W = x.shape
+    cs = (Cc + 7) // 8 * 8 if cstride is None else cstride
+    out = torch.empty(B, H, W, cs, device=x.device, dtype=torch.bfloat16)
+    if scale_bc is not None:
+        scale_bc = scale_bc.contiguous().to(torch.float32)
+    with torch.cuda.device(x.device):
+        st = _lib.lib().fm_nchw_to_nhwc_bf16(_ptr(out), _ptr(x), _ptr(scale_bc), B, Cc, H, W, cs, _stream())
+    _lib.check(st, "fm_nchw_to_nhwc_bf16")
+    return out
+
+
+def nhwc_bf16_to_nchw(x, channels, inv_scale_bc=None):
+    _check_cuda(x, "input")
+    B, H, W, cs = x.shape
+    out = torch.empty(B, channels, H, W, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        st = _lib.lib().fm_nhwc_bf16_to_nchw(_ptr(out), _ptr(x), _ptr(inv_scale_bc), B, channels, H, W, cs, _stream())
+    _lib.check(st, "fm_nhwc_bf16_to_nchw")
+    return out
+
+
+def blur_act_nhwc(t, kernel4x4, tab, noise, noise_per_sample, noise_w, C_, out=None):
+    """t bf16 [B,OH+1,OW+1,cs] -> bf16 [B,OH,OW,cs] (see fm_blur_act_nhwc)."""
+    B, IH, IW, cs = t.shape
+    OH, OW = IH - 1, IW - 1
+    if out is None:
+        out = torch.empty(B, OH, OW, cs, device=t.device, dtype=torch.bfloat16)
+    with torch.cuda.device(t.device):
+        st = _lib.lib().fm_blur_act_nhwc(_ptr(out), _ptr(t), _ptr(kernel4x4), _ptr(tab), _ptr(noise),
+                                         1 if noise_per_sample else 0, _ptr(noise_w), B, OH, OW, C_, cs, _stream())
+    _lib.check(st, "fm_blur_act_nhwc")
+    return out
+
+
+def rgb_finalize(acc, bias3, skip, kernel4x4, out=None):
+    """acc fp32 [B,H,W,4] (+bias +Upsample(skip)) -> fp32 NCHW [B,3,H,W]; acc is zeroed."""
+    B, H, W, _ = acc.shape
+    if out is None:
+        out = torch.empty(B, 3, H, W, device=acc.device, dtype=torch.float32)
+    with torch.cuda.device(acc.device):
+        st = _lib.lib().fm_rgb_finalize(_ptr(out), _ptr(acc), _ptr(bias3), _ptr(skip), _ptr(kernel4x4), B, H, W, _stream())
+    _lib.check(st, "fm_rgb_finalize")
+    return out

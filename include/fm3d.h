@@ -1,0 +1,199 @@
+/*
+ * fm3d.h -- C ABI of libfm3d.so: the B200 (sm_100a) kernels behind 3D-FM GAN's
+ * StyleGAN2 synthesis hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain C: raw device pointers, sizes, a cudaStream_t passed as void*; no torch types;
+ *   - return 0 on success, non-zero fm_status on error; fm_last_error() gives the text
+ *     (thread-local).  No exceptions cross the boundary;
+ *   - the callee never allocates device memory, never synchronises, and enqueues all
+ *     work on the stream it is given (the reference ops use the current torch stream,
+ *     op/fused_bias_act_kernel.cu:54-56, op/upfirdn2d_kernel.cu:213-215);
+ *   - the caller owns every buffer; outputs must be pre-allocated and contiguous;
+ *   - re-entrant and thread-safe (the reference is called from nn.DataParallel worker
+ *     threads, train_3_encoder.py:355-362).
+ *
+ * Each declaration cites the reference interface it replaces (file:line in
+ * adobe/3D-FM-GAN).
+ */
+#ifndef FM3D_H_
+#define FM3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { FM_F32 = 0, FM_F16 = 1, FM_BF16 = 2 } fm_dtype;
+
+typedef enum {
+  FM_OK = 0,
+  FM_ERR_INVALID = 1,      /* bad argument (shape, alignment, enum) */
+  FM_ERR_UNSUPPORTED = 2,  /* valid but outside what the kernels cover */
+  FM_ERR_CUDA = 3,         /* a CUDA runtime / driver call failed */
+  FM_ERR_NO_DEVICE = 4     /* no sm_100 device / driver entry point missing */
+} fm_status;
+
+/* Library identification. */
+int fm_version(void);
+const char* fm_last_error(void);
+/* Number of kernel launches issued by this library since load (all threads). */
+int64_t fm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * fused bias + activation.
+ * Replaces: fused_bias_act(input, bias, refer, act, grad, alpha, scale) -> Tensor
+ *           op/fused_bias_act.cpp:11-17, kernel op/fused_bias_act_kernel.cu:18-49.
+ * x is viewed as [n_outer, channels, inner] (bias broadcasts along dim 1; inner =
+ * prod(dims[2:]), .cu:67-71).  bias / ref may be NULL (= the reference's empty tensor,
+ * .cu:62-63).  act: 1 linear, 3 leaky-ReLU; grad: 0 forward, 1 first derivative w.r.t.
+ * ref, 2 second derivative (zero).  Indexing is 64-bit (the reference overflows at 2^31
+ * elements, .cu:65).  bias has the same dtype as x.
+ * ---------------------------------------------------------------------------------- */
+int fm_bias_act(void* out, const void* x, const void* bias, const void* ref,
+                int64_t n_outer, int64_t channels, int64_t inner,
+                int act, int grad, float alpha, float scale, int dtype, void* stream);
+
+/* Gradient mode (act, grad=1, no bias) fused with the bias-gradient reduction that the
+ * reference runs as a separate torch sum (op/fused_act.py:42-48).
+ * grad_bias_f32[channels] must be zero-initialised by the caller; it is accumulated in fp32. */
+int fm_bias_act_grad_bias(void* grad_in, float* grad_bias_f32, const void* grad_out,
+                          const void* ref, int64_t n_outer, int64_t channels, int64_t inner,
+                          int act, float alpha, float scale, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * upfirdn2d: zero-stuff x up, pad/crop, correlate with the flipped kernel, decimate.
+ * Replaces: upfirdn2d(input[major,H,W,minor], kernel[kh,kw], up_x, up_y, down_x, down_y,
+ *                     pad_x0, pad_x1, pad_y0, pad_y1) -> Tensor[major,out_h,out_w,minor]
+ *           op/upfirdn2d.cpp:12-19, kernels op/upfirdn2d_kernel.cu:49-105,107-207.
+ * The Python wrapper always passes minor = 1 and major = N*C (op/upfirdn2d.py:108), so
+ * the ABI takes `planes` = N*C contiguous [in_h, in_w] images.  The kernel taps are fp32
+ * (host or device pointer is NOT accepted: device pointer, kh*kw floats).
+ * out must hold planes*out_h*out_w elements with
+ *   out_h = (in_h*up_y + pad_y0 + pad_y1 - kh) / down_y + 1   (op/upfirdn2d_kernel.cu:237-240).
+ * ---------------------------------------------------------------------------------- */
+int fm_upfirdn2d(void* out, const void* x, const float* kernel,
+                 int64_t planes, int in_h, int in_w, int kh, int kw,
+                 int up_x, int up_y, int down_x, int down_y,
+                 int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                 int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM).
+ * Replaces the reference's ATen calls F.conv2d / F.conv_transpose2d(groups=batch) on the
+ * materialised per-sample weights (stylegan2.py:276,285,291), the EqualConv2d call
+ * (stylegan2.py:129) and the encoders' nn.Conv2d (resnet_encoder.py:36,42,193;
+ * psp_encoder_model/encoders/helpers.py:80-82,124-131; psp_encoders.py:27-31).
+ *
+ * Data layout: activations NHWC bf16 with a physical channel stride (multiple of 8);
+ * weights bf16 [ntaps][cout_rows][cin_stride] (K-major).  Style modulation is applied to
+ * the activations by the producer (x * s[b,i]) and demodulation d[b,o] in the epilogue, so
+ * the weight operand is shared by the whole batch and B*H*W is the GEMM M dimension
+ * (SURVEY.md 7.3 algebra; identical to stylegan2.py:257-262 up to rounding order).
+ *
+ * Epilogue per output element (b, y, x, o), with table row T = tab[(b*tab_bstride + o)*8]:
+ *   v = acc * T[0] + T[1] + noise[b*noise_bstride + y*OWfull + x] * (*noise_w)  [+ residual]
+ *   v = v > 0 ? v : v * T[2]
+ *   rgb[b,y,x,0..2] += v * T[4..6]            (optional fused ToRGB, stylegan2.py:393)
+ *   out[b,y,x,o]     = v * T[3]
+ * ---------------------------------------------------------------------------------- */
+#define FM_MAX_TAPS 49
+
+typedef struct {
+  /* input activations */
+  const void* x;            /* bf16 NHWC */
+  int32_t B, H, W, Cin;     /* logical sizes */
+  int32_t x_cstride;        /* physical channel stride in elements (multiple of 8) */
+  /* weights */
+  const void* w;            /* bf16 [ntaps][w_rows][w_cstride] */
+  int32_t ntaps, Cout, w_rows, w_cstride;
+  int8_t tap_dy[FM_MAX_TAPS];   /* input row offset of each tap relative to oy*stride */
+  int8_t tap_dx[FM_MAX_TAPS];
+  int8_t tap_widx[FM_MAX_TAPS]; /* which [w_rows][w_cstride] slab of w each tap multiplies */
+  int32_t stride;           /* convolution stride (1 or 2) */
+  /* logical output grid computed by this launch */
+  int32_t OH, OW;
+  /* placement of that grid inside the output tensor: pixel (oy,ox) is written to
+   * (oy*out_ys + out_y0, ox*out_xs + out_x0) of a [B,out_H,out_W,out_cstride] tensor */
+  void* out;                /* bf16 NHWC, or fp32 NCHW when out_nchw_f32 != 0 */
+  int32_t out_H, out_W, out_cstride, out_y0, out_x0, out_ys, out_xs;
+  int32_t out_nchw_f32;
+  /* epilogue */
+  const float* tab;         /* [tab_rows][Cout][8] fp32 (see above); tab_bstride = Cout or 0 */
+  int32_t tab_bstride;      /* 0: one table shared by the batch; 1: per-sample tables */
+  const float* noise;       /* fp32 [B or 1][out_H][out_W] or NULL */
+  int32_t noise_bstride;    /* 0 shared / 1 per-sample */
+  const float* noise_w;     /* device scalar or NULL (=> 1.0) */
+  const void* residual;     /* bf16 NHWC like out, or NULL */
+  float* rgb;               /* fp32 [B][out_H][out_W][4] accumulated with atomics, or NULL */
+  /* tiling hints (0 = choose) */
+  int32_t block_n;          /* 64, 128 or 256 */
+  int32_t tile_w, tile_h;   /* tile_w*tile_h*tile_b = 128 output pixels */
+} fm_conv_desc;
+
+int fm_conv_igemm(const fm_conv_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Synthesis-path helper kernels (all bandwidth-bound).
+ * ---------------------------------------------------------------------------------- */
+
+/* s[b,i] = latent[b, latent_idx, :] . wmod[i,:] / sqrt(D) + bmod[i]     (EqualLinear with
+ * bias_init=1, stylegan2.py:165-175,240,257) for a batch of layers in one launch. */
+typedef struct {
+  const float* wmod;   /* [cin][style_dim] */
+  const float* bmod;   /* [cin] */
+  float* s;            /* out [B][cin] */
+  int32_t cin, latent_idx;
+} fm_style_layer;
+int fm_style_affine(const fm_style_layer* layers_dev, int n_layers, int max_cin,
+                    const float* latent, int B, int n_latent, int style_dim, void* stream);
+
+/* Epilogue tables for one modulated conv (stylegan2.py:258-262,312,371,393-394):
+ *   T[0] = demod ? rsqrt(sum_i s[b,i]^2 wsq[o,i] + 1e-8) : 1
+ *   T[1] = act_bias[o] (or 0), T[2] = slope, T[3] = gain * (s_next ? s_next[b,o] : 1)
+ *   T[4..6] = gain * wrgb[j,o] * s_rgb[b,o] / sqrt(cout)   (when wrgb != NULL) */
+typedef struct {
+  const float* s;        /* [B][cin] this layer's style */
+  const float* wsq;      /* [cout][cin] sum_k (scale*W)^2, or NULL (no demod) */
+  const float* act_bias; /* [cout] or NULL */
+  const float* s_next;   /* [B][cout] style of the 3x3 consumer or NULL */
+  const float* wrgb;     /* [3][cout] ToRGB weight or NULL */
+  const float* s_rgb;    /* [B][cout] */
+  float* tab;            /* out [B][cout][8] */
+  int32_t cin, cout;
+  float slope, gain;
+} fm_table_layer;
+int fm_build_tables(const fm_table_layer* layers_dev, int n_layers, int max_cout, int B, void* stream);
+
+/* NCHW fp32 -> NHWC bf16 with optional per-(b,c) scale; pad channels are zero-filled. */
+int fm_nchw_to_nhwc_bf16(void* out, const float* x, const float* scale_bc,
+                         int B, int C, int H, int W, int out_cstride, void* stream);
+/* NHWC bf16 -> NCHW fp32 with optional per-(b,c) inverse scale. */
+int fm_nhwc_bf16_to_nchw(float* out, const void* x, const float* inv_scale_bc,
+                         int B, int C, int H, int W, int x_cstride, void* stream);
+
+/* Blur after the stride-2 transposed modulated conv, fused with demod, noise, bias,
+ * leaky-ReLU and the next layer's style (stylegan2.py:279,312,371):
+ *   t[b,2h+1,2w+1,C] bf16 NHWC  ->  out[b,2h,2w,C] bf16 NHWC
+ *   v = (sum_{a,b} k[a,b] t[..]) * T[0] + T[1] + noise*noise_w ; lrelu(T[2]) ; * T[3] */
+int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4,
+                     const float* tab, const float* noise, int noise_bstride, const float* noise_w,
+                     int B, int OH, int OW, int C, int cstride, void* stream);
+
+/* ToRGB tail (stylegan2.py:394-399): rgb_out[b,:,y,x] = acc[b,y,x,:] + bias + up2(skip).
+ * acc fp32 [B][H][W][4] (from the fused epilogue), skip fp32 NCHW [B,3,H/2,W/2] or NULL,
+ * kernel4x4 = Upsample.kernel (k*4).  Output fp32 NCHW [B,3,H,W].  acc is re-zeroed. */
+int fm_rgb_finalize(float* rgb_out, float* acc, const float* bias3, const float* skip,
+                    const float* kernel4x4, int B, int H, int W, void* stream);
+
+/* Weight preparation (derived caches; never state):
+ *   wq [kh*kw][cout_rows][cin_stride] bf16 = scale * W[o,i,ky,kx] (slab index ky*kw+kx),
+ *   wsq[cout][cin] fp32 = sum_taps (scale*W)^2. */
+int fm_prep_weight(void* wq, float* wsq, const float* w_oikk, int cout, int cin, int kh, int kw,
+                   float scale, int cout_rows, int cin_stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FM3D_H_ */

@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Generate golden vectors by importing the UNMODIFIED reference (CPU op path).
+
+TEST INFRASTRUCTURE -- not part of the product path.
+
+Runs only in the build container, where ``/root/reference`` exists.  The
+reference JIT-compiles its CUDA ops at import time (``op/fused_act.py:20-26``,
+``op/upfirdn2d.py:19-25``); we stub ``torch.utils.cpp_extension.load`` so the
+import succeeds and every op takes the reference's own pure-PyTorch CPU branch
+(``op/fused_act.py:114-125``, ``op/upfirdn2d.py:155-158,168-209``).
+
+Outputs small ``.npz`` fixtures into ``tests/golden/``; the fixtures (not the
+reference) travel to the GPU box.  Re-run:  ``python oracle/make_golden.py``.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("FM3D_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def import_reference():
+    import torch.utils.cpp_extension as ce
+    ce.load = lambda *a, **k: types.SimpleNamespace()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import stylegan2  # noqa
+    import resnet_encoder  # noqa
+    from psp_encoder_model.encoders import psp_encoders  # noqa
+    from Util import network_util  # noqa
+    import op  # noqa
+    return stylegan2, resnet_encoder, psp_encoders, network_util, op
+
+
+def sd_to_np(sd, prefix=""):
+    return {prefix + k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def checksum(sd):
+    s = 0.0
+    a = 0.0
+    for k in sorted(sd.keys()):
+        v = sd[k].detach().double()
+        s += float(v.sum())
+        a += float(v.abs().sum())
+    return np.array([s, a], dtype=np.float64)
+
+
+def randomize_fused_terms(g, seed):
+    """NoiseInjection.weight initialises to 0 (stylegan2.py:305) and biases to 0;
+    give them non-zero values so the fused terms are exercised."""
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in g.named_parameters():
+            if name.endswith("noise.weight") or name.endswith("activate.bias") or \
+               (name.endswith(".bias") and "to_rgb" in name and p.ndim == 4):
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.1)
+
+
+def gen_upfirdn2d(op):
+    from op.upfirdn2d import upfirdn2d_native
+    g = torch.Generator().manual_seed(100)
+    out = {}
+    k1 = torch.tensor([1., 3., 3., 1.])
+    k2 = k1[None, :] * k1[:, None]
+    k2 = k2 / k2.sum()
+    cases = [
+        # name, shape, kernel, (upx,upy,downx,downy,px0,px1,py0,py1)
+        ("g_blur", (2, 3, 9, 9), k2 * 4, (1, 1, 1, 1, 1, 1, 1, 1)),        # stylegan2.py:279 (2h+1 -> 2h)
+        ("rgb_up", (2, 3, 8, 8), k2 * 4, (2, 2, 1, 1, 2, 1, 2, 1)),        # stylegan2.py:397
+        ("d_blur22", (1, 4, 8, 8), k2, (1, 1, 1, 1, 2, 2, 2, 2)),          # stylegan2.py:705-711
+        ("d_blur11", (1, 4, 8, 8), k2, (1, 1, 1, 1, 1, 1, 1, 1)),          # stylegan2.py:748-750
+        ("down2", (2, 2, 16, 16), k2, (1, 1, 2, 2, 1, 1, 1, 1)),           # bwd of Upsample / Downsample
+        ("up2_k2", (1, 2, 5, 7), torch.tensor([[1., 2.], [3., 4.]]), (2, 2, 1, 1, 1, 0, 1, 0)),
+        ("down2_k2", (1, 2, 8, 6), torch.tensor([[1., 2.], [3., 4.]]), (1, 1, 2, 2, 0, 0, 0, 0)),
+        ("k3", (1, 3, 7, 5), torch.randn(3, 3, generator=g), (1, 1, 1, 1, 1, 1, 1, 1)),
+        ("negpad", (1, 2, 10, 10), k2, (1, 1, 1, 1, -1, 2, 1, -2)),
+        ("aniso", (1, 2, 6, 9), torch.randn(3, 5, generator=g), (3, 2, 2, 3, 2, 1, 0, 3)),
+        ("big_fallback", (1, 1, 12, 12), torch.randn(6, 6, generator=g), (1, 1, 1, 1, 3, 2, 3, 2)),
+        ("odd33", (3, 5, 33, 33), k2 * 4, (1, 1, 1, 1, 1, 1, 1, 1)),
+        ("grad_of_blur", (2, 3, 8, 8), torch.flip(k2 * 4, [0, 1]), (1, 1, 1, 1, 2, 2, 2, 2)),
+    ]
+    names = []
+    for name, shape, k, cfg in cases:
+        x = torch.randn(*shape, generator=g)
+        y = upfirdn2d_native(x, k, *cfg)
+        out[f"{name}.x"] = x.numpy()
+        out[f"{name}.k"] = k.numpy()
+        out[f"{name}.cfg"] = np.array(cfg, dtype=np.int64)
+        out[f"{name}.y"] = y.numpy()
+        names.append(name)
+    # public-API form (scalar up/down, 2-tuple pad, op/upfirdn2d.py:154-165)
+    x = torch.randn(2, 3, 8, 8, generator=g)
+    out["api.x"] = x.numpy()
+    out["api.k"] = (k2 * 4).numpy()
+    out["api.y"] = op.upfirdn2d(x, k2 * 4, up=2, down=1, pad=(2, 1)).numpy()
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "upfirdn2d.npz"), **out)
+    print("upfirdn2d:", len(names), "cases")
+
+
+def gen_bias_act(op):
+    g = torch.Generator().manual_seed(200)
+    out = {}
+    names = []
+    for name, shape, has_bias in [("nchw", (2, 6, 5, 7), True), ("nc", (3, 16), True),
+                                  ("nobias", (2, 4, 3, 3), False), ("ncl", (2, 5, 9), True),
+                                  ("odd", (1, 3, 1, 1), True)]:
+        x = torch.randn(*shape, generator=g, requires_grad=True)
+        b = torch.randn(shape[1], generator=g, requires_grad=True) if has_bias else None
+        y = op.fused_leaky_relu(x, b)          # op/fused_act.py:113-125 (CPU branch)
+        gy = torch.randn(*shape, generator=g)
+        grads = torch.autograd.grad(y, [x] + ([b] if has_bias else []), gy)
+        out[f"{name}.x"] = x.detach().numpy()
+        if has_bias:
+            out[f"{name}.b"] = b.detach().numpy()
+            out[f"{name}.gb"] = grads[1].numpy()
+        out[f"{name}.y"] = y.detach().numpy()
+        out[f"{name}.gy"] = gy.numpy()
+        out[f"{name}.gx"] = grads[0].numpy()
+        names.append(name)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "bias_act.npz"), **out)
+    print("bias_act:", len(names), "cases")
+
+
+def gen_modconv(sg):
+    out = {}
+    names = []
+    cfgs = [
+        # name, cin, cout, k, style_dim, demod, up, down, H
+        ("plain", 16, 24, 3, 32, True, False, False, 8),
+        ("up", 16, 24, 3, 32, True, True, False, 8),
+        ("down", 16, 24, 3, 32, True, False, True, 8),
+        ("torgb", 16, 3, 1, 32, False, False, False, 8),
+        ("plain_odd", 10, 6, 3, 20, True, False, False, 5),
+    ]
+    for i, (name, cin, cout, k, sd, demod, up, down, H) in enumerate(cfgs):
+        torch.manual_seed(300 + i)
+        m = sg.ModulatedConv2d(cin, cout, k, sd, demodulate=demod, upsample=up, downsample=down)
+        with torch.no_grad():
+            m.modulation.bias.add_(torch.randn_like(m.modulation.bias) * 0.3)
+        x = torch.randn(3, cin, H, H)
+        s = torch.randn(3, sd)
+        y = m(x, s)
+        for kk, v in m.state_dict().items():
+            out[f"{name}.sd.{kk}"] = v.numpy()
+        out[f"{name}.x"] = x.numpy()
+        out[f"{name}.style"] = s.numpy()
+        out[f"{name}.y"] = y.detach().numpy()
+        out[f"{name}.cfg"] = np.array([cin, cout, k, sd, int(demod), int(up), int(down)], dtype=np.int64)
+        names.append(name)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "modconv.npz"), **out)
+    print("modconv:", len(names), "cases")
+
+
+def gen_generator_small(sg):
+    """Pruned generator (generator_net_shape, stylegan2.py:461-466,508-527) at 32x32 so
+    the whole state dict fits in the fixture."""
+    out = {}
+    torch.manual_seed(400)
+    shape = [32, 32, 32, 32, 24, 24, 16, 16]
+    g = sg.Generator(32, 64, 2, generator_net_shape=shape)
+    randomize_fused_terms(g, 401)
+    g.eval()
+    gen = torch.Generator().manual_seed(402)
+    B = 3
+    z = torch.randn(B, 64, generator=gen)
+    latent = torch.randn(B, g.n_latent, 64, generator=gen)
+    ext = torch.randn(B, shape[0], 4, 4, generator=gen)
+    noise = [torch.randn(B, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), generator=gen)
+             for i in range(g.num_layers)]
+    with torch.no_grad():
+        # z-mode with stored noise buffers (stylegan2.py:583-594)
+        y_z = g([z], randomize_noise=False)
+        # 3-encoder mode (Util/network_util.py:329-330)
+        y_l, rgbs = g(None, latent_styles=[latent], input_is_latent=True, noise=noise,
+                      use_external_input_tensor=True, external_input_tensor=ext,
+                      return_rgb_list=True), None
+        rgbs = y_l
+        y_l = rgbs[-1]
+        # truncation + style mixing branch (stylegan2.py:596-625)
+        z2 = torch.randn(B, 64, generator=gen)
+        mean_lat = g.style(torch.randn(64, 64, generator=gen)).mean(0, keepdim=True)
+        y_mix = g([z, z2], inject_index=3, truncation=0.7, truncation_latent=mean_lat,
+                  randomize_noise=False)
+    # per-layer activations in 3-encoder mode via hooks
+    acts = {}
+    hooks = []
+    for name, mod in g.named_modules():
+        if isinstance(mod, (sg.StyledConv, sg.ToRGB)):
+            hooks.append(mod.register_forward_hook(
+                lambda m, i, o, name=name: acts.__setitem__(name, o.detach().numpy())))
+    with torch.no_grad():
+        g(None, latent_styles=[latent], input_is_latent=True, noise=noise,
+          use_external_input_tensor=True, external_input_tensor=ext)
+    for h in hooks:
+        h.remove()
+    # PPL branch (stylegan2.py:683-688): image + path lengths; the randn_like draw is seeded
+    latent_g = latent.clone().requires_grad_(True)
+    torch.manual_seed(403)
+    img_p, pl = g(None, latent_styles=[latent_g], input_is_latent=True, noise=noise,
+                  use_external_input_tensor=True, external_input_tensor=ext, PPL_regularize=True)
+    for k, v in g.state_dict().items():
+        out[f"sd.{k}"] = v.numpy()
+    out["shape"] = np.array(shape)
+    out["z"] = z.numpy(); out["z2"] = z2.numpy(); out["mean_latent"] = mean_lat.detach().numpy()
+    out["latent"] = latent.numpy(); out["ext"] = ext.numpy()
+    for i, n in enumerate(noise):
+        out[f"noise.{i}"] = n.numpy()
+    out["y_z"] = y_z.numpy(); out["y_latent"] = y_l.numpy(); out["y_mix"] = y_mix.numpy()
+    for i, r in enumerate(rgbs):
+        out[f"rgb.{i}"] = r.numpy()
+    for k, v in acts.items():
+        out[f"act.{k}"] = v
+    out["ppl.path_lengths"] = pl.detach().numpy()
+    out["ppl.image"] = img_p.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "generator_small.npz"), **out)
+    print("generator_small: keys", len(out))
+
+
+def gen_generator_cfg1(sg):
+    """BASELINE config 1: Generator(256,512,8), batch 4, CPU fp32.  Weights are too big
+    for a fixture (120 MB): they are re-created from the seed; a checksum guards that."""
+    out = {}
+    torch.manual_seed(0)
+    g = sg.Generator(256, 512, 8, channel_multiplier=2)
+    randomize_fused_terms(g, 1)
+    g.eval()
+    out["sd_checksum"] = checksum(g.state_dict())
+    gen = torch.Generator().manual_seed(2)
+    B = 4
+    z = torch.randn(B, 512, generator=gen)
+    latent = torch.randn(B, 14, 512, generator=gen)
+    ext = torch.randn(B, 512, 4, 4, generator=gen)
+    gen3 = torch.Generator().manual_seed(3)
+    noise = [torch.randn(B, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), generator=gen3)
+             for i in range(13)]
+    with torch.no_grad():
+        y_z = g([z], randomize_noise=False)
+        rgbs = g(None, latent_styles=[latent], input_is_latent=True, noise=noise,
+                 use_external_input_tensor=True, external_input_tensor=ext, return_rgb_list=True)
+    y_l = rgbs[-1]
+    out["y_z.stats"] = np.array([float(y_z.mean()), float(y_z.std())])
+    out["y_latent.stats"] = np.array([float(y_l.mean()), float(y_l.std())])
+    out["y_z.img0"] = y_z[0].numpy().astype(np.float16)
+    out["y_latent.img0"] = y_l[0].numpy().astype(np.float16)
+    out["y_latent.ds8"] = y_l[:, :, ::8, ::8].numpy()
+    out["y_z.ds8"] = y_z[:, :, ::8, ::8].numpy()
+    for i, r in enumerate(rgbs):
+        out[f"rgb{i}.stats"] = np.array([float(r.mean()), float(r.std()), float(r.abs().max())])
+    np.savez_compressed(os.path.join(OUT, "generator_cfg1.npz"), **out)
+    print("generator_cfg1: y_z stats", out["y_z.stats"], " y_latent stats", out["y_latent.stats"])
+
+
+def gen_discriminator(sg):
+    out = {}
+    torch.manual_seed(500)
+    d = sg.Discriminator(32)
+    with torch.no_grad():
+        for n, p in d.named_parameters():
+            if n.endswith("bias"):
+                p.add_(torch.randn_like(p) * 0.1)
+    out["sd_checksum"] = checksum(d.state_dict())
+    gen = torch.Generator().manual_seed(501)
+    x = torch.randn(8, 3, 32, 32, generator=gen)
+    with torch.no_grad():
+        y = d(x)
+    # R1 penalty (Util/training_util.py:46-52) -> double backward through D
+    xr = x.clone().requires_grad_(True)
+    pred = d(xr)
+    grad_real, = torch.autograd.grad(outputs=pred.sum(), inputs=xr, create_graph=True)
+    r1 = grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
+    gw = torch.autograd.grad(r1, d.convs[0][0].weight)[0]
+    out["x"] = x.numpy(); out["y"] = y.numpy()
+    out["r1"] = np.array(float(r1)); out["r1.grad_conv0"] = gw.numpy()
+    np.savez_compressed(os.path.join(OUT, "discriminator32.npz"), **out)
+    print("discriminator32: y", y.flatten()[:4].tolist(), "r1", float(r1))
+
+
+def gen_encoders(sg, rn, psp, nu):
+    out = {}
+    torch.manual_seed(600)
+    e_tsr = rn.resnet18(tensor_encoding=True).eval()
+    e_w = rn.resnet18(tensor_encoding=False).eval()
+    opts = types.SimpleNamespace(input_nc=3, n_styles=14)
+    e_wp = psp.GradualStyleEncoder(18, 'ir_se', opts).eval()
+    g = sg.Generator(256, 512, 8, channel_multiplier=2).eval()
+    randomize_fused_terms(g, 601)
+    # non-trivial BN running stats / PReLU slopes so the folded forms are exercised
+    gen = torch.Generator().manual_seed(602)
+    with torch.no_grad():
+        for m in list(e_tsr.modules()) + list(e_w.modules()) + list(e_wp.modules()):
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen) * 0.1)
+                m.running_var.copy_(1.0 + 0.2 * torch.rand(m.running_var.shape, generator=gen))
+                m.weight.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=gen))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=gen))
+    out["cs.e_tsr"] = checksum(e_tsr.state_dict())
+    out["cs.e_w"] = checksum(e_w.state_dict())
+    out["cs.e_wp"] = checksum(e_wp.state_dict())
+    out["cs.g"] = checksum(g.state_dict())
+    B = 2
+    p = (torch.rand(B, 3, 256, 256, generator=gen) * 2 - 1)
+    r = (torch.rand(B, 3, 256, 256, generator=gen) * 2 - 1)
+    gen3 = torch.Generator().manual_seed(603)
+    noise = [torch.randn(B, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), generator=gen3)
+             for i in range(13)]
+    with torch.no_grad():
+        t = e_tsr(r); w = e_w(r); wp = e_wp(p)
+        # Forward_Inference_3_Encoder (Util/network_util.py:293-338) requires g_ema.module
+        g_dp = types.SimpleNamespace(module=g)
+        # noise is drawn inside (randomize_noise=True); to be reproducible, re-implement the
+        # call with explicit noise AND run the real funnel under a seed.
+        lat = torch.stack([w * wp[:, i, :] for i in range(14)]).transpose(0, 1)
+        img = g(None, latent_styles=[lat], input_is_latent=True, noise=noise,
+                use_external_input_tensor=True, external_input_tensor=t)
+
+        class _G(torch.nn.Module):
+            def __init__(s, m):
+                super().__init__(); s.module = m
+            def forward(s, *a, **k):
+                k["noise"] = noise
+                return s.module(*a, **k)
+        img2 = nu.Forward_Inference_3_Encoder(p, r, e_tsr, e_w, e_wp, _G(g), tsr_encode='Render Image')
+    assert torch.equal(img, img2)
+    out["p.ds"] = p[:, :, ::16, ::16].numpy(); out["r.ds"] = r[:, :, ::16, ::16].numpy()
+    out["e_tsr"] = t.numpy(); out["e_w"] = w.numpy(); out["e_wp"] = wp.numpy()
+    out["latent"] = lat.numpy()
+    out["img.stats"] = np.array([float(img.mean()), float(img.std())])
+    out["img.ds8"] = img[:, :, ::8, ::8].numpy()
+    out["img0"] = img[0].numpy().astype(np.float16)
+    np.savez_compressed(os.path.join(OUT, "three_encoder.npz"), **out)
+    print("three_encoder: img stats", out["img.stats"])
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    sg, rn, psp, nu, op = import_reference()
+    torch.set_num_threads(os.cpu_count())
+    gen_upfirdn2d(op)
+    gen_bias_act(op)
+    gen_modconv(sg)
+    gen_generator_small(sg)
+    gen_discriminator(sg)
+    gen_generator_cfg1(sg)
+    gen_encoders(sg, rn, psp, nu)
+
+
+if __name__ == "__main__":
+    main()

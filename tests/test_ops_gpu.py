@@ -1,0 +1,172 @@
+"""Parity of the CUDA ops (through the C ABI) with the oracle and the golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fm_oracle as orc  # noqa: E402  (test infrastructure)
+
+
+def _t(a, dev, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dtype)
+
+
+# ----------------------------------------------------------------------------- upfirdn2d
+def test_upfirdn2d_golden(cuda):
+    from fm3d import ops
+    g = load_golden("upfirdn2d.npz")
+    for name in g["names"]:
+        x, k, cfg, y = g[f"{name}.x"], g[f"{name}.k"], g[f"{name}.cfg"], g[f"{name}.y"]
+        out = ops.upfirdn2d_planes(_t(x, cuda), _t(k, cuda), *[int(c) for c in cfg])
+        assert tuple(out.shape) == y.shape, name
+        # fp32 tolerance: same taps, different summation order / FMA contraction
+        np.testing.assert_allclose(out.cpu().numpy(), y, rtol=1e-5, atol=1e-5, err_msg=str(name))
+
+
+def test_upfirdn2d_api_and_analytic(cuda):
+    import op
+    g = load_golden("upfirdn2d.npz")
+    out = op.upfirdn2d(_t(g["api.x"], cuda), _t(g["api.k"], cuda), up=2, down=1, pad=(2, 1))
+    np.testing.assert_allclose(out.cpu().numpy(), g["api.y"], rtol=1e-5, atol=1e-5)
+    # analytic KATs: DC gain of the x4 kernel
+    k = orc.make_kernel_ref([1, 3, 3, 1]).to(cuda) * 4
+    up = op.upfirdn2d(torch.ones(1, 1, 8, 8, device=cuda), k, up=2, pad=(2, 1))
+    assert up.shape == (1, 1, 16, 16)
+    assert torch.allclose(up[0, 0, 2:-2, 2:-2], torch.ones(12, 12, device=cuda), atol=1e-6)
+    assert abs(float(up[0, 0, 0, 0]) - 0.5625) < 1e-6
+    bl = op.upfirdn2d(torch.ones(1, 1, 17, 17, device=cuda), k, pad=(1, 1))
+    assert bl.shape == (1, 1, 16, 16)
+    assert torch.allclose(bl[0, 0, 2:-2, 2:-2], torch.full((12, 12), 4.0, device=cuda), atol=1e-5)
+
+
+@pytest.mark.parametrize("shape,cfg", [
+    ((4, 128, 257, 257), (1, 1, 1, 1, 1, 1, 1, 1)),     # largest G blur (per-sample slice)
+    ((8, 3, 128, 128), (2, 2, 1, 1, 2, 1, 2, 1)),       # ToRGB skip upsample
+    ((2, 3, 256, 256), (1, 1, 2, 2, 1, 1, 1, 1)),       # bwd of Upsample
+    ((2, 7, 33, 130), (1, 1, 1, 1, 2, 2, 2, 2)),        # D blur, ragged tile edge
+    ((1, 1, 1, 1), (1, 1, 1, 1, 2, 2, 2, 2)),           # minimum size
+    ((2, 2, 5, 300), (2, 2, 1, 1, 2, 1, 2, 1)),
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_upfirdn2d_vs_oracle(cuda, shape, cfg, dtype):
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(sum(shape) + cfg[0])
+    x = torch.randn(*shape, generator=gen).to(dtype)
+    k = orc.make_kernel_ref([1, 3, 3, 1]) * (4 if cfg[0] == 2 or cfg[4] == 1 else 1)
+    ref = orc.upfirdn2d_ref(x.float(), k, *cfg)
+    out = ops.upfirdn2d_planes(x.to(cuda), k.to(cuda), *cfg)
+    assert out.dtype == dtype and tuple(out.shape) == tuple(ref.shape)
+    tol = 1e-5 if dtype == torch.float32 else (2e-2 if dtype == torch.bfloat16 else 3e-3)
+    torch.testing.assert_close(out.float().cpu(), ref, rtol=tol, atol=tol * 4)
+
+
+def test_upfirdn2d_empty(cuda):
+    from fm3d import ops
+    k = orc.make_kernel_ref([1, 3, 3, 1]).to(cuda)
+    out = ops.upfirdn2d_planes(torch.zeros(0, 3, 8, 8, device=cuda), k, 1, 1, 1, 1, 1, 1, 1, 1)
+    assert out.shape == (0, 3, 7, 7)
+    out = ops.upfirdn2d_planes(torch.zeros(1, 1, 2, 2, device=cuda), k, 1, 1, 1, 1, 0, 0, 0, 0)
+    assert out.numel() == 0
+
+
+def test_upfirdn2d_grad_and_gradgrad(cuda):
+    """first and second order through UpFirDn2d vs autograd of the oracle (double backward
+    is what R1 / path-length regularisation need, op/upfirdn2d.py:71-94)."""
+    import op
+    k = orc.make_kernel_ref([1, 3, 3, 1]) * 4
+    for up, down, pad, hw in [(1, 1, (1, 1), 9), (2, 1, (2, 1), 6), (1, 2, (1, 1), 8), (1, 1, (2, 2), 8)]:
+        x = torch.randn(2, 3, hw, hw, dtype=torch.float32)
+        xr = x.clone().requires_grad_(True)
+        yr = orc.upfirdn2d_api_ref(xr, k, up, down, pad)
+        w = torch.randn_like(yr)
+        gr, = torch.autograd.grad((yr * w).sum(), xr, create_graph=True)
+        v = torch.randn_like(gr)
+        xg = x.to(cuda).requires_grad_(True)
+        yg = op.upfirdn2d(xg, k.to(cuda), up=up, down=down, pad=pad)
+        wg = w.to(cuda).requires_grad_(True)
+        gg, = torch.autograd.grad((yg * wg).sum(), xg, create_graph=True)
+        torch.testing.assert_close(yg.detach().cpu(), yr.detach(), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(gg.detach().cpu(), gr.detach(), rtol=1e-5, atol=1e-5)
+        # second order: d/dw (g . v) = upfirdn(v)
+        h, = torch.autograd.grad((gg * v.to(cuda)).sum(), wg)
+        href = orc.upfirdn2d_api_ref(v, k, up, down, pad)
+        torch.testing.assert_close(h.cpu(), href, rtol=1e-5, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------- bias_act
+def test_bias_act_golden(cuda):
+    import op
+    g = load_golden("bias_act.npz")
+    for name in g["names"]:
+        x = _t(g[f"{name}.x"], cuda).requires_grad_(True)
+        has_b = f"{name}.b" in g
+        b = _t(g[f"{name}.b"], cuda).requires_grad_(True) if has_b else None
+        y = op.fused_leaky_relu(x, b)
+        np.testing.assert_allclose(y.detach().cpu().numpy(), g[f"{name}.y"], rtol=1e-6, atol=1e-6, err_msg=str(name))
+        grads = torch.autograd.grad(y, [x] + ([b] if has_b else []), _t(g[f"{name}.gy"], cuda))
+        np.testing.assert_allclose(grads[0].cpu().numpy(), g[f"{name}.gx"], rtol=1e-6, atol=1e-6)
+        if has_b:
+            np.testing.assert_allclose(grads[1].cpu().numpy(), g[f"{name}.gb"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(32, 512, 4, 4), (4, 128, 64, 64), (3, 5, 7, 11), (32, 512), (2, 3, 1, 1), (5,)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_bias_act_modes_vs_oracle(cuda, shape, dtype):
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(len(shape) * 7 + shape[0])
+    x = torch.randn(*shape, generator=gen).to(dtype)
+    ch = shape[1] if len(shape) > 1 else shape[0]
+    b = torch.randn(ch, generator=gen).to(dtype)
+    r = torch.randn(*shape, generator=gen).to(dtype)
+    tol = 1e-6 if dtype == torch.float32 else (1.6e-2 if dtype == torch.bfloat16 else 2e-3)
+    for act, grad, use_b, use_r in [(3, 0, True, False), (3, 0, False, False), (3, 1, False, True), (3, 1, True, True),
+                                    (1, 0, True, False), (1, 1, False, True), (3, 2, False, True), (1, 2, True, False)]:
+        xs = x if len(shape) > 1 else x.view(1, -1)
+        rs = r if len(shape) > 1 else r.view(1, -1)
+        ref = orc.fused_bias_act_ref(xs.float(), b.float() if use_b else None, rs.float() if use_r else None,
+                                     act, grad, 0.2, 2 ** 0.5).view(shape)
+        out = ops.bias_act(x.to(cuda), b.to(cuda) if use_b else None, r.to(cuda) if use_r else None, act, grad, 0.2, 2 ** 0.5)
+        assert out.dtype == dtype
+        torch.testing.assert_close(out.float().cpu(), ref, rtol=tol, atol=tol, msg=f"act{act} grad{grad}")
+
+
+def test_bias_act_unaligned_and_empty(cuda):
+    from fm3d import ops
+    base = torch.randn(4 * 6 * 9 + 1, device=cuda)
+    x = base[1:].view(4, 6, 9)              # 4-byte aligned only, inner not a multiple of 4
+    b = torch.randn(6, device=cuda)
+    ref = orc.fused_leaky_relu_ref(x.cpu(), b.cpu())
+    torch.testing.assert_close(ops.bias_act(x, b).cpu(), ref, rtol=1e-6, atol=1e-6)
+    assert ops.bias_act(torch.zeros(0, 4, 2, 2, device=cuda), torch.zeros(4, device=cuda)).shape == (0, 4, 2, 2)
+
+
+def test_fused_leaky_relu_double_backward(cuda):
+    """Second-order path (op/fused_act.py:55-62) against autograd of the oracle."""
+    import op
+    x = torch.randn(3, 6, 5, 5)
+    b = torch.randn(6)
+    xr, br = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = orc.fused_leaky_relu_ref(xr, br)
+    gxr, gbr = torch.autograd.grad(yr.pow(2).sum(), [xr, br], create_graph=True)
+    lr = gxr.pow(2).sum() + gbr.pow(2).sum()
+    ggr = torch.autograd.grad(lr, [xr, br])
+    xg, bg = x.to(cuda).requires_grad_(True), b.to(cuda).requires_grad_(True)
+    yg = op.fused_leaky_relu(xg, bg)
+    gxg, gbg = torch.autograd.grad(yg.pow(2).sum(), [xg, bg], create_graph=True)
+    lg = gxg.pow(2).sum() + gbg.pow(2).sum()
+    ggg = torch.autograd.grad(lg, [xg, bg])
+    torch.testing.assert_close(gxg.detach().cpu(), gxr.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(gbg.detach().cpu(), gbr.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ggg[0].cpu(), ggr[0], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ggg[1].cpu(), ggr[1], rtol=1e-4, atol=1e-3)
+
+
+def test_cpu_tensor_is_rejected():
+    import op
+    with pytest.raises(RuntimeError):
+        op.fused_leaky_relu(torch.zeros(1, 2, 3, 3))
+    with pytest.raises(RuntimeError):
+        op.upfirdn2d(torch.zeros(1, 2, 3, 3), torch.ones(2, 2))
