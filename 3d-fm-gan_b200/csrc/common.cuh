@@ -103,9 +103,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (visible as a launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
       printf("fm3d: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
