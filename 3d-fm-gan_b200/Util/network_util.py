@@ -1,0 +1,47 @@
+"""3-encoder forward funnel (mirror of the reference's Util/network_util.py:293-338).
+
+``Forward_Inference_3_Encoder`` is the single entry every training step and evaluation loop
+of the reference goes through; same name, arguments and return structure here.  The W / W+
+product that the reference builds with a 14-iteration Python loop + stack + transpose is one
+broadcast multiply.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def _n_latent(g_ema):
+    return (g_ema.module if hasattr(g_ema, "module") else g_ema).n_latent
+
+
+def Forward_Inference_3_Encoder(p_input, r_input, E_Tsr, E_W, E_W_Plus, g_ema, tsr_encode='Photo Image',
+                                sliced_layer=None, use_tanh=False, PPL_regularize=False):
+    """p_input / r_input: normalised photo and rendered-face batches [B,3,H,W].
+    E_Tsr -> 4x4 start tensor (from the photo or the render, per ``tsr_encode``), E_W(render) -> W,
+    E_W_Plus(photo) -> W+;  latent[b,i] = W[b] * W+[b,i] for i in ``sliced_layer`` (default: all),
+    else W[b].  Returns the generator output (``(image, path_lengths)`` under PPL_regularize)."""
+    if tsr_encode == 'Photo Image':
+        encoded_tensor = E_Tsr(p_input)
+    elif tsr_encode == 'Render Image':
+        encoded_tensor = E_Tsr(r_input)
+    else:
+        raise ValueError(f"unknown tsr_encode {tsr_encode!r}")
+    encoded_W = E_W(r_input)
+    encoded_W_plus = E_W_Plus(p_input)
+
+    n = encoded_W_plus.shape[1]
+    if sliced_layer is None:
+        sliced_layer = range(_n_latent(g_ema))
+    gate = torch.tensor([1.0 if i in sliced_layer else 0.0 for i in range(n)], device=encoded_W.device,
+                        dtype=encoded_W.dtype).view(1, n, 1)
+    w = encoded_W.unsqueeze(1)
+    encoded_latent = w * encoded_W_plus * gate + w * (1.0 - gate)
+
+    g_output = g_ema(noise_z=None, latent_styles=[encoded_latent], input_is_latent=True,
+                     use_external_input_tensor=True, external_input_tensor=encoded_tensor,
+                     PPL_regularize=PPL_regularize)
+    if use_tanh:
+        if PPL_regularize:
+            g_output = (torch.tanh(g_output[0]), g_output[1])
+        else:
+            g_output = torch.tanh(g_output)
+    return g_output

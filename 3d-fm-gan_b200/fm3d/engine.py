@@ -1,0 +1,248 @@
+"""Fused bf16 synthesis engine: runs a whole ``stylegan2.Generator`` synthesis network
+(stylegan2.py:627-668 of the reference) on the tcgen05 implicit-GEMM kernel.
+
+Dataflow per forward (B samples, activations NHWC bf16, never NCHW fp32 in between):
+
+  style_affine   all 20 modulation EqualLinears in ONE launch        -> s[layer][B,Cin]
+  build_tables   demod d[b,o], bias, lrelu slope, gain*s_next, fused ToRGB weights (ONE launch)
+  nchw->nhwc     external 4x4 tensor * s_conv1                        -> bf16 NHWC
+  conv1          igemm 3x3 (+noise +bias +lrelu*sqrt2, *s_next, RGB)  -> x, rgb_acc
+  per resolution:
+     up-conv     stride-2 transposed conv as 4 output-parity phases (4/2/2/1 taps: exactly the
+                 algorithmic FLOPs, no zero-stuffing work) -> T[(2h+1)^2] bf16
+     blur_act    4x4 FIR + demod + noise + bias + lrelu, *s_next      -> x
+     conv        igemm 3x3 with fused epilogue and fused ToRGB        -> x, rgb_acc
+     rgb_finalize  rgb_acc + bias + Upsample(skip)                    -> skip (fp32 NCHW)
+
+Style modulation is applied to the *activations* by the producing layer's epilogue, so all
+convolutions use weights shared across the batch (see stylegan2.ModulatedConv2d).  Derived
+tensors (bf16 K-major weights, sum-of-squares tables, descriptor arrays) are caches keyed on
+the parameters' version counters -- they are never part of the state dict.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib, ops
+from ._lib import StyleLayer, TableLayer
+
+
+def _up_phase_taps(py, px):
+    """Taps of output parity (py,px) of a stride-2 transposed 3x3 conv:
+    T[2y+py, 2x+px] = sum_{ky=py (mod 2), kx=px (mod 2)} x[y + (py-ky)/2, x + (px-kx)/2] * W[ky,kx]."""
+    taps = []
+    for ky in range(3):
+        if (ky - py) % 2:
+            continue
+        for kx in range(3):
+            if (kx - px) % 2:
+                continue
+            taps.append(((py - ky) // 2, (px - kx) // 2, ky * 3 + kx))
+    return taps
+
+
+class _ConvLayer:
+    """One modulated 3x3 conv of the plan."""
+    __slots__ = ("mod", "act_bias", "noise_w", "cin", "cout", "up", "res_in", "res_out", "latent_idx",
+                 "wq", "wsq", "s", "tab", "rgb_mod", "next_idx", "kernel", "name")
+
+
+class SynthesisPlan:
+    def __init__(self, gen, batch, device):
+        self.gen = gen
+        self.B = batch
+        self.device = device
+        self.style_dim = gen.style_dim
+        lib = _lib.lib()  # fail early if the library is missing
+        assert lib is not None
+
+        # ---- walk the generator: conv1, then (up, conv) per resolution; ToRGB after each plain conv
+        convs = []
+
+        def add(styled, latent_idx, res_in, up, name):
+            L = _ConvLayer()
+            L.mod = styled.conv
+            L.act_bias = styled.activate.bias
+            L.noise_w = styled.noise.weight
+            L.cin, L.cout = styled.conv.in_channel, styled.conv.out_channel
+            L.up = up
+            L.res_in = res_in
+            L.res_out = res_in * 2 if up else res_in
+            L.latent_idx = latent_idx
+            L.rgb_mod = None
+            L.kernel = styled.conv.blur.kernel if up else None
+            L.name = name
+            convs.append(L)
+            return L
+
+        first = add(gen.conv1, 0, 4, False, "conv1")
+        self.rgbs = [(gen.to_rgb1, 1, first)]
+        res, li = 4, 1
+        for j, to_rgb in enumerate(gen.to_rgbs):
+            add(gen.convs[2 * j], li, res, True, f"convs.{2 * j}")
+            res *= 2
+            last = add(gen.convs[2 * j + 1], li + 1, res, False, f"convs.{2 * j + 1}")
+            self.rgbs.append((to_rgb, li + 2, last))
+            li += 2
+        self.convs = convs
+        for (to_rgb, lidx, L) in self.rgbs:
+            L.rgb_mod = (to_rgb, lidx)
+
+        B = batch
+        f32 = dict(device=device, dtype=torch.float32)
+        bf16 = dict(device=device, dtype=torch.bfloat16)
+        cs = lambda c: (c + 7) // 8 * 8
+
+        # ---- per-layer buffers
+        for L in convs:
+            L.s = torch.empty(B, L.cin, **f32)
+            L.tab = torch.empty(B, L.cout, 8, **f32)
+        self.rgb_s = [torch.empty(B, L.cout, **f32) for (_, _, L) in self.rgbs]
+        self.acts = [torch.empty(B, L.res_out, L.res_out, cs(L.cout), **bf16) for L in convs]
+        self.tbuf = {i: torch.empty(B, L.res_out + 1, L.res_out + 1, cs(L.cout), **bf16)
+                     for i, L in enumerate(convs) if L.up}
+        self.x0 = torch.empty(B, 4, 4, cs(convs[0].cin), **bf16)
+        self.rgb_acc = [torch.zeros(B, L.res_out, L.res_out, 4, **f32) for (_, _, L) in self.rgbs]
+        self.ident_tabs = {}
+        for L in convs:
+            if L.up and L.cout not in self.ident_tabs:
+                t = torch.zeros(1, L.cout, 8, **f32)
+                t[..., 0] = 1.0; t[..., 2] = 1.0; t[..., 3] = 1.0
+                self.ident_tabs[L.cout] = t
+        self._versions = None
+        self._desc_keepalive = None
+        self._refresh_weights()
+
+    # ------------------------------------------------------------------ derived caches
+    def _param_versions(self):
+        v = []
+        for L in self.convs:
+            v += [L.mod.weight._version, L.mod.weight.data_ptr(), L.mod.modulation.weight.data_ptr(),
+                  L.mod.modulation.bias.data_ptr(), L.act_bias.data_ptr(), L.noise_w.data_ptr()]
+        for (to_rgb, _, _) in self.rgbs:
+            v += [to_rgb.conv.weight._version, to_rgb.conv.weight.data_ptr(), to_rgb.bias.data_ptr(),
+                  to_rgb.conv.modulation.weight.data_ptr(), to_rgb.conv.modulation.bias.data_ptr()]
+        return v
+
+    def _refresh_weights(self):
+        vers = self._param_versions()
+        if vers == self._versions:
+            return
+        self._versions = vers
+        dev = self.device
+        for L in self.convs:
+            w = L.mod.weight.detach()[0]
+            L.wq, L.wsq = ops.prep_weight(w, L.mod.scale, want_wsq=True)
+        self.rgb_w = [to_rgb.conv.weight.detach().reshape(3, -1).contiguous().float() for (to_rgb, _, _) in self.rgbs]
+        # descriptor arrays (device resident)
+        n_style = len(self.convs) + len(self.rgbs)
+        sl = (StyleLayer * n_style)()
+        k = 0
+        for L in self.convs:
+            m = L.mod.modulation
+            sl[k].wmod, sl[k].bmod, sl[k].s = m.weight.data_ptr(), m.bias.data_ptr(), L.s.data_ptr()
+            sl[k].cin, sl[k].latent_idx = L.cin, L.latent_idx
+            k += 1
+        for (to_rgb, lidx, L), s in zip(self.rgbs, self.rgb_s):
+            m = to_rgb.conv.modulation
+            sl[k].wmod, sl[k].bmod, sl[k].s = m.weight.data_ptr(), m.bias.data_ptr(), s.data_ptr()
+            sl[k].cin, sl[k].latent_idx = L.cout, lidx
+            k += 1
+        self.n_style = n_style
+        self.max_cin = max(max(L.cin for L in self.convs), max(L.cout for (_, _, L) in self.rgbs))
+        tl = (TableLayer * len(self.convs))()
+        rgb_of = {id(L): (w, s) for (_, _, L), w, s in zip(self.rgbs, self.rgb_w, self.rgb_s)}
+        for i, L in enumerate(self.convs):
+            nxt = self.convs[i + 1] if i + 1 < len(self.convs) else None
+            tl[i].s, tl[i].wsq = L.s.data_ptr(), L.wsq.data_ptr()
+            tl[i].act_bias = L.act_bias.data_ptr()
+            tl[i].s_next = nxt.s.data_ptr() if nxt is not None else None
+            if id(L) in rgb_of:
+                tl[i].wrgb, tl[i].s_rgb = rgb_of[id(L)][0].data_ptr(), rgb_of[id(L)][1].data_ptr()
+            tl[i].tab = L.tab.data_ptr()
+            tl[i].cin, tl[i].cout = L.cin, L.cout
+            tl[i].slope, tl[i].gain = 0.2, math.sqrt(2.0)
+        self.max_cout = max(L.cout for L in self.convs)
+
+        def to_dev(arr):
+            raw = bytes(arr)
+            t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+            return t
+        self.style_desc = to_dev(sl)
+        self.table_desc = to_dev(tl)
+        self._desc_keepalive = (sl, tl)
+
+    # ------------------------------------------------------------------ forward
+    def run(self, latent, start, noise):
+        """latent [B,n_latent,D] fp32, start [B,C0,4,4] fp32 NCHW, noise: list (None = fresh
+        N(0,1) drawn in the reference's order) -> list of fp32 NCHW RGB images per resolution."""
+        self._refresh_weights()
+        lib = _lib.lib()
+        B = self.B
+        dev = self.device
+        latent = latent.contiguous()
+        st = torch.cuda.current_stream().cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.fm_style_affine(self.style_desc.data_ptr(), self.n_style, self.max_cin, latent.data_ptr(), B,
+                                           latent.shape[1], self.style_dim, st), "fm_style_affine")
+            _lib.check(lib.fm_build_tables(self.table_desc.data_ptr(), len(self.convs), self.max_cout, B, st),
+                       "fm_build_tables")
+            first = self.convs[0]
+            _lib.check(lib.fm_nchw_to_nhwc_bf16(self.x0.data_ptr(), start.contiguous().float().data_ptr(),
+                                                first.s.data_ptr(), B, first.cin, 4, 4, self.x0.shape[-1], st),
+                       "fm_nchw_to_nhwc_bf16")
+        x = self.x0
+        outs = []
+        skip = None
+        rgb_i = 0
+        for i, L in enumerate(self.convs):
+            nz = noise[i]
+            if nz is None:
+                nz = torch.empty(B, 1, L.res_out, L.res_out, device=dev, dtype=torch.float32).normal_()
+            nz = nz.contiguous().float()
+            per_sample = nz.shape[0] != 1
+            if nz.shape[0] not in (1, B):
+                raise RuntimeError(f"noise batch {nz.shape[0]} does not match batch {B}")
+            y = self.acts[i]
+            h = L.res_in
+            if L.up:
+                t = self.tbuf[i]
+                ident = self.ident_tabs[L.cout]
+                for py in (0, 1):
+                    for px in (0, 1):
+                        ops.conv_igemm(x, L.wq, _up_phase_taps(py, px), t, ident, B=B, H=h, W=h, Cin=L.cin, Cout=L.cout,
+                                       OH=h + 1 - py, OW=h + 1 - px, out_H=2 * h + 1, out_W=2 * h + 1,
+                                       out_y0=py, out_x0=px, out_ys=2, out_xs=2, tab_per_sample=False,
+                                       tile_w=min(16, _pow2_ge(h + 1)), tile_h=max(1, min(8, 128 // min(16, _pow2_ge(h + 1)))))
+                ops.blur_act_nhwc(t, L.kernel, L.tab, nz, per_sample, L.noise_w, L.cout, out=y)
+            else:
+                rgb = self.rgb_acc[rgb_i] if L.rgb_mod is not None else None
+                ops.conv_igemm(x, L.wq, ops.conv_taps(3, 3, 1), y, L.tab, B=B, H=h, W=h, Cin=L.cin, Cout=L.cout,
+                               OH=h, OW=h, tab_per_sample=True, noise=nz, noise_per_sample=per_sample,
+                               noise_w=L.noise_w, rgb=rgb)
+                if L.rgb_mod is not None:
+                    to_rgb = L.rgb_mod[0]
+                    kern = to_rgb.upsample.kernel if skip is not None else None
+                    skip = ops.rgb_finalize(rgb, to_rgb.bias.detach().reshape(3).contiguous(), skip, kern)
+                    outs.append(skip)
+                    rgb_i += 1
+            x = y
+        return outs
+
+
+def _pow2_ge(n):
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
+def run_synthesis(gen, latent, start, noise):
+    """Entry used by ``stylegan2.Generator.forward``: cached plan per (batch, device)."""
+    key = (latent.shape[0], latent.device.index)
+    plan = gen._engine_plans.get(key)
+    if plan is None:
+        plan = SynthesisPlan(gen, latent.shape[0], latent.device)
+        gen._engine_plans[key] = plan
+    return plan.run(latent, start, noise)

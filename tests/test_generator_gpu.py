@@ -1,0 +1,192 @@
+"""Generator / Discriminator / 3-encoder funnel on the B200 path vs golden vectors + oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, build_three_encoder_models
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fm_oracle as orc  # noqa: E402
+
+
+def _small_generator(cuda):
+    import stylegan2
+    g = load_golden("generator_small.npz")
+    gen = stylegan2.Generator(32, 64, 2, generator_net_shape=[int(v) for v in g["shape"]])
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    gen.load_state_dict(sd)          # strict: key names and shapes are the reference's
+    return gen.to(cuda).eval(), g
+
+
+def _inputs(g, cuda):
+    noise = [torch.from_numpy(g[f"noise.{i}"]).to(cuda) for i in range(7)]
+    return torch.from_numpy(g["latent"]).to(cuda), torch.from_numpy(g["ext"]).to(cuda), noise
+
+
+def test_generator_small_fp32_composition(cuda, monkeypatch):
+    """Differentiable fp32 path (shared-weight modulated conv + libfm3d ops) vs the reference."""
+    monkeypatch.setenv("FM3D_ENGINE", "0")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen, g = _small_generator(cuda)
+    lat, ext, noise = _inputs(g, cuda)
+    with torch.no_grad():
+        rgbs = gen(None, latent_styles=[lat], input_is_latent=True, noise=noise, use_external_input_tensor=True,
+                   external_input_tensor=ext, return_rgb_list=True)
+        for i, r in enumerate(rgbs):
+            np.testing.assert_allclose(r.cpu().numpy(), g[f"rgb.{i}"], rtol=1e-4, atol=1e-4)   # fp32 tolerance
+        y_z = gen([torch.from_numpy(g["z"]).to(cuda)], randomize_noise=False)
+        np.testing.assert_allclose(y_z.cpu().numpy(), g["y_z"], rtol=1e-4, atol=1e-4)
+        y_mix = gen([torch.from_numpy(g["z"]).to(cuda), torch.from_numpy(g["z2"]).to(cuda)], inject_index=3,
+                    truncation=0.7, truncation_latent=torch.from_numpy(g["mean_latent"]).to(cuda), randomize_noise=False)
+        np.testing.assert_allclose(y_mix.cpu().numpy(), g["y_mix"], rtol=1e-4, atol=1e-4)
+        out, scal = gen(None, latent_styles=[lat], input_is_latent=True, noise=noise, use_external_input_tensor=True,
+                        external_input_tensor=ext, return_style_scalars=True)
+        assert len(scal) == 8 and scal[0].shape == (3, 1, 32, 1, 1)
+        np.testing.assert_allclose(out.cpu().numpy(), g["y_latent"], rtol=1e-4, atol=1e-4)
+
+
+def test_generator_small_ppl_branch(cuda):
+    """PPL_regularize=True: (image, path_lengths) with a double-backward-capable graph."""
+    torch.backends.cudnn.allow_tf32 = False
+    gen, g = _small_generator(cuda)
+    lat, ext, noise = _inputs(g, cuda)
+    lat = lat.clone().requires_grad_(True)
+    torch.manual_seed(11)
+    img, pl = gen(None, latent_styles=[lat], input_is_latent=True, noise=noise, use_external_input_tensor=True,
+                  external_input_tensor=ext, PPL_regularize=True)
+    torch.manual_seed(11)
+    pl_noise = torch.randn(img.shape, device=cuda)
+    sd = {k: v.detach().cpu() for k, v in gen.state_dict().items()}
+    img_r, pl_r = orc.generator_ppl_ref(sd, lat.detach().cpu(), [n.cpu() for n in noise], ext.cpu(), pl_noise.cpu())
+    np.testing.assert_allclose(img.detach().cpu().numpy(), img_r.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(pl.detach().cpu().numpy(), pl_r.numpy(), rtol=1e-3, atol=1e-5)
+    # second order: the path-length penalty back-propagates into the weights (train_3_encoder.py:593)
+    ((pl - pl.mean().detach()).pow(2).mean()).backward()
+    gw = gen.convs[0].conv.weight.grad
+    assert gw is not None and torch.isfinite(gw).all() and float(gw.abs().sum()) > 0
+
+
+def _rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def test_generator_small_engine_bf16(cuda):
+    """Fused bf16 engine (tcgen05 implicit GEMM) vs the fp32 reference; per-layer tolerance
+    2^-6 of the activation's max magnitude, final image 3e-2 of its max (stated in DESIGN.md)."""
+    gen, g = _small_generator(cuda)
+    lat, ext, noise = _inputs(g, cuda)
+    with torch.no_grad():
+        rgbs = gen(None, latent_styles=[lat], input_is_latent=True, noise=noise, use_external_input_tensor=True,
+                   external_input_tensor=ext, return_rgb_list=True)
+    assert len(rgbs) == 4
+    for i, r in enumerate(rgbs):
+        ref = torch.from_numpy(g[f"rgb.{i}"])
+        assert r.shape == ref.shape and r.dtype == torch.float32
+        assert _rel_err(r.cpu(), ref) < 3e-2, (i, _rel_err(r.cpu(), ref))
+    # stored-noise ([1,1,r,r] buffers) + mapping network + ConstantInput path
+    with torch.no_grad():
+        y_z = gen([torch.from_numpy(g["z"]).to(cuda)], randomize_noise=False)
+    assert _rel_err(y_z.cpu(), torch.from_numpy(g["y_z"])) < 3e-2
+
+
+def test_generator_engine_random_noise_matches_torch_rng(cuda):
+    """noise=None draws N(0,1) per layer with the same torch calls, in the same order, as
+    NoiseInjection (stylegan2.py:308-310): the engine and the composed path agree for a seed."""
+    gen, g = _small_generator(cuda)
+    lat, ext, _ = _inputs(g, cuda)
+    with torch.no_grad():
+        torch.manual_seed(5)
+        a = gen(None, latent_styles=[lat], input_is_latent=True, use_external_input_tensor=True, external_input_tensor=ext)
+        os.environ["FM3D_ENGINE"] = "0"
+        try:
+            torch.manual_seed(5)
+            b = gen(None, latent_styles=[lat], input_is_latent=True, use_external_input_tensor=True, external_input_tensor=ext)
+        finally:
+            os.environ.pop("FM3D_ENGINE")
+    assert _rel_err(a, b) < 3e-2
+
+
+def test_generator_cfg1_engine(cuda):
+    """BASELINE config 1 (Generator(256,512,8), batch 4) on the engine vs the reference's CPU output."""
+    import stylegan2
+    from conftest import state_checksum
+    g = load_golden("generator_cfg1.npz")
+    torch.manual_seed(0)
+    gen = stylegan2.Generator(256, 512, 8, channel_multiplier=2)
+    rg = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p in gen.named_parameters():
+            if name.endswith("noise.weight") or name.endswith("activate.bias") or \
+               (name.endswith(".bias") and "to_rgb" in name and p.ndim == 4):
+                p.copy_(torch.randn(p.shape, generator=rg) * 0.1)
+    np.testing.assert_allclose(state_checksum(gen.state_dict()), g["sd_checksum"], rtol=1e-12)
+    gen = gen.to(cuda).eval()
+    rg = torch.Generator().manual_seed(2)
+    z = torch.randn(4, 512, generator=rg); lat = torch.randn(4, 14, 512, generator=rg); ext = torch.randn(4, 512, 4, 4, generator=rg)
+    rg3 = torch.Generator().manual_seed(3)
+    noise = [torch.randn(4, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), generator=rg3).to(cuda) for i in range(13)]
+    with torch.no_grad():
+        y = gen(None, latent_styles=[lat.to(cuda)], input_is_latent=True, noise=noise, use_external_input_tensor=True,
+                external_input_tensor=ext.to(cuda))
+        yz = gen([z.to(cuda)], randomize_noise=False)
+    assert y.shape == (4, 3, 256, 256)
+    ref0 = torch.from_numpy(g["y_latent.img0"].astype(np.float32))
+    e_img = _rel_err(y[0].cpu(), ref0)
+    e_ds = _rel_err(y[:, :, ::8, ::8].cpu(), torch.from_numpy(g["y_latent.ds8"]))
+    e_z = _rel_err(yz[:, :, ::8, ::8].cpu(), torch.from_numpy(g["y_z.ds8"]))
+    print(f"cfg1 engine rel err: img0 {e_img:.4f} ds8 {e_ds:.4f} z {e_z:.4f}")
+    assert max(e_img, e_ds, e_z) < 3e-2
+    np.testing.assert_allclose([float(y.mean()), float(y.std())], g["y_latent.stats"], rtol=0, atol=2e-2)
+
+
+def test_discriminator_and_r1(cuda):
+    import stylegan2
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load_golden("discriminator32.npz")
+    torch.manual_seed(500)
+    d = stylegan2.Discriminator(32)
+    with torch.no_grad():
+        for n, p in d.named_parameters():
+            if n.endswith("bias"):
+                p.add_(torch.randn_like(p) * 0.1)
+    d = d.to(cuda)
+    x = torch.from_numpy(g["x"]).to(cuda)
+    with torch.no_grad():
+        y = d(x)
+    np.testing.assert_allclose(y.cpu().numpy(), g["y"], rtol=1e-3, atol=1e-4)
+    # R1 (Util/training_util.py:46-52): double backward through blur / bias-act kernels
+    xr = x.clone().requires_grad_(True)
+    grad_real, = torch.autograd.grad(outputs=d(xr).sum(), inputs=xr, create_graph=True)
+    r1 = grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
+    gw = torch.autograd.grad(r1, d.convs[0][0].weight)[0]
+    np.testing.assert_allclose(float(r1), float(g["r1"]), rtol=2e-3)
+    np.testing.assert_allclose(gw.cpu().numpy(), g["r1.grad_conv0"], rtol=5e-3, atol=1e-6)
+
+
+def test_three_encoder_forward(cuda):
+    """Forward_Inference_3_Encoder (a16) end to end vs the reference run (golden), B=2."""
+    from Util.network_util import Forward_Inference_3_Encoder
+    g = load_golden("three_encoder.npz")
+    (e_tsr, e_w, e_wp, gen), p, r, noise = build_three_encoder_models(cuda)
+
+    class _G(torch.nn.Module):       # the funnel only needs .module.n_latent and a call (nn.DataParallel shape)
+        def __init__(s, m):
+            super().__init__(); s.module = m
+        def forward(s, *a, **k):
+            k["noise"] = [n.to(cuda) for n in noise]
+            return s.module(*a, **k)
+    with torch.no_grad():
+        img = Forward_Inference_3_Encoder(p.to(cuda), r.to(cuda), e_tsr, e_w, e_wp, _G(gen), tsr_encode='Render Image')
+        t = e_tsr(r.to(cuda)); w = e_w(r.to(cuda)); wp = e_wp(p.to(cuda))
+    for name, got, tol in (("e_tsr", t, 3e-2), ("e_w", w, 3e-2), ("e_wp", wp, 3e-2)):
+        e = _rel_err(got.cpu(), torch.from_numpy(g[name]))
+        print(f"{name} rel err {e:.4f}")
+        assert e < tol, (name, e)
+    e = _rel_err(img[:, :, ::8, ::8].cpu(), torch.from_numpy(g["img.ds8"]))
+    print(f"3-encoder image rel err {e:.4f}")
+    assert e < 5e-2
