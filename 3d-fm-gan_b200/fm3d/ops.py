@@ -10,6 +10,9 @@ import torch
 from . import _lib
 from ._lib import ConvDesc, FM_BF16, FM_F16, FM_F32
 
+# bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops) per conv launch
+PROFILE = None
+
 _DTYPES = {torch.float32: FM_F32, torch.float16: FM_F16, torch.bfloat16: FM_BF16}
 
 
@@ -146,8 +149,15 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     d.residual = _ptr(residual)
     d.rgb = _ptr(rgb)
     d.block_n, d.tile_w, d.tile_h = block_n, tile_w, tile_h
+    prof = PROFILE
     with torch.cuda.device(x.device):
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         st = _lib.lib().fm_conv_igemm(C.byref(d), _stream())
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1, 2.0 * B * OH * OW * Cin * Cout * len(taps)))
     _lib.check(st, "fm_conv_igemm")
     return out
 
