@@ -1,0 +1,297 @@
+// Bandwidth-bound NHWC bf16 helpers for the encoder path (ResNet-18 and pSp IR-SE encoders):
+// stem input packing, max/avg pooling, squeeze-and-excitation, bilinear FPN upsampling.
+// Each replaces a separate ATen kernel of the reference graph (resnet_encoder.py:258-280,
+// psp_encoder_model/encoders/helpers.py:76-139, psp_encoders.py:81-98).
+#include "common.cuh"
+
+namespace fm {
+
+__device__ __forceinline__ void unpack8(const uint4& w, float (&v)[8]) {
+  float2 f;
+  f = unpack_bf16x2(w.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(w.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(w.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(w.w); v[6] = f.x; v[7] = f.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 w;
+  w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+  w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+  return w;
+}
+
+static inline unsigned grid_for2(int64_t total, int waves = 16) {
+  int64_t want = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * waves;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<unsigned>(want);
+}
+
+// fp32 NCHW image (C <= 8) -> zero-padded bf16 [B, Hp, Wp, 8]
+__global__ void __launch_bounds__(256) image_pack_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x, int C,
+                                                         int H, int W, int pad_t, int pad_l, int Hp, int Wp, int64_t total) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int xp = static_cast<int>(idx % Wp);
+    const int yp = static_cast<int>((idx / Wp) % Hp);
+    const int64_t b = idx / (static_cast<int64_t>(Wp) * Hp);
+    const int y = yp - pad_t, xx = xp - pad_l;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (y >= 0 && y < H && xx >= 0 && xx < W) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < C) v[c] = x[((b * C + c) * H + y) * static_cast<int64_t>(W) + xx];
+    }
+    *reinterpret_cast<uint4*>(out + idx * 8) = pack8(v);
+  }
+}
+
+// 3x3 stride-2 pad-1 max pooling, NHWC bf16
+__global__ void __launch_bounds__(256) maxpool_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ x,
+                                                      int H, int W, int OH, int OW, int cs, int64_t total) {
+  const int groups = cs / 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int g = static_cast<int>(idx % groups);
+    int64_t r = idx / groups;
+    const int ox = static_cast<int>(r % OW); r /= OW;
+    const int oy = static_cast<int>(r % OH);
+    const int64_t b = r / OH;
+    float m[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) m[c] = -INFINITY;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((b * H + iy) * W + ix) * cs + g * 8)), v);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m[c] = fmaxf(m[c], v[c]);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + ((b * OH + oy) * OW + ox) * cs + g * 8) = pack8(m);
+  }
+}
+
+// non-overlapping ph x pw average pooling, NHWC bf16 -> NCHW fp32
+__global__ void __launch_bounds__(256) avgpool_kernel(float* __restrict__ out, const __nv_bfloat16* __restrict__ x, int H, int W,
+                                                      int C, int cs, int ph, int pw, int64_t total) {
+  const int OH = H / ph, OW = W / pw;
+  const float inv = 1.f / (ph * pw);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    // idx enumerates (b, oy, ox, c) so that reads are channel-contiguous
+    const int c = static_cast<int>(idx % C);
+    int64_t r = idx / C;
+    const int ox = static_cast<int>(r % OW); r /= OW;
+    const int oy = static_cast<int>(r % OH);
+    const int64_t b = r / OH;
+    float acc = 0.f;
+    for (int dy = 0; dy < ph; ++dy)
+      for (int dx = 0; dx < pw; ++dx)
+        acc += __bfloat162float(x[((b * H + oy * ph + dy) * W + ox * pw + dx) * cs + c]);
+    out[((b * C + c) * OH + oy) * OW + ox] = acc * inv;
+  }
+}
+
+// sum over pixels per (b, c): grid (chunks, B); fp32 atomics into sum[B][C] (zeroed by the caller)
+__global__ void __launch_bounds__(256) channel_sum_kernel(float* __restrict__ sum, const __nv_bfloat16* __restrict__ x, int HW,
+                                                          int C, int cs, int chunk) {
+  __shared__ float s_part[256 * 8];
+  const int groups = cs / 8;
+  const int lanes = 256 / groups;               // pixel lanes per block (groups <= 64 -> >= 4)
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * chunk;
+  const int p1 = min(p0 + chunk, HW);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (pl < lanes) {
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + (static_cast<int64_t>(b) * HW + p) * cs + g * 8)), v);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] += v[c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s_part[threadIdx.x * 8 + c] = (pl < lanes) ? acc[c] : 0.f;
+  __syncthreads();
+  if (threadIdx.x < groups * 8) {
+    const int gg = threadIdx.x / 8, c = threadIdx.x % 8;
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += s_part[(l * groups + gg) * 8 + c];
+    const int ch = gg * 8 + c;
+    if (ch < C) atomicAdd(sum + static_cast<int64_t>(b) * C + ch, t);
+  }
+}
+
+// gate[b,c] = sigmoid(w2[c,:] . relu(w1 . mean[b,:]));  one block per sample.  Clears sum afterwards.
+__global__ void __launch_bounds__(256) se_gate_kernel(float* __restrict__ gate, float* __restrict__ sum, float inv_hw,
+                                                      const float* __restrict__ w1, const float* __restrict__ w2, int C, int Cr) {
+  __shared__ float s_mean[1024];
+  __shared__ float s_hid[64];
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    s_mean[c] = sum[static_cast<int64_t>(b) * C + c] * inv_hw;
+    sum[static_cast<int64_t>(b) * C + c] = 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < Cr; j += 8) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(w1 + static_cast<int64_t>(j) * C + c), s_mean[c], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) s_hid[j] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float acc = 0.f;
+    for (int j = 0; j < Cr; ++j) acc = fmaf(__ldg(w2 + static_cast<int64_t>(c) * Cr + j), s_hid[j], acc);
+    gate[static_cast<int64_t>(b) * C + c] = 1.f / (1.f + __expf(-acc));
+  }
+}
+
+// out = r * gate[b,c] + shortcut[b, y*ss, x*ss, c]
+__global__ void __launch_bounds__(256) se_combine_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ r,
+                                                         const float* __restrict__ gate, const __nv_bfloat16* __restrict__ sc,
+                                                         int H, int W, int C, int cs, int sc_H, int sc_W, int sc_cs, int ss,
+                                                         int64_t total) {
+  const int groups = cs / 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int g = static_cast<int>(idx % groups);
+    int64_t t = idx / groups;
+    const int x = static_cast<int>(t % W); t /= W;
+    const int y = static_cast<int>(t % H);
+    const int64_t b = t / H;
+    float rv[8], sv[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(r + ((b * H + y) * W + x) * cs + g * 8)), rv);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(sc + ((b * sc_H + y * ss) * sc_W + x * ss) * sc_cs + g * 8)), sv);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int ch = g * 8 + c;
+      o[c] = ch < C ? fmaf(rv[c], __ldg(gate + b * C + ch), sv[c]) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(out + ((b * H + y) * W + x) * cs + g * 8) = pack8(o);
+  }
+}
+
+// bilinear resize with align_corners=True (F.interpolate, psp_encoders.py:98), NHWC bf16
+__global__ void __launch_bounds__(256) bilinear_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ x,
+                                                       int IH, int IW, int OH, int OW, int cs, float ry, float rx,
+                                                       int64_t total) {
+  const int groups = cs / 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int g = static_cast<int>(idx % groups);
+    int64_t t = idx / groups;
+    const int ox = static_cast<int>(t % OW); t /= OW;
+    const int oy = static_cast<int>(t % OH);
+    const int64_t b = t / OH;
+    const float fy = ry * oy, fx = rx * ox;
+    const int y0 = min(static_cast<int>(fy), IH - 1), x0 = min(static_cast<int>(fx), IW - 1);
+    const int y1 = min(y0 + 1, IH - 1), x1 = min(x0 + 1, IW - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    float a[8], bq[8], c[8], d[8], o[8];
+    const __nv_bfloat16* base = x + b * IH * IW * static_cast<int64_t>(cs) + g * 8;
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y0) * IW + x0) * cs)), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y0) * IW + x1) * cs)), bq);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y1) * IW + x0) * cs)), c);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(y1) * IW + x1) * cs)), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      o[k] = (1.f - ly) * ((1.f - lx) * a[k] + lx * bq[k]) + ly * ((1.f - lx) * c[k] + lx * d[k]);
+    *reinterpret_cast<uint4*>(out + ((b * OH + oy) * OW + ox) * cs + g * 8) = pack8(o);
+  }
+}
+
+}  // namespace fm
+
+using namespace fm;
+#define ST static_cast<cudaStream_t>(stream)
+
+extern "C" int fm_image_to_nhwc8_padded(void* out, const float* x, int B, int C, int H, int W, int pad_t, int pad_l, int Hp,
+                                        int Wp, void* stream) {
+  FM_CHECK_ARG(out && x && B > 0 && C > 0 && C <= 8 && H > 0 && W > 0, "fm_image_to_nhwc8_padded: bad args");
+  FM_CHECK_ARG(pad_t >= 0 && pad_l >= 0 && Hp >= H + pad_t && Wp >= W + pad_l, "fm_image_to_nhwc8_padded: bad padding");
+  const int64_t total = static_cast<int64_t>(B) * Hp * Wp;
+  image_pack_kernel<<<grid_for2(total), 256, 0, ST>>>(static_cast<__nv_bfloat16*>(out), x, C, H, W, pad_t, pad_l, Hp, Wp, total);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_maxpool3x3s2_nhwc(void* out, const void* x, int B, int H, int W, int cs, void* stream) {
+  FM_CHECK_ARG(out && x && B > 0 && H > 0 && W > 0 && cs > 0 && cs % 8 == 0, "fm_maxpool3x3s2_nhwc: bad args");
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  const int64_t total = static_cast<int64_t>(B) * OH * OW * (cs / 8);
+  maxpool_kernel<<<grid_for2(total), 256, 0, ST>>>(static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(x), H, W,
+                                                   OH, OW, cs, total);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_avgpool_nhwc_to_nchw(float* out, const void* x, int B, int H, int W, int C, int cs, int ph, int pw,
+                                       void* stream) {
+  FM_CHECK_ARG(out && x && B > 0 && H > 0 && W > 0 && C > 0 && cs >= C && ph > 0 && pw > 0 && H % ph == 0 && W % pw == 0,
+               "fm_avgpool_nhwc_to_nchw: bad args");
+  const int64_t total = static_cast<int64_t>(B) * (H / ph) * (W / pw) * C;
+  avgpool_kernel<<<grid_for2(total), 256, 0, ST>>>(out, static_cast<const __nv_bfloat16*>(x), H, W, C, cs, ph, pw, total);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_channel_sum_nhwc(float* sum_bc, const void* x, int B, int HW, int C, int cs, void* stream) {
+  FM_CHECK_ARG(sum_bc && x && B > 0 && HW > 0 && C > 0 && cs >= C && cs % 8 == 0 && cs <= 512 && 256 % (cs / 8) == 0,
+               "fm_channel_sum_nhwc: bad args (cs must be 8*2^k <= 512)");
+  const int chunk = 1024;
+  dim3 grid((HW + chunk - 1) / chunk, B);
+  channel_sum_kernel<<<grid, 256, 0, ST>>>(sum_bc, static_cast<const __nv_bfloat16*>(x), HW, C, cs, chunk);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_se_gate(float* gate_bc, float* sum_bc, float inv_hw, const float* w1, const float* w2, int B, int C, int Cr,
+                          void* stream) {
+  FM_CHECK_ARG(gate_bc && sum_bc && w1 && w2 && B > 0 && C > 0 && C <= 1024 && Cr > 0 && Cr <= 64, "fm_se_gate: bad args");
+  se_gate_kernel<<<B, 256, 0, ST>>>(gate_bc, sum_bc, inv_hw, w1, w2, C, Cr);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_se_combine_nhwc(void* out, const void* r, const float* gate_bc, const void* sc, int B, int H, int W, int C,
+                                  int cs, int sc_H, int sc_W, int sc_cs, int sc_stride, void* stream) {
+  FM_CHECK_ARG(out && r && gate_bc && sc && B > 0 && H > 0 && W > 0 && C > 0 && cs >= C && cs % 8 == 0 && sc_cs >= cs - 7 &&
+                   sc_cs % 8 == 0 && sc_stride >= 1, "fm_se_combine_nhwc: bad args");
+  FM_CHECK_ARG((H - 1) * sc_stride < sc_H && (W - 1) * sc_stride < sc_W, "fm_se_combine_nhwc: shortcut too small");
+  const int64_t total = static_cast<int64_t>(B) * H * W * (cs / 8);
+  se_combine_kernel<<<grid_for2(total), 256, 0, ST>>>(static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(r),
+                                                      gate_bc, static_cast<const __nv_bfloat16*>(sc), H, W, C, cs, sc_H, sc_W,
+                                                      sc_cs, sc_stride, total);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
+extern "C" int fm_bilinear_up_nhwc(void* out, const void* x, int B, int IH, int IW, int OH, int OW, int cs, void* stream) {
+  FM_CHECK_ARG(out && x && B > 0 && IH > 0 && IW > 0 && OH > 0 && OW > 0 && cs > 0 && cs % 8 == 0, "fm_bilinear_up_nhwc: bad args");
+  const float ry = OH > 1 ? static_cast<float>(IH - 1) / (OH - 1) : 0.f;
+  const float rx = OW > 1 ? static_cast<float>(IW - 1) / (OW - 1) : 0.f;
+  const int64_t total = static_cast<int64_t>(B) * OH * OW * (cs / 8);
+  bilinear_kernel<<<grid_for2(total), 256, 0, ST>>>(static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(x), IH,
+                                                    IW, OH, OW, cs, ry, rx, total);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}

@@ -30,7 +30,12 @@ struct IgemmParams {
   int OH, OW, B;
   int tw, th, tb;                  // tile dims, tw*th*tb == 128
   int tiles_x, tiles_y, tiles_b, tiles_n, num_tiles;
-  int kchunks, ntaps, stride, w_rows, Cout;
+  int kchunks, ntaps, stride_x, stride_y, w_rows, Cout;
+  int rows;                        // tw*th*tb (<= 128) valid rows of the A tile
+  int Bg, nslabs;                  // images per group, weight slabs per group
+  const float* border_tab;
+  int out_cgroup;
+  long long out_gstride;
   void* out;
   int out_H, out_W, out_cstride, out_y0, out_x0, out_ys, out_xs, out_nchw_f32;
   const float* tab;
@@ -108,7 +113,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int bx = m % p.tiles_x; m /= p.tiles_x;
       const int by = m % p.tiles_y;
       const int bb = m / p.tiles_y;
-      const int x0 = bx * p.tw * p.stride, y0 = by * p.th * p.stride, b0 = bb * p.tb, n0 = nt * BN;
+      const int x0 = bx * p.tw * p.stride_x, y0 = by * p.th * p.stride_y, b0 = bb * p.tb, n0 = nt * BN;
+      const int wrow0 = (b0 / p.Bg) * p.nslabs;
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.rows) * (IG_BK * 2) + Cfg::B_BYTES;
       for (int it = 0; it < kiters; ++it) {
         const int tap = it / p.kchunks;
         const int kc = it - tap * p.kchunks;
@@ -116,9 +123,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
           uint8_t* sa = s_stage + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_4d(sa, &tmA, &full_bar[stage], kc * IG_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kc * IG_BK, p.tap_widx[tap] * p.w_rows + n0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0);
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -176,15 +183,16 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int ly = (row / p.tw) % p.th;
       const int lb = row / (p.tw * p.th);
       const int ox = bx * p.tw + lx, oy = by * p.th + ly, b = bb * p.tb + lb;
-      const bool valid = ox < p.OW && oy < p.OH && b < p.B;
+      const bool valid = row < p.rows && ox < p.OW && oy < p.OH && b < p.B;
+      const int grp = (bb * p.tb) / p.Bg;
 
       // ---- stage this tile's epilogue tables (overlaps the tile's MMAs)
       for (int i = etid; i < tbe * BN; i += 128) {
         const int sb = i / BN, j = i - sb * BN;
         const int o = n0 + j;
-        const int bsrc = p.tab_bstride ? (bb * p.tb + sb) : 0;
+        const int bsrc = p.tab_bstride ? (bb * p.tb + sb) : grp;
         float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
-        if (o < p.Cout && bsrc < p.B) {
+        if (o < p.Cout && (!p.tab_bstride || bsrc < p.B)) {
           const float4* src = reinterpret_cast<const float4*>(p.tab + (static_cast<size_t>(bsrc) * p.Cout + o) * 8);
           t0 = __ldg(src);
           t1 = __ldg(src + 1);
@@ -201,6 +209,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const size_t pix = (static_cast<size_t>(b) * p.out_H + Y) * p.out_W + X;
       const float4* trow = s_tab + static_cast<size_t>(p.tab_bstride ? lb : 0) * BN * 2;
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      const float* btab = nullptr;      // folded-input-BN border correction (per-thread: thread = pixel)
+      if (p.border_tab) {
+        const int cls = (oy == 0 ? 1 : (oy == p.OH - 1 ? 2 : 0)) * 3 + (ox == 0 ? 1 : (ox == p.OW - 1 ? 2 : 0));
+        if (cls) btab = p.border_tab + static_cast<size_t>(cls) * p.Cout;
+      }
 
       mbar_wait(&tfull_bar[buf], aphase);
       tc_fence_after();
@@ -210,18 +223,23 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c * 32, acc);
         tmem_ld_wait();
         const int o0 = n0 + c * 32;
-        if (o0 >= p.out_cstride && !(p.out_nchw_f32 && o0 < p.Cout)) continue;   // nothing to write (warp-uniform)
+        // position inside the output tensor (concatenated-N outputs are written group-major)
+        const int og = p.out_cgroup ? o0 / p.out_cgroup : 0;
+        const int ol0 = o0 - og * p.out_cgroup;
+        // chunks past Cout only zero-fill the pad channels of an NHWC tensor (warp-uniform test)
+        if (o0 >= p.Cout && (p.out_nchw_f32 || p.out_cgroup || ol0 >= p.out_cstride)) continue;
         float v[32];
         uint4 resv[4];
         if (p.residual && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.out_cstride + o0);
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.out_cstride + ol0);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) resv[g] = (o0 + 8 * g < p.out_cstride) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
+          for (int g = 0; g < 4; ++g) resv[g] = (ol0 + 8 * g < p.out_cstride) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float4 t0 = trow[2 * (c * 32 + j)];
           float x = fmaf(__uint_as_float(acc[j]), t0.x, t0.y + nz);
+          if (btab && o0 + j < p.Cout) x += __ldg(btab + o0 + j);
           if (p.residual) {
             const uint32_t w = reinterpret_cast<const uint32_t*>(resv)[j >> 1];
             const float2 f = unpack_bf16x2(w);
@@ -244,10 +262,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (o0 + j < p.Cout)
                 op[((static_cast<size_t>(b) * p.Cout + o0 + j) * p.out_H + Y) * p.out_W + X] = v[j];
           } else {
-            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.out_cstride + o0);
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + og * p.out_gstride +
+                                                 pix * p.out_cstride + ol0);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              if (o0 + 8 * g < p.out_cstride) {
+              if (ol0 + 8 * g < p.out_cstride) {
                 uint4 w;
                 w.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
                 w.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
@@ -326,38 +345,53 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   FM_CHECK_ARG(d->x && d->w && d->out && d->tab, "fm_conv_igemm: null tensor");
   FM_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "fm_conv_igemm: bad sizes");
   FM_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= FM_MAX_TAPS, "fm_conv_igemm: ntaps %d out of range", d->ntaps);
-  FM_CHECK_ARG(d->stride == 1 || d->stride == 2, "fm_conv_igemm: stride must be 1 or 2");
-  FM_CHECK_ARG(d->x_cstride % 8 == 0 && d->x_cstride >= d->Cin, "fm_conv_igemm: x_cstride must be a multiple of 8 and >= Cin");
+  const int sx = d->stride_x > 0 ? d->stride_x : d->stride;
+  const int sy = d->stride_y > 0 ? d->stride_y : d->stride;
+  FM_CHECK_ARG(sx >= 1 && sx <= 8 && sy >= 1 && sy <= 8, "fm_conv_igemm: strides must be in 1..8 (got %d, %d)", sx, sy);
+  const int64_t pixs = d->x_pixstride > 0 ? d->x_pixstride : d->x_cstride;
+  const int64_t rows_ = d->x_rowstride > 0 ? d->x_rowstride : pixs * d->W;
+  const int64_t imgs = d->x_imgstride > 0 ? d->x_imgstride : rows_ * d->H;
+  FM_CHECK_ARG(pixs % 8 == 0 && rows_ % 8 == 0 && imgs % 8 == 0, "fm_conv_igemm: input strides must be multiples of 8 elements");
+  FM_CHECK_ARG(d->x_pixstride > 0 || d->x_cstride >= d->Cin, "fm_conv_igemm: x_cstride < Cin");
   FM_CHECK_ARG(d->w_cstride % 8 == 0 && d->w_cstride >= d->Cin, "fm_conv_igemm: w_cstride must be a multiple of 8 and >= Cin");
   FM_CHECK_ARG(d->w_rows >= d->Cout, "fm_conv_igemm: w_rows < Cout");
   FM_CHECK_ARG((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "fm_conv_igemm: tensors must be 16-byte aligned");
-  FM_CHECK_ARG(d->out_nchw_f32 || (d->out_cstride % 8 == 0 && d->out_cstride >= d->Cout),
+  FM_CHECK_ARG(d->out_nchw_f32 || d->out_cgroup || (d->out_cstride % 8 == 0 && d->out_cstride >= d->Cout),
                "fm_conv_igemm: out_cstride must be a multiple of 8 and >= Cout");
   FM_CHECK_ARG(d->OH > 0 && d->OW > 0 && d->out_ys >= 1 && d->out_xs >= 1, "fm_conv_igemm: bad output grid");
   FM_CHECK_ARG((d->OH - 1) * d->out_ys + d->out_y0 < d->out_H && (d->OW - 1) * d->out_xs + d->out_x0 < d->out_W,
                "fm_conv_igemm: output grid does not fit the output tensor");
-  FM_CHECK_ARG(!(d->residual && d->out_nchw_f32), "fm_conv_igemm: residual needs NHWC output");
+  FM_CHECK_ARG(!(d->residual && (d->out_nchw_f32 || d->out_cgroup)), "fm_conv_igemm: residual needs a plain NHWC output");
+  FM_CHECK_ARG(!d->border_tab || (d->OH >= 2 && d->OW >= 2), "fm_conv_igemm: border_tab needs OH, OW >= 2");
+  FM_CHECK_ARG(!d->out_cgroup || (!d->out_nchw_f32 && d->out_cgroup % 32 == 0 && d->Cout % d->out_cgroup == 0 &&
+                                  d->out_cstride % 8 == 0 && d->out_cstride >= d->out_cgroup && d->out_gstride % 8 == 0),
+               "fm_conv_igemm: bad grouped-output parameters");
+  const int G = d->groups > 1 ? d->groups : 1;
+  FM_CHECK_ARG(d->B % G == 0, "fm_conv_igemm: batch %d not divisible by groups %d", d->B, G);
+  const int Bg = d->B / G;
 
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) { set_error("fm_conv_igemm: cuTensorMapEncodeTiled driver entry point unavailable"); return FM_ERR_NO_DEVICE; }
 
   IgemmParams p{};
-  p.OH = d->OH; p.OW = d->OW; p.B = d->B;
-  // ---- tile shape: tw*th*tb = 128 pixels
+  p.OH = d->OH; p.OW = d->OW; p.B = d->B; p.Bg = Bg;
+  // ---- tile shape: tw*th*tb <= 128 pixels (a tile never straddles two groups)
   int tw = d->tile_w, th = d->tile_h;
   if (tw <= 0 || th <= 0) {
     tw = 1; while (tw < d->OW && tw < 128) tw <<= 1;
     th = 1; while (th < d->OH && tw * th < 128) th <<= 1;
   }
   FM_CHECK_ARG(tw >= 1 && th >= 1 && 128 % (tw * th) == 0, "fm_conv_igemm: tile %dx%d does not divide 128", tw, th);
-  p.tw = tw; p.th = th; p.tb = 128 / (tw * th);
-  FM_CHECK_ARG(tw * d->stride <= 256 && th * d->stride <= 256 && p.tb <= 256, "fm_conv_igemm: TMA box too large");
+  int tb = 128 / (tw * th);
+  if (G > 1) while (tb > 1 && (tb > Bg || Bg % tb != 0)) tb >>= 1;
+  p.tw = tw; p.th = th; p.tb = tb; p.rows = tw * th * tb;
+  FM_CHECK_ARG(tw * sx <= 256 && th * sy <= 256 && tb <= 256, "fm_conv_igemm: TMA box too large");
   p.tiles_x = (d->OW + tw - 1) / tw;
   p.tiles_y = (d->OH + th - 1) / th;
-  p.tiles_b = (d->B + p.tb - 1) / p.tb;
+  p.tiles_b = (d->B + tb - 1) / tb;
   // ---- block_n
-  const int tbe = d->tab_bstride ? p.tb : 1;
+  const int tbe = d->tab_bstride ? tb : 1;
   int bn = d->block_n;
   if (bn <= 0) {
     bn = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
@@ -368,12 +402,13 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   while (bn > 64 && tbe * bn > IG_TAB_ROWS) bn >>= 1;
   FM_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "fm_conv_igemm: block_n must be 64/128/256");
   FM_CHECK_ARG(tbe * bn <= IG_TAB_ROWS, "fm_conv_igemm: per-sample tables do not fit (tile_b %d x block_n %d)", tbe, bn);
+  FM_CHECK_ARG(!d->out_cgroup || d->out_cgroup % bn == 0 || bn % d->out_cgroup == 0, "fm_conv_igemm: out_cgroup vs block_n");
   p.tiles_n = (d->Cout + bn - 1) / bn;
   const int64_t nt = static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.tiles_b * p.tiles_n;
   FM_CHECK_ARG(nt < 0x7FFFFFFF, "fm_conv_igemm: too many tiles");
   p.num_tiles = static_cast<int>(nt);
   p.kchunks = (d->Cin + IG_BK - 1) / IG_BK;
-  p.ntaps = d->ntaps; p.stride = d->stride; p.w_rows = d->w_rows; p.Cout = d->Cout;
+  p.ntaps = d->ntaps; p.stride_x = sx; p.stride_y = sy; p.w_rows = d->w_rows; p.Cout = d->Cout;
   p.out = d->out; p.out_H = d->out_H; p.out_W = d->out_W; p.out_cstride = d->out_cstride;
   p.out_y0 = d->out_y0; p.out_x0 = d->out_x0; p.out_ys = d->out_ys; p.out_xs = d->out_xs;
   p.out_nchw_f32 = d->out_nchw_f32;
@@ -381,31 +416,34 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   p.noise = d->noise; p.noise_bstride = d->noise_bstride ? 1 : 0; p.noise_w = d->noise_w;
   p.residual = static_cast<const __nv_bfloat16*>(d->residual);
   p.rgb = d->rgb;
+  p.border_tab = d->border_tab;
+  p.out_cgroup = d->out_cgroup; p.out_gstride = d->out_gstride;
   int max_widx = 0;
   for (int i = 0; i < d->ntaps; ++i) {
     p.tap_dy[i] = d->tap_dy[i]; p.tap_dx[i] = d->tap_dx[i]; p.tap_widx[i] = d->tap_widx[i];
     FM_CHECK_ARG(d->tap_widx[i] >= 0, "fm_conv_igemm: negative tap_widx");
     if (d->tap_widx[i] > max_widx) max_widx = d->tap_widx[i];
   }
+  p.nslabs = max_widx + 1;
 
   // ---- tensor maps
   CUtensorMap tmA, tmB;
   {
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->Cin), static_cast<cuuint64_t>(d->W), static_cast<cuuint64_t>(d->H),
                                 static_cast<cuuint64_t>(d->B)};
-    const cuuint64_t cs = static_cast<cuuint64_t>(d->x_cstride) * 2;
-    const cuuint64_t strides[3] = {cs, cs * d->W, cs * d->W * d->H};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(pixs) * 2, static_cast<cuuint64_t>(rows_) * 2,
+                                   static_cast<cuuint64_t>(imgs) * 2};
     // with an element stride s TMA loads ceil(box/s) elements: box = n*s loads n
-    const cuuint32_t box[4] = {IG_BK, static_cast<cuuint32_t>(tw * d->stride), static_cast<cuuint32_t>(th * d->stride),
-                               static_cast<cuuint32_t>(p.tb)};
-    const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d->stride), static_cast<cuuint32_t>(d->stride), 1};
+    const cuuint32_t box[4] = {IG_BK, static_cast<cuuint32_t>(tw * sx), static_cast<cuuint32_t>(th * sy),
+                               static_cast<cuuint32_t>(tb)};
+    const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(sx), static_cast<cuuint32_t>(sy), 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("fm_conv_igemm: cuTensorMapEncodeTiled(A) failed with CUresult %d", (int)r); return FM_ERR_CUDA; }
   }
   {
-    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d->Cin), static_cast<cuuint64_t>(max_widx + 1) * d->w_rows};
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d->Cin), static_cast<cuuint64_t>(G) * p.nslabs * d->w_rows};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d->w_cstride) * 2};
     const cuuint32_t box[2] = {IG_BK, static_cast<cuuint32_t>(bn)};
     const cuuint32_t estr[2] = {1, 1};

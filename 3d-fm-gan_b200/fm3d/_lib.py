@@ -20,7 +20,9 @@ class ConvDesc(C.Structure):
         ("x_cstride", C.c_int32),
         ("w", C.c_void_p), ("ntaps", C.c_int32), ("Cout", C.c_int32), ("w_rows", C.c_int32), ("w_cstride", C.c_int32),
         ("tap_dy", C.c_int8 * FM_MAX_TAPS), ("tap_dx", C.c_int8 * FM_MAX_TAPS), ("tap_widx", C.c_int8 * FM_MAX_TAPS),
-        ("stride", C.c_int32),
+        ("stride", C.c_int32), ("stride_x", C.c_int32), ("stride_y", C.c_int32),
+        ("x_pixstride", C.c_int64), ("x_rowstride", C.c_int64), ("x_imgstride", C.c_int64),
+        ("groups", C.c_int32),
         ("OH", C.c_int32), ("OW", C.c_int32),
         ("out", C.c_void_p),
         ("out_H", C.c_int32), ("out_W", C.c_int32), ("out_cstride", C.c_int32), ("out_y0", C.c_int32),
@@ -28,6 +30,7 @@ class ConvDesc(C.Structure):
         ("tab", C.c_void_p), ("tab_bstride", C.c_int32),
         ("noise", C.c_void_p), ("noise_bstride", C.c_int32), ("noise_w", C.c_void_p),
         ("residual", C.c_void_p), ("rgb", C.c_void_p),
+        ("border_tab", C.c_void_p), ("out_cgroup", C.c_int32), ("out_gstride", C.c_int64),
         ("block_n", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32),
     ]
 
@@ -64,6 +67,13 @@ _SIGNATURES = {
     "fm_rgb_finalize": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p]),
     "fm_prep_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                  C.c_int, C.c_int, C.c_void_p]),
+    "fm_image_to_nhwc8_padded": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]),
+    "fm_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "fm_avgpool_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),
+    "fm_channel_sum_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "fm_se_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p]),
+    "fm_se_combine_nhwc": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 9 + [C.c_void_p]),
+    "fm_bilinear_up_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())

@@ -124,7 +124,8 @@ def conv_taps(kh, kw, pad):
 def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_rows=None,
                out_H=None, out_W=None, out_y0=0, out_x0=0, out_ys=1, out_xs=1, out_nchw_f32=False,
                tab_per_sample=False, noise=None, noise_per_sample=True, noise_w=None, residual=None,
-               rgb=None, block_n=0, tile_w=0, tile_h=0):
+               rgb=None, block_n=0, tile_w=0, tile_h=0, stride_x=0, stride_y=0, x_pixstride=0, x_rowstride=0,
+               x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None):
     """Launch fm_conv_igemm.  x: bf16 NHWC [B,H,W,cs]; w: bf16 [slabs, w_rows, cin_stride];
     out: bf16 NHWC [B,out_H,out_W,cs_out] or fp32 NCHW; tab: fp32 [B|1, Cout, 8]."""
     d = ConvDesc()
@@ -136,11 +137,16 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     for i, (dy, dx, wi) in enumerate(taps):
         d.tap_dy[i] = dy; d.tap_dx[i] = dx; d.tap_widx[i] = wi
     d.stride = stride
+    d.stride_x, d.stride_y = stride_x, stride_y
+    d.x_pixstride, d.x_rowstride, d.x_imgstride = x_pixstride, x_rowstride, x_imgstride
+    d.groups = groups
+    d.border_tab = _ptr(border_tab)
+    d.out_cgroup, d.out_gstride = out_cgroup, out_gstride
     d.OH, d.OW = OH, OW
     d.out = out.data_ptr()
     d.out_H = OH if out_H is None else out_H
     d.out_W = OW if out_W is None else out_W
-    d.out_cstride = Cout if out_nchw_f32 else out.shape[-1]
+    d.out_cstride = out_cstride if out_cstride is not None else (Cout if out_nchw_f32 else out.shape[-1])
     d.out_y0, d.out_x0, d.out_ys, d.out_xs = out_y0, out_x0, out_ys, out_xs
     d.out_nchw_f32 = 1 if out_nchw_f32 else 0
     d.tab = tab.data_ptr(); d.tab_bstride = 1 if tab_per_sample else 0
@@ -222,4 +228,54 @@ def rgb_finalize(acc, bias3, skip, kernel4x4, out=None):
     with torch.cuda.device(acc.device):
         st = _lib.lib().fm_rgb_finalize(_ptr(out), _ptr(acc), _ptr(bias3), _ptr(skip), _ptr(kernel4x4), B, H, W, _stream())
     _lib.check(st, "fm_rgb_finalize")
+    return out
+
+
+# ------------------------------------------------------------------ encoder helpers
+def _call(name, *args):
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+
+def image_to_nhwc8_padded(x, pad_t, pad_l, Hp, Wp, out=None):
+    _check_cuda(x, "input")
+    x = x.contiguous().float()
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty(B, Hp, Wp, 8, device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _call("fm_image_to_nhwc8_padded", _ptr(out), _ptr(x), B, Cc, H, W, pad_t, pad_l, Hp, Wp, _stream())
+    return out
+
+
+def maxpool3x3s2_nhwc(x, out):
+    B, H, W, cs = x.shape
+    with torch.cuda.device(x.device):
+        _call("fm_maxpool3x3s2_nhwc", _ptr(out), _ptr(x), B, H, W, cs, _stream())
+    return out
+
+
+def avgpool_nhwc_to_nchw(x, channels, ph, pw):
+    B, H, W, cs = x.shape
+    out = torch.empty(B, channels, H // ph, W // pw, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _call("fm_avgpool_nhwc_to_nchw", _ptr(out), _ptr(x), B, H, W, channels, cs, ph, pw, _stream())
+    return out
+
+
+def se_block_nhwc(r, channels, w1, w2, shortcut, sc_stride, sum_buf, gate_buf, out):
+    """out = r * sigmoid(w2 relu(w1 mean_hw(r))) + shortcut[:, ::s, ::s]  (3 launches)."""
+    B, H, W, cs = r.shape
+    st = _stream()
+    with torch.cuda.device(r.device):
+        _call("fm_channel_sum_nhwc", _ptr(sum_buf), _ptr(r), B, H * W, channels, cs, st)
+        _call("fm_se_gate", _ptr(gate_buf), _ptr(sum_buf), 1.0 / (H * W), _ptr(w1), _ptr(w2), B, channels, w1.shape[0], st)
+        _call("fm_se_combine_nhwc", _ptr(out), _ptr(r), _ptr(gate_buf), _ptr(shortcut), B, H, W, channels, cs,
+              shortcut.shape[1], shortcut.shape[2], shortcut.shape[3], sc_stride, st)
+    return out
+
+
+def bilinear_up_nhwc(x, OH, OW, out):
+    B, IH, IW, cs = x.shape
+    with torch.cuda.device(x.device):
+        _call("fm_bilinear_up_nhwc", _ptr(out), _ptr(x), B, IH, IW, OH, OW, cs, _stream())
     return out

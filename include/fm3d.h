@@ -111,7 +111,14 @@ typedef struct {
   int8_t tap_dy[FM_MAX_TAPS];   /* input row offset of each tap relative to oy*stride */
   int8_t tap_dx[FM_MAX_TAPS];
   int8_t tap_widx[FM_MAX_TAPS]; /* which [w_rows][w_cstride] slab of w each tap multiplies */
-  int32_t stride;           /* convolution stride (1 or 2) */
+  int32_t stride;           /* convolution stride (1 or 2), both axes unless stride_x/stride_y are set */
+  int32_t stride_x, stride_y;   /* 0 = use `stride` */
+  /* optional custom input strides in elements (0 = dense NHWC): lets a "pixel" be an overlapping
+   * window of a padded row (3-channel stems: 8 px x 8 ch = one 64-wide K chunk) */
+  int64_t x_pixstride, x_rowstride, x_imgstride;
+  /* groups: x holds groups*Bg images (group-major), w holds groups*[slabs][w_rows][w_cstride],
+   * a shared table holds groups*[Cout][8].  0/1 = ungrouped. */
+  int32_t groups;
   /* logical output grid computed by this launch */
   int32_t OH, OW;
   /* placement of that grid inside the output tensor: pixel (oy,ox) is written to
@@ -127,6 +134,13 @@ typedef struct {
   const float* noise_w;     /* device scalar or NULL (=> 1.0) */
   const void* residual;     /* bf16 NHWC like out, or NULL */
   float* rgb;               /* fp32 [B][out_H][out_W][4] accumulated with atomics, or NULL */
+  /* 3x3/pad-1 convs fed by a folded input BatchNorm: additive correction per border class
+   * ((y==0?1:y==OH-1?2:0)*3 + (x==0?1:x==OW-1?2:0)), fp32 [9][Cout], or NULL */
+  const float* border_tab;
+  /* concatenated-N output: channels [g*out_cgroup,(g+1)*out_cgroup) go to out + g*out_gstride
+   * elements (a [G*B,H,W,out_cstride] group-major tensor); 0 = off */
+  int32_t out_cgroup;
+  int64_t out_gstride;
   /* tiling hints (0 = choose) */
   int32_t block_n;          /* 64, 128 or 256 */
   int32_t tile_w, tile_h;   /* tile_w*tile_h*tile_b = 128 output pixels */
@@ -192,6 +206,33 @@ int fm_rgb_finalize(float* rgb_out, float* acc, const float* bias3, const float*
  *   wsq[cout][cin] fp32 = sum_taps (scale*W)^2. */
 int fm_prep_weight(void* wq, float* wsq, const float* w_oikk, int cout, int cin, int kh, int kw,
                    float scale, int cout_rows, int cin_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Encoder-path helpers (NHWC bf16, bandwidth-bound).  They replace the ATen kernels behind
+ * resnet_encoder.py:258-280 (stem, MaxPool2d, AvgPool2d / AdaptiveAvgPool2d),
+ * psp_encoder_model/encoders/helpers.py:76-139 (SEModule, residual add, MaxPool2d(1,s)
+ * shortcut) and psp_encoders.py:81-98 (bilinear FPN upsample).
+ * ---------------------------------------------------------------------------------- */
+/* fp32 NCHW image with C <= 8 channels -> zero-padded bf16 [B,Hp,Wp,8] (image at (pad_t,pad_l)). */
+int fm_image_to_nhwc8_padded(void* out, const float* x, int B, int C, int H, int W,
+                             int pad_t, int pad_l, int Hp, int Wp, void* stream);
+/* MaxPool2d(3, stride 2, padding 1): [B,H,W,cs] -> [B,(H-1)/2+1,(W-1)/2+1,cs]. */
+int fm_maxpool3x3s2_nhwc(void* out, const void* x, int B, int H, int W, int cs, void* stream);
+/* Non-overlapping ph x pw average pooling, output fp32 NCHW [B,C,H/ph,W/pw]. */
+int fm_avgpool_nhwc_to_nchw(float* out, const void* x, int B, int H, int W, int C, int cs,
+                            int ph, int pw, void* stream);
+/* sum_bc[b,c] += sum over pixels (fp32 atomics; caller zero-initialises once, fm_se_gate re-zeroes). */
+int fm_channel_sum_nhwc(float* sum_bc, const void* x, int B, int HW, int C, int cs, void* stream);
+/* gate[b,c] = sigmoid(w2[C,Cr] relu(w1[Cr,C] (sum[b,:]*inv_hw))). */
+int fm_se_gate(float* gate_bc, float* sum_bc, float inv_hw, const float* w1, const float* w2,
+               int B, int C, int Cr, void* stream);
+/* out = r * gate[b,c] + shortcut[b, y*sc_stride, x*sc_stride, c]. */
+int fm_se_combine_nhwc(void* out, const void* r, const float* gate_bc, const void* sc,
+                       int B, int H, int W, int C, int cs, int sc_H, int sc_W, int sc_cs,
+                       int sc_stride, void* stream);
+/* F.interpolate(mode='bilinear', align_corners=True). */
+int fm_bilinear_up_nhwc(void* out, const void* x, int B, int IH, int IW, int OH, int OW, int cs,
+                        void* stream);
 
 #ifdef __cplusplus
 }

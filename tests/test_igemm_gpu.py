@@ -125,3 +125,127 @@ def test_conv_epilogue_tables_noise_residual_rgb(cuda):
     torch.cuda.synchronize()
     torch.testing.assert_close(out.float().permute(0, 3, 1, 2).cpu(), ref, rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(rgb[..., :3].permute(0, 3, 1, 2).cpu(), ref_rgb, rtol=2e-3, atol=2e-3)
+
+
+# ------------------------------------------------------------------ generalisations used by the encoders
+def _tab(cout, dev, groups=1, shift=None, slope=1.0):
+    t = torch.zeros(groups, cout, 8, device=dev)
+    t[..., 0] = 1.0; t[..., 2] = slope; t[..., 3] = 1.0
+    if shift is not None:
+        t[..., 1] = shift.to(dev)
+    return t
+
+
+@pytest.mark.parametrize("Bg,H,stride", [(4, 8, 2), (2, 2, 2), (32, 1, 1), (3, 16, 1)])
+def test_conv_grouped(cuda, Bg, H, stride):
+    """groups: per-group weights and tables over a group-major batch (pSp map2style heads)."""
+    from fm3d import ops
+    G, C = 3, 64
+    gen = torch.Generator().manual_seed(Bg * 10 + H)
+    k = 3 if H > 1 else 1
+    pad = k // 2
+    x = torch.randn(G * Bg, C, H, H, generator=gen)
+    w = torch.randn(G, C, C, k, k, generator=gen) / (C * k * k) ** 0.5
+    bias = torch.randn(G, C, generator=gen)
+    ref = torch.cat([F.leaky_relu(F.conv2d(x[g * Bg:(g + 1) * Bg].to(torch.bfloat16).float(), w[g].to(torch.bfloat16).float(),
+                                           bias[g], stride=stride, padding=pad), 0.01) for g in range(G)], 0)
+    OH = ref.shape[2]
+    wq = torch.cat([ops.prep_weight(w[g].to(cuda), 1.0, want_wsq=False)[0] for g in range(G)], 0).contiguous()
+    out = torch.zeros(G * Bg, C, OH, OH, device=cuda)
+    ops.conv_igemm(ops.nchw_to_nhwc_bf16(x.to(cuda)), wq, ops.conv_taps(k, k, pad), out, _tab(C, cuda, G, bias, 0.01),
+                   B=G * Bg, H=H, W=H, Cin=C, Cout=C, OH=OH, OW=OH, stride=stride, groups=G, w_rows=C, out_nchw_f32=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.cpu(), ref, rtol=2e-3, atol=2e-3)
+
+
+def test_conv_concatenated_output(cuda):
+    """out_cgroup: one launch computes n heads that share an input, written head-major."""
+    from fm3d import ops
+    B, C, H, n = 2, 64, 8, 3
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(B, C, H, H, generator=gen)
+    w = torch.randn(n * C, C, 3, 3, generator=gen) / (C * 9) ** 0.5
+    ref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), stride=2, padding=1)     # [B, n*C, 4, 4]
+    wq, _ = ops.prep_weight(w.to(cuda), 1.0, want_wsq=False)
+    out = torch.zeros(n * B, 4, 4, C, device=cuda, dtype=torch.bfloat16)
+    ops.conv_igemm(ops.nchw_to_nhwc_bf16(x.to(cuda)), wq, ops.conv_taps(3, 3, 1), out, _tab(n * C, cuda), B=B, H=H, W=H,
+                   Cin=C, Cout=n * C, OH=4, OW=4, stride=2, out_cgroup=C, out_gstride=B * 16 * C, out_cstride=C)
+    torch.cuda.synchronize()
+    got = out.float().view(n, B, 4, 4, C).permute(1, 0, 4, 2, 3).reshape(B, n * C, 4, 4).cpu()
+    torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2)
+
+
+def test_conv_input_bn_border_table(cuda):
+    """BatchNorm in front of a zero-padded 3x3 conv folded into weights + 9-class border table."""
+    from fm3d import ops
+    from fm3d.encoder_engine import _border_table, _table
+    B, C, O, H = 2, 64, 128, 12
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(B, C, H, H, generator=gen)
+    a = torch.rand(C, generator=gen) + 0.5
+    b = torch.randn(C, generator=gen) * 0.5
+    w = torch.randn(O, C, 3, 3, generator=gen) / (C * 9) ** 0.5
+    xq = x.to(torch.bfloat16).float()
+    wf = (w * a.view(1, -1, 1, 1)).to(torch.bfloat16).float()
+    # reference: conv(zero_pad(a*x + b)) with the same rounded operands
+    ref = F.conv2d(xq, wf, padding=1) + F.conv2d(torch.ones(B, C, H, H) * b.view(1, -1, 1, 1), w, padding=1)
+    full, corr = _border_table(w.to(cuda), b.to(cuda))
+    wq, _ = ops.prep_weight((w * a.view(1, -1, 1, 1)).to(cuda), 1.0, want_wsq=False)
+    out = torch.zeros(B, O, H, H, device=cuda)
+    ops.conv_igemm(ops.nchw_to_nhwc_bf16(x.to(cuda)), wq, ops.conv_taps(3, 3, 1), out, _table(O, cuda, None, full, 1.0),
+                   B=B, H=H, W=H, Cin=C, Cout=O, OH=H, OW=H, border_tab=corr, out_nchw_f32=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.cpu(), ref, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("k,stride,pad,S", [(7, 2, 3, 64), (3, 1, 1, 32)])
+def test_conv_stem_window(cuda, k, stride, pad, S):
+    """3-channel stems: 8 pixels x 8 channels of a padded row as one 64-wide K chunk."""
+    from fm3d import ops
+    from fm3d.encoder_engine import _stem_weight, _table
+    B, O = 2, 64
+    gen = torch.Generator().manual_seed(k)
+    x = torch.randn(B, 3, S, S, generator=gen)
+    w = torch.randn(O, 3, k, k, generator=gen) / (3 * k * k) ** 0.5
+    ref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), stride=stride, padding=pad)
+    oh = ref.shape[2]
+    Hp, Wp = S + 2 * pad, max(S + 2 * pad, stride * (oh - 1) + 8)
+    packed = ops.image_to_nhwc8_padded(x.to(cuda), pad, pad, Hp, Wp)
+    out = torch.zeros(B, O, oh, oh, device=cuda)
+    ops.conv_igemm(packed, _stem_weight(w.to(cuda)), [(ky, 0, ky) for ky in range(k)], out, _table(O, cuda), B=B, H=Hp, W=oh,
+                   Cin=64, Cout=O, OH=oh, OW=oh, stride_x=1, stride_y=stride, x_pixstride=8 * stride, x_rowstride=Wp * 8,
+                   x_imgstride=Hp * Wp * 8, out_nchw_f32=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.cpu(), ref, rtol=2e-3, atol=2e-3)
+
+
+def test_encoder_helper_kernels(cuda):
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(9)
+    B, C, H = 3, 64, 10
+    x = torch.randn(B, C, H, H, generator=gen).to(torch.bfloat16)
+    xg = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+    # max pool
+    out = torch.empty(B, 5, 5, C, device=cuda, dtype=torch.bfloat16)
+    ops.maxpool3x3s2_nhwc(xg, out)
+    ref = F.max_pool2d(x.float(), 3, 2, 1)
+    assert torch.equal(out.float().permute(0, 3, 1, 2).cpu(), ref)
+    # avg pool -> NCHW fp32
+    torch.testing.assert_close(ops.avgpool_nhwc_to_nchw(xg, C, 2, 2).cpu(), F.avg_pool2d(x.float(), 2, 2), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ops.avgpool_nhwc_to_nchw(xg, C, H, H).cpu(), x.float().mean((2, 3), keepdim=True), rtol=1e-5, atol=1e-5)
+    # bilinear align_corners
+    up = torch.empty(B, 20, 20, C, device=cuda, dtype=torch.bfloat16)
+    ops.bilinear_up_nhwc(xg, 20, 20, up)
+    refu = F.interpolate(x.float(), size=(20, 20), mode="bilinear", align_corners=True)
+    torch.testing.assert_close(up.float().permute(0, 3, 1, 2).cpu(), refu, rtol=1e-2, atol=1e-2)
+    # SE block with a strided identity shortcut
+    w1 = torch.randn(C // 16, C, generator=gen) * 0.3
+    w2 = torch.randn(C, C // 16, generator=gen) * 0.3
+    sc = torch.randn(B, C, 2 * H, 2 * H, generator=gen).to(torch.bfloat16)
+    gate = torch.sigmoid(F.linear(F.relu(F.linear(x.float().mean((2, 3)), w1)), w2))
+    refse = x.float() * gate[:, :, None, None] + sc.float()[:, :, ::2, ::2]
+    sums = torch.zeros(B, 512, device=cuda); gbuf = torch.empty(B, 512, device=cuda)
+    o = torch.empty_like(xg)
+    ops.se_block_nhwc(xg, C, w1.to(cuda), w2.to(cuda), sc.permute(0, 2, 3, 1).contiguous().to(cuda), 2, sums, gbuf, o)
+    torch.testing.assert_close(o.float().permute(0, 3, 1, 2).cpu(), refse, rtol=1e-2, atol=2e-2)
+    assert float(sums.abs().sum()) == 0.0          # re-zeroed for the next block
