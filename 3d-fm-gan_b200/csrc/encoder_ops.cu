@@ -253,7 +253,11 @@ extern "C" int fm_avgpool_nhwc_to_nchw(float* out, const void* x, int B, int H, 
 extern "C" int fm_channel_sum_nhwc(float* sum_bc, const void* x, int B, int HW, int C, int cs, void* stream) {
   FM_CHECK_ARG(sum_bc && x && B > 0 && HW > 0 && C > 0 && cs >= C && cs % 8 == 0 && cs <= 512 && 256 % (cs / 8) == 0,
                "fm_channel_sum_nhwc: bad args (cs must be 8*2^k <= 512)");
-  const int chunk = 1024;
+  // enough CTAs to fill the chip even for small maps (16x16: one CTA per sample would idle 116 SMs)
+  int per_sample = (4 * sm_count() + B - 1) / B;
+  if (per_sample < 1) per_sample = 1;
+  int chunk = (HW + per_sample - 1) / per_sample;
+  if (chunk < 32) chunk = 32;
   dim3 grid((HW + chunk - 1) / chunk, B);
   channel_sum_kernel<<<grid, 256, 0, ST>>>(sum_bc, static_cast<const __nv_bfloat16*>(x), HW, C, cs, chunk);
   count_launch();

@@ -23,7 +23,6 @@ namespace fm {
 
 constexpr int IG_BM = 128;     // pixels per tile (UMMA M)
 constexpr int IG_BK = 64;      // channels per k-step (128 B rows, SWIZZLE_128B)
-constexpr int IG_THREADS = 192;
 constexpr int IG_TAB_ROWS = 512;  // staged table rows per tile (tile_b_eff * BLOCK_N <= 512)
 
 struct IgemmParams {
@@ -50,26 +49,33 @@ struct IgemmParams {
   int8_t tap_widx[FM_MAX_TAPS];
 };
 
+constexpr int IG_EPI_WARPS = 8;                       // two warps per TMEM lane quarter
+constexpr int IG_THREADS2 = 64 + 32 * IG_EPI_WARPS;   // producer + MMA + epilogue warps
+
+// epilogue feature flags (template: dead paths cost nothing)
+constexpr int EPI_RGB = 1, EPI_RES = 2, EPI_BTAB = 4;
+
 template <int BN> struct IgemmCfg {
   static constexpr int A_BYTES = IG_BM * IG_BK * 2;        // 16 KB
   static constexpr int B_BYTES = BN * IG_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TAB_BYTES = IG_TAB_ROWS * 32;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + TAB_BYTES + 256 /*barriers*/;
+  static constexpr int RGB_BYTES = IG_BM * 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAB_BYTES + RGB_BYTES + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(IG_THREADS, 1)
+template <int BN, int EPI>
+__global__ void __launch_bounds__(IG_THREADS2, 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
   using Cfg = IgemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operand tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // SWIZZLE_128B operand tiles need 1024-byte alignment; declaring it keeps the shared address space
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_stage = smem;
   float4* s_tab = reinterpret_cast<float4*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAB_BYTES);
+  float4* s_rgb = reinterpret_cast<float4*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAB_BYTES + Cfg::RGB_BYTES);
   uint64_t* full_bar = bars;                        // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + Cfg::STAGES;         // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;     // [2]       MMA -> epilogue
@@ -80,6 +86,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) { printf("fm3d: dynamic smem base not 1024-aligned\n"); __trap(); }
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -88,7 +95,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], IG_EPI_WARPS);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -107,6 +114,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ============================== TMA producer ==============================
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t tx_bytes = static_cast<uint32_t>(p.rows) * (IG_BK * 2) + Cfg::B_BYTES;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
       int m = tile / p.tiles_n;
@@ -115,7 +123,6 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int bb = m / p.tiles_y;
       const int x0 = bx * p.tw * p.stride_x, y0 = by * p.th * p.stride_y, b0 = bb * p.tb, n0 = nt * BN;
       const int wrow0 = (b0 / p.Bg) * p.nslabs;
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.rows) * (IG_BK * 2) + Cfg::B_BYTES;
       for (int it = 0; it < kiters; ++it) {
         const int tap = it / p.kchunks;
         const int kc = it - tap * p.kchunks;
@@ -163,12 +170,18 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ============================== epilogue ==============================
+    // ============================== epilogue (8 warps) ==============================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which half of the column chunks this warp takes
     const int row = q * 32 + lane;          // pixel index inside the tile
-    const int etid = threadIdx.x - 64;      // 0..127
+    const int etid = threadIdx.x - 64;      // 0..255
     const int tbe = p.tab_bstride ? p.tb : 1;
     const float nw = p.noise ? (p.noise_w ? __ldg(p.noise_w) : 1.f) : 0.f;
+    const int lx = row % p.tw;
+    const int ly = (row / p.tw) % p.th;
+    const int lb = row / (p.tw * p.th);
+    const float4* trow = s_tab + static_cast<size_t>(p.tab_bstride ? lb : 0) * BN * 2;
+    int tab_key = -1;
     int titer = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++titer) {
       const int buf = titer & 1;
@@ -179,75 +192,79 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int by = m % p.tiles_y;
       const int bb = m / p.tiles_y;
       const int n0 = nt * BN;
-      const int lx = row % p.tw;
-      const int ly = (row / p.tw) % p.th;
-      const int lb = row / (p.tw * p.th);
       const int ox = bx * p.tw + lx, oy = by * p.th + ly, b = bb * p.tb + lb;
       const bool valid = row < p.rows && ox < p.OW && oy < p.OH && b < p.B;
       const int grp = (bb * p.tb) / p.Bg;
 
-      // ---- stage this tile's epilogue tables (overlaps the tile's MMAs)
-      for (int i = etid; i < tbe * BN; i += 128) {
-        const int sb = i / BN, j = i - sb * BN;
-        const int o = n0 + j;
-        const int bsrc = p.tab_bstride ? (bb * p.tb + sb) : grp;
-        float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
-        if (o < p.Cout && (!p.tab_bstride || bsrc < p.B)) {
-          const float4* src = reinterpret_cast<const float4*>(p.tab + (static_cast<size_t>(bsrc) * p.Cout + o) * 8);
-          t0 = __ldg(src);
-          t1 = __ldg(src + 1);
+      // ---- epilogue tables: re-staged only when (sample block | group, n-tile) changes
+      const int key = (p.tab_bstride ? bb : grp) * p.tiles_n + nt;
+      if (key != tab_key) {
+        tab_key = key;
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done with the old tables
+        for (int i = etid; i < tbe * BN; i += 256) {
+          const int sb = i / BN, j = i - sb * BN;
+          const int o = n0 + j;
+          const int bsrc = p.tab_bstride ? (bb * p.tb + sb) : grp;
+          float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+          if (o < p.Cout && (!p.tab_bstride || bsrc < p.B)) {
+            const float4* src = reinterpret_cast<const float4*>(p.tab + (static_cast<size_t>(bsrc) * p.Cout + o) * 8);
+            t0 = __ldg(src);
+            t1 = __ldg(src + 1);
+          }
+          s_tab[2 * i] = t0;
+          s_tab[2 * i + 1] = t1;
         }
-        s_tab[2 * i] = t0;
-        s_tab[2 * i + 1] = t1;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
 
       const int Y = oy * p.out_ys + p.out_y0, X = ox * p.out_xs + p.out_x0;
       float nz = 0.f;
       if (valid && p.noise)
         nz = nw * __ldg(p.noise + (static_cast<size_t>(p.noise_bstride ? b : 0) * p.out_H + Y) * p.out_W + X);
       const size_t pix = (static_cast<size_t>(b) * p.out_H + Y) * p.out_W + X;
-      const float4* trow = s_tab + static_cast<size_t>(p.tab_bstride ? lb : 0) * BN * 2;
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
       const float* btab = nullptr;      // folded-input-BN border correction (per-thread: thread = pixel)
-      if (p.border_tab) {
+      if (EPI & EPI_BTAB) {
         const int cls = (oy == 0 ? 1 : (oy == p.OH - 1 ? 2 : 0)) * 3 + (ox == 0 ? 1 : (ox == p.OW - 1 ? 2 : 0));
-        if (cls) btab = p.border_tab + static_cast<size_t>(cls) * p.Cout;
+        if (cls && p.border_tab) btab = p.border_tab + static_cast<size_t>(cls) * p.Cout;
       }
 
       mbar_wait(&tfull_bar[buf], aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t acc[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c * 32, acc);
-        tmem_ld_wait();
-        const int o0 = n0 + c * 32;
+      for (int c = half; c < BN / 16; c += 2) {     // 16-column chunks, alternating between the two warps
+        uint32_t acc[16];
+        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c * 16, acc);
+        const int o0 = n0 + c * 16;
         // position inside the output tensor (concatenated-N outputs are written group-major)
         const int og = p.out_cgroup ? o0 / p.out_cgroup : 0;
         const int ol0 = o0 - og * p.out_cgroup;
-        // chunks past Cout only zero-fill the pad channels of an NHWC tensor (warp-uniform test)
-        if (o0 >= p.Cout && (p.out_nchw_f32 || p.out_cgroup || ol0 >= p.out_cstride)) continue;
-        float v[32];
-        uint4 resv[4];
-        if (p.residual && valid) {
+        uint4 resv[2];
+        if (EPI & EPI_RES) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.out_cstride + ol0);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) resv[g] = (ol0 + 8 * g < p.out_cstride) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
+          for (int g = 0; g < 2; ++g)
+            resv[g] = (valid && p.residual && ol0 + 8 * g < p.out_cstride) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
         }
+        tmem_ld_wait();
+        // chunks past Cout only zero-fill the pad channels of an NHWC tensor (warp-uniform test)
+        if (o0 >= p.Cout && (p.out_nchw_f32 || p.out_cgroup || ol0 >= p.out_cstride)) continue;
+        const float4* tr = trow + 2 * (c * 16);
+        float v[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float4 t0 = trow[2 * (c * 32 + j)];
+        for (int j = 0; j < 16; ++j) {
+          const float4 t0 = tr[2 * j];
           float x = fmaf(__uint_as_float(acc[j]), t0.x, t0.y + nz);
-          if (btab && o0 + j < p.Cout) x += __ldg(btab + o0 + j);
-          if (p.residual) {
-            const uint32_t w = reinterpret_cast<const uint32_t*>(resv)[j >> 1];
-            const float2 f = unpack_bf16x2(w);
-            x += (j & 1) ? f.y : f.x;
+          if (EPI & EPI_BTAB) {
+            if (btab != nullptr && o0 + j < p.Cout) x += __ldg(btab + o0 + j);
+          }
+          if (EPI & EPI_RES) {
+            const uint32_t w = (&resv[0].x)[j >> 1];
+            x += __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
           }
           x = x > 0.f ? x : x * t0.z;
-          if (p.rgb) {
-            const float4 t1 = trow[2 * (c * 32 + j) + 1];
+          if (EPI & EPI_RGB) {
+            const float4 t1 = tr[2 * j + 1];
             r0 = fmaf(x, t1.x, r0);
             r1 = fmaf(x, t1.y, r1);
             r2 = fmaf(x, t1.z, r2);
@@ -256,16 +273,17 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (valid) {
           if (p.out_nchw_f32) {
-            float* op = static_cast<float*>(p.out);
+            const size_t plane = static_cast<size_t>(p.out_H) * p.out_W;
+            float* op = static_cast<float*>(p.out) + (static_cast<size_t>(b) * p.Cout + o0) * plane +
+                        static_cast<size_t>(Y) * p.out_W + X;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (o0 + j < p.Cout)
-                op[((static_cast<size_t>(b) * p.Cout + o0 + j) * p.out_H + Y) * p.out_W + X] = v[j];
+            for (int j = 0; j < 16; ++j)
+              if (o0 + j < p.Cout) op[j * plane] = v[j];
           } else {
             uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + og * p.out_gstride +
                                                  pix * p.out_cstride + ol0);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 2; ++g) {
               if (ol0 + 8 * g < p.out_cstride) {
                 uint4 w;
                 w.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
@@ -282,17 +300,23 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-      if (p.rgb && valid) {
-        float* rp = p.rgb + pix * 4;
-        if (p.tiles_n == 1) {
-          *reinterpret_cast<float4*>(rp) = make_float4(r0, r1, r2, 0.f);
-        } else {
-          atomicAdd(rp + 0, r0);
-          atomicAdd(rp + 1, r1);
-          atomicAdd(rp + 2, r2);
+      if (EPI & EPI_RGB) {
+        // combine the two column halves of each pixel through smem (deterministic), then write
+        if (half == 1) s_rgb[row] = make_float4(r0, r1, r2, 0.f);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (half == 0 && valid && p.rgb) {
+          const float4 o = s_rgb[row];
+          float* rp = p.rgb + pix * 4;
+          if (p.tiles_n == 1) {
+            *reinterpret_cast<float4*>(rp) = make_float4(r0 + o.x, r1 + o.y, r2 + o.z, 0.f);
+          } else {
+            atomicAdd(rp + 0, r0 + o.x);
+            atomicAdd(rp + 1, r1 + o.y);
+            atomicAdd(rp + 2, r2 + o.z);
+          }
         }
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // s_rgb may be overwritten by the next tile
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");   // tables are free to be overwritten
     }
   }
 
@@ -321,20 +345,33 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN>
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
+template <int BN, int EPI>
+static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
   using Cfg = IgemmCfg<BN>;
   static bool attr_set = false;   // per-process, per-instantiation; benign race
   if (!attr_set) {
-    FM_CUDA_OK(cudaFuncSetAttribute(igemm_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    FM_CUDA_OK(cudaFuncSetAttribute(igemm_conv_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int sms = sm_count();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  igemm_conv_kernel<BN><<<grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  igemm_conv_kernel<BN, EPI><<<grid, IG_THREADS2, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;
+}
+
+template <int BN>
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
+  // one instantiation per epilogue feature set in use (generator: RGB; ResNet: RES; IR block: BTAB)
+  const int epi = (p.rgb ? EPI_RGB : 0) | (p.residual ? EPI_RES : 0) | (p.border_tab ? EPI_BTAB : 0);
+  switch (epi) {
+    case 0: return launch_igemm2<BN, 0>(tmA, tmB, p, st);
+    case EPI_RGB: return launch_igemm2<BN, EPI_RGB>(tmA, tmB, p, st);
+    case EPI_RES: return launch_igemm2<BN, EPI_RES>(tmA, tmB, p, st);
+    case EPI_BTAB: return launch_igemm2<BN, EPI_BTAB>(tmA, tmB, p, st);
+    default: return launch_igemm2<BN, EPI_RGB | EPI_RES | EPI_BTAB>(tmA, tmB, p, st);
+  }
 }
 
 }  // namespace fm

@@ -131,102 +131,140 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(float* __restrict__ o
 // blur (4x4 FIR, pad (1,1)) + demod + noise + bias + lrelu + next style, NHWC bf16.
 // t [B, OH+1, OW+1, cs] -> out [B, OH, OW, cs].  Replaces Blur (stylegan2.py:279 ->
 // upfirdn2d mode 1), NoiseInjection (:312) and FusedLeakyReLU (:371) after the stride-2
-// transposed conv.  Each thread owns 8 channels of a 2x2 output block: 25 16-byte loads
-// feed 4 outputs (6.25 loads/output instead of 16).
+// transposed conv.
+// One CTA = 16x16 output pixels x 64 channels: the 19x19x128 B input patch is staged in
+// shared memory with 16-byte coalesced loads; a thread owns 8 channels of a vertical strip of
+// 8 outputs and walks the 11 input rows it needs (4 LDS.128 per row), so every staged value
+// is reused from registers.  Rank-1 kernels (the default [1,3,3,1] outer product) take the
+// separable path: half the FMAs.
 // Algorithmic bytes per output pixel-channel: 2 B read ((OH+1)(OW+1)/(OH*OW) ~ 1) + 2 B write.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) blur_act_nhwc_kernel(__nv_bfloat16* __restrict__ out,
-                                                            const __nv_bfloat16* __restrict__ t,
-                                                            const float* __restrict__ kernel, const float* __restrict__ tab,
-                                                            const float* __restrict__ noise, int noise_bstride,
-                                                            const float* __restrict__ noise_w, int B, int OH, int OW, int C,
-                                                            int cs, int64_t total) {
+constexpr int BL_T = 16;            // output tile edge
+constexpr int BL_P = BL_T + 3;      // patch edge
+
+template <bool SEP>
+__global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(__nv_bfloat16* __restrict__ out,
+                                                               const __nv_bfloat16* __restrict__ t,
+                                                               const float* __restrict__ kernel, const float* __restrict__ tab,
+                                                               const float* __restrict__ noise, int noise_bstride,
+                                                               const float* __restrict__ noise_w, int OH, int OW, int C, int cs,
+                                                               int tiles_x, int tiles_y, int cblocks) {
+  __shared__ __align__(16) uint4 s_patch[BL_P * BL_P * 8];   // [row][px][8 groups of 8 ch]
+  __shared__ float4 s_tab[64];
   __shared__ float s_k[16];
-  if (threadIdx.x < 16) {
-    const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
-    s_k[threadIdx.x] = kernel[(3 - a) * 4 + (3 - b)];   // flipped taps (true convolution)
+  __shared__ float s_kv[4], s_kh[4];
+  int bid = blockIdx.x;
+  const int cb = bid % cblocks; bid /= cblocks;
+  const int tx = bid % tiles_x; bid /= tiles_x;
+  const int ty = bid % tiles_y;
+  const int b = bid / tiles_y;
+  const int X0 = tx * BL_T, Y0 = ty * BL_T, c0 = cb * 64;
+  const int IH = OH + 1, IW = OW + 1;
+  const int tid = threadIdx.x;
+  if (tid < 16) {
+    const int a = tid >> 2, bb = tid & 3;
+    s_k[tid] = kernel[(3 - a) * 4 + (3 - bb)];   // flipped taps (true convolution)
+  }
+  if (SEP && tid < 4) {
+    // rank-1: k[a][b] = kv[a] * kh[b] with kh = row sums / total... use first non-zero row/col
+    float tot = 0.f;
+    for (int i = 0; i < 16; ++i) tot += kernel[i];
+    float rs = 0.f, csum = 0.f;
+    for (int j = 0; j < 4; ++j) { rs += kernel[(3 - tid) * 4 + j]; csum += kernel[j * 4 + (3 - tid)]; }
+    s_kv[tid] = rs;                 // sum over columns of flipped row a
+    s_kh[tid] = csum / tot;         // k[a][b] = rs[a] * cs[b] / tot for a rank-1 matrix
+  }
+  if (tid < 64) {
+    const int o = c0 + tid;
+    s_tab[tid] = o < C ? __ldg(reinterpret_cast<const float4*>(tab + (static_cast<size_t>(b) * C + o) * 8))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // ---- stage the patch (rows Y0-1 .. Y0+17, cols X0-1 .. X0+17), zero outside the image
+  const __nv_bfloat16* tb = t + static_cast<size_t>(b) * IH * IW * cs;
+  for (int i = tid; i < BL_P * BL_P * 8; i += 256) {
+    const int g = i & 7;
+    const int px = (i >> 3) % BL_P, py = (i >> 3) / BL_P;
+    const int iy = Y0 - 1 + py, ix = X0 - 1 + px;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < IH && ix >= 0 && ix < IW && c0 + g * 8 < cs)
+      v = __ldg(reinterpret_cast<const uint4*>(tb + (static_cast<size_t>(iy) * IW + ix) * cs + c0 + g * 8));
+    s_patch[i] = v;
   }
   __syncthreads();
-  const int groups = cs / 8;
-  const int bw = (OW + 1) / 2, bh = (OH + 1) / 2;
-  const int IH = OH + 1, IW = OW + 1;
-  const float nw = noise ? (noise_w ? __ldg(noise_w) : 1.f) : 0.f;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int g = static_cast<int>(idx % groups);
-    int64_t r = idx / groups;
-    const int bxp = static_cast<int>(r % bw); r /= bw;
-    const int byp = static_cast<int>(r % bh);
-    const int b = static_cast<int>(r / bh);
-    const int X0 = bxp * 2, Y0 = byp * 2;
-    float acc[2][2][8];
+
+  const int g = tid & 7;
+  const int sx = (tid >> 3) & 15;      // output column inside the tile
+  const int sy = (tid >> 7) * 8;       // first output row of this thread's strip
+  float acc[8][8];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+    for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[i][j][c] = 0.f;
-    const __nv_bfloat16* tb = t + static_cast<size_t>(b) * IH * IW * cs + g * 8;
+  for (int r = 0; r < 11; ++r) {        // patch rows sy + r feed outputs sy + r - a, a = 0..3
+    float v[4][8];
 #pragma unroll
-    for (int ry = 0; ry < 5; ++ry) {
-      const int iy = Y0 - 1 + ry;
-      if (iy < 0 || iy >= IH) continue;
+    for (int q = 0; q < 4; ++q) {
+      const uint4 w = s_patch[((sy + r) * BL_P + sx + q) * 8 + g];
+      float2 f;
+      f = unpack_bf16x2(w.x); v[q][0] = f.x; v[q][1] = f.y;
+      f = unpack_bf16x2(w.y); v[q][2] = f.x; v[q][3] = f.y;
+      f = unpack_bf16x2(w.z); v[q][4] = f.x; v[q][5] = f.y;
+      f = unpack_bf16x2(w.w); v[q][6] = f.x; v[q][7] = f.y;
+    }
+    if (SEP) {
+      float hrow[8];
 #pragma unroll
-      for (int rx = 0; rx < 5; ++rx) {
-        const int ix = X0 - 1 + rx;
-        if (ix < 0 || ix >= IW) continue;
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(tb + (static_cast<size_t>(iy) * IW + ix) * cs));
-        float v[8];
-        float2 f;
-        f = unpack_bf16x2(w.x); v[0] = f.x; v[1] = f.y;
-        f = unpack_bf16x2(w.y); v[2] = f.x; v[3] = f.y;
-        f = unpack_bf16x2(w.z); v[4] = f.x; v[5] = f.y;
-        f = unpack_bf16x2(w.w); v[6] = f.x; v[7] = f.y;
+      for (int c = 0; c < 8; ++c)
+        hrow[c] = fmaf(s_kh[3], v[3][c], fmaf(s_kh[2], v[2][c], fmaf(s_kh[1], v[1][c], s_kh[0] * v[0][c])));
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int a = ry - i;           // tap row for output row Y0+i
-          if (a < 0 || a > 3) continue;
+      for (int a = 0; a < 4; ++a) {
+        const int i = r - a;
+        if (i < 0 || i > 7) continue;
+        const float kv = s_kv[a];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int bb = rx - j;
-            if (bb < 0 || bb > 3) continue;
-            const float kv = s_k[a * 4 + bb];
+        for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(kv, hrow[c], acc[i][c]);
+      }
+    } else {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[i][j][c] = fmaf(v[c], kv, acc[i][j][c]);
-          }
+      for (int a = 0; a < 4; ++a) {
+        const int i = r - a;
+        if (i < 0 || i > 7) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float kv = s_k[a * 4 + q];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(kv, v[q][c], acc[i][c]);
         }
       }
     }
-    float4 tabv[8];
+  }
+
+  if (c0 + g * 8 >= cs) return;
+  const int X = X0 + sx;
+  if (X >= OW) return;
+  const float nw = noise ? (noise_w ? __ldg(noise_w) : 1.f) : 0.f;
+  float4 tv[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) tv[c] = s_tab[g * 8 + c];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int Y = Y0 + sy + i;
+    if (Y >= OH) break;
+    float nz = 0.f;
+    if (noise) nz = nw * __ldg(noise + (static_cast<size_t>(noise_bstride ? b : 0) * OH + Y) * OW + X);
+    float o[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const int o = g * 8 + c;
-      tabv[c] = o < C ? __ldg(reinterpret_cast<const float4*>(tab + (static_cast<size_t>(b) * C + o) * 8))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      float x = fmaf(acc[i][c], tv[c].x, tv[c].y + nz);
+      x = x > 0.f ? x : x * tv[c].z;
+      o[c] = x * tv[c].w;
     }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int Y = Y0 + i;
-      if (Y >= OH) continue;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int X = X0 + j;
-        if (X >= OW) continue;
-        float nz = 0.f;
-        if (noise) nz = nw * __ldg(noise + (static_cast<size_t>(noise_bstride ? b : 0) * OH + Y) * OW + X);
-        float v[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float x = fmaf(acc[i][j][c], tabv[c].x, tabv[c].y + nz);
-          x = x > 0.f ? x : x * tabv[c].z;
-          v[c] = x * tabv[c].w;
-        }
-        uint4 w;
-        w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
-        w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * OH + Y) * OW + X) * cs + g * 8) = w;
-      }
-    }
+    uint4 w;
+    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+    w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * OH + Y) * OW + X) * cs + c0 + g * 8) = w;
   }
 }
 
@@ -358,13 +396,21 @@ extern "C" int fm_nhwc_bf16_to_nchw(float* out, const void* x, const float* inv_
 
 extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4, const float* tab, const float* noise,
                                 int noise_bstride, const float* noise_w, int B, int OH, int OW, int C, int cstride,
-                                void* stream) {
+                                int separable, void* stream) {
   FM_CHECK_ARG(out && t && kernel4x4 && tab && B > 0 && OH > 0 && OW > 0 && C > 0, "fm_blur_act_nhwc: bad args");
   FM_CHECK_ARG(cstride % 8 == 0 && cstride >= C, "fm_blur_act_nhwc: cstride must be a multiple of 8 >= C");
-  const int64_t total = static_cast<int64_t>(B) * ((OH + 1) / 2) * ((OW + 1) / 2) * (cstride / 8);
-  blur_act_nhwc_kernel<<<grid_for(total, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(t), kernel4x4, tab, noise, noise_bstride, noise_w,
-      B, OH, OW, C, cstride, total);
+  const int tiles_x = (OW + BL_T - 1) / BL_T, tiles_y = (OH + BL_T - 1) / BL_T, cblocks = (cstride + 63) / 64;
+  const int64_t blocks = static_cast<int64_t>(B) * tiles_x * tiles_y * cblocks;
+  FM_CHECK_ARG(blocks < 0x7FFFFFFF, "fm_blur_act_nhwc: too many blocks");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (separable)
+    blur_act_nhwc_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(t), kernel4x4, tab, noise, noise_bstride, noise_w,
+        OH, OW, C, cstride, tiles_x, tiles_y, cblocks);
+  else
+    blur_act_nhwc_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(t), kernel4x4, tab, noise, noise_bstride, noise_w,
+        OH, OW, C, cstride, tiles_x, tiles_y, cblocks);
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;

@@ -63,7 +63,7 @@ _SIGNATURES = {
     "fm_nchw_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "fm_nhwc_bf16_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "fm_blur_act_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
-                         + [C.c_int] * 5 + [C.c_void_p]),
+                         + [C.c_int] * 6 + [C.c_void_p]),
     "fm_rgb_finalize": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p]),
     "fm_prep_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                  C.c_int, C.c_int, C.c_void_p]),

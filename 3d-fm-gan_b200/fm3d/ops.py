@@ -207,15 +207,32 @@ def nhwc_bf16_to_nchw(x, channels, inv_scale_bc=None):
     return out
 
 
+def _is_rank1(k):
+    """True when the (host-inspected) 4x4 kernel is an outer product: enables the separable path."""
+    kk = k.detach().double().cpu()
+    tot = kk.sum()
+    if float(tot.abs()) < 1e-12:
+        return False
+    return bool(torch.allclose(torch.outer(kk.sum(1), kk.sum(0)) / tot, kk, rtol=1e-6, atol=1e-9))
+
+
+_RANK1_CACHE = {}
+
+
 def blur_act_nhwc(t, kernel4x4, tab, noise, noise_per_sample, noise_w, C_, out=None):
     """t bf16 [B,OH+1,OW+1,cs] -> bf16 [B,OH,OW,cs] (see fm_blur_act_nhwc)."""
     B, IH, IW, cs = t.shape
     OH, OW = IH - 1, IW - 1
     if out is None:
         out = torch.empty(B, OH, OW, cs, device=t.device, dtype=torch.bfloat16)
+    key = (kernel4x4.data_ptr(), kernel4x4._version)
+    sep = _RANK1_CACHE.get(key)
+    if sep is None:                       # one host sync per kernel buffer (cached)
+        sep = _RANK1_CACHE[key] = _is_rank1(kernel4x4)
     with torch.cuda.device(t.device):
         st = _lib.lib().fm_blur_act_nhwc(_ptr(out), _ptr(t), _ptr(kernel4x4), _ptr(tab), _ptr(noise),
-                                         1 if noise_per_sample else 0, _ptr(noise_w), B, OH, OW, C_, cs, _stream())
+                                         1 if noise_per_sample else 0, _ptr(noise_w), B, OH, OW, C_, cs,
+                                         1 if sep else 0, _stream())
     _lib.check(st, "fm_blur_act_nhwc")
     return out
 

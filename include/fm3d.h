@@ -190,10 +190,11 @@ int fm_nhwc_bf16_to_nchw(float* out, const void* x, const float* inv_scale_bc,
 /* Blur after the stride-2 transposed modulated conv, fused with demod, noise, bias,
  * leaky-ReLU and the next layer's style (stylegan2.py:279,312,371):
  *   t[b,2h+1,2w+1,C] bf16 NHWC  ->  out[b,2h,2w,C] bf16 NHWC
- *   v = (sum_{a,b} k[a,b] t[..]) * T[0] + T[1] + noise*noise_w ; lrelu(T[2]) ; * T[3] */
+ *   v = (sum_{a,b} k[a,b] t[..]) * T[0] + T[1] + noise*noise_w ; lrelu(T[2]) ; * T[3]
+ * separable != 0 asserts that kernel4x4 is rank-1 (outer product): half the FMAs. */
 int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4,
                      const float* tab, const float* noise, int noise_bstride, const float* noise_w,
-                     int B, int OH, int OW, int C, int cstride, void* stream);
+                     int B, int OH, int OW, int C, int cstride, int separable, void* stream);
 
 /* ToRGB tail (stylegan2.py:394-399): rgb_out[b,:,y,x] = acc[b,y,x,:] + bias + up2(skip).
  * acc fp32 [B][H][W][4] (from the fused epilogue), skip fp32 NCHW [B,3,H/2,W/2] or NULL,
