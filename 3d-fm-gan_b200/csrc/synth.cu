@@ -143,13 +143,13 @@ constexpr int BL_T = 16;            // output tile edge
 constexpr int BL_P = BL_T + 3;      // patch edge
 
 template <bool SEP>
-__global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(__nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(512, 2) blur_act_nhwc_kernel(__nv_bfloat16* __restrict__ out,
                                                                const __nv_bfloat16* __restrict__ t,
                                                                const float* __restrict__ kernel, const float* __restrict__ tab,
                                                                const float* __restrict__ noise, int noise_bstride,
                                                                const float* __restrict__ noise_w, int OH, int OW, int C, int cs,
                                                                int tiles_x, int tiles_y, int cblocks) {
-  __shared__ __align__(16) uint4 s_patch[BL_P * BL_P * 8];   // [row][px][8 groups of 8 ch]
+  __shared__ __align__(16) uint4 s_patch[BL_P * BL_P * 8];   // [row][px][64 ch]
   __shared__ float4 s_tab[64];
   __shared__ float s_k[16];
   __shared__ float s_kv[4], s_kh[4];
@@ -166,13 +166,13 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(__nv_bfloat16* __
     s_k[tid] = kernel[(3 - a) * 4 + (3 - bb)];   // flipped taps (true convolution)
   }
   if (SEP && tid < 4) {
-    // rank-1: k[a][b] = kv[a] * kh[b] with kh = row sums / total... use first non-zero row/col
+    // rank-1 kernel: k[a][b] = rowsum[a] * colsum[b] / total
     float tot = 0.f;
     for (int i = 0; i < 16; ++i) tot += kernel[i];
     float rs = 0.f, csum = 0.f;
     for (int j = 0; j < 4; ++j) { rs += kernel[(3 - tid) * 4 + j]; csum += kernel[j * 4 + (3 - tid)]; }
-    s_kv[tid] = rs;                 // sum over columns of flipped row a
-    s_kh[tid] = csum / tot;         // k[a][b] = rs[a] * cs[b] / tot for a rank-1 matrix
+    s_kv[tid] = rs;
+    s_kh[tid] = csum / tot;
   }
   if (tid < 64) {
     const int o = c0 + tid;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(__nv_bfloat16* __
   }
   // ---- stage the patch (rows Y0-1 .. Y0+17, cols X0-1 .. X0+17), zero outside the image
   const __nv_bfloat16* tb = t + static_cast<size_t>(b) * IH * IW * cs;
-  for (int i = tid; i < BL_P * BL_P * 8; i += 256) {
+  for (int i = tid; i < BL_P * BL_P * 8; i += 512) {
     const int g = i & 7;
     const int px = (i >> 3) % BL_P, py = (i >> 3) / BL_P;
     const int iy = Y0 - 1 + py, ix = X0 - 1 + px;
@@ -192,31 +192,30 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(__nv_bfloat16* __
   }
   __syncthreads();
 
-  const int g = tid & 7;
-  const int sx = (tid >> 3) & 15;      // output column inside the tile
-  const int sy = (tid >> 7) * 8;       // first output row of this thread's strip
-  float acc[8][8];
+  // thread = 4 channels x one column x a strip of 8 rows  (512 threads: 16 ch-quads x 16 cols x 2 strips)
+  const int g = tid & 15;
+  const int sx = (tid >> 4) & 15;
+  const int sy = (tid >> 8) * 8;
+  const uint2* patch2 = reinterpret_cast<const uint2*>(s_patch);
+  float acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
 
 #pragma unroll
   for (int r = 0; r < 11; ++r) {        // patch rows sy + r feed outputs sy + r - a, a = 0..3
-    float v[4][8];
+    float v[4][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint4 w = s_patch[((sy + r) * BL_P + sx + q) * 8 + g];
-      float2 f;
-      f = unpack_bf16x2(w.x); v[q][0] = f.x; v[q][1] = f.y;
-      f = unpack_bf16x2(w.y); v[q][2] = f.x; v[q][3] = f.y;
-      f = unpack_bf16x2(w.z); v[q][4] = f.x; v[q][5] = f.y;
-      f = unpack_bf16x2(w.w); v[q][6] = f.x; v[q][7] = f.y;
+      const uint2 w = patch2[((sy + r) * BL_P + sx + q) * 16 + g];
+      v[q][0] = __uint_as_float(w.x << 16); v[q][1] = __uint_as_float(w.x & 0xffff0000u);
+      v[q][2] = __uint_as_float(w.y << 16); v[q][3] = __uint_as_float(w.y & 0xffff0000u);
     }
     if (SEP) {
-      float hrow[8];
+      float hrow[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
+      for (int c = 0; c < 4; ++c)
         hrow[c] = fmaf(s_kh[3], v[3][c], fmaf(s_kh[2], v[2][c], fmaf(s_kh[1], v[1][c], s_kh[0] * v[0][c])));
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
@@ -224,7 +223,7 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(__nv_bfloat16* __
         if (i < 0 || i > 7) continue;
         const float kv = s_kv[a];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(kv, hrow[c], acc[i][c]);
+        for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(kv, hrow[c], acc[i][c]);
       }
     } else {
 #pragma unroll
@@ -235,36 +234,39 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(__nv_bfloat16* __
         for (int q = 0; q < 4; ++q) {
           const float kv = s_k[a * 4 + q];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(kv, v[q][c], acc[i][c]);
+          for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(kv, v[q][c], acc[i][c]);
         }
       }
     }
   }
 
-  if (c0 + g * 8 >= cs) return;
+  if (c0 + g * 4 >= cs) return;
   const int X = X0 + sx;
   if (X >= OW) return;
   const float nw = noise ? (noise_w ? __ldg(noise_w) : 1.f) : 0.f;
-  float4 tv[8];
+  float4 tv[4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) tv[c] = s_tab[g * 8 + c];
+  for (int c = 0; c < 4; ++c) tv[c] = s_tab[g * 4 + c];
+  float nzv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int Y = Y0 + sy + i;
+    nzv[i] = (noise && Y < OH) ? nw * __ldg(noise + (static_cast<size_t>(noise_bstride ? b : 0) * OH + Y) * OW + X) : 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int Y = Y0 + sy + i;
     if (Y >= OH) break;
-    float nz = 0.f;
-    if (noise) nz = nw * __ldg(noise + (static_cast<size_t>(noise_bstride ? b : 0) * OH + Y) * OW + X);
-    float o[8];
+    float o[4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float x = fmaf(acc[i][c], tv[c].x, tv[c].y + nz);
+    for (int c = 0; c < 4; ++c) {
+      float x = fmaf(acc[i][c], tv[c].x, tv[c].y + nzv[i]);
       x = x > 0.f ? x : x * tv[c].z;
       o[c] = x * tv[c].w;
     }
-    uint4 w;
+    uint2 w;
     w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
-    w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * OH + Y) * OW + X) * cs + c0 + g * 8) = w;
+    *reinterpret_cast<uint2*>(out + ((static_cast<size_t>(b) * OH + Y) * OW + X) * cs + c0 + g * 4) = w;
   }
 }
 
@@ -404,11 +406,11 @@ extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4
   FM_CHECK_ARG(blocks < 0x7FFFFFFF, "fm_blur_act_nhwc: too many blocks");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (separable)
-    blur_act_nhwc_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+    blur_act_nhwc_kernel<true><<<static_cast<unsigned>(blocks), 512, 0, st>>>(
         static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(t), kernel4x4, tab, noise, noise_bstride, noise_w,
         OH, OW, C, cstride, tiles_x, tiles_y, cblocks);
   else
-    blur_act_nhwc_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+    blur_act_nhwc_kernel<false><<<static_cast<unsigned>(blocks), 512, 0, st>>>(
         static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(t), kernel4x4, tab, noise, noise_bstride, noise_w,
         OH, OW, C, cstride, tiles_x, tiles_y, cblocks);
   count_launch();
