@@ -204,6 +204,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                         // layout = SWIZZLE_128B
   return d;
 }
+// Same, for an operand whose first row sits `row_off` (0..7) 128-byte rows into a 1024-byte swizzle
+// atom (a shifted view of a larger staged patch): the matrix-descriptor base_offset field [49,52).
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128_off(uint32_t smem_addr, uint32_t row_off) {
+  return umma_smem_desc_sw128(smem_addr) | (static_cast<uint64_t>(row_off & 7) << 49);
+}
 // Instruction descriptor: D=f32, A=B=bf16, both K-major, dense, M x N.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);

@@ -17,6 +17,8 @@
 // encoders folded BatchNorm + ReLU/PReLU/LeakyReLU + residual add.
 //
 // Algorithmic FLOPs per launch: 2 * B*OH*OW * Cin * Cout * ntaps   (SURVEY.md 8d).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fm {
@@ -31,6 +33,9 @@ struct IgemmParams {
   int tiles_x, tiles_y, tiles_b, tiles_n, num_tiles;
   int kchunks, ntaps, stride_x, stride_y, w_rows, Cout;
   int rows;                        // tw*th*tb (<= 128) valid rows of the A tile
+  int patch;                       // 3x3/s1/p1 row-patch mode: one 130-pixel A load serves the 3 horizontal taps
+  int prows;                       // output rows per tile in patch mode (R accumulators share each weight load)
+  int patch_a_bytes, patch_stage_bytes, patch_stages;
   int Bg, nslabs;                  // images per group, weight slabs per group
   const float* border_tab;
   int out_cgroup;
@@ -60,10 +65,12 @@ template <int BN> struct IgemmCfg {
   static constexpr int B_BYTES = BN * IG_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  // row-patch mode carves the same ring into stages of (R 130-pixel input rows + 3 weight tiles)
+  static constexpr int RING_BYTES = 200 * 1024;
   static constexpr int TAB_BYTES = IG_TAB_ROWS * 32;
   static constexpr int RGB_BYTES = IG_BM * 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAB_BYTES + RGB_BYTES + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = RING_BYTES + TAB_BYTES + RGB_BYTES + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 512;   // 2 buffers x R rows x BN columns; one CTA per SM owns all of TMEM
 };
 
 template <int BN, int EPI>
@@ -73,9 +80,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // SWIZZLE_128B operand tiles need 1024-byte alignment; declaring it keeps the shared address space
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_stage = smem;
-  float4* s_tab = reinterpret_cast<float4*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  float4* s_rgb = reinterpret_cast<float4*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAB_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAB_BYTES + Cfg::RGB_BYTES);
+  float4* s_tab = reinterpret_cast<float4*>(smem + Cfg::RING_BYTES);
+  float4* s_rgb = reinterpret_cast<float4*>(smem + Cfg::RING_BYTES + Cfg::TAB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES + Cfg::TAB_BYTES + Cfg::RGB_BYTES);
   uint64_t* full_bar = bars;                        // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + Cfg::STAGES;         // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;     // [2]       MMA -> epilogue
@@ -123,6 +130,27 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int bb = m / p.tiles_y;
       const int x0 = bx * p.tw * p.stride_x, y0 = by * p.th * p.stride_y, b0 = bb * p.tb, n0 = nt * BN;
       const int wrow0 = (b0 / p.Bg) * p.nslabs;
+      if (p.patch) {
+        // stage = (kernel row ky, channel chunk): R 130-pixel input rows + the 3 weight tiles of that kernel row
+        const uint32_t ptx = static_cast<uint32_t>(p.prows) * 130u * (IG_BK * 2) + 3u * Cfg::B_BYTES;
+        for (int it = 0; it < 3 * p.kchunks; ++it) {
+          const int ky = it / p.kchunks;
+          const int kc = it - ky * p.kchunks;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (lane == 0) {
+            uint8_t* sa = s_stage + stage * p.patch_stage_bytes;
+            uint8_t* sb = sa + p.patch_a_bytes;
+            mbar_arrive_expect_tx(&full_bar[stage], ptx);
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * IG_BK, x0 - 1, by * p.prows + ky - 1, b0);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+              tma_load_2d(sb + kx * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + ky * 3 + kx) * p.w_rows + n0);
+          }
+          __syncwarp();
+          if (++stage == p.patch_stages) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       for (int it = 0; it < kiters; ++it) {
         const int tap = it / p.kchunks;
         const int kc = it - tap * p.kchunks;
@@ -150,6 +178,34 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tempty_bar[buf], aphase ^ 1);     // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * BN;
+      if (p.patch) {
+        const int nst = 3 * p.kchunks;
+        const uint32_t tmem_t = tmem_base + buf * (p.prows * BN);
+        for (int it = 0; it < nst; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(s_stage + stage * p.patch_stage_bytes);
+            for (int r = 0; r < p.prows; ++r) {
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                // the tap's A operand is staged row r shifted by kx pixels (= kx 128-byte rows); the
+                // 128B swizzle is a function of the smem address, so a shifted start address just works
+                const uint64_t adesc = umma_smem_desc_sw128(sa + r * (130 * 128) + kx * 128);
+                const uint64_t bdesc = umma_smem_desc_sw128(sa + p.patch_a_bytes + kx * Cfg::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < IG_BK / 16; ++k)
+                  umma_bf16(tmem_t + r * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || kx > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (it == nst - 1) umma_commit(&tfull_bar[buf]);
+          }
+          __syncwarp();
+          if (++stage == p.patch_stages) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&full_bar[stage], phase);        // TMA bytes have landed
         tc_fence_after();
@@ -192,8 +248,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int by = m % p.tiles_y;
       const int bb = m / p.tiles_y;
       const int n0 = nt * BN;
-      const int ox = bx * p.tw + lx, oy = by * p.th + ly, b = bb * p.tb + lb;
-      const bool valid = row < p.rows && ox < p.OW && oy < p.OH && b < p.B;
+      const int ox = bx * p.tw + lx, b = bb * p.tb + lb;
       const int grp = (bb * p.tb) / p.Bg;
 
       // ---- epilogue tables: re-staged only when (sample block | group, n-tile) changes
@@ -217,6 +272,14 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
 
+      mbar_wait(&tfull_bar[buf], aphase);
+      tc_fence_after();
+      const int nrows = p.patch ? p.prows : 1;
+#pragma unroll 1
+      for (int r = 0; r < nrows; ++r) {
+      const int oy = p.patch ? by * p.prows + r : by * p.th + ly;
+      const bool valid = row < p.rows && ox < p.OW && oy < p.OH && b < p.B;
+      const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (nrows * BN) + r * BN;
       const int Y = oy * p.out_ys + p.out_y0, X = ox * p.out_xs + p.out_x0;
       float nz = 0.f;
       if (valid && p.noise)
@@ -229,12 +292,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (cls && p.border_tab) btab = p.border_tab + static_cast<size_t>(cls) * p.Cout;
       }
 
-      mbar_wait(&tfull_bar[buf], aphase);
-      tc_fence_after();
 #pragma unroll 1
       for (int c = half; c < BN / 16; c += 2) {     // 16-column chunks, alternating between the two warps
         uint32_t acc[16];
-        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c * 16, acc);
+        tmem_ld_32x16(tmem_acc + c * 16, acc);
         const int o0 = n0 + c * 16;
         // position inside the output tensor (concatenated-N outputs are written group-major)
         const int og = p.out_cgroup ? o0 / p.out_cgroup : 0;
@@ -296,10 +357,6 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       }
-      // accumulator drained -> hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
       if (EPI & EPI_RGB) {
         // combine the two column halves of each pixel through smem (deterministic), then write
         if (half == 1) s_rgb[row] = make_float4(r0, r1, r2, 0.f);
@@ -317,6 +374,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");   // s_rgb may be overwritten by the next tile
       }
+      }   // rows of the tile
+      // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
   }
 
@@ -462,7 +524,32 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     if (d->tap_widx[i] > max_widx) max_widx = d->tap_widx[i];
   }
   p.nslabs = max_widx + 1;
-
+  // ---- row-patch mode: plain 3x3 / stride 1 / pad 1, 128-pixel output rows, N <= 128.  A tile is R
+  // output rows (R accumulators in TMEM) so each weight tile loaded from L2 feeds R*128 pixels.
+  {
+    static const int env_patch = []() { const char* e = getenv("FM3D_PATCH"); return e ? atoi(e) : 1; }();
+    static const int env_rows = []() { const char* e = getenv("FM3D_PATCH_ROWS"); return e ? atoi(e) : 0; }();
+    bool std33 = d->ntaps == 9 && sx == 1 && sy == 1 && d->x_pixstride == 0 && d->x_rowstride == 0 && d->x_imgstride == 0;
+    for (int i = 0; std33 && i < 9; ++i)
+      std33 = d->tap_dy[i] == i / 3 - 1 && d->tap_dx[i] == i % 3 - 1 && d->tap_widx[i] == i;
+    p.patch = (env_patch && std33 && tw == 128 && th == 1 && tb == 1 && bn <= 128) ? 1 : 0;
+    if (p.patch) {
+      int R = env_rows > 0 ? env_rows : (bn == 64 ? 4 : 2);
+      while (R > 1 && (2 * R * bn > 512 || R > d->OH)) R >>= 1;
+      p.prows = R;
+      p.patch_a_bytes = (R * 130 * 128 + 1023) & ~1023;
+      p.patch_stage_bytes = p.patch_a_bytes + 3 * bn * 128;
+      p.patch_stages = (200 * 1024) / p.patch_stage_bytes;
+      if (p.patch_stages > 8) p.patch_stages = 8;
+      if (p.patch_stages < 2) { p.patch = 0; p.prows = 1; }
+    }
+    if (p.patch) {
+      p.tiles_y = (d->OH + p.prows - 1) / p.prows;
+      p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+    } else {
+      p.prows = 1;
+    }
+  }
   // ---- tensor maps
   CUtensorMap tmA, tmB;
   {
@@ -471,8 +558,8 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(pixs) * 2, static_cast<cuuint64_t>(rows_) * 2,
                                    static_cast<cuuint64_t>(imgs) * 2};
     // with an element stride s TMA loads ceil(box/s) elements: box = n*s loads n
-    const cuuint32_t box[4] = {IG_BK, static_cast<cuuint32_t>(tw * sx), static_cast<cuuint32_t>(th * sy),
-                               static_cast<cuuint32_t>(tb)};
+    const cuuint32_t box[4] = {IG_BK, static_cast<cuuint32_t>(p.patch ? 130 : tw * sx),
+                               static_cast<cuuint32_t>(p.patch ? p.prows : th * sy), static_cast<cuuint32_t>(tb)};
     const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(sx), static_cast<cuuint32_t>(sy), 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

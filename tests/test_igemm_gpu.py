@@ -249,3 +249,20 @@ def test_encoder_helper_kernels(cuda):
     ops.se_block_nhwc(xg, C, w1.to(cuda), w2.to(cuda), sc.permute(0, 2, 3, 1).contiguous().to(cuda), 2, sums, gbuf, o)
     torch.testing.assert_close(o.float().permute(0, 3, 1, 2).cpu(), refse, rtol=1e-2, atol=2e-2)
     assert float(sums.abs().sum()) == 0.0          # re-zeroed for the next block
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 6, 128, 64, 64), (1, 9, 256, 128, 128), (2, 5, 200, 72, 40), (1, 3, 130, 192, 128)])
+def test_conv_row_patch_mode(cuda, B, H, W, Cin, Cout):
+    """3x3/s1/p1 with 128-pixel row tiles: one 130-pixel patch feeds the three horizontal taps
+    through shifted UMMA descriptors."""
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(W + Cin)
+    x = torch.randn(B, Cin, H, W, generator=gen)
+    w = torch.randn(Cout, Cin, 3, 3, generator=gen) / (Cin * 9) ** 0.5
+    ref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), padding=1)
+    wq, _ = ops.prep_weight(w.to(cuda), 1.0, want_wsq=False)
+    out = torch.zeros(B, Cout, H, W, device=cuda)
+    ops.conv_igemm(ops.nchw_to_nhwc_bf16(x.to(cuda)), wq, ops.conv_taps(3, 3, 1), out, _tab(Cout, cuda), B=B, H=H, W=W,
+                   Cin=Cin, Cout=Cout, OH=H, OW=W, out_nchw_f32=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.cpu(), ref, rtol=2e-3, atol=2e-3)
