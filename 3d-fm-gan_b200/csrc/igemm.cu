@@ -34,6 +34,9 @@ struct IgemmParams {
   int kchunks, ntaps, stride_x, stride_y, w_rows, Cout;
   int rows;                        // tw*th*tb (<= 128) valid rows of the A tile
   int patch;                       // 3x3/s1/p1 row-patch mode: one 130-pixel A load serves the 3 horizontal taps
+  int ksplit, kper;                // split-K: CTAs per (m,n) tile and k-iterations per CTA
+  float* ws;                       // split-K fp32 workspace [B*OH*OW][ws_cs]
+  int ws_cs;
   int prows;                       // output rows per tile in patch mode (R accumulators share each weight load)
   int patch_a_bytes, patch_stage_bytes, patch_stages;
   int Bg, nslabs;                  // images per group, weight slabs per group
@@ -58,7 +61,7 @@ constexpr int IG_EPI_WARPS = 8;                       // two warps per TMEM lane
 constexpr int IG_THREADS2 = 64 + 32 * IG_EPI_WARPS;   // producer + MMA + epilogue warps
 
 // epilogue feature flags (template: dead paths cost nothing)
-constexpr int EPI_RGB = 1, EPI_RES = 2, EPI_BTAB = 4;
+constexpr int EPI_RGB = 1, EPI_RES = 2, EPI_BTAB = 4, EPI_SPLIT = 8;
 
 template <int BN> struct IgemmCfg {
   static constexpr int A_BYTES = IG_BM * IG_BK * 2;        // 16 KB
@@ -125,10 +128,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
       int m = tile / p.tiles_n;
+      const int ks = m % p.ksplit; m /= p.ksplit;
       const int bx = m % p.tiles_x; m /= p.tiles_x;
       const int by = m % p.tiles_y;
       const int bb = m / p.tiles_y;
       const int x0 = bx * p.tw * p.stride_x, y0 = by * p.th * p.stride_y, b0 = bb * p.tb, n0 = nt * BN;
+      const int it0 = ks * p.kper, it1 = min(kiters, it0 + p.kper);
       const int wrow0 = (b0 / p.Bg) * p.nslabs;
       if (p.patch) {
         // stage = (kernel row ky, channel chunk): R 130-pixel input rows + the 3 weight tiles of that kernel row
@@ -151,7 +156,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
-      for (int it = 0; it < kiters; ++it) {
+      for (int it = it0; it < it1; ++it) {
         const int tap = it / p.kchunks;
         const int kc = it - tap * p.kchunks;
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -178,6 +183,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tempty_bar[buf], aphase ^ 1);     // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * BN;
+      const int ks = (tile / p.tiles_n) % p.ksplit;
+      const int it0 = ks * p.kper, it1 = min(kiters, it0 + p.kper);
       if (p.patch) {
         const int nst = 3 * p.kchunks;
         const uint32_t tmem_t = tmem_base + buf * (p.prows * BN);
@@ -206,7 +213,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
-      for (int it = 0; it < kiters; ++it) {
+      for (int it = it0; it < it1; ++it) {
         mbar_wait(&full_bar[stage], phase);        // TMA bytes have landed
         tc_fence_after();
         if (lane == 0) {
@@ -216,10 +223,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < IG_BK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs finish
-          if (it == kiters - 1) umma_commit(&tfull_bar[buf]);
+          if (it == it1 - 1) umma_commit(&tfull_bar[buf]);
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -244,6 +251,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t aphase = (titer >> 1) & 1;
       const int nt = tile % p.tiles_n;
       int m = tile / p.tiles_n;
+      m /= p.ksplit;
       const int bx = m % p.tiles_x; m /= p.tiles_x;
       const int by = m % p.tiles_y;
       const int bb = m / p.tiles_y;
@@ -253,7 +261,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       // ---- epilogue tables: re-staged only when (sample block | group, n-tile) changes
       const int key = (p.tab_bstride ? bb : grp) * p.tiles_n + nt;
-      if (key != tab_key) {
+      if (!(EPI & EPI_SPLIT) && key != tab_key) {
         tab_key = key;
         asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done with the old tables
         for (int i = etid; i < tbe * BN; i += 256) {
@@ -287,9 +295,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const size_t pix = (static_cast<size_t>(b) * p.out_H + Y) * p.out_W + X;
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
       const float* btab = nullptr;      // folded-input-BN border correction (per-thread: thread = pixel)
+      bool warp_has_border = false;
       if (EPI & EPI_BTAB) {
         const int cls = (oy == 0 ? 1 : (oy == p.OH - 1 ? 2 : 0)) * 3 + (ox == 0 ? 1 : (ox == p.OW - 1 ? 2 : 0));
         if (cls && p.border_tab) btab = p.border_tab + static_cast<size_t>(cls) * p.Cout;
+        warp_has_border = __any_sync(0xffffffffu, btab != nullptr);   // interior warps skip the correction code
       }
 
 #pragma unroll 1
@@ -297,6 +307,23 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t acc[16];
         tmem_ld_32x16(tmem_acc + c * 16, acc);
         const int o0 = n0 + c * 16;
+        if (EPI & EPI_SPLIT) {
+          // split-K partial: raw fp32 accumulators are reduced into the workspace with vector atomics;
+          // igemm_splitk_finalize_kernel applies the epilogue
+          tmem_ld_wait();
+          if (valid && o0 < p.Cout) {
+            float* wp = p.ws + (static_cast<size_t>(b) * p.OH * p.OW + static_cast<size_t>(oy) * p.OW + ox) * p.ws_cs + o0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              if (o0 + j < p.Cout)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wp + j), "f"(__uint_as_float(acc[j])),
+                             "f"(__uint_as_float(acc[j + 1])), "f"(__uint_as_float(acc[j + 2])),
+                             "f"(__uint_as_float(acc[j + 3]))
+                             : "memory");
+            }
+          }
+          continue;
+        }
         // position inside the output tensor (concatenated-N outputs are written group-major)
         const int og = p.out_cgroup ? o0 / p.out_cgroup : 0;
         const int ol0 = o0 - og * p.out_cgroup;
@@ -317,7 +344,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const float4 t0 = tr[2 * j];
           float x = fmaf(__uint_as_float(acc[j]), t0.x, t0.y + nz);
           if (EPI & EPI_BTAB) {
-            if (btab != nullptr && o0 + j < p.Cout) x += __ldg(btab + o0 + j);
+            if (warp_has_border) {
+              if (btab != nullptr && o0 + j < p.Cout) x += __ldg(btab + o0 + j);
+            }
           }
           if (EPI & EPI_RES) {
             const uint32_t w = (&resv[0].x)[j >> 1];
@@ -390,6 +419,54 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// Split-K tail: workspace (fp32 sums) -> epilogue -> bf16 NHWC, and re-zero the workspace.
+// All loads of a thread (2 workspace vectors, 8 table rows, residual, noise) are issued up front.
+__global__ void __launch_bounds__(256) igemm_splitk_finalize_kernel(const IgemmParams p, int64_t total) {
+  const int groups8 = p.ws_cs / 8;
+  const float nw = p.noise ? (p.noise_w ? __ldg(p.noise_w) : 1.f) : 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int g = static_cast<int>(idx % groups8);
+    const int64_t pixlin = idx / groups8;
+    const int ox = static_cast<int>(pixlin % p.OW);
+    const int oy = static_cast<int>((pixlin / p.OW) % p.OH);
+    const int b = static_cast<int>(pixlin / (static_cast<int64_t>(p.OW) * p.OH));
+    const int o0 = g * 8;
+    float4* wp = reinterpret_cast<float4*>(p.ws + pixlin * p.ws_cs + o0);
+    const float4 a0 = wp[0], a1 = wp[1];
+    const int Y = oy * p.out_ys + p.out_y0, X = ox * p.out_xs + p.out_x0;
+    const size_t pix = (static_cast<size_t>(b) * p.out_H + Y) * p.out_W + X;
+    const bool store = o0 < p.out_cstride;
+    const int trow = p.tab_bstride ? b : b / p.Bg;
+    const float4* tp = reinterpret_cast<const float4*>(p.tab + static_cast<size_t>(trow) * p.Cout * 8);
+    float4 t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = __ldg(tp + 2 * min(o0 + j, p.Cout - 1));     // clamped: no branch, loads batch
+    uint4 res = make_uint4(0, 0, 0, 0);
+    if (p.residual && store) res = __ldg(reinterpret_cast<const uint4*>(p.residual + pix * p.out_cstride + o0));
+    float nz = 0.f;
+    if (p.noise) nz = nw * __ldg(p.noise + (static_cast<size_t>(p.noise_bstride ? b : 0) * p.out_H + Y) * p.out_W + X);
+    wp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!store) continue;
+    const float r0 = __uint_as_float(res.x << 16), r1 = __uint_as_float(res.x & 0xffff0000u);
+    const float r2 = __uint_as_float(res.y << 16), r3 = __uint_as_float(res.y & 0xffff0000u);
+    const float r4 = __uint_as_float(res.z << 16), r5 = __uint_as_float(res.z & 0xffff0000u);
+    const float r6 = __uint_as_float(res.w << 16), r7 = __uint_as_float(res.w & 0xffff0000u);
+#define FM_FIN(J, ACC, RES)                                              \
+    float v##J = fmaf(ACC, t[J].x, t[J].y + nz) + RES;                   \
+    v##J = v##J > 0.f ? v##J : v##J * t[J].z;                            \
+    v##J = (o0 + J < p.Cout) ? v##J * t[J].w : 0.f;
+    FM_FIN(0, a0.x, r0) FM_FIN(1, a0.y, r1) FM_FIN(2, a0.z, r2) FM_FIN(3, a0.w, r3)
+    FM_FIN(4, a1.x, r4) FM_FIN(5, a1.y, r5) FM_FIN(6, a1.z, r6) FM_FIN(7, a1.w, r7)
+#undef FM_FIN
+    uint4 w;
+    w.x = pack_bf16x2(v0, v1); w.y = pack_bf16x2(v2, v3);
+    w.z = pack_bf16x2(v4, v5); w.w = pack_bf16x2(v6, v7);
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.out_cstride + o0) = w;
+  }
+}
+
 // ------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -426,6 +503,18 @@ static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const I
 template <int BN>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
   // one instantiation per epilogue feature set in use (generator: RGB; ResNet: RES; IR block: BTAB)
+  if (p.ksplit > 1) {
+    const int rc = launch_igemm2<BN, EPI_SPLIT>(tmA, tmB, p, st);
+    if (rc != FM_OK) return rc;
+    const int64_t total = static_cast<int64_t>(p.B) * p.OH * p.OW * (p.ws_cs / 8);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
+    if (blocks > cap) blocks = cap;
+    igemm_splitk_finalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(p, total);
+    count_launch();
+    FM_LAUNCH_OK();
+    return FM_OK;
+  }
   const int epi = (p.rgb ? EPI_RGB : 0) | (p.residual ? EPI_RES : 0) | (p.border_tab ? EPI_BTAB : 0);
   switch (epi) {
     case 0: return launch_igemm2<BN, 0>(tmA, tmB, p, st);
@@ -489,21 +578,50 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   p.tiles_x = (d->OW + tw - 1) / tw;
   p.tiles_y = (d->OH + th - 1) / th;
   p.tiles_b = (d->B + tb - 1) / tb;
+  // ---- split-K for small-M problems: with few (m,n) tiles every CTA would stream the whole K loop of
+  // its tile alone; splitting K over idle SMs with the widest N tile divides the per-SM operand bytes
+  const int kiters_total = d->ntaps * ((d->Cin + IG_BK - 1) / IG_BK);
+  int ksplit = 1;
+  {
+    static const int env_split = []() { const char* e = getenv("FM3D_SPLITK"); return e ? atoi(e) : 1; }();
+    const bool eligible = env_split && d->ksplit != 1 && d->splitk_ws && !d->rgb && !d->border_tab && !d->out_nchw_f32 &&
+                          !d->out_cgroup && d->block_n <= 0;
+    if (eligible) {
+      const int bn_wide = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
+      const int64_t tiles_wide = static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.tiles_b * ((d->Cout + bn_wide - 1) / bn_wide);
+      const int sms = sm_count();
+      int want = d->ksplit > 1 ? d->ksplit : static_cast<int>(sms / (tiles_wide > 0 ? tiles_wide : 1));
+      if (want > kiters_total / 6) want = kiters_total / 6;       // keep >= 6 k-iterations per CTA
+      if (want > 16) want = 16;
+      const int ws_cs = (d->Cout + 15) / 16 * 16;
+      const int64_t need = static_cast<int64_t>(d->B) * d->OH * d->OW * ws_cs * 4;
+      if (want >= 2 && need <= d->splitk_ws_bytes && (d->ksplit > 1 || tiles_wide * 2 <= sms)) {
+        ksplit = want;
+        p.ws = d->splitk_ws;
+        p.ws_cs = ws_cs;
+      }
+    }
+  }
   // ---- block_n
   const int tbe = d->tab_bstride ? tb : 1;
   int bn = d->block_n;
-  if (bn <= 0) {
+  if (ksplit > 1) {
+    bn = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
+  } else if (bn <= 0) {
     bn = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
     // small problems: more, narrower tiles fill more SMs
     const int sms = sm_count();
     while (bn > 64 && static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.tiles_b * ((d->Cout + bn - 1) / bn) < sms) bn >>= 1;
   }
-  while (bn > 64 && tbe * bn > IG_TAB_ROWS) bn >>= 1;
+  if (ksplit == 1) while (bn > 64 && tbe * bn > IG_TAB_ROWS) bn >>= 1;
   FM_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "fm_conv_igemm: block_n must be 64/128/256");
-  FM_CHECK_ARG(tbe * bn <= IG_TAB_ROWS, "fm_conv_igemm: per-sample tables do not fit (tile_b %d x block_n %d)", tbe, bn);
+  FM_CHECK_ARG(ksplit > 1 || tbe * bn <= IG_TAB_ROWS, "fm_conv_igemm: per-sample tables do not fit (tile_b %d x block_n %d)", tbe, bn);
   FM_CHECK_ARG(!d->out_cgroup || d->out_cgroup % bn == 0 || bn % d->out_cgroup == 0, "fm_conv_igemm: out_cgroup vs block_n");
   p.tiles_n = (d->Cout + bn - 1) / bn;
-  const int64_t nt = static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.tiles_b * p.tiles_n;
+  p.ksplit = ksplit;
+  p.kper = (kiters_total + ksplit - 1) / ksplit;
+  p.ksplit = (kiters_total + p.kper - 1) / p.kper;        // no empty k-slices
+  const int64_t nt = static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.tiles_b * p.tiles_n * p.ksplit;
   FM_CHECK_ARG(nt < 0x7FFFFFFF, "fm_conv_igemm: too many tiles");
   p.num_tiles = static_cast<int>(nt);
   p.kchunks = (d->Cin + IG_BK - 1) / IG_BK;
@@ -532,7 +650,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     bool std33 = d->ntaps == 9 && sx == 1 && sy == 1 && d->x_pixstride == 0 && d->x_rowstride == 0 && d->x_imgstride == 0;
     for (int i = 0; std33 && i < 9; ++i)
       std33 = d->tap_dy[i] == i / 3 - 1 && d->tap_dx[i] == i % 3 - 1 && d->tap_widx[i] == i;
-    p.patch = (env_patch && std33 && tw == 128 && th == 1 && tb == 1 && bn <= 128) ? 1 : 0;
+    p.patch = (env_patch && std33 && tw == 128 && th == 1 && tb == 1 && bn <= 128 && p.ksplit == 1) ? 1 : 0;
     if (p.patch) {
       int R = env_rows > 0 ? env_rows : (bn == 64 ? 4 : 2);
       while (R > 1 && (2 * R * bn > 512 || R > d->OH)) R >>= 1;

@@ -33,3 +33,6 @@ int sm_count() {
 extern "C" int fm_version(void) { return 100; }
 extern "C" const char* fm_last_error(void) { return fm::g_err; }
 extern "C" int64_t fm_launch_count(void) { return fm::g_launches.load(std::memory_order_relaxed); }
+// A captured CUDA graph replays kernels without passing through the launch wrappers: the host
+// runtime credits the launches of each replay here.
+extern "C" void fm_add_launches(int64_t n) { fm::g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -6,67 +6,119 @@
 namespace fm {
 
 // ------------------------------------------------------------------------------------
-// s[b,i] = latent[b, idx, :] . (wmod[i,:] * 1/sqrt(D)) + bmod[i]
-// EqualLinear(style_dim, cin, bias_init=1), stylegan2.py:165-175, 240, 257.
-// grid (ceil(max_cin/8), n_layers); one warp per output channel, all samples.
+// Small "NT" GEMMs of the modulation path:  C[b][o] = sum_k A[b][k] * W[o][k]  with B <= a few
+// dozen samples.  lane = sample; the A rows of a 32-sample chunk sit in shared memory (padded, so
+// the per-lane float4 reads are conflict-free); W values are warp-uniform broadcast loads.  Each
+// warp produces 4 output channels per pass: no shuffles, 1 LDS.128 + 4 LDG.128 per 16 FMAs.
+//   style_affine : A = latent[:, idx, :], W = modulation weight  (stylegan2.py:165-175,240,257)
+//   build_tables : A = s^2,               W = wsq                 (stylegan2.py:258-262)
+// grid (ceil(max_out/64), n_layers), 256 threads, dynamic smem 32*(K+4)*4 bytes.
 // ------------------------------------------------------------------------------------
+template <bool SQUARE>
+__device__ __forceinline__ void stage_rows(float* s_a, const float* __restrict__ a, int64_t row_stride, int b0, int B, int K,
+                                           int KP) {
+  // s_a[r][k] for r = 0..31 (sample b0 + r), zero beyond B and beyond K
+  for (int i = threadIdx.x; i < 32 * KP; i += blockDim.x) {
+    const int r = i / KP, k = i - r * KP;
+    float v = 0.f;
+    if (b0 + r < B && k < K) v = __ldg(a + static_cast<int64_t>(b0 + r) * row_stride + k);
+    s_a[i] = SQUARE ? v * v : v;
+  }
+}
+
+__device__ __forceinline__ void dot4x4(const float* s_row, const float* __restrict__ w, int K, int o_valid, float (&acc)[4]) {
+  // acc[c] = sum_k s_row[k] * w[c*K + k], c < o_valid (rows beyond are clamped by the caller)
+  if ((K & 3) == 0) {
+#pragma unroll 8
+    for (int k = 0; k < K; k += 4) {      // unrolled: 32 independent broadcast loads in flight per thread
+      const float4 av = *reinterpret_cast<const float4*>(s_row + k);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(min(c, o_valid - 1)) * K + k));
+        acc[c] = fmaf(av.x, wv.x, fmaf(av.y, wv.y, fmaf(av.z, wv.z, fmaf(av.w, wv.w, acc[c]))));
+      }
+    }
+  } else {
+    for (int k = 0; k < K; ++k) {
+      const float av = s_row[k];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c] = fmaf(av, __ldg(w + static_cast<size_t>(min(c, o_valid - 1)) * K + k), acc[c]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) style_affine_kernel(const fm_style_layer* __restrict__ layers,
                                                            const float* __restrict__ latent, int B, int n_latent,
                                                            int D, float scale) {
+  extern __shared__ __align__(16) float s_a[];
   const fm_style_layer L = layers[blockIdx.y];
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (i >= L.cin) return;
-  const float* w = L.wmod + static_cast<size_t>(i) * D;
-  const float bias = __ldg(L.bmod + i);
-  for (int b = 0; b < B; ++b) {
-    const float* x = latent + (static_cast<size_t>(b) * n_latent + L.latent_idx) * D;
-    float acc = 0.f;
-    for (int k = lane; k < D; k += 32) acc = fmaf(__ldg(w + k) * scale, __ldg(x + k), acc);
+  if (blockIdx.x * 64 >= L.cin) return;
+  const int KP = ((D + 3) & ~3) + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    __syncthreads();
+    stage_rows<false>(s_a, latent + static_cast<int64_t>(L.latent_idx) * D, static_cast<int64_t>(n_latent) * D, b0, B, D, KP);
+    __syncthreads();
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int o = blockIdx.x * 64 + warp * 8 + pass * 4;
+      if (o >= L.cin) break;
+      const int nv = min(4, L.cin - o);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      dot4x4(s_a + lane * KP, L.wmod + static_cast<size_t>(o) * D, D, nv, acc);
+      if (b0 + lane < B) {
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) L.s[static_cast<size_t>(b) * L.cin + i] = acc + bias;
+        for (int c = 0; c < 4; ++c)
+          if (c < nv) L.s[static_cast<size_t>(b0 + lane) * L.cin + o + c] = fmaf(acc[c], scale, __ldg(L.bmod + o + c));
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------
-// Epilogue tables, one warp per (layer, out channel), all samples.
+// Epilogue tables: T[b][o] = (d, bias, slope, gain*s_next, rgb weights...)
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) build_tables_kernel(const fm_table_layer* __restrict__ layers, int B) {
+  extern __shared__ __align__(16) float s_a[];
   const fm_table_layer L = layers[blockIdx.y];
-  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (o >= L.cout) return;
+  if (blockIdx.x * 64 >= L.cout) return;
+  const int KP = ((L.cin + 3) & ~3) + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float rgb_scale = rsqrtf(static_cast<float>(L.cout));   // ToRGB fan_in = cout*1*1 (stylegan2.py:232-233)
-  for (int b = 0; b < B; ++b) {
-    float d = 1.f;
+  for (int b0 = 0; b0 < B; b0 += 32) {
     if (L.wsq) {
-      const float* s = L.s + static_cast<size_t>(b) * L.cin;
-      const float* q = L.wsq + static_cast<size_t>(o) * L.cin;
-      float acc = 0.f;
-      for (int i = lane; i < L.cin; i += 32) {
-        const float sv = __ldg(s + i);
-        acc = fmaf(sv * sv, __ldg(q + i), acc);
-      }
-#pragma unroll
-      for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
-      d = rsqrtf(acc + 1e-8f);                                   // stylegan2.py:261 (literal 1e-8)
+      __syncthreads();
+      stage_rows<true>(s_a, L.s, L.cin, b0, B, L.cin, KP);
+      __syncthreads();
     }
-    if (lane == 0) {
-      float* t = L.tab + (static_cast<size_t>(b) * L.cout + o) * 8;
-      float4 t0, t1 = make_float4(0.f, 0.f, 0.f, 0.f);
-      t0.x = d;
-      t0.y = L.act_bias ? __ldg(L.act_bias + o) : 0.f;
-      t0.z = L.slope;
-      t0.w = L.gain * (L.s_next ? __ldg(L.s_next + static_cast<size_t>(b) * L.cout + o) : 1.f);
-      if (L.wrgb) {
-        const float sr = __ldg(L.s_rgb + static_cast<size_t>(b) * L.cout + o) * L.gain;
-        t1.x = rgb_scale * __ldg(L.wrgb + o) * sr;
-        t1.y = rgb_scale * __ldg(L.wrgb + L.cout + o) * sr;
-        t1.z = rgb_scale * __ldg(L.wrgb + 2 * L.cout + o) * sr;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int o = blockIdx.x * 64 + warp * 8 + pass * 4;
+      if (o >= L.cout) break;
+      const int nv = min(4, L.cout - o);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (L.wsq) dot4x4(s_a + lane * KP, L.wsq + static_cast<size_t>(o) * L.cin, L.cin, nv, acc);
+      const int b = b0 + lane;
+      if (b >= B) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c >= nv) break;
+        const int oc = o + c;
+        float* t = L.tab + (static_cast<size_t>(b) * L.cout + oc) * 8;
+        float4 t0, t1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        t0.x = L.wsq ? rsqrtf(acc[c] + 1e-8f) : 1.f;                   // stylegan2.py:261 (literal 1e-8)
+        t0.y = L.act_bias ? __ldg(L.act_bias + oc) : 0.f;
+        t0.z = L.slope;
+        t0.w = L.gain * (L.s_next ? __ldg(L.s_next + static_cast<size_t>(b) * L.cout + oc) : 1.f);
+        if (L.wrgb) {
+          const float sr = __ldg(L.s_rgb + static_cast<size_t>(b) * L.cout + oc) * L.gain;
+          t1.x = rgb_scale * __ldg(L.wrgb + oc) * sr;
+          t1.y = rgb_scale * __ldg(L.wrgb + L.cout + oc) * sr;
+          t1.z = rgb_scale * __ldg(L.wrgb + 2 * L.cout + oc) * sr;
+        }
+        *reinterpret_cast<float4*>(t) = t0;
+        *reinterpret_cast<float4*>(t + 4) = t1;
       }
-      *reinterpret_cast<float4*>(t) = t0;
-      *reinterpret_cast<float4*>(t + 4) = t1;
     }
   }
 }
@@ -284,6 +336,7 @@ __global__ void __launch_bounds__(256) rgb_finalize_kernel(float* __restrict__ r
   }
   __syncthreads();
   const int h2 = H / 2, w2 = W / 2;
+  const float b0 = __ldg(bias3 + 0), b1 = __ldg(bias3 + 1), b2 = __ldg(bias3 + 2);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
     const int x = static_cast<int>(idx % W);
@@ -292,29 +345,33 @@ __global__ void __launch_bounds__(256) rgb_finalize_kernel(float* __restrict__ r
     float4* ap = reinterpret_cast<float4*>(acc + idx * 4);
     const float4 a = *ap;
     *ap = make_float4(0.f, 0.f, 0.f, 0.f);
-    float v[3] = {a.x + __ldg(bias3 + 0), a.y + __ldg(bias3 + 1), a.z + __ldg(bias3 + 2)};
+    float v[3] = {a.x + b0, a.y + b1, a.z + b2};
     if (skip) {
-      float up[3] = {0.f, 0.f, 0.f};
+      // zero-stuffed row u = y + ta - 2 is live when even: ta has the parity of y -> 2 of the 4 taps per axis
+      const size_t plane = static_cast<size_t>(h2) * w2;
+      const float* sp = skip + b * 3 * plane;
 #pragma unroll
-      for (int ta = 0; ta < 4; ++ta) {
-        const int u = y + ta - 2;             // row in the zero-stuffed image
-        if (u < 0 || (u & 1) || (u >> 1) >= h2) continue;
+      for (int ia = 0; ia < 2; ++ia) {
+        const int ta = (y & 1) + 2 * ia;
+        const int sy = (y + ta - 2) >> 1;
+        if (y + ta - 2 < 0 || sy >= h2) continue;
 #pragma unroll
-        for (int tb = 0; tb < 4; ++tb) {
-          const int w = x + tb - 2;
-          if (w < 0 || (w & 1) || (w >> 1) >= w2) continue;
+        for (int ib = 0; ib < 2; ++ib) {
+          const int tb = (x & 1) + 2 * ib;
+          const int sx = (x + tb - 2) >> 1;
+          if (x + tb - 2 < 0 || sx >= w2) continue;
           const float kv = s_k[ta * 4 + tb];
-          const size_t off = (static_cast<size_t>(u >> 1)) * w2 + (w >> 1);
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            up[c] = fmaf(__ldg(skip + (b * 3 + c) * static_cast<size_t>(h2) * w2 + off), kv, up[c]);
+          const size_t off = static_cast<size_t>(sy) * w2 + sx;
+          v[0] = fmaf(__ldg(sp + off), kv, v[0]);
+          v[1] = fmaf(__ldg(sp + plane + off), kv, v[1]);
+          v[2] = fmaf(__ldg(sp + 2 * plane + off), kv, v[2]);
         }
       }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) v[c] += up[c];
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) rgb_out[((b * 3 + c) * H + y) * static_cast<size_t>(W) + x] = v[c];
+    const size_t o = (b * 3 * H + y) * static_cast<size_t>(W) + x;
+    rgb_out[o] = v[0];
+    rgb_out[o + static_cast<size_t>(H) * W] = v[1];
+    rgb_out[o + 2 * static_cast<size_t>(H) * W] = v[2];
   }
 }
 
@@ -352,21 +409,32 @@ static inline unsigned grid_for(int64_t total, int per_block = 256, int waves = 
 
 using namespace fm;
 
+static int small_gemm_smem(const void* fn, int K) {
+  const int bytes = 32 * (((K + 3) & ~3) + 4) * 4;
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return bytes;
+}
+
 extern "C" int fm_style_affine(const fm_style_layer* layers_dev, int n_layers, int max_cin, const float* latent, int B,
                                int n_latent, int style_dim, void* stream) {
   FM_CHECK_ARG(layers_dev && latent && n_layers > 0 && max_cin > 0 && B > 0 && style_dim > 0, "fm_style_affine: bad args");
-  dim3 grid((max_cin + 7) / 8, n_layers);
-  style_affine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(layers_dev, latent, B, n_latent, style_dim,
-                                                                           1.0f / sqrtf(static_cast<float>(style_dim)));
+  FM_CHECK_ARG(style_dim <= 1700, "fm_style_affine: style_dim %d too large for the shared-memory tile", style_dim);
+  const int smem = small_gemm_smem(reinterpret_cast<const void*>(style_affine_kernel), style_dim);
+  dim3 grid((max_cin + 63) / 64, n_layers);
+  style_affine_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(layers_dev, latent, B, n_latent, style_dim,
+                                                                              1.0f / sqrtf(static_cast<float>(style_dim)));
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;
 }
 
-extern "C" int fm_build_tables(const fm_table_layer* layers_dev, int n_layers, int max_cout, int B, void* stream) {
-  FM_CHECK_ARG(layers_dev && n_layers > 0 && max_cout > 0 && B > 0, "fm_build_tables: bad args");
-  dim3 grid((max_cout + 7) / 8, n_layers);
-  build_tables_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(layers_dev, B);
+extern "C" int fm_build_tables(const fm_table_layer* layers_dev, int n_layers, int max_cout, int max_cin, int B,
+                               void* stream) {
+  FM_CHECK_ARG(layers_dev && n_layers > 0 && max_cout > 0 && max_cin > 0 && B > 0, "fm_build_tables: bad args");
+  FM_CHECK_ARG(max_cin <= 1700, "fm_build_tables: cin %d too large for the shared-memory tile", max_cin);
+  const int smem = small_gemm_smem(reinterpret_cast<const void*>(build_tables_kernel), max_cin);
+  dim3 grid((max_cout + 63) / 64, n_layers);
+  build_tables_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(layers_dev, B);
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;
@@ -423,7 +491,7 @@ extern "C" int fm_rgb_finalize(float* rgb_out, float* acc, const float* bias3, c
   FM_CHECK_ARG(rgb_out && acc && bias3 && B > 0 && H > 0 && W > 0, "fm_rgb_finalize: bad args");
   FM_CHECK_ARG(!skip || (kernel4x4 && H % 2 == 0 && W % 2 == 0), "fm_rgb_finalize: skip needs a kernel and even H, W");
   const int64_t total = static_cast<int64_t>(B) * H * W;
-  rgb_finalize_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(rgb_out, acc, bias3, skip, kernel4x4,
+  rgb_finalize_kernel<<<grid_for(total, 256, 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(rgb_out, acc, bias3, skip, kernel4x4,
                                                                                      H, W, total);
   count_launch();
   FM_LAUNCH_OK();

@@ -31,6 +31,7 @@ class ConvDesc(C.Structure):
         ("noise", C.c_void_p), ("noise_bstride", C.c_int32), ("noise_w", C.c_void_p),
         ("residual", C.c_void_p), ("rgb", C.c_void_p),
         ("border_tab", C.c_void_p), ("out_cgroup", C.c_int32), ("out_gstride", C.c_int64),
+        ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64), ("ksplit", C.c_int32),
         ("block_n", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32),
     ]
 
@@ -52,6 +53,7 @@ _SIGNATURES = {
     "fm_version": (C.c_int, []),
     "fm_last_error": (C.c_char_p, []),
     "fm_launch_count": (C.c_int64, []),
+    "fm_add_launches": (None, [C.c_int64]),
     "fm_bias_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                               C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "fm_bias_act_grad_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
@@ -59,7 +61,7 @@ _SIGNATURES = {
     "fm_upfirdn2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int] * 12 + [C.c_int, C.c_void_p]),
     "fm_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "fm_style_affine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "fm_build_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fm_build_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fm_nchw_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "fm_nhwc_bf16_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "fm_blur_act_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

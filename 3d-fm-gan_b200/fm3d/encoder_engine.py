@@ -19,6 +19,7 @@ import math
 import torch
 
 from . import ops
+from .graphs import GraphRunner
 
 
 def _versions(module):
@@ -90,6 +91,7 @@ class ResNetPlan:
         ph, pw = (self.oh - 1) // 2 + 1, (self.ow - 1) // 2 + 1
         self.pool_out = torch.empty(B, ph, pw, 64, **bf)
         self.bufs = {}
+        self.runner = GraphRunner(self._run)
         self.refresh()
 
     def _buf(self, key, B, h, w, c):
@@ -104,6 +106,7 @@ class ResNetPlan:
         if v == self.versions:
             return
         self.versions = v
+        self.runner.invalidate()
         m, dev = self.model, self.device
         a, b = _fold_bn(m.bn1)
         self.stem_w = _stem_weight(m.conv1.weight)
@@ -124,6 +127,9 @@ class ResNetPlan:
 
     def run(self, x):
         self.refresh()
+        return self.runner(x.contiguous().float())
+
+    def _run(self, x):
         B = self.B
         ops.image_to_nhwc8_padded(x, 3, 3, self.Hp, self.Wp, out=self.packed)
         ops.conv_igemm(self.packed, self.stem_w, [(ky, 0, ky) for ky in range(7)], self.stem_out, self.stem_tab,
@@ -196,6 +202,7 @@ class PspPlan:
         self.bufs = {}
         self.sum_buf = torch.zeros(B, 512, device=device, dtype=torch.float32)
         self.gate_buf = torch.empty(B, 512, device=device, dtype=torch.float32)
+        self.runner = GraphRunner(self._run)
         self.refresh()
 
     def _buf(self, key, n, h, w, c):
@@ -210,6 +217,7 @@ class PspPlan:
         if v == self.versions:
             return
         self.versions = v
+        self.runner.invalidate()
         m, dev = self.model, self.device
         conv0, bn0, prelu0 = m.input_layer[0], m.input_layer[1], m.input_layer[2]
         a, b = _fold_bn(bn0)
@@ -279,6 +287,9 @@ class PspPlan:
 
     def run(self, x):
         self.refresh()
+        return self.runner(x.contiguous().float())
+
+    def _run(self, x):
         B, S = self.B, self.S
         m = self.model
         ops.image_to_nhwc8_padded(x, 1, 1, self.Hp, self.Wp, out=self.packed)

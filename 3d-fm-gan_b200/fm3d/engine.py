@@ -25,6 +25,7 @@ import math
 import torch
 
 from . import _lib, ops
+from .graphs import GraphRunner
 from ._lib import StyleLayer, TableLayer
 
 
@@ -112,6 +113,7 @@ class SynthesisPlan:
                 self.ident_tabs[L.cout] = t
         self._versions = None
         self._desc_keepalive = None
+        self._runner = GraphRunner(self._run_flat)
         self._refresh_weights()
 
     # ------------------------------------------------------------------ derived caches
@@ -130,6 +132,7 @@ class SynthesisPlan:
         if vers == self._versions:
             return
         self._versions = vers
+        self._runner.invalidate()          # derived buffers are re-created: captured graphs are stale
         dev = self.device
         for L in self.convs:
             w = L.mod.weight.detach()[0]
@@ -178,6 +181,10 @@ class SynthesisPlan:
         """latent [B,n_latent,D] fp32, start [B,C0,4,4] fp32 NCHW, noise: list (None = fresh
         N(0,1) drawn in the reference's order) -> list of fp32 NCHW RGB images per resolution."""
         self._refresh_weights()
+        noise = [None if n is None else n.contiguous().float() for n in noise]
+        return self._runner(latent.contiguous().float(), start.contiguous().float(), *noise)
+
+    def _run_flat(self, latent, start, *noise):
         lib = _lib.lib()
         B = self.B
         dev = self.device
@@ -186,7 +193,7 @@ class SynthesisPlan:
         with torch.cuda.device(dev):
             _lib.check(lib.fm_style_affine(self.style_desc.data_ptr(), self.n_style, self.max_cin, latent.data_ptr(), B,
                                            latent.shape[1], self.style_dim, st), "fm_style_affine")
-            _lib.check(lib.fm_build_tables(self.table_desc.data_ptr(), len(self.convs), self.max_cout, B, st),
+            _lib.check(lib.fm_build_tables(self.table_desc.data_ptr(), len(self.convs), self.max_cout, self.max_cin, B, st),
                        "fm_build_tables")
             first = self.convs[0]
             _lib.check(lib.fm_nchw_to_nhwc_bf16(self.x0.data_ptr(), start.contiguous().float().data_ptr(),

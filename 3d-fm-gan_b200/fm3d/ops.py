@@ -116,6 +116,18 @@ def upfirdn2d_planes(x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_
 
 
 # ------------------------------------------------------------------ implicit-GEMM conv
+_SPLITK_WS = {}
+SPLITK_WS_BYTES = 64 << 20
+
+
+def _splitk_workspace(device):
+    """Per-device fp32 zero workspace shared by all convs on the stream (each user re-zeroes it)."""
+    ws = _SPLITK_WS.get(device)
+    if ws is None:
+        ws = _SPLITK_WS[device] = torch.zeros(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32)
+    return ws
+
+
 def conv_taps(kh, kw, pad):
     """Tap list (dy, dx, weight slab) of a plain correlation (F.conv2d semantics)."""
     return [(ky - pad, kx - pad, ky * kw + kx) for ky in range(kh) for kx in range(kw)]
@@ -125,7 +137,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
                out_H=None, out_W=None, out_y0=0, out_x0=0, out_ys=1, out_xs=1, out_nchw_f32=False,
                tab_per_sample=False, noise=None, noise_per_sample=True, noise_w=None, residual=None,
                rgb=None, block_n=0, tile_w=0, tile_h=0, stride_x=0, stride_y=0, x_pixstride=0, x_rowstride=0,
-               x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None):
+               x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None, ksplit=0):
     """Launch fm_conv_igemm.  x: bf16 NHWC [B,H,W,cs]; w: bf16 [slabs, w_rows, cin_stride];
     out: bf16 NHWC [B,out_H,out_W,cs_out] or fp32 NCHW; tab: fp32 [B|1, Cout, 8]."""
     d = ConvDesc()
@@ -155,6 +167,8 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     d.residual = _ptr(residual)
     d.rgb = _ptr(rgb)
     d.block_n, d.tile_w, d.tile_h = block_n, tile_w, tile_h
+    ws = _splitk_workspace(x.device)
+    d.splitk_ws, d.splitk_ws_bytes, d.ksplit = ws.data_ptr(), ws.numel() * 4, ksplit
     prof = PROFILE
     with torch.cuda.device(x.device):
         if prof is not None:

@@ -40,6 +40,8 @@ int fm_version(void);
 const char* fm_last_error(void);
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t fm_launch_count(void);
+/* Credit n launches replayed by a captured CUDA graph (they bypass the launch wrappers). */
+void fm_add_launches(int64_t n);
 
 /* ------------------------------------------------------------------------------------
  * fused bias + activation.
@@ -141,6 +143,12 @@ typedef struct {
    * elements (a [G*B,H,W,out_cstride] group-major tensor); 0 = off */
   int32_t out_cgroup;
   int64_t out_gstride;
+  /* split-K workspace: fp32 zeros, at least B*OH*OW*roundup(Cout,16)*4 bytes when used.  Small-M
+   * layers split the K loop over several CTAs (fp32 atomics into the workspace) and a second
+   * tiny kernel applies the epilogue and re-zeroes it.  NULL disables split-K. */
+  float* splitk_ws;
+  int64_t splitk_ws_bytes;
+  int32_t ksplit;           /* 0 = choose automatically, 1 = off, k > 1 = force */
   /* tiling hints (0 = choose) */
   int32_t block_n;          /* 64, 128 or 256 */
   int32_t tile_w, tile_h;   /* tile_w*tile_h*tile_b = 128 output pixels */
@@ -178,7 +186,8 @@ typedef struct {
   int32_t cin, cout;
   float slope, gain;
 } fm_table_layer;
-int fm_build_tables(const fm_table_layer* layers_dev, int n_layers, int max_cout, int B, void* stream);
+int fm_build_tables(const fm_table_layer* layers_dev, int n_layers, int max_cout, int max_cin, int B,
+                    void* stream);
 
 /* NCHW fp32 -> NHWC bf16 with optional per-(b,c) scale; pad channels are zero-filled. */
 int fm_nchw_to_nhwc_bf16(void* out, const float* x, const float* scale_bc,
