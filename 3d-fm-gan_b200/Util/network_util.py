@@ -5,8 +5,19 @@ of the reference goes through; same name, arguments and return structure here.  
 product that the reference builds with a 14-iteration Python loop + stack + transpose is one
 broadcast multiply.
 """
+import os
+
 import torch
 import torch.nn.functional as F
+
+_SIDE_STREAMS = {}
+
+
+def _side_streams(device):
+    st = _SIDE_STREAMS.get(device)
+    if st is None:
+        st = _SIDE_STREAMS[device] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+    return st
 
 
 def _n_latent(g_ema):
@@ -20,13 +31,33 @@ def Forward_Inference_3_Encoder(p_input, r_input, E_Tsr, E_W, E_W_Plus, g_ema, t
     E_W_Plus(photo) -> W+;  latent[b,i] = W[b] * W+[b,i] for i in ``sliced_layer`` (default: all),
     else W[b].  Returns the generator output (``(image, path_lengths)`` under PPL_regularize)."""
     if tsr_encode == 'Photo Image':
-        encoded_tensor = E_Tsr(p_input)
+        tsr_in = p_input
     elif tsr_encode == 'Render Image':
-        encoded_tensor = E_Tsr(r_input)
+        tsr_in = r_input
     else:
         raise ValueError(f"unknown tsr_encode {tsr_encode!r}")
-    encoded_W = E_W(r_input)
-    encoded_W_plus = E_W_Plus(p_input)
+    concurrent = (p_input.is_cuda and not torch.is_grad_enabled() and os.environ.get("FM3D_STREAMS", "1") != "0"
+                  and not torch.cuda.is_current_stream_capturing())
+    if concurrent:
+        # the three encoders are independent: the two small ResNets run on side streams and fill the
+        # tails / launch gaps of the large W+ encoder
+        main = torch.cuda.current_stream(p_input.device)
+        s1, s2 = _side_streams(p_input.device)
+        s1.wait_stream(main)
+        s2.wait_stream(main)
+        with torch.cuda.stream(s1):
+            encoded_tensor = E_Tsr(tsr_in)
+        with torch.cuda.stream(s2):
+            encoded_W = E_W(r_input)
+        encoded_W_plus = E_W_Plus(p_input)
+        main.wait_stream(s1)
+        main.wait_stream(s2)
+        for t in (encoded_tensor, encoded_W, p_input, r_input):
+            t.record_stream(main)
+    else:
+        encoded_tensor = E_Tsr(tsr_in)
+        encoded_W = E_W(r_input)
+        encoded_W_plus = E_W_Plus(p_input)
 
     n = encoded_W_plus.shape[1]
     if sliced_layer is None:

@@ -121,10 +121,12 @@ SPLITK_WS_BYTES = 64 << 20
 
 
 def _splitk_workspace(device):
-    """Per-device fp32 zero workspace shared by all convs on the stream (each user re-zeroes it)."""
-    ws = _SPLITK_WS.get(device)
+    """fp32 zero workspace per (device, stream): convs on one stream run in order and each user
+    re-zeroes what it touched; concurrent streams (the three encoders) get their own buffer."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _SPLITK_WS.get(key)
     if ws is None:
-        ws = _SPLITK_WS[device] = torch.zeros(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32)
+        ws = _SPLITK_WS[key] = torch.zeros(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32)
     return ws
 
 
