@@ -37,6 +37,8 @@ struct IgemmParams {
   int ksplit, kper;                // split-K: CTAs per (m,n) tile and k-iterations per CTA
   float* ws;                       // split-K fp32 workspace [B*OH*OW][ws_cs]
   int ws_cs;
+  int upmode;                      // fused stride-2 transposed 3x3 conv: 4 output-parity accumulators share the A tiles
+  int nbuf;                        // TMEM accumulator buffers (2, or 1 when 4 x BN x 2 columns do not fit)
   int prows;                       // output rows per tile in patch mode (R accumulators share each weight load)
   int patch_a_bytes, patch_stage_bytes, patch_stages;
   int Bg, nslabs;                  // images per group, weight slabs per group
@@ -75,6 +77,17 @@ template <int BN> struct IgemmCfg {
   static constexpr int SMEM_BYTES = RING_BYTES + TAB_BYTES + RGB_BYTES + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 512;   // 2 buffers x R rows x BN columns; one CTA per SM owns all of TMEM
 };
+
+// Up mode (stride-2 transposed 3x3 conv, stylegan2.py:276): with T[2y+py, 2x+px] = sum over the kernel
+// taps of matching parity, the four output parities need only four shifted views of the input
+// (dy,dx in {0,-1}^2).  Stage s loads view s once and the weight taps that multiply it:
+//   s=0 (0,0): W00->P00 W01->P01 W10->P10 W11->P11 | s=1 (0,-1): W02->P00 W12->P10
+//   s=2 (-1,0): W20->P00 W21->P01                  | s=3 (-1,-1): W22->P00
+__constant__ int8_t c_up_nb[4] = {4, 2, 2, 1};
+__constant__ int8_t c_up_w[4][4] = {{0, 1, 3, 4}, {2, 5, 0, 0}, {6, 7, 0, 0}, {8, 0, 0, 0}};
+__constant__ int8_t c_up_acc[4][4] = {{0, 1, 2, 3}, {0, 2, 0, 0}, {0, 1, 0, 0}, {0, 0, 0, 0}};
+__constant__ int8_t c_up_dy[4] = {0, 0, -1, -1};
+__constant__ int8_t c_up_dx[4] = {0, -1, 0, -1};
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(IG_THREADS2, 1)
@@ -135,6 +148,24 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int x0 = bx * p.tw * p.stride_x, y0 = by * p.th * p.stride_y, b0 = bb * p.tb, n0 = nt * BN;
       const int it0 = ks * p.kper, it1 = min(kiters, it0 + p.kper);
       const int wrow0 = (b0 / p.Bg) * p.nslabs;
+      if (p.upmode) {
+        for (int it = 0; it < 4 * p.kchunks; ++it) {
+          const int kc = it >> 2, sft = it & 3;
+          const int nb = c_up_nb[sft];
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (lane == 0) {
+            uint8_t* sa = s_stage + stage * (Cfg::A_BYTES + 4 * Cfg::B_BYTES);
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.rows) * (IG_BK * 2) + nb * Cfg::B_BYTES);
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * IG_BK, x0 + c_up_dx[sft], y0 + c_up_dy[sft], b0);
+            for (int j = 0; j < nb; ++j)
+              tma_load_2d(sb + j * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + c_up_w[sft][j]) * p.w_rows + n0);
+          }
+          __syncwarp();
+          if (++stage == p.patch_stages) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       if (p.patch) {
         // stage = (kernel row ky, channel chunk): R 130-pixel input rows + the 3 weight tiles of that kernel row
         const uint32_t ptx = static_cast<uint32_t>(p.prows) * 130u * (IG_BK * 2) + 3u * Cfg::B_BYTES;
@@ -178,11 +209,37 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t phase = 0;
     int titer = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++titer) {
-      const int buf = titer & 1;
-      const uint32_t aphase = (titer >> 1) & 1;
+      const int buf = titer % p.nbuf;
+      const uint32_t aphase = (titer / p.nbuf) & 1;
       mbar_wait(&tempty_bar[buf], aphase ^ 1);     // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * BN;
+      if (p.upmode) {
+        const int nst = 4 * p.kchunks;
+        const uint32_t tmem_t = tmem_base + buf * (4 * BN);
+        for (int it = 0; it < nst; ++it) {
+          const int sft = it & 3;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(s_stage + stage * (Cfg::A_BYTES + 4 * Cfg::B_BYTES));
+            const uint64_t adesc = umma_smem_desc_sw128(sa);
+            const int nb = c_up_nb[sft];
+            for (int j = 0; j < nb; ++j) {
+              const uint64_t bdesc = umma_smem_desc_sw128(sa + Cfg::A_BYTES + j * Cfg::B_BYTES);
+              const uint32_t dcol = tmem_t + c_up_acc[sft][j] * BN;
+#pragma unroll
+              for (int k = 0; k < IG_BK / 16; ++k)
+                umma_bf16(dcol, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (it == nst - 1) umma_commit(&tfull_bar[buf]);
+          }
+          __syncwarp();
+          if (++stage == p.patch_stages) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       const int ks = (tile / p.tiles_n) % p.ksplit;
       const int it0 = ks * p.kper, it1 = min(kiters, it0 + p.kper);
       if (p.patch) {
@@ -247,8 +304,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int tab_key = -1;
     int titer = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++titer) {
-      const int buf = titer & 1;
-      const uint32_t aphase = (titer >> 1) & 1;
+      const int buf = titer % p.nbuf;
+      const uint32_t aphase = (titer / p.nbuf) & 1;
       const int nt = tile % p.tiles_n;
       int m = tile / p.tiles_n;
       m /= p.ksplit;
@@ -282,13 +339,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       mbar_wait(&tfull_bar[buf], aphase);
       tc_fence_after();
-      const int nrows = p.patch ? p.prows : 1;
+      const int nrows = p.upmode ? 4 : (p.patch ? p.prows : 1);
 #pragma unroll 1
       for (int r = 0; r < nrows; ++r) {
       const int oy = p.patch ? by * p.prows + r : by * p.th + ly;
-      const bool valid = row < p.rows && ox < p.OW && oy < p.OH && b < p.B;
+      // up mode: accumulator r holds output parity (r>>1, r&1); odd parities have one row/column less
+      const int upy = p.upmode ? (r >> 1) : 0, upx = p.upmode ? (r & 1) : 0;
+      const bool valid = row < p.rows && ox < p.OW - upx && oy < p.OH - upy && b < p.B;
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (nrows * BN) + r * BN;
-      const int Y = oy * p.out_ys + p.out_y0, X = ox * p.out_xs + p.out_x0;
+      const int Y = oy * p.out_ys + p.out_y0 + upy, X = ox * p.out_xs + p.out_x0 + upx;
       float nz = 0.f;
       if (valid && p.noise)
         nz = nw * __ldg(p.noise + (static_cast<size_t>(p.noise_bstride ? b : 0) * p.out_H + Y) * p.out_W + X);
@@ -585,7 +644,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   {
     static const int env_split = []() { const char* e = getenv("FM3D_SPLITK"); return e ? atoi(e) : 1; }();
     const bool eligible = env_split && d->ksplit != 1 && d->splitk_ws && !d->rgb && !d->border_tab && !d->out_nchw_f32 &&
-                          !d->out_cgroup && d->block_n <= 0;
+                          !d->out_cgroup && d->block_n <= 0 && !d->upmode;
     if (eligible) {
       const int bn_wide = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
       const int64_t tiles_wide = static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.tiles_b * ((d->Cout + bn_wide - 1) / bn_wide);
@@ -613,6 +672,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     const int sms = sm_count();
     while (bn > 64 && static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.tiles_b * ((d->Cout + bn - 1) / bn) < sms) bn >>= 1;
   }
+  if (d->upmode && bn > 128) bn = 128;      // 4 accumulators x BN columns must fit the 512 TMEM columns
   if (ksplit == 1) while (bn > 64 && tbe * bn > IG_TAB_ROWS) bn >>= 1;
   FM_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "fm_conv_igemm: block_n must be 64/128/256");
   FM_CHECK_ARG(ksplit > 1 || tbe * bn <= IG_TAB_ROWS, "fm_conv_igemm: per-sample tables do not fit (tile_b %d x block_n %d)", tbe, bn);
@@ -642,6 +702,17 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     if (d->tap_widx[i] > max_widx) max_widx = d->tap_widx[i];
   }
   p.nslabs = max_widx + 1;
+  p.nbuf = 2;
+  if (d->upmode) {
+    FM_CHECK_ARG(d->ntaps == 9 && sx == 1 && sy == 1 && G == 1 && d->out_ys == 2 && d->out_xs == 2 && !d->out_nchw_f32 &&
+                     !d->out_cgroup && !d->residual && !d->rgb && !d->border_tab && d->OH == d->H + 1 && d->OW == d->W + 1,
+                 "fm_conv_igemm: bad upmode configuration");
+    p.upmode = 1;
+    p.nslabs = 9;
+    p.nbuf = (4 * bn * 2 <= 512) ? 2 : 1;
+    p.patch_stages = (200 * 1024) / (16384 + 4 * bn * 128);
+    if (p.patch_stages > 8) p.patch_stages = 8;
+  }
   // ---- row-patch mode: plain 3x3 / stride 1 / pad 1, 128-pixel output rows, N <= 128.  A tile is R
   // output rows (R accumulators in TMEM) so each weight tile loaded from L2 feeds R*128 pixels.
   {
@@ -650,7 +721,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     bool std33 = d->ntaps == 9 && sx == 1 && sy == 1 && d->x_pixstride == 0 && d->x_rowstride == 0 && d->x_imgstride == 0;
     for (int i = 0; std33 && i < 9; ++i)
       std33 = d->tap_dy[i] == i / 3 - 1 && d->tap_dx[i] == i % 3 - 1 && d->tap_widx[i] == i;
-    p.patch = (env_patch && std33 && tw == 128 && th == 1 && tb == 1 && bn <= 128 && p.ksplit == 1) ? 1 : 0;
+    p.patch = (env_patch && std33 && tw == 128 && th == 1 && tb == 1 && bn <= 128 && p.ksplit == 1 && !d->upmode) ? 1 : 0;
     if (p.patch) {
       int R = env_rows > 0 ? env_rows : (bn == 64 ? 4 : 2);
       while (R > 1 && (2 * R * bn > 512 || R > d->OH)) R >>= 1;

@@ -29,6 +29,11 @@ from .graphs import GraphRunner
 from ._lib import StyleLayer, TableLayer
 
 
+import os
+
+_FUSED_UP = os.environ.get("FM3D_UPMODE", "1") != "0"
+
+
 def _up_phase_taps(py, px):
     """Taps of output parity (py,px) of a stride-2 transposed 3x3 conv:
     T[2y+py, 2x+px] = sum_{ky=py (mod 2), kx=px (mod 2)} x[y + (py-ky)/2, x + (px-kx)/2] * W[ky,kx]."""
@@ -216,12 +221,20 @@ class SynthesisPlan:
             if L.up:
                 t = self.tbuf[i]
                 ident = self.ident_tabs[L.cout]
-                for py in (0, 1):
-                    for px in (0, 1):
-                        ops.conv_igemm(x, L.wq, _up_phase_taps(py, px), t, ident, B=B, H=h, W=h, Cin=L.cin, Cout=L.cout,
-                                       OH=h + 1 - py, OW=h + 1 - px, out_H=2 * h + 1, out_W=2 * h + 1,
-                                       out_y0=py, out_x0=px, out_ys=2, out_xs=2, tab_per_sample=False,
-                                       tile_w=min(16, _pow2_ge(h + 1)), tile_h=max(1, min(8, 128 // min(16, _pow2_ge(h + 1)))))
+                tw_ = min(16, _pow2_ge(h + 1))
+                th_ = max(1, min(8, 128 // tw_))
+                if _FUSED_UP:
+                    # all four output parities in one launch: the input is read once
+                    ops.conv_igemm(x, L.wq, ops.conv_taps(3, 3, 1), t, ident, B=B, H=h, W=h, Cin=L.cin, Cout=L.cout,
+                                   OH=h + 1, OW=h + 1, out_H=2 * h + 1, out_W=2 * h + 1, out_ys=2, out_xs=2,
+                                   tab_per_sample=False, tile_w=tw_, tile_h=th_, upmode=True)
+                else:
+                    for py in (0, 1):
+                        for px in (0, 1):
+                            ops.conv_igemm(x, L.wq, _up_phase_taps(py, px), t, ident, B=B, H=h, W=h, Cin=L.cin,
+                                           Cout=L.cout, OH=h + 1 - py, OW=h + 1 - px, out_H=2 * h + 1, out_W=2 * h + 1,
+                                           out_y0=py, out_x0=px, out_ys=2, out_xs=2, tab_per_sample=False,
+                                           tile_w=tw_, tile_h=th_)
                 ops.blur_act_nhwc(t, L.kernel, L.tab, nz, per_sample, L.noise_w, L.cout, out=y)
             else:
                 rgb = self.rgb_acc[rgb_i] if L.rgb_mod is not None else None

@@ -139,7 +139,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
                out_H=None, out_W=None, out_y0=0, out_x0=0, out_ys=1, out_xs=1, out_nchw_f32=False,
                tab_per_sample=False, noise=None, noise_per_sample=True, noise_w=None, residual=None,
                rgb=None, block_n=0, tile_w=0, tile_h=0, stride_x=0, stride_y=0, x_pixstride=0, x_rowstride=0,
-               x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None, ksplit=0):
+               x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None, ksplit=0, upmode=False):
     """Launch fm_conv_igemm.  x: bf16 NHWC [B,H,W,cs]; w: bf16 [slabs, w_rows, cin_stride];
     out: bf16 NHWC [B,out_H,out_W,cs_out] or fp32 NCHW; tab: fp32 [B|1, Cout, 8]."""
     d = ConvDesc()
@@ -171,6 +171,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     d.block_n, d.tile_w, d.tile_h = block_n, tile_w, tile_h
     ws = _splitk_workspace(x.device)
     d.splitk_ws, d.splitk_ws_bytes, d.ksplit = ws.data_ptr(), ws.numel() * 4, ksplit
+    d.upmode = 1 if upmode else 0
     prof = PROFILE
     with torch.cuda.device(x.device):
         if prof is not None:
@@ -179,7 +180,8 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
         st = _lib.lib().fm_conv_igemm(C.byref(d), _stream())
         if prof is not None:
             e1.record()
-            prof.append((e0, e1, 2.0 * B * OH * OW * Cin * Cout * len(taps)))
+            # up mode: algorithmic FLOPs of the stride-2 transposed conv = 9 taps at the INPUT resolution
+            prof.append((e0, e1, 2.0 * B * (H * W if upmode else OH * OW) * Cin * Cout * len(taps)))
     _lib.check(st, "fm_conv_igemm")
     return out
 

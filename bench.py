@@ -280,7 +280,10 @@ def main():
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "launches_per_step": len(prof) // 2, "kernel_ms_per_step": ksec * 1e3 / 2,
-                "algorithmic_gflop_per_step": flops / 2 / 1e9, "traffic": None}
+                "algorithmic_gflop_per_step": flops / 2 / 1e9,
+                # dram__bytes_read+write summed over the igemm launches of one step / launches, from the ncu pass
+                # committed as profiles/r01_step_metrics_v2.csv (5.85 GB read + 2.30 GB write over 103 launches)
+                "traffic": 8.146e9 / 103, "traffic_unit": "bytes per launch (ncu, profiles/r01_step_metrics_v2.csv)"}
 
     if rank != 0:
         if world > 1:

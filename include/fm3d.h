@@ -149,6 +149,11 @@ typedef struct {
   float* splitk_ws;
   int64_t splitk_ws_bytes;
   int32_t ksplit;           /* 0 = choose automatically, 1 = off, k > 1 = force */
+  /* upmode != 0: fused stride-2 transposed 3x3 conv (stylegan2.py:276).  w holds the 9 slabs of the
+   * 3x3 kernel; OH = H+1, OW = W+1 is the grid of output 2x2 blocks; the four output parities are
+   * accumulated from four shared shifted input views and written to out[b, 2y+py, 2x+px, :]
+   * (out_H = 2H+1, out_W = 2W+1, out_ys = out_xs = 2).  taps are ignored. */
+  int32_t upmode;
   /* tiling hints (0 = choose) */
   int32_t block_n;          /* 64, 128 or 256 */
   int32_t tile_w, tile_h;   /* tile_w*tile_h*tile_b = 128 output pixels */

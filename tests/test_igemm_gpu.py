@@ -266,3 +266,24 @@ def test_conv_row_patch_mode(cuda, B, H, W, Cin, Cout):
                    Cin=Cin, Cout=Cout, OH=H, OW=W, out_nchw_f32=True)
     torch.cuda.synchronize()
     torch.testing.assert_close(out.cpu(), ref, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("B,h,Cin,Cout", [(2, 8, 64, 64), (1, 16, 128, 128), (3, 4, 512, 512), (2, 32, 256, 128), (1, 7, 72, 40)])
+def test_conv_fused_upsample_mode(cuda, B, h, Cin, Cout):
+    """upmode: stride-2 transposed 3x3 conv (F.conv_transpose2d, stylegan2.py:276) as four output
+    parities accumulated from four shared shifted input views in one launch."""
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(h + Cin)
+    x = torch.randn(B, Cin, h, h, generator=gen)
+    w = torch.randn(Cout, Cin, 3, 3, generator=gen) / (Cin * 9) ** 0.5
+    ref = F.conv_transpose2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float().transpose(0, 1), stride=2)
+    assert ref.shape[-1] == 2 * h + 1
+    wq, _ = ops.prep_weight(w.to(cuda), 1.0, want_wsq=False)
+    cs = (Cout + 7) // 8 * 8
+    out = torch.zeros(B, 2 * h + 1, 2 * h + 1, cs, device=cuda, dtype=torch.bfloat16)
+    tw = min(16, 1 << (h).bit_length())
+    ops.conv_igemm(ops.nchw_to_nhwc_bf16(x.to(cuda)), wq, ops.conv_taps(3, 3, 1), out, _tab(Cout, cuda), B=B, H=h, W=h,
+                   Cin=Cin, Cout=Cout, OH=h + 1, OW=h + 1, out_H=2 * h + 1, out_W=2 * h + 1, out_ys=2, out_xs=2,
+                   tile_w=tw, tile_h=max(1, min(8, 128 // tw)), upmode=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out[..., :Cout].float().permute(0, 3, 1, 2).cpu(), ref, rtol=1e-2, atol=1e-2)
