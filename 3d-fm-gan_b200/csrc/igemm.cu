@@ -37,6 +37,9 @@ struct IgemmParams {
   int ksplit, kper;                // split-K: CTAs per (m,n) tile and k-iterations per CTA
   float* ws;                       // split-K fp32 workspace [B*OH*OW][ws_cs]
   int ws_cs;
+  int cluster;                     // CTAs per cluster (1, 2 or 4): weight tiles are TMA-multicast to the cluster
+  int num_super;                   // tiles_n * ksplit * ceil(m_tiles / cluster)
+  int m_tiles;
   int upmode;                      // fused stride-2 transposed 3x3 conv: 4 output-parity accumulators share the A tiles
   int nbuf;                        // TMEM accumulator buffers (2, or 1 when 4 x BN x 2 columns do not fit)
   int prows;                       // output rows per tile in patch mode (R accumulators share each weight load)
@@ -114,7 +117,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], p.cluster);       // every CTA of the cluster releases the slot (multicast commit)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -128,8 +131,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();           // barriers of every CTA are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  const int crank = p.cluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / p.cluster, num_clusters = gridDim.x / p.cluster;
+  const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1);
 
   const int kiters = p.ntaps * p.kchunks;
 
@@ -138,10 +145,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t tx_bytes = static_cast<uint32_t>(p.rows) * (IG_BK * 2) + Cfg::B_BYTES;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nt = tile % p.tiles_n;
-      int m = tile / p.tiles_n;
+    for (int st = cluster_id; st < p.num_super; st += num_clusters) {
+      const int nt = st % p.tiles_n;
+      int m = st / p.tiles_n;
       const int ks = m % p.ksplit; m /= p.ksplit;
+      m = m * p.cluster + crank;                  // CTAs of a cluster take adjacent m-tiles of the same n-tile
       const int bx = m % p.tiles_x; m /= p.tiles_x;
       const int by = m % p.tiles_y;
       const int bb = m / p.tiles_y;
@@ -159,7 +167,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.rows) * (IG_BK * 2) + nb * Cfg::B_BYTES);
             tma_load_4d(sa, &tmA, &full_bar[stage], kc * IG_BK, x0 + c_up_dx[sft], y0 + c_up_dy[sft], b0);
             for (int j = 0; j < nb; ++j)
-              tma_load_2d(sb + j * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + c_up_w[sft][j]) * p.w_rows + n0);
+              { if (p.cluster == 1) tma_load_2d(sb + j * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + c_up_w[sft][j]) * p.w_rows + n0); else if (crank == 0) tma_load_2d_mcast(sb + j * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + c_up_w[sft][j]) * p.w_rows + n0, cmask); }
           }
           __syncwarp();
           if (++stage == p.patch_stages) { stage = 0; phase ^= 1; }
@@ -180,7 +188,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_4d(sa, &tmA, &full_bar[stage], kc * IG_BK, x0 - 1, by * p.prows + ky - 1, b0);
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
-              tma_load_2d(sb + kx * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + ky * 3 + kx) * p.w_rows + n0);
+              { if (p.cluster == 1) tma_load_2d(sb + kx * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + ky * 3 + kx) * p.w_rows + n0); else if (crank == 0) tma_load_2d_mcast(sb + kx * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + ky * 3 + kx) * p.w_rows + n0, cmask); }
           }
           __syncwarp();
           if (++stage == p.patch_stages) { stage = 0; phase ^= 1; }
@@ -196,7 +204,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_4d(sa, &tmA, &full_bar[stage], kc * IG_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0);
+          { if (p.cluster == 1) tma_load_2d(sb, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0); else if (crank == 0) tma_load_2d_mcast(sb, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0, cmask); }
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -208,7 +216,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     int titer = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++titer) {
+    for (int st = cluster_id; st < p.num_super; st += num_clusters, ++titer) {
       const int buf = titer % p.nbuf;
       const uint32_t aphase = (titer / p.nbuf) & 1;
       mbar_wait(&tempty_bar[buf], aphase ^ 1);     // epilogue has drained this accumulator
@@ -232,7 +240,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               for (int k = 0; k < IG_BK / 16; ++k)
                 umma_bf16(dcol, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);
+            if (p.cluster == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
             if (it == nst - 1) umma_commit(&tfull_bar[buf]);
           }
           __syncwarp();
@@ -240,7 +248,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
-      const int ks = (tile / p.tiles_n) % p.ksplit;
+      const int ks = (st / p.tiles_n) % p.ksplit;
       const int it0 = ks * p.kper, it1 = min(kiters, it0 + p.kper);
       if (p.patch) {
         const int nst = 3 * p.kchunks;
@@ -262,7 +270,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   umma_bf16(tmem_t + r * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || kx > 0 || k > 0) ? 1u : 0u);
               }
             }
-            umma_commit(&empty_bar[stage]);
+            if (p.cluster == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
             if (it == nst - 1) umma_commit(&tfull_bar[buf]);
           }
           __syncwarp();
@@ -282,7 +290,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
             umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs finish
+          if (p.cluster == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
           if (it == it1 - 1) umma_commit(&tfull_bar[buf]);
         }
         __syncwarp();
@@ -303,18 +311,19 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const float4* trow = s_tab + static_cast<size_t>(p.tab_bstride ? lb : 0) * BN * 2;
     int tab_key = -1;
     int titer = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++titer) {
+    for (int st = cluster_id; st < p.num_super; st += num_clusters, ++titer) {
       const int buf = titer % p.nbuf;
       const uint32_t aphase = (titer / p.nbuf) & 1;
-      const int nt = tile % p.tiles_n;
-      int m = tile / p.tiles_n;
+      const int nt = st % p.tiles_n;
+      int m = st / p.tiles_n;
       m /= p.ksplit;
+      m = m * p.cluster + crank;
       const int bx = m % p.tiles_x; m /= p.tiles_x;
       const int by = m % p.tiles_y;
       const int bb = m / p.tiles_y;
       const int n0 = nt * BN;
       const int ox = bx * p.tw + lx, b = bb * p.tb + lb;
-      const int grp = (bb * p.tb) / p.Bg;
+      const int grp = min((bb * p.tb) / p.Bg, p.B / p.Bg - 1);   // padded cluster tiles clamp to the last group
 
       // ---- epilogue tables: re-staged only when (sample block | group, n-tile) changes
       const int key = (p.tab_bstride ? bb : grp) * p.tiles_n + nt;
@@ -420,7 +429,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           v[j] = x * t0.w;
         }
-        if (valid) {
+        if (valid && p.out) {      // out == NULL: only the fused ToRGB sums are wanted (last synthesis layer)
           if (p.out_nchw_f32) {
             const size_t plane = static_cast<size_t>(p.out_H) * p.out_W;
             float* op = static_cast<float*>(p.out) + (static_cast<size_t>(b) * p.Cout + o0) * plane +
@@ -472,6 +481,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();           // no CTA exits while a peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -527,11 +537,7 @@ __global__ void __launch_bounds__(256) igemm_splitk_finalize_kernel(const IgemmP
 }
 
 // ------------------------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
+EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = []() -> EncodeTiledFn {
     void* f = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -552,8 +558,21 @@ static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const I
     attr_set = true;
   }
   const int sms = sm_count();
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  igemm_conv_kernel<BN, EPI><<<grid, IG_THREADS2, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  const int max_clusters = sms / p.cluster;
+  const int nclusters = p.num_super < max_clusters ? p.num_super : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(nclusters * p.cluster));
+  cfg.blockDim = dim3(IG_THREADS2);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(p.cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FM_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_conv_kernel<BN, EPI>, tmA, tmB, p));
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;
@@ -589,7 +608,8 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
 extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   using namespace fm;
   FM_CHECK_ARG(d != nullptr, "fm_conv_igemm: null desc");
-  FM_CHECK_ARG(d->x && d->w && d->out && d->tab, "fm_conv_igemm: null tensor");
+  FM_CHECK_ARG(d->x && d->w && (d->out || d->rgb) && d->tab, "fm_conv_igemm: null tensor");
+  FM_CHECK_ARG(d->out || (!d->out_nchw_f32 && !d->out_cgroup && !d->upmode), "fm_conv_igemm: out may be NULL only for a plain NHWC conv with a fused RGB output");
   FM_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "fm_conv_igemm: bad sizes");
   FM_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= FM_MAX_TAPS, "fm_conv_igemm: ntaps %d out of range", d->ntaps);
   const int sx = d->stride_x > 0 ? d->stride_x : d->stride;
@@ -738,6 +758,17 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     } else {
       p.prows = 1;
     }
+  }
+  // ---- clusters: CTAs of a cluster work on adjacent m-tiles of the same n-tile and share each weight
+  // tile through one multicast TMA load (weights are the dominant L2->SM stream for N <= 128)
+  {
+    static const int env_cluster = []() { const char* e = getenv("FM3D_CLUSTER"); return e ? atoi(e) : 2; }();
+    p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+    int cs = env_cluster;
+    if (cs != 1 && cs != 2 && cs != 4) cs = 1;
+    while (cs > 1 && (p.m_tiles % cs != 0 || G > 1)) cs >>= 1;   // no padded m-tiles, one weight slab per cluster
+    p.cluster = cs;
+    p.num_super = p.tiles_n * p.ksplit * ((p.m_tiles + cs - 1) / cs);
   }
   // ---- tensor maps
   CUtensorMap tmA, tmB;

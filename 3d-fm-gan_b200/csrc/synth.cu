@@ -1,6 +1,8 @@
 // Bandwidth-bound helper kernels of the synthesis path (sm_100a): style affine, epilogue
 // tables (demodulation), layout converts, the fused blur+noise+bias+lrelu pass after the
 // stride-2 transposed conv, the ToRGB tail and weight preparation.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace fm {
@@ -12,8 +14,11 @@ namespace fm {
 // warp produces 4 output channels per pass: no shuffles, 1 LDS.128 + 4 LDG.128 per 16 FMAs.
 //   style_affine : A = latent[:, idx, :], W = modulation weight  (stylegan2.py:165-175,240,257)
 //   build_tables : A = s^2,               W = wsq                 (stylegan2.py:258-262)
-// grid (ceil(max_out/64), n_layers), 256 threads, dynamic smem 32*(K+4)*4 bytes.
+// grid (ceil(max_out/SG_CH), n_layers), 256 threads, dynamic smem 32*(K+4)*4 bytes.  The op is latency
+// bound (a dependent chain of K/4 steps per warp), so CTAs are kept small: 32 output channels each
+// gives ~4 CTAs per SM for the generator's 20 layers.
 // ------------------------------------------------------------------------------------
+constexpr int SG_CH = 32;   // output channels per CTA (8 warps x 4)
 template <bool SQUARE>
 __device__ __forceinline__ void stage_rows(float* s_a, const float* __restrict__ a, int64_t row_stride, int b0, int B, int K,
                                            int KP) {
@@ -52,7 +57,7 @@ __global__ void __launch_bounds__(256) style_affine_kernel(const fm_style_layer*
                                                            int D, float scale) {
   extern __shared__ __align__(16) float s_a[];
   const fm_style_layer L = layers[blockIdx.y];
-  if (blockIdx.x * 64 >= L.cin) return;
+  if (blockIdx.x * SG_CH >= L.cin) return;
   const int KP = ((D + 3) & ~3) + 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b0 = 0; b0 < B; b0 += 32) {
@@ -60,8 +65,8 @@ __global__ void __launch_bounds__(256) style_affine_kernel(const fm_style_layer*
     stage_rows<false>(s_a, latent + static_cast<int64_t>(L.latent_idx) * D, static_cast<int64_t>(n_latent) * D, b0, B, D, KP);
     __syncthreads();
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const int o = blockIdx.x * 64 + warp * 8 + pass * 4;
+    for (int pass = 0; pass < SG_CH / 32; ++pass) {
+      const int o = blockIdx.x * SG_CH + warp * (SG_CH / 8) + pass * 4;
       if (o >= L.cin) break;
       const int nv = min(4, L.cin - o);
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(256) style_affine_kernel(const fm_style_layer*
 __global__ void __launch_bounds__(256) build_tables_kernel(const fm_table_layer* __restrict__ layers, int B) {
   extern __shared__ __align__(16) float s_a[];
   const fm_table_layer L = layers[blockIdx.y];
-  if (blockIdx.x * 64 >= L.cout) return;
+  if (blockIdx.x * SG_CH >= L.cout) return;
   const int KP = ((L.cin + 3) & ~3) + 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float rgb_scale = rsqrtf(static_cast<float>(L.cout));   // ToRGB fan_in = cout*1*1 (stylegan2.py:232-233)
@@ -92,8 +97,8 @@ __global__ void __launch_bounds__(256) build_tables_kernel(const fm_table_layer*
       __syncthreads();
     }
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const int o = blockIdx.x * 64 + warp * 8 + pass * 4;
+    for (int pass = 0; pass < SG_CH / 32; ++pass) {
+      const int o = blockIdx.x * SG_CH + warp * (SG_CH / 8) + pass * 4;
       if (o >= L.cout) break;
       const int nv = min(4, L.cout - o);
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -184,25 +189,35 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(float* __restrict__ o
 // t [B, OH+1, OW+1, cs] -> out [B, OH, OW, cs].  Replaces Blur (stylegan2.py:279 ->
 // upfirdn2d mode 1), NoiseInjection (:312) and FusedLeakyReLU (:371) after the stride-2
 // transposed conv.
-// One CTA = 16x16 output pixels x 64 channels: the 19x19x128 B input patch is staged in
-// shared memory with 16-byte coalesced loads; a thread owns 8 channels of a vertical strip of
-// 8 outputs and walks the 11 input rows it needs (4 LDS.128 per row), so every staged value
-// is reused from registers.  Rank-1 kernels (the default [1,3,3,1] outer product) take the
-// separable path: half the FMAs.
+// The op moves 4 B per output element and needs ~11 fp32 operations for it, so it is bound by HBM
+// only if (a) enough bytes are in flight and (b) the instruction count is cut to the bone:
+//  (a) a CTA owns a 64-column x 64-channel strip and streams down BL_ROWS output rows; TMA
+//      (cp.async.bulk.tensor, out-of-bounds = the blur's zero padding) stages 2 input rows
+//      (67 px x 128 B each) per mbarrier stage into a 4-stage ring: ~50 KB of loads in flight per
+//      CTA from ONE issuing thread, nothing is fetched twice.
+//  (b) a thread owns 4 adjacent columns x 4 channels: 7 LDS.64 feed 4 outputs, the horizontal pass
+//      and the rolling window of 4 vertical partial sums (statically renamed, 4 rows per unrolled
+//      step) run on packed fp32 pairs (FFMA2), the epilogue on FFMA2/FMUL2/FMNMX.
+// Rank-1 kernels (the default [1,3,3,1] outer product) take the separable path.
 // Algorithmic bytes per output pixel-channel: 2 B read ((OH+1)(OW+1)/(OH*OW) ~ 1) + 2 B write.
 // ------------------------------------------------------------------------------------
-constexpr int BL_T = 16;            // output tile edge
-constexpr int BL_P = BL_T + 3;      // patch edge
+constexpr int BL_TW = 64;                        // output columns per CTA
+constexpr int BL_IW = BL_TW + 3;                 // staged input columns
+constexpr int BL_SR = 2;                         // input rows per stage
+constexpr int BL_NST = 4;                        // ring stages
+constexpr int BL_STAGE_BYTES = BL_SR * BL_IW * 128;
+constexpr int BL_ROWS = 64;                      // output rows per strip
+constexpr int BL_SMEM = BL_NST * BL_STAGE_BYTES;
 
 template <bool SEP>
-__global__ void __launch_bounds__(512, 2) blur_act_nhwc_kernel(__nv_bfloat16* __restrict__ out,
-                                                               const __nv_bfloat16* __restrict__ t,
+__global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap tmT,
+                                                               __nv_bfloat16* __restrict__ out,
                                                                const float* __restrict__ kernel, const float* __restrict__ tab,
                                                                const float* __restrict__ noise, int noise_bstride,
                                                                const float* __restrict__ noise_w, int OH, int OW, int C, int cs,
                                                                int tiles_x, int tiles_y, int cblocks) {
-  __shared__ __align__(16) uint4 s_patch[BL_P * BL_P * 8];   // [row][px][64 ch]
-  __shared__ float4 s_tab[64];
+  extern __shared__ __align__(128) uint8_t bl_smem[];
+  __shared__ __align__(8) uint64_t s_full[BL_NST];
   __shared__ float s_k[16];
   __shared__ float s_kv[4], s_kh[4];
   int bid = blockIdx.x;
@@ -210,14 +225,15 @@ __global__ void __launch_bounds__(512, 2) blur_act_nhwc_kernel(__nv_bfloat16* __
   const int tx = bid % tiles_x; bid /= tiles_x;
   const int ty = bid % tiles_y;
   const int b = bid / tiles_y;
-  const int X0 = tx * BL_T, Y0 = ty * BL_T, c0 = cb * 64;
-  const int IH = OH + 1, IW = OW + 1;
+  const int c0 = cb * 64, x0 = tx * BL_TW;
+  const int Y0 = ty * BL_ROWS;
+  const int Y1 = min(OH, Y0 + BL_ROWS);
   const int tid = threadIdx.x;
   if (tid < 16) {
     const int a = tid >> 2, bb = tid & 3;
     s_k[tid] = kernel[(3 - a) * 4 + (3 - bb)];   // flipped taps (true convolution)
   }
-  if (SEP && tid < 4) {
+  if (tid < 4) {
     // rank-1 kernel: k[a][b] = rowsum[a] * colsum[b] / total
     float tot = 0.f;
     for (int i = 0; i < 16; ++i) tot += kernel[i];
@@ -226,99 +242,148 @@ __global__ void __launch_bounds__(512, 2) blur_act_nhwc_kernel(__nv_bfloat16* __
     s_kv[tid] = rs;
     s_kh[tid] = csum / tot;
   }
-  if (tid < 64) {
-    const int o = c0 + tid;
-    s_tab[tid] = o < C ? __ldg(reinterpret_cast<const float4*>(tab + (static_cast<size_t>(b) * C + o) * 8))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  // ---- stage the patch (rows Y0-1 .. Y0+17, cols X0-1 .. X0+17), zero outside the image
-  const __nv_bfloat16* tb = t + static_cast<size_t>(b) * IH * IW * cs;
-  for (int i = tid; i < BL_P * BL_P * 8; i += 512) {
-    const int g = i & 7;
-    const int px = (i >> 3) % BL_P, py = (i >> 3) / BL_P;
-    const int iy = Y0 - 1 + py, ix = X0 - 1 + px;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (iy >= 0 && iy < IH && ix >= 0 && ix < IW && c0 + g * 8 < cs)
-      v = __ldg(reinterpret_cast<const uint4*>(tb + (static_cast<size_t>(iy) * IW + ix) * cs + c0 + g * 8));
-    s_patch[i] = v;
+  const int nrows_in = (Y1 - Y0) + 3;                       // input rows Y0-1 .. Y1+1
+  const int nstages = (nrows_in + BL_SR - 1) / BL_SR;
+  auto issue = [&](int s) {                                  // thread 0 only
+    const int slot = s % BL_NST;
+    fence_proxy_async();                                     // generic reads of this slot precede the async refill
+    mbar_arrive_expect_tx(&s_full[slot], BL_STAGE_BYTES);
+    tma_load_4d(bl_smem + slot * BL_STAGE_BYTES, &tmT, &s_full[slot], c0, x0 - 1, Y0 - 1 + s * BL_SR, b);
+  };
+  if (tid == 0) {
+    tma_prefetch_desc(&tmT);
+    for (int i = 0; i < BL_NST; ++i) mbar_init(&s_full[i], 1);
+    fence_barrier_init();
+    for (int s = 0; s < BL_NST && s < nstages; ++s) issue(s);
   }
   __syncthreads();
 
-  // thread = 4 channels x one column x a strip of 8 rows  (512 threads: 16 ch-quads x 16 cols x 2 strips)
-  const int g = tid & 15;
-  const int sx = (tid >> 4) & 15;
-  const int sy = (tid >> 8) * 8;
-  const uint2* patch2 = reinterpret_cast<const uint2*>(s_patch);
-  float acc[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+  const int g = tid & 15;                 // 4-channel group inside the 64-channel block
+  const int cg = tid >> 4;                // 4-column group inside the 64-column tile
+  const int X = x0 + 4 * cg;
+  const int ch = c0 + g * 4;
+  const bool active = X < OW && ch < cs;
+  const float nw = noise ? (noise_w ? __ldg(noise_w) : 1.f) : 0.f;
+  const float* nzp = noise ? noise + static_cast<size_t>(noise_bstride ? b : 0) * OH * OW + X : nullptr;
+  const bool nz_vec = (OW & 3) == 0;
 
+  // epilogue table of this thread's 4 channels as pairs: v = acc*d + bias (+noise); lrelu; * post
+  f32x2 td[2], tb[2], ts[2], tp[2];
 #pragma unroll
-  for (int r = 0; r < 11; ++r) {        // patch rows sy + r feed outputs sy + r - a, a = 0..3
-    float v[4][4];
+  for (int pr = 0; pr < 2; ++pr) {
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+    if (ch + 2 * pr < C) t0 = __ldg(reinterpret_cast<const float4*>(tab + (static_cast<size_t>(b) * C + ch + 2 * pr) * 8));
+    if (ch + 2 * pr + 1 < C) t1 = __ldg(reinterpret_cast<const float4*>(tab + (static_cast<size_t>(b) * C + ch + 2 * pr + 1) * 8));
+    td[pr] = f2_pack(t0.x, t1.x); tb[pr] = f2_pack(t0.y, t1.y); ts[pr] = f2_pack(t0.z, t1.z); tp[pr] = f2_pack(t0.w, t1.w);
+  }
+  f32x2 kh2[4], kv2[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint2 w = patch2[((sy + r) * BL_P + sx + q) * 16 + g];
-      v[q][0] = __uint_as_float(w.x << 16); v[q][1] = __uint_as_float(w.x & 0xffff0000u);
-      v[q][2] = __uint_as_float(w.y << 16); v[q][3] = __uint_as_float(w.y & 0xffff0000u);
+  for (int i = 0; i < 4; ++i) { kh2[i] = f2_pack(s_kh[i], s_kh[i]); kv2[i] = f2_pack(s_kv[i], s_kv[i]); }
+
+  // Input row j (relative, iy = Y0-1+j) feeds output row Y0 + j - a with vertical tap a; its partial sum
+  // sits in slot (j - a) & 3, and tap 3 closes output row Y0 + j - 3 (slot (j + 1) & 3).
+  f32x2 acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c][0] = acc[i][c][1] = 0ull;
+
+  const uint8_t* my = bl_smem + (4 * cg) * 128 + g * 8;
+  __nv_bfloat16* orow0 = out + (static_cast<size_t>(b) * OH * OW + X) * cs + ch;
+
+  auto do_row = [&](auto uc, int j, const uint8_t* rowp) {
+    constexpr int u = decltype(uc)::value;
+    f32x2 v[7][2];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const uint2 w = *reinterpret_cast<const uint2*>(rowp + i * 128);
+      v[i][0] = f2_from_bf16x2(w.x);
+      v[i][1] = f2_from_bf16x2(w.y);
     }
     if (SEP) {
-      float hrow[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        hrow[c] = fmaf(s_kh[3], v[3][c], fmaf(s_kh[2], v[2][c], fmaf(s_kh[1], v[1][c], s_kh[0] * v[0][c])));
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int i = r - a;
-        if (i < 0 || i > 7) continue;
-        const float kv = s_kv[a];
+        for (int pr = 0; pr < 2; ++pr) {
+          f32x2 h = f2_mul(kh2[0], v[c][pr]);
+          h = f2_fma(kh2[1], v[c + 1][pr], h);
+          h = f2_fma(kh2[2], v[c + 2][pr], h);
+          h = f2_fma(kh2[3], v[c + 3][pr], h);
+          acc[u & 3][c][pr] = f2_mul(kv2[0], h);            // tap 0 opens a new output row: no zeroing pass
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(kv, hrow[c], acc[i][c]);
-      }
+          for (int a = 1; a < 4; ++a) acc[(u - a) & 3][c][pr] = f2_fma(kv2[a], h, acc[(u - a) & 3][c][pr]);
+        }
     } else {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int i = r - a;
-        if (i < 0 || i > 7) continue;
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float kv = s_k[a * 4 + q];
+          const float kk = s_k[a * 4 + q];
+          const f32x2 k2 = f2_pack(kk, kk);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(kv, v[q][c], acc[i][c]);
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr)
+              acc[(u - a) & 3][c][pr] = (a == 0 && q == 0) ? f2_mul(k2, v[c + q][pr]) : f2_fma(k2, v[c + q][pr], acc[(u - a) & 3][c][pr]);
+        }
+    }
+    const int Y = Y0 + j - 3;
+    if (j >= 3 && Y < Y1) {
+      float nz[4] = {0.f, 0.f, 0.f, 0.f};
+      if (nzp) {
+        const float* np = nzp + static_cast<size_t>(Y) * OW;
+        if (nz_vec) {
+          const float4 n4 = __ldg(reinterpret_cast<const float4*>(np));
+          nz[0] = n4.x * nw; nz[1] = n4.y * nw; nz[2] = n4.z * nw; nz[3] = n4.w * nw;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) nz[c] = X + c < OW ? nw * __ldg(np + c) : 0.f;
         }
       }
+      __nv_bfloat16* orow = orow0 + static_cast<size_t>(Y) * OW * cs;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o2[2];
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          f32x2 x = f2_fma(acc[(u + 1) & 3][c][pr], td[pr], f2_add(tb[pr], f2_pack(nz[c], nz[c])));
+          const f32x2 xs = f2_mul(x, ts[pr]);
+          float xl, xh, sl, sh;
+          f2_unpack(x, xl, xh);
+          f2_unpack(xs, sl, sh);
+          // x > 0 ? x : x*slope
+          const f32x2 y = f2_mul(f2_pack(xl > 0.f ? xl : sl, xh > 0.f ? xh : sh), tp[pr]);
+          float yl, yh;
+          f2_unpack(y, yl, yh);
+          o2[pr] = pack_bf16x2(yl, yh);
+        }
+        if (X + c < OW) *reinterpret_cast<uint2*>(orow + static_cast<size_t>(c) * cs) = make_uint2(o2[0], o2[1]);
+      }
     }
-  }
+  };
 
-  if (c0 + g * 4 >= cs) return;
-  const int X = X0 + sx;
-  if (X >= OW) return;
-  const float nw = noise ? (noise_w ? __ldg(noise_w) : 1.f) : 0.f;
-  float4 tv[4];
+  // two stages (4 input rows) per iteration keep the slot renaming static
+  for (int s = 0; s < nstages; s += 2) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) tv[c] = s_tab[g * 4 + c];
-  float nzv[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int Y = Y0 + sy + i;
-    nzv[i] = (noise && Y < OH) ? nw * __ldg(noise + (static_cast<size_t>(noise_bstride ? b : 0) * OH + Y) * OW + X) : 0.f;
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int Y = Y0 + sy + i;
-    if (Y >= OH) break;
-    float o[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float x = fmaf(acc[i][c], tv[c].x, tv[c].y + nzv[i]);
-      x = x > 0.f ? x : x * tv[c].z;
-      o[c] = x * tv[c].w;
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int sc = s + h2;
+      if (sc >= nstages) break;
+      const int slot = sc % BL_NST;
+      mbar_wait(&s_full[slot], (sc / BL_NST) & 1);
+      if (active) {
+        const uint8_t* base = my + slot * BL_STAGE_BYTES;
+        const int j0 = sc * BL_SR;
+        if (h2 == 0) {
+          do_row(std::integral_constant<int, 0>{}, j0, base);
+          if (j0 + 1 < nrows_in) do_row(std::integral_constant<int, 1>{}, j0 + 1, base + BL_IW * 128);
+        } else {
+          do_row(std::integral_constant<int, 2>{}, j0, base);
+          if (j0 + 1 < nrows_in) do_row(std::integral_constant<int, 3>{}, j0 + 1, base + BL_IW * 128);
+        }
+      }
+      __syncthreads();                                   // the slot is drained
+      if (tid == 0 && sc + BL_NST < nstages) issue(sc + BL_NST);
     }
-    uint2 w;
-    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
-    *reinterpret_cast<uint2*>(out + ((static_cast<size_t>(b) * OH + Y) * OW + X) * cs + c0 + g * 4) = w;
   }
 }
 
@@ -326,52 +391,66 @@ __global__ void __launch_bounds__(512, 2) blur_act_nhwc_kernel(__nv_bfloat16* __
 // ToRGB tail: rgb_out = acc + bias + Upsample(skip)   (stylegan2.py:394-399; Upsample =
 // upfirdn2d(up=2, pad=(2,1)) with kernel*4, stylegan2.py:52-63).  One thread per pixel.
 // ------------------------------------------------------------------------------------
+// A thread owns 4 horizontally adjacent pixels: 4 LDG.128 of the accumulator (re-zeroed for the next
+// forward), the 4x2 skip samples per plane its 2x-upsampled footprint needs, 3 STG.128 (one per plane).
 __global__ void __launch_bounds__(256) rgb_finalize_kernel(float* __restrict__ rgb_out, float* __restrict__ acc,
                                                            const float* __restrict__ bias3, const float* __restrict__ skip,
-                                                           const float* __restrict__ kernel, int H, int W, int64_t total) {
+                                                           const float* __restrict__ kernel, int H, int W, int total_quads) {
   __shared__ float s_k[16];
   if (threadIdx.x < 16) {
     const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
     s_k[threadIdx.x] = kernel ? kernel[(3 - a) * 4 + (3 - b)] : 0.f;
   }
   __syncthreads();
-  const int h2 = H / 2, w2 = W / 2;
-  const float b0 = __ldg(bias3 + 0), b1 = __ldg(bias3 + 1), b2 = __ldg(bias3 + 2);
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int x = static_cast<int>(idx % W);
-    const int y = static_cast<int>((idx / W) % H);
-    const int64_t b = idx / (static_cast<int64_t>(W) * H);
-    float4* ap = reinterpret_cast<float4*>(acc + idx * 4);
-    const float4 a = *ap;
-    *ap = make_float4(0.f, 0.f, 0.f, 0.f);
-    float v[3] = {a.x + b0, a.y + b1, a.z + b2};
+  const int qw = W >> 2;
+  const int h2 = H >> 1, w2 = W >> 1;
+  const float bias[3] = {__ldg(bias3 + 0), __ldg(bias3 + 1), __ldg(bias3 + 2)};
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total_quads; idx += gridDim.x * blockDim.x) {
+    const int xq = idx % qw;
+    const int t = idx / qw;
+    const int y = t % H;
+    const int b = t / H;
+    const int x0 = xq * 4;
+    float4* ap = reinterpret_cast<float4*>(acc) + (static_cast<size_t>(t) * W + x0);
+    float v[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = ap[j];
+      ap[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      v[0][j] = a.x + bias[0]; v[1][j] = a.y + bias[1]; v[2][j] = a.z + bias[2];
+    }
     if (skip) {
-      // zero-stuffed row u = y + ta - 2 is live when even: ta has the parity of y -> 2 of the 4 taps per axis
+      // zero-stuffed row u = y + ta - 2 is live when even: ta has the parity of y -> 2 of the 4 taps per axis;
+      // pixel x0+j reads skip columns (x0+j + tb - 2) / 2 with tb = (j & 1) + 2*ib -> columns x0/2 - 1 .. x0/2 + 2
       const size_t plane = static_cast<size_t>(h2) * w2;
-      const float* sp = skip + b * 3 * plane;
+      const float* sp = skip + static_cast<size_t>(b) * 3 * plane;
+      const int sx0 = (x0 >> 1) - 1;
 #pragma unroll
       for (int ia = 0; ia < 2; ++ia) {
         const int ta = (y & 1) + 2 * ia;
         const int sy = (y + ta - 2) >> 1;
         if (y + ta - 2 < 0 || sy >= h2) continue;
+        float kx[4];
 #pragma unroll
-        for (int ib = 0; ib < 2; ++ib) {
-          const int tb = (x & 1) + 2 * ib;
-          const int sx = (x + tb - 2) >> 1;
-          if (x + tb - 2 < 0 || sx >= w2) continue;
-          const float kv = s_k[ta * 4 + tb];
-          const size_t off = static_cast<size_t>(sy) * w2 + sx;
-          v[0] = fmaf(__ldg(sp + off), kv, v[0]);
-          v[1] = fmaf(__ldg(sp + plane + off), kv, v[1]);
-          v[2] = fmaf(__ldg(sp + 2 * plane + off), kv, v[2]);
+        for (int i = 0; i < 4; ++i) kx[i] = s_k[ta * 4 + i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* row = sp + c * plane + static_cast<size_t>(sy) * w2;
+          float sv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sv[i] = (sx0 + i >= 0 && sx0 + i < w2) ? __ldg(row + sx0 + i) : 0.f;
+          // j even: tb in {0,2} -> columns (j/2 - 1, j/2) + x0/2 ; j odd: tb in {1,3} -> ((j-1)/2, (j+1)/2) + x0/2
+          v[c][0] = fmaf(sv[0], kx[0], fmaf(sv[1], kx[2], v[c][0]));
+          v[c][1] = fmaf(sv[1], kx[1], fmaf(sv[2], kx[3], v[c][1]));
+          v[c][2] = fmaf(sv[1], kx[0], fmaf(sv[2], kx[2], v[c][2]));
+          v[c][3] = fmaf(sv[2], kx[1], fmaf(sv[3], kx[3], v[c][3]));
         }
       }
     }
-    const size_t o = (b * 3 * H + y) * static_cast<size_t>(W) + x;
-    rgb_out[o] = v[0];
-    rgb_out[o + static_cast<size_t>(H) * W] = v[1];
-    rgb_out[o + 2 * static_cast<size_t>(H) * W] = v[2];
+    const size_t hw = static_cast<size_t>(H) * W;
+    float* op = rgb_out + static_cast<size_t>(b) * 3 * hw + static_cast<size_t>(y) * W + x0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(op + c * hw) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
   }
 }
 
@@ -420,7 +499,7 @@ extern "C" int fm_style_affine(const fm_style_layer* layers_dev, int n_layers, i
   FM_CHECK_ARG(layers_dev && latent && n_layers > 0 && max_cin > 0 && B > 0 && style_dim > 0, "fm_style_affine: bad args");
   FM_CHECK_ARG(style_dim <= 1700, "fm_style_affine: style_dim %d too large for the shared-memory tile", style_dim);
   const int smem = small_gemm_smem(reinterpret_cast<const void*>(style_affine_kernel), style_dim);
-  dim3 grid((max_cin + 63) / 64, n_layers);
+  dim3 grid((max_cin + SG_CH - 1) / SG_CH, n_layers);
   style_affine_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(layers_dev, latent, B, n_latent, style_dim,
                                                                               1.0f / sqrtf(static_cast<float>(style_dim)));
   count_launch();
@@ -433,7 +512,7 @@ extern "C" int fm_build_tables(const fm_table_layer* layers_dev, int n_layers, i
   FM_CHECK_ARG(layers_dev && n_layers > 0 && max_cout > 0 && max_cin > 0 && B > 0, "fm_build_tables: bad args");
   FM_CHECK_ARG(max_cin <= 1700, "fm_build_tables: cin %d too large for the shared-memory tile", max_cin);
   const int smem = small_gemm_smem(reinterpret_cast<const void*>(build_tables_kernel), max_cin);
-  dim3 grid((max_cout + 63) / 64, n_layers);
+  dim3 grid((max_cout + SG_CH - 1) / SG_CH, n_layers);
   build_tables_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(layers_dev, B);
   count_launch();
   FM_LAUNCH_OK();
@@ -469,18 +548,41 @@ extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4
                                 int separable, void* stream) {
   FM_CHECK_ARG(out && t && kernel4x4 && tab && B > 0 && OH > 0 && OW > 0 && C > 0, "fm_blur_act_nhwc: bad args");
   FM_CHECK_ARG(cstride % 8 == 0 && cstride >= C, "fm_blur_act_nhwc: cstride must be a multiple of 8 >= C");
-  const int tiles_x = (OW + BL_T - 1) / BL_T, tiles_y = (OH + BL_T - 1) / BL_T, cblocks = (cstride + 63) / 64;
+  FM_CHECK_ARG((reinterpret_cast<uintptr_t>(t) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "fm_blur_act_nhwc: tensors must be 16-byte aligned");
+  const int tiles_x = (OW + BL_TW - 1) / BL_TW, tiles_y = (OH + BL_ROWS - 1) / BL_ROWS, cblocks = (cstride + 63) / 64;
   const int64_t blocks = static_cast<int64_t>(B) * tiles_x * tiles_y * cblocks;
   FM_CHECK_ARG(blocks < 0x7FFFFFFF, "fm_blur_act_nhwc: too many blocks");
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) { set_error("fm_blur_act_nhwc: cuTensorMapEncodeTiled driver entry point unavailable"); return FM_ERR_NO_DEVICE; }
+  CUtensorMap tmT;
+  {
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(cstride), static_cast<cuuint64_t>(OW + 1), static_cast<cuuint64_t>(OH + 1),
+                                static_cast<cuuint64_t>(B)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(cstride) * 2, static_cast<cuuint64_t>(cstride) * 2 * (OW + 1),
+                                   static_cast<cuuint64_t>(cstride) * 2 * (OW + 1) * (OH + 1)};
+    const cuuint32_t box[4] = {64, BL_IW, BL_SR, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(t), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("fm_blur_act_nhwc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return FM_ERR_CUDA; }
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_SMEM));
+    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_SMEM));
+    attr_set = true;
+  }
   if (separable)
-    blur_act_nhwc_kernel<true><<<static_cast<unsigned>(blocks), 512, 0, st>>>(
-        static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(t), kernel4x4, tab, noise, noise_bstride, noise_w,
-        OH, OW, C, cstride, tiles_x, tiles_y, cblocks);
+    blur_act_nhwc_kernel<true><<<static_cast<unsigned>(blocks), 256, BL_SMEM, st>>>(
+        tmT, static_cast<__nv_bfloat16*>(out), kernel4x4, tab, noise, noise_bstride, noise_w, OH, OW, C, cstride, tiles_x, tiles_y,
+        cblocks);
   else
-    blur_act_nhwc_kernel<false><<<static_cast<unsigned>(blocks), 512, 0, st>>>(
-        static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(t), kernel4x4, tab, noise, noise_bstride, noise_w,
-        OH, OW, C, cstride, tiles_x, tiles_y, cblocks);
+    blur_act_nhwc_kernel<false><<<static_cast<unsigned>(blocks), 256, BL_SMEM, st>>>(
+        tmT, static_cast<__nv_bfloat16*>(out), kernel4x4, tab, noise, noise_bstride, noise_w, OH, OW, C, cstride, tiles_x, tiles_y,
+        cblocks);
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;
@@ -490,9 +592,11 @@ extern "C" int fm_rgb_finalize(float* rgb_out, float* acc, const float* bias3, c
                                int B, int H, int W, void* stream) {
   FM_CHECK_ARG(rgb_out && acc && bias3 && B > 0 && H > 0 && W > 0, "fm_rgb_finalize: bad args");
   FM_CHECK_ARG(!skip || (kernel4x4 && H % 2 == 0 && W % 2 == 0), "fm_rgb_finalize: skip needs a kernel and even H, W");
-  const int64_t total = static_cast<int64_t>(B) * H * W;
-  rgb_finalize_kernel<<<grid_for(total, 256, 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(rgb_out, acc, bias3, skip, kernel4x4,
-                                                                                     H, W, total);
+  FM_CHECK_ARG(W % 4 == 0, "fm_rgb_finalize: W must be a multiple of 4");
+  const int64_t total = static_cast<int64_t>(B) * H * (W / 4);
+  FM_CHECK_ARG(total < 0x7FFFFFFF, "fm_rgb_finalize: too many pixels");
+  rgb_finalize_kernel<<<grid_for(total, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rgb_out, acc, bias3, skip, kernel4x4, H, W, static_cast<int>(total));
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;

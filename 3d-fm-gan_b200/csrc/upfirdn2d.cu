@@ -8,6 +8,8 @@
 // adjacent outputs so each staged input is reused from registers, accumulation is fp32
 // for every dtype, and the strip is written with one 16-byte store when aligned.
 // Algorithmic bytes: (planes*in_h*in_w + planes*out_h*out_w) * sizeof(T); roofline = HBM.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fm {
@@ -125,6 +127,218 @@ __global__ void __launch_bounds__(256) upfirdn2d_tile_kernel(T* __restrict__ out
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Streaming kernel for up = down = 1 (every Blur of the generator and the discriminator:
+// stylegan2.py:95-105 -> op/upfirdn2d.py:154 with pad (1,1) / (2,2) / (2,1)), kernel <= 4x4.
+// A work item is a full-width strip of R output rows of one plane (or, for small images, a group of
+// P whole planes): its input footprint is ONE contiguous byte range of the [planes, H, W] tensor, so a
+// single thread fetches it with 1-D bulk async copies (cp.async.bulk, 16-byte aligned superset of the
+// range) into a double-buffered shared-memory ring while the other threads filter the previous item.
+// This is the only way to get wide loads here: rows are W*sizeof(T) bytes with W odd (2h+1), so
+// neither vector loads nor tensor-map TMA (16-byte strides) apply.
+// Compute: a thread owns COLS adjacent output columns and walks down the rows with a rolling window
+// of 4 partial sums (statically renamed, 4 rows per unrolled step): COLS+3 conflict-free LDS and
+// 16*COLS FMAs per row, one coalesced store per row.  fp32 accumulation for every dtype.
+// ------------------------------------------------------------------------------------
+constexpr int UFS_THREADS = 512;
+constexpr int UFS_BUF_BYTES = 48 * 1024;        // per ring slot (2 slots): 2 CTAs of 512 threads per SM
+constexpr int UFS_CHUNK = 16 * 1024;            // bytes per bulk copy
+
+struct UfsItem {
+  int64_t plane0;      // first plane
+  int nplanes;         // planes in the item (1 in strip mode)
+  int oy0, oy1;        // output rows [oy0, oy1)
+  int r_lo, r_hi;      // staged input rows [r_lo, r_hi] of each plane
+};
+
+__device__ __forceinline__ UfsItem ufs_item(int64_t i, const UpfirdnParams& p, int64_t planes, int R, int P, int strips) {
+  UfsItem it;
+  if (strips > 1) {
+    it.plane0 = i / strips;
+    it.nplanes = 1;
+    const int s = static_cast<int>(i - it.plane0 * strips);
+    it.oy0 = s * R;
+    it.oy1 = min(p.out_h, it.oy0 + R);
+    it.r_lo = max(0, it.oy0 - p.pad_y0);
+    it.r_hi = min(p.in_h - 1, it.oy1 - 1 - p.pad_y0 + 3);
+  } else {
+    it.plane0 = i * P;
+    it.nplanes = static_cast<int>(min(static_cast<int64_t>(P), planes - it.plane0));
+    it.oy0 = 0; it.oy1 = p.out_h;
+    it.r_lo = 0; it.r_hi = p.in_h - 1;
+  }
+  return it;
+}
+
+template <typename T, int COLS>
+__global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __restrict__ out, const T* __restrict__ x,
+                                                                       const float* __restrict__ kernel, UpfirdnParams p,
+                                                                       int64_t planes, int R, int P, int strips,
+                                                                       int64_t n_items) {
+  extern __shared__ __align__(128) uint8_t ufs_smem[];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ float s_k[16];
+  const int tid = threadIdx.x;
+  if (tid < 16) {
+    const int ky = tid >> 2, kx = tid & 3;
+    // flipped: tap (ky,kx) of the correlation = k[kh-1-ky][kw-1-kx]  (op/upfirdn2d_kernel.cu:137)
+    s_k[tid] = (ky < p.kh && kx < p.kw) ? kernel[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)] : 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  float w[4][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i >> 2][i & 3] = s_k[i];
+
+  const int64_t plane_elems = static_cast<int64_t>(p.in_h) * p.in_w;
+  const uintptr_t xbase = reinterpret_cast<uintptr_t>(x);
+
+  // byte range of an item, widened to 16-byte boundaries (the extra bytes stay inside the 16-byte
+  // granules that hold the first / last wanted byte, so they are always mapped)
+  auto issue = [&](const UfsItem& it, int slot) {
+    const uintptr_t lo = xbase + static_cast<uintptr_t>((it.plane0 * plane_elems + static_cast<int64_t>(it.r_lo) * p.in_w) * sizeof(T));
+    const uintptr_t hi = xbase + static_cast<uintptr_t>(((it.plane0 + it.nplanes - 1) * plane_elems +
+                                                         static_cast<int64_t>(it.r_hi + 1) * p.in_w) * sizeof(T));
+    const uintptr_t lo_a = lo & ~static_cast<uintptr_t>(15);
+    const uint32_t bytes = static_cast<uint32_t>(((hi + 15) & ~static_cast<uintptr_t>(15)) - lo_a);
+    uint8_t* dst = ufs_smem + slot * UFS_BUF_BYTES;
+    fence_proxy_async();                       // earlier generic reads of this slot precede the async writes
+    mbar_arrive_expect_tx(&s_bar[slot], bytes);
+    for (uint32_t off = 0; off < bytes; off += UFS_CHUNK)
+      bulk_load_1d(dst + off, reinterpret_cast<const void*>(lo_a + off), min(static_cast<uint32_t>(UFS_CHUNK), bytes - off),
+                   &s_bar[slot]);
+  };
+
+  const int colgroups = (p.out_w + COLS - 1) / COLS;
+  int64_t item = blockIdx.x;
+  if (item < n_items && tid == 0) issue(ufs_item(item, p, planes, R, P, strips), 0);
+  for (int k = 0; item < n_items; item += gridDim.x, ++k) {
+    const int slot = k & 1;
+    const UfsItem it = ufs_item(item, p, planes, R, P, strips);
+    if (tid == 0 && item + gridDim.x < n_items) issue(ufs_item(item + gridDim.x, p, planes, R, P, strips), slot ^ 1);
+    mbar_wait(&s_bar[slot], (k >> 1) & 1);
+
+    const uintptr_t lo = xbase + static_cast<uintptr_t>((it.plane0 * plane_elems + static_cast<int64_t>(it.r_lo) * p.in_w) * sizeof(T));
+    const T* sbuf = reinterpret_cast<const T*>(ufs_smem + slot * UFS_BUF_BYTES + (lo & 15));
+    // thread tasks: (plane of the item, column group, row split)
+    const int nrows = it.oy1 - it.oy0;
+    const int ncg = it.nplanes * colgroups;
+    int rs = UFS_THREADS / ncg;
+    rs = rs < 1 ? 1 : (rs > 4 ? 4 : rs);
+    const int rows_per = (nrows + rs - 1) / rs;
+    for (int task = tid; task < ncg * rs; task += UFS_THREADS) {
+      const int part = task / ncg;
+      const int cgi = task - part * ncg;
+      const int pl = cgi / colgroups;
+      const int ox = (cgi - pl * colgroups) * COLS;
+      const int ty0 = it.oy0 + part * rows_per;
+      const int ty1 = min(it.oy1, ty0 + rows_per);
+      if (ty0 >= ty1) continue;
+      const T* sp = sbuf + static_cast<int64_t>(pl) * plane_elems - static_cast<int64_t>(it.r_lo) * p.in_w;   // row iy at sp + iy*in_w
+      const int ix0 = ox - p.pad_x0;
+      bool cok[COLS + 3];
+#pragma unroll
+      for (int q = 0; q < COLS + 3; ++q) cok[q] = ix0 + q >= 0 && ix0 + q < p.in_w;
+      T* op = out + ((it.plane0 + pl) * p.out_h) * static_cast<int64_t>(p.out_w) + ox;
+
+      float acc[4][COLS];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) acc[j][c] = 0.f;
+      // relative input row j <-> iy = ty0 - pad_y0 + j feeds output row ty0 + j - ky; slot (j - ky) & 3
+      const int jn = (ty1 - ty0) + 3;
+      for (int jb = 0; jb < jn; jb += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = jb + u;
+          if (j >= jn) break;
+          const int iy = ty0 - p.pad_y0 + j;
+          float v[COLS + 3];
+          const bool rok = iy >= it.r_lo && iy <= it.r_hi;
+          const T* rp = sp + static_cast<int64_t>(rok ? iy : it.r_lo) * p.in_w + ix0;
+#pragma unroll
+          for (int q = 0; q < COLS + 3; ++q) v[q] = (rok && cok[q]) ? to_f32<T>(rp[q]) : 0.f;
+#pragma unroll
+          for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) {
+              float a = acc[(u - ky) & 3][c];
+#pragma unroll
+              for (int kx = 0; kx < 4; ++kx) a = fmaf(v[c + kx], w[ky][kx], a);
+              acc[(u - ky) & 3][c] = a;
+            }
+          // tap row 3 closes output row ty0 + j - 3 (slot (u + 1) & 3)
+          float (&done)[COLS] = acc[(u + 1) & 3];
+          const int oy = ty0 + j - 3;
+          if (j >= 3) {
+            T* orow = op + static_cast<int64_t>(oy) * p.out_w;
+            if (COLS == 2 && sizeof(T) == 2 && ox + 1 < p.out_w && (reinterpret_cast<uintptr_t>(orow) & 3) == 0) {
+              T q2[2] = {from_f32<T>(done[0]), from_f32<T>(done[COLS - 1])};
+              *reinterpret_cast<uint32_t*>(orow) = *reinterpret_cast<uint32_t*>(q2);
+            } else {
+#pragma unroll
+              for (int c = 0; c < COLS; ++c)
+                if (ox + c < p.out_w) orow[c] = from_f32<T>(done[c]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < COLS; ++c) done[c] = 0.f;
+        }
+      }
+    }
+    __syncthreads();      // everyone is done with this slot before it is refilled (two items ahead)
+  }
+}
+
+template <typename T>
+static bool stream_eligible(const UpfirdnParams& p, int pad_x1, int pad_y1) {
+  if (p.up_x != 1 || p.up_y != 1 || p.down_x != 1 || p.down_y != 1) return false;
+  if (p.kh > 4 || p.kw > 4) return false;
+  if (p.pad_x0 < 0 || p.pad_y0 < 0 || pad_x1 < 0 || pad_y1 < 0 || p.pad_x0 > 16 || p.pad_y0 > 16) return false;
+  // at least 4 output rows (+3 halo rows) of a full-width strip must fit one ring slot
+  return static_cast<int64_t>(7) * p.in_w * static_cast<int64_t>(sizeof(T)) + 32 <= UFS_BUF_BYTES;
+}
+
+template <typename T>
+static int launch_stream(void* out, const void* x, const float* kernel, const UpfirdnParams& p, int64_t planes, cudaStream_t st) {
+  constexpr int COLS = sizeof(T) == 4 ? 1 : 2;
+  const int64_t row_bytes = static_cast<int64_t>(p.in_w) * sizeof(T);
+  const int64_t plane_bytes = row_bytes * p.in_h;
+  int R, P, strips;
+  if (plane_bytes + 32 <= UFS_BUF_BYTES) {
+    strips = 1; R = p.out_h;
+    P = static_cast<int>((UFS_BUF_BYTES - 32) / plane_bytes);
+    // keep enough items to fill the machine
+    const int64_t want_items = static_cast<int64_t>(sm_count()) * 4;
+    while (P > 1 && (planes + P - 1) / P < want_items) P >>= 1;
+  } else {
+    P = 1;
+    R = static_cast<int>((UFS_BUF_BYTES - 32) / row_bytes) - 3;
+    if (R > 40) R = 40;
+    strips = (p.out_h + R - 1) / R;
+    R = (p.out_h + strips - 1) / strips;          // balance the strips
+  }
+  const int64_t n_items = strips > 1 ? planes * strips : (planes + P - 1) / P;
+  static bool attr_set = false;
+  auto fn = upfirdn2d_stream_kernel<T, COLS>;
+  if (!attr_set) {
+    FM_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * UFS_BUF_BYTES));
+    attr_set = true;
+  }
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 2;
+  const unsigned grid = static_cast<unsigned>(n_items < cap ? n_items : cap);
+  fn<<<grid, UFS_THREADS, 2 * UFS_BUF_BYTES, st>>>(static_cast<T*>(out), static_cast<const T*>(x), kernel, p, planes, R, P, strips,
+                                                   n_items);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
 // Generic kernel: any up/down (per axis), any kernel size, one thread per output.
 template <typename T>
 __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(T* __restrict__ out, const T* __restrict__ x,
@@ -172,10 +386,12 @@ static int launch_tile(void* out, const void* x, const float* kernel, UpfirdnPar
 }
 
 template <typename T>
-static int upfirdn2d_dispatch(void* out, const void* x, const float* kernel, int64_t planes, UpfirdnParams p,
-                              cudaStream_t st) {
+static int upfirdn2d_dispatch(void* out, const void* x, const float* kernel, int64_t planes, UpfirdnParams p, int pad_x1,
+                              int pad_y1, cudaStream_t st) {
   const int64_t total = planes * p.out_h * p.out_w;
   if (total == 0) return FM_OK;
+  static const int env_stream = []() { const char* e = getenv("FM3D_UPFIRDN_STREAM"); return e ? atoi(e) : 1; }();
+  if (env_stream && stream_eligible<T>(p, pad_x1, pad_y1)) return launch_stream<T>(out, x, kernel, p, planes, st);
   const bool sq = p.up_x == p.up_y && p.down_x == p.down_y;
   const int kmax = p.kh > p.kw ? p.kh : p.kw;
   // small images: shorter tiles keep more CTAs busy
@@ -220,9 +436,9 @@ extern "C" int fm_upfirdn2d(void* out, const void* x, const float* kernel, int64
   FM_CHECK_ARG(out && x && kernel, "fm_upfirdn2d: null tensor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (dtype) {
-    case FM_F32: return fm::upfirdn2d_dispatch<float>(out, x, kernel, planes, p, st);
-    case FM_F16: return fm::upfirdn2d_dispatch<__half>(out, x, kernel, planes, p, st);
-    case FM_BF16: return fm::upfirdn2d_dispatch<__nv_bfloat16>(out, x, kernel, planes, p, st);
+    case FM_F32: return fm::upfirdn2d_dispatch<float>(out, x, kernel, planes, p, pad_x1, pad_y1, st);
+    case FM_F16: return fm::upfirdn2d_dispatch<__half>(out, x, kernel, planes, p, pad_x1, pad_y1, st);
+    case FM_BF16: return fm::upfirdn2d_dispatch<__nv_bfloat16>(out, x, kernel, planes, p, pad_x1, pad_y1, st);
     default: fm::set_error("fm_upfirdn2d: bad dtype %d", dtype); return FM_ERR_INVALID;
   }
 }

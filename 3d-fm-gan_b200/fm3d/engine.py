@@ -31,7 +31,8 @@ from ._lib import StyleLayer, TableLayer
 
 import os
 
-_FUSED_UP = os.environ.get("FM3D_UPMODE", "1") != "0"
+# fused 4-parity launch: correct but not faster than four phase launches yet (weight re-streaming bound)
+_FUSED_UP = os.environ.get("FM3D_UPMODE", "0") == "1"
 
 
 def _up_phase_taps(py, px):
@@ -105,7 +106,9 @@ class SynthesisPlan:
             L.s = torch.empty(B, L.cin, **f32)
             L.tab = torch.empty(B, L.cout, 8, **f32)
         self.rgb_s = [torch.empty(B, L.cout, **f32) for (_, _, L) in self.rgbs]
-        self.acts = [torch.empty(B, L.res_out, L.res_out, cs(L.cout), **bf16) for L in convs]
+        # the last layer's activations feed nothing but its fused ToRGB: they are never stored
+        self.acts = [torch.empty(B, L.res_out, L.res_out, cs(L.cout), **bf16) if i + 1 < len(convs) else None
+                     for i, L in enumerate(convs)]
         self.tbuf = {i: torch.empty(B, L.res_out + 1, L.res_out + 1, cs(L.cout), **bf16)
                      for i, L in enumerate(convs) if L.up}
         self.x0 = torch.empty(B, 4, 4, cs(convs[0].cin), **bf16)

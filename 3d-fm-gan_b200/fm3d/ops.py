@@ -5,6 +5,8 @@ shims do (op/fused_bias_act.cpp:11-17, op/upfirdn2d.cpp:12-19): CUDA checks, con
 """
 import ctypes as C
 
+import weakref
+
 import torch
 
 from . import _lib
@@ -157,10 +159,10 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     d.border_tab = _ptr(border_tab)
     d.out_cgroup, d.out_gstride = out_cgroup, out_gstride
     d.OH, d.OW = OH, OW
-    d.out = out.data_ptr()
+    d.out = out.data_ptr() if out is not None else None
     d.out_H = OH if out_H is None else out_H
     d.out_W = OW if out_W is None else out_W
-    d.out_cstride = out_cstride if out_cstride is not None else (Cout if out_nchw_f32 else out.shape[-1])
+    d.out_cstride = out_cstride if out_cstride is not None else (Cout if out_nchw_f32 else (out.shape[-1] if out is not None else (Cout + 7) // 8 * 8))
     d.out_y0, d.out_x0, d.out_ys, d.out_xs = out_y0, out_x0, out_ys, out_xs
     d.out_nchw_f32 = 1 if out_nchw_f32 else 0
     d.tab = tab.data_ptr(); d.tab_bstride = 1 if tab_per_sample else 0
@@ -234,7 +236,8 @@ def _is_rank1(k):
     return bool(torch.allclose(torch.outer(kk.sum(1), kk.sum(0)) / tot, kk, rtol=1e-6, atol=1e-9))
 
 
-_RANK1_CACHE = {}
+# keyed on the tensor OBJECT (weakly): a data_ptr key would go stale when the allocator re-uses the address
+_RANK1_CACHE = weakref.WeakKeyDictionary()
 
 
 def blur_act_nhwc(t, kernel4x4, tab, noise, noise_per_sample, noise_w, C_, out=None):
@@ -243,10 +246,10 @@ def blur_act_nhwc(t, kernel4x4, tab, noise, noise_per_sample, noise_w, C_, out=N
     OH, OW = IH - 1, IW - 1
     if out is None:
         out = torch.empty(B, OH, OW, cs, device=t.device, dtype=torch.bfloat16)
-    key = (kernel4x4.data_ptr(), kernel4x4._version)
-    sep = _RANK1_CACHE.get(key)
-    if sep is None:                       # one host sync per kernel buffer (cached)
-        sep = _RANK1_CACHE[key] = _is_rank1(kernel4x4)
+    ent = _RANK1_CACHE.get(kernel4x4)
+    if ent is None or ent[0] != (kernel4x4.data_ptr(), kernel4x4._version):   # one host sync per kernel buffer (cached)
+        ent = _RANK1_CACHE[kernel4x4] = ((kernel4x4.data_ptr(), kernel4x4._version), _is_rank1(kernel4x4))
+    sep = ent[1]
     with torch.cuda.device(t.device):
         st = _lib.lib().fm_blur_act_nhwc(_ptr(out), _ptr(t), _ptr(kernel4x4), _ptr(tab), _ptr(noise),
                                          1 if noise_per_sample else 0, _ptr(noise_w), B, OH, OW, C_, cs,

@@ -125,7 +125,8 @@ typedef struct {
   int32_t OH, OW;
   /* placement of that grid inside the output tensor: pixel (oy,ox) is written to
    * (oy*out_ys + out_y0, ox*out_xs + out_x0) of a [B,out_H,out_W,out_cstride] tensor */
-  void* out;                /* bf16 NHWC, or fp32 NCHW when out_nchw_f32 != 0 */
+  void* out;                /* bf16 NHWC, or fp32 NCHW when out_nchw_f32 != 0; NULL (with rgb != NULL) = only the
+                             * fused ToRGB sums are produced: the last synthesis layer's activations feed nothing else */
   int32_t out_H, out_W, out_cstride, out_y0, out_x0, out_ys, out_xs;
   int32_t out_nchw_f32;
   /* epilogue */

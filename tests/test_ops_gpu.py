@@ -63,6 +63,35 @@ def test_upfirdn2d_vs_oracle(cuda, shape, cfg, dtype):
     torch.testing.assert_close(out.float().cpu(), ref, rtol=tol, atol=tol * 4)
 
 
+@pytest.mark.parametrize("shape,kshape,pads", [
+    ((3, 5, 17, 17), (4, 4), (1, 1, 1, 1)),        # several whole planes per work item
+    ((2, 2, 300, 1000), (3, 3), (2, 0, 1, 3)),     # wide rows: few rows per strip, asymmetric pads
+    ((1, 3, 131, 67), (2, 4), (0, 3, 2, 1)),       # non-square kernel, odd sizes
+    ((5, 1, 4, 4), (1, 1), (0, 0, 0, 0)),          # 1x1 kernel (identity scale)
+    ((2, 1, 6, 9), (4, 4), (3, 3, 3, 3)),          # pads as large as the kernel allows
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_upfirdn2d_stream_cases(cuda, shape, kshape, pads, dtype):
+    """up = down = 1 takes the bulk-copy streaming kernel: non-separable random taps, ragged sizes and a
+    source tensor that is only element-aligned (the copy widens its byte range to 16-byte granules)."""
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(sum(shape) * 3 + kshape[0])
+    numel = 1
+    for d in shape:
+        numel *= d
+    base = torch.randn(numel + 3, generator=gen).to(dtype)
+    k = torch.randn(*kshape, generator=gen)
+    cfg = (1, 1, 1, 1) + pads
+    for off in (0, 1, 3):
+        x = base[off:off + numel].view(*shape)
+        ref = orc.upfirdn2d_ref(x.float(), k, *cfg)
+        xd = base.to(cuda)[off:off + numel].view(*shape)
+        out = ops.upfirdn2d_planes(xd, k.to(cuda), *cfg)
+        assert tuple(out.shape) == tuple(ref.shape)
+        tol = 1e-5 if dtype == torch.float32 else 2e-2
+        torch.testing.assert_close(out.float().cpu(), ref, rtol=tol, atol=tol * 8)
+
+
 def test_upfirdn2d_empty(cuda):
     from fm3d import ops
     k = orc.make_kernel_ref([1, 3, 3, 1]).to(cuda)

@@ -29,8 +29,76 @@ def timeit(fn, iters=10, warm=3):
     return ts[len(ts) // 2] * 1e-3
 
 
+def bench_synth(res):
+    """blur_act_nhwc / rgb_finalize at the generator's shapes (B=32), fused up-conv vs 4 phase launches."""
+    B = 32
+    k = torch.tensor([1., 3., 3., 1.]); k = (k[None] * k[:, None]); k = (k / k.sum() * 4).to(dev)
+    for (OH, C) in [(256, 128), (128, 256), (64, 512), (32, 512)]:
+        t_in = torch.randn(B, OH + 1, OH + 1, C, device=dev).to(torch.bfloat16)
+        tab = torch.zeros(B, C, 8, device=dev); tab[..., 0] = 1; tab[..., 2] = 0.2; tab[..., 3] = 1
+        noise = torch.randn(B, 1, OH, OH, device=dev)
+        nw = torch.ones(1, device=dev)
+        out = torch.empty(B, OH, OH, C, device=dev, dtype=torch.bfloat16)
+        t = timeit(lambda: ops.blur_act_nhwc(t_in, k, tab, noise, True, nw, C, out=out))
+        res.append(dict(kernel="blur_act_nhwc", OH=OH, C=C, ms=t * 1e3, GBs=(t_in.numel() + out.numel()) * 2 / t / 1e9))
+        del t_in, out
+    for H in (256, 128, 64):
+        acc = torch.randn(B, H, H, 4, device=dev)
+        skip = torch.randn(B, 3, H // 2, H // 2, device=dev)
+        bias = torch.zeros(3, device=dev)
+        out = torch.empty(B, 3, H, H, device=dev)
+        t = timeit(lambda: ops.rgb_finalize(acc, bias, skip, k, out=out))
+        byts = acc.numel() * 4 * 2 + skip.numel() * 4 + out.numel() * 4
+        res.append(dict(kernel="rgb_finalize", H=H, ms=t * 1e3, GBs=byts / t / 1e9))
+
+
+def bench_upconv(res):
+    """Stride-2 transposed 3x3 conv: four parity-phase launches vs the fused 4-accumulator launch."""
+    sys.path.insert(0, os.path.join(ROOT, "3d-fm-gan_b200"))
+    from fm3d import engine
+    B = 32
+    for (h, Cin, Cout) in [(128, 256, 128), (64, 512, 256), (32, 512, 512), (16, 512, 512)]:
+        x = torch.randn(B, h, h, Cin, device=dev).to(torch.bfloat16)
+        w = (torch.randn(9, Cout, Cin, device=dev) / (Cin * 9) ** 0.5).to(torch.bfloat16)
+        tab = torch.zeros(1, Cout, 8, device=dev); tab[..., 0] = 1; tab[..., 2] = 1; tab[..., 3] = 1
+        t_out = torch.empty(B, 2 * h + 1, 2 * h + 1, Cout, device=dev, dtype=torch.bfloat16)
+        tw_ = min(16, engine._pow2_ge(h + 1)); th_ = max(1, min(8, 128 // tw_))
+
+        def phases():
+            for py in (0, 1):
+                for px in (0, 1):
+                    ops.conv_igemm(x, w, engine._up_phase_taps(py, px), t_out, tab, B=B, H=h, W=h, Cin=Cin, Cout=Cout,
+                                   OH=h + 1 - py, OW=h + 1 - px, out_H=2 * h + 1, out_W=2 * h + 1, out_y0=py, out_x0=px,
+                                   out_ys=2, out_xs=2, tab_per_sample=False, tile_w=tw_, tile_h=th_)
+
+        def fused():
+            ops.conv_igemm(x, w, ops.conv_taps(3, 3, 1), t_out, tab, B=B, H=h, W=h, Cin=Cin, Cout=Cout, OH=h + 1, OW=h + 1,
+                           out_H=2 * h + 1, out_W=2 * h + 1, out_ys=2, out_xs=2, tab_per_sample=False, tile_w=tw_, tile_h=th_,
+                           upmode=True)
+        fl = 2.0 * B * h * h * Cin * Cout * 9
+        for name, fn in (("upconv_phases", phases), ("upconv_fused", fused)):
+            t = timeit(fn)
+            res.append(dict(kernel=name, h=h, Cin=Cin, Cout=Cout, ms=t * 1e3, TFLOPs=fl / t / 1e12,
+                            cluster=os.environ.get("FM3D_CLUSTER", "default")))
+        del x, t_out
+
+
 def main():
     res = []
+    which = sys.argv[1:] or ["ops", "igemm", "synth", "upconv"]
+    if "synth" in which:
+        bench_synth(res)
+    if "upconv" in which:
+        bench_upconv(res)
+    if "ops" in which:
+        bench_ops(res)
+    if "igemm" in which:
+        bench_igemm(res)
+    for r in res:
+        print(json.dumps(r))
+
+
+def bench_ops(res):
     # ---- bias_act
     for shape, dt in [((32, 128, 256, 256), torch.float32), ((32, 128, 256, 256), torch.bfloat16),
                       ((32, 512, 64, 64), torch.float32)]:
@@ -58,6 +126,9 @@ def main():
         res.append(dict(kernel="upfirdn2d", shape=shape, cfg=cfg, dtype=str(dt), ms=t * 1e3,
                         GBs=(x.numel() + y.numel()) * x.element_size() / t / 1e9))
         del x, y
+
+
+def bench_igemm(res):
     # ---- igemm conv at the generator's shapes (B=32)
     B = 32
     for (H, Cin, Cout) in [(4, 512, 512), (8, 512, 512), (16, 512, 512), (32, 512, 512), (64, 512, 512),
@@ -74,8 +145,6 @@ def main():
         fl = 2.0 * B * H * H * Cin * Cout * 9
         res.append(dict(kernel="igemm3x3", H=H, Cin=Cin, Cout=Cout, ms=t * 1e3, TFLOPs=fl / t / 1e12))
         del x, out
-    for r in res:
-        print(json.dumps(r))
 
 
 if __name__ == "__main__":
