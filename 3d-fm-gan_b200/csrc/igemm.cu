@@ -25,6 +25,7 @@ namespace fm {
 
 constexpr int IG_BM = 128;     // pixels per tile (UMMA M)
 constexpr int IG_BK = 64;      // channels per k-step (128 B rows, SWIZZLE_128B)
+constexpr int IG_HP_MAXA = 8;      // halo-patch slots (barrier pairs reserved)
 constexpr int IG_TAB_ROWS = 512;  // staged table rows per tile (tile_b_eff * BLOCK_N <= 512)
 
 struct IgemmParams {
@@ -44,6 +45,10 @@ struct IgemmParams {
   int nbuf;                        // TMEM accumulator buffers (2, or 1 when 4 x BN x 2 columns do not fit)
   int prows;                       // output rows per tile in patch mode (R accumulators share each weight load)
   int patch_a_bytes, patch_stage_bytes, patch_stages;
+  // halo-patch mode (stride-1 tap sets): tile = 8 x 16 pixels of one image; ONE (16+dy span) x (8+dx span)
+  // input patch per channel chunk serves every tap as a shifted UMMA descriptor (group stride = patch row)
+  int hp, hp_pw, hp_ph, hp_bytes, hp_dx0, hp_dy0, hp_stages, hp_na, hp_dist;
+  int16_t hp_aoff[FM_MAX_TAPS];    // per-tap start offset of the A descriptor inside the patch (16-byte units)
   int Bg, nslabs;                  // images per group, weight slabs per group
   const float* border_tab;
   int out_cgroup;
@@ -77,7 +82,7 @@ template <int BN> struct IgemmCfg {
   static constexpr int RING_BYTES = 200 * 1024;
   static constexpr int TAB_BYTES = IG_TAB_ROWS * 32;
   static constexpr int RGB_BYTES = IG_BM * 16;
-  static constexpr int SMEM_BYTES = RING_BYTES + TAB_BYTES + RGB_BYTES + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = RING_BYTES + TAB_BYTES + RGB_BYTES + 512 /*barriers*/;
   static constexpr int TMEM_COLS = 512;   // 2 buffers x R rows x BN columns; one CTA per SM owns all of TMEM
 };
 
@@ -107,6 +112,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;     // [2]       MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]     epilogue -> MMA
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+  uint64_t* afull_bar = bars + 2 * Cfg::STAGES + 5;   // [IG_HP_MAXA] halo-patch slots: TMA -> MMA
+  uint64_t* aempty_bar = afull_bar + IG_HP_MAXA;      // [IG_HP_MAXA] MMA -> TMA
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,6 +125,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], p.cluster);       // every CTA of the cluster releases the slot (multicast commit)
+    }
+    for (int i = 0; i < IG_HP_MAXA; ++i) {
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&aempty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -145,6 +156,28 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t tx_bytes = static_cast<uint32_t>(p.rows) * (IG_BK * 2) + Cfg::B_BYTES;
+    // halo-patch mode: patch cursor (tile, chunk) runs hp_dist chunks ahead of the weight cursor, across tiles
+    int pst = cluster_id, pkc = 0, pslot = 0;
+    uint32_t pphase = 0;
+    const uint32_t patch_tx = static_cast<uint32_t>(p.hp_pw) * p.hp_ph * (IG_BK * 2);
+    auto hp_prefetch = [&]() {
+      if (pst >= p.num_super) return;
+      int m = pst / p.tiles_n;                     // ksplit == cluster == 1 in this mode
+      const int bx = m % p.tiles_x; m /= p.tiles_x;
+      const int by = m % p.tiles_y;
+      const int bb = m / p.tiles_y;
+      mbar_wait(&aempty_bar[pslot], pphase ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&afull_bar[pslot], patch_tx);
+        tma_load_4d(s_stage + pslot * p.hp_bytes, &tmA, &afull_bar[pslot], pkc * IG_BK,
+                    bx * 8 + p.hp_dx0, by * 16 + p.hp_dy0, bb);
+      }
+      __syncwarp();
+      if (++pkc == p.kchunks) { pkc = 0; pst += num_clusters; }
+      if (++pslot == p.hp_na) { pslot = 0; pphase ^= 1; }
+    };
+    if (p.hp)
+      for (int i = 0; i < p.hp_dist; ++i) hp_prefetch();
     for (int st = cluster_id; st < p.num_super; st += num_clusters) {
       const int nt = st % p.tiles_n;
       int m = st / p.tiles_n;
@@ -195,6 +228,24 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
+      if (p.hp) {
+        // chunk-major weight stages; the input patch of chunk c + hp_dist is requested when chunk c starts
+        // (its slot was last read hp_na - hp_dist >= 2 chunks ago, so the wait below never blocks the weights)
+        uint8_t* sb0 = s_stage + p.hp_na * p.hp_bytes;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          hp_prefetch();
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (lane == 0) {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_BYTES);
+              tma_load_2d(sb0 + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0);
+            }
+            __syncwarp();
+            if (++stage == p.hp_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        continue;
+      }
       for (int it = it0; it < it1; ++it) {
         const int tap = it / p.kchunks;
         const int kc = it - tap * p.kchunks;
@@ -212,10 +263,18 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
+    // The whole warp walks the loop in uniform control flow (so ptxas keeps stage indices and descriptors in
+    // uniform registers) and one elected lane issues; the four K=16 MMAs of a 64-channel stage go out of one
+    // asm block.  At N <= 128 a K=16 MMA lasts only 32-64 tensor-pipe cycles: every instruction between two
+    // UTCHMMAs is on the critical path of the kernel.
     constexpr uint32_t idesc = umma_idesc_bf16(IG_BM, BN);
+    constexpr uint32_t dhi = umma_desc_hi_sw128(1024);
     int stage = 0;
     uint32_t phase = 0;
     int titer = 0;
+    int aslot = 0;
+    uint32_t aslot_phase = 0;
+    const uint32_t ring = smem_u32(s_stage);
     for (int st = cluster_id; st < p.num_super; st += num_clusters, ++titer) {
       const int buf = titer % p.nbuf;
       const uint32_t aphase = (titer / p.nbuf) & 1;
@@ -225,21 +284,17 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (p.upmode) {
         const int nst = 4 * p.kchunks;
         const uint32_t tmem_t = tmem_base + buf * (4 * BN);
+        const uint32_t sbytes = Cfg::A_BYTES + 4 * Cfg::B_BYTES;
         for (int it = 0; it < nst; ++it) {
           const int sft = it & 3;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(s_stage + stage * (Cfg::A_BYTES + 4 * Cfg::B_BYTES));
-            const uint64_t adesc = umma_smem_desc_sw128(sa);
-            const int nb = c_up_nb[sft];
-            for (int j = 0; j < nb; ++j) {
-              const uint64_t bdesc = umma_smem_desc_sw128(sa + Cfg::A_BYTES + j * Cfg::B_BYTES);
-              const uint32_t dcol = tmem_t + c_up_acc[sft][j] * BN;
-#pragma unroll
-              for (int k = 0; k < IG_BK / 16; ++k)
-                umma_bf16(dcol, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-            }
+          const uint32_t sa = ring + stage * sbytes;
+          const int nb = c_up_nb[sft];
+          if (elect_one()) {
+            for (int j = 0; j < nb; ++j)
+              umma_bf16_x4(tmem_t + c_up_acc[sft][j] * BN, umma_desc_lo(sa), dhi, umma_desc_lo(sa + Cfg::A_BYTES + j * Cfg::B_BYTES),
+                           dhi, idesc, it > 0 ? 1u : 0u);
             if (p.cluster == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
             if (it == nst - 1) umma_commit(&tfull_bar[buf]);
           }
@@ -248,27 +303,23 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
-      const int ks = (st / p.tiles_n) % p.ksplit;
-      const int it0 = ks * p.kper, it1 = min(kiters, it0 + p.kper);
       if (p.patch) {
         const int nst = 3 * p.kchunks;
         const uint32_t tmem_t = tmem_base + buf * (p.prows * BN);
         for (int it = 0; it < nst; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(s_stage + stage * p.patch_stage_bytes);
+          const uint32_t sa = ring + stage * p.patch_stage_bytes;
+          const uint32_t blo = umma_desc_lo(sa + p.patch_a_bytes);
+          if (elect_one()) {
             for (int r = 0; r < p.prows; ++r) {
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                // the tap's A operand is staged row r shifted by kx pixels (= kx 128-byte rows); the
-                // 128B swizzle is a function of the smem address, so a shifted start address just works
-                const uint64_t adesc = umma_smem_desc_sw128(sa + r * (130 * 128) + kx * 128);
-                const uint64_t bdesc = umma_smem_desc_sw128(sa + p.patch_a_bytes + kx * Cfg::B_BYTES);
-#pragma unroll
-                for (int k = 0; k < IG_BK / 16; ++k)
-                  umma_bf16(tmem_t + r * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || kx > 0 || k > 0) ? 1u : 0u);
-              }
+              // the tap's A operand is staged row r shifted by kx pixels (= kx 128-byte rows); the
+              // 128B swizzle is a function of the smem address, so a shifted start address just works
+              const uint32_t alo = umma_desc_lo(sa + r * (130 * 128));
+              const uint32_t td = tmem_t + r * BN;
+              umma_bf16_x4(td, alo, dhi, blo, dhi, idesc, it > 0 ? 1u : 0u);
+              umma_bf16_x4(td, alo + (128 >> 4), dhi, blo + (Cfg::B_BYTES >> 4), dhi, idesc, 1u);
+              umma_bf16_x4(td, alo + (256 >> 4), dhi, blo + 2 * (Cfg::B_BYTES >> 4), dhi, idesc, 1u);
             }
             if (p.cluster == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
             if (it == nst - 1) umma_commit(&tfull_bar[buf]);
@@ -278,18 +329,42 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
+      if (p.hp) {
+        const uint32_t sb0 = ring + p.hp_na * p.hp_bytes;
+        const uint32_t ahi = umma_desc_hi_sw128(static_cast<uint32_t>(p.hp_pw) * 128u);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&afull_bar[aslot], aslot_phase);          // this chunk's input patch has landed
+          const uint32_t alo0 = umma_desc_lo(ring + aslot * p.hp_bytes);
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t alo = alo0 + static_cast<uint32_t>(p.hp_aoff[tap]);
+            const uint32_t blo = umma_desc_lo(sb0 + stage * Cfg::B_BYTES);
+            if (elect_one()) {
+              umma_bf16_x4(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tap > 0) ? 1u : 0u);
+              umma_commit(&empty_bar[stage]);
+              if (tap == p.ntaps - 1) {
+                umma_commit(&aempty_bar[aslot]);              // patch slot is free once these MMAs retire
+                if (kc == p.kchunks - 1) umma_commit(&tfull_bar[buf]);
+              }
+            }
+            __syncwarp();
+            if (++stage == p.hp_stages) { stage = 0; phase ^= 1; }
+          }
+          if (++aslot == p.hp_na) { aslot = 0; aslot_phase ^= 1; }
+        }
+        continue;
+      }
+      const int ks = (st / p.tiles_n) % p.ksplit;
+      const int it0 = ks * p.kper, it1 = min(kiters, it0 + p.kper);
       for (int it = it0; it < it1; ++it) {
         mbar_wait(&full_bar[stage], phase);        // TMA bytes have landed
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(s_stage + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = umma_smem_desc_sw128(sa);
-          const uint64_t bdesc = umma_smem_desc_sw128(sa + Cfg::A_BYTES);
-#pragma unroll
-          for (int k = 0; k < IG_BK / 16; ++k) {
-            // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
-          }
+        const uint32_t sa = ring + stage * Cfg::STAGE_BYTES;
+        const uint32_t alo = umma_desc_lo(sa), blo = umma_desc_lo(sa + Cfg::A_BYTES);
+        if (elect_one()) {
+          // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
+          umma_bf16_x4(tmem_d, alo, dhi, blo, dhi, idesc, it > it0 ? 1u : 0u);
           if (p.cluster == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
           if (it == it1 - 1) umma_commit(&tfull_bar[buf]);
         }
@@ -402,6 +477,25 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int g = 0; g < 2; ++g)
             resv[g] = (valid && p.residual && ol0 + 8 * g < p.out_cstride) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
         }
+        float bcor[16];
+        if (EPI & EPI_BTAB) {
+          // border pixels (one warp in four on a 128-px row tile) fetch their 16 corrections as 4 vector loads
+          if (warp_has_border) {
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (btab != nullptr && (p.Cout & 3) == 0 && o0 + 4 * g4 + 3 < p.Cout) {
+                bv = __ldg(reinterpret_cast<const float4*>(btab + o0 + 4 * g4));
+              } else if (btab != nullptr) {
+                if (o0 + 4 * g4 + 0 < p.Cout) bv.x = __ldg(btab + o0 + 4 * g4 + 0);
+                if (o0 + 4 * g4 + 1 < p.Cout) bv.y = __ldg(btab + o0 + 4 * g4 + 1);
+                if (o0 + 4 * g4 + 2 < p.Cout) bv.z = __ldg(btab + o0 + 4 * g4 + 2);
+                if (o0 + 4 * g4 + 3 < p.Cout) bv.w = __ldg(btab + o0 + 4 * g4 + 3);
+              }
+              bcor[4 * g4 + 0] = bv.x; bcor[4 * g4 + 1] = bv.y; bcor[4 * g4 + 2] = bv.z; bcor[4 * g4 + 3] = bv.w;
+            }
+          }
+        }
         tmem_ld_wait();
         // chunks past Cout only zero-fill the pad channels of an NHWC tensor (warp-uniform test)
         if (o0 >= p.Cout && (p.out_nchw_f32 || p.out_cgroup || ol0 >= p.out_cstride)) continue;
@@ -412,9 +506,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const float4 t0 = tr[2 * j];
           float x = fmaf(__uint_as_float(acc[j]), t0.x, t0.y + nz);
           if (EPI & EPI_BTAB) {
-            if (warp_has_border) {
-              if (btab != nullptr && o0 + j < p.Cout) x += __ldg(btab + o0 + j);
-            }
+            if (warp_has_border) x += bcor[j];
           }
           if (EPI & EPI_RES) {
             const uint32_t w = (&resv[0].x)[j >> 1];
@@ -759,6 +851,60 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       p.prows = 1;
     }
   }
+  // ---- halo-patch mode: any stride-1 tap set on images at least 16 rows tall.  Tile = 8 x 16 output pixels;
+  // the (16 + dy span) x (8 + dx span) input patch of a channel chunk is loaded ONCE and every tap reads it
+  // through a shifted descriptor, so the activation traffic L2 -> SM drops from ntaps x to ~1.4x per chunk
+  // (the chip-wide L2 -> SM rate, not the tensor pipe, bounds the per-tap scheme for N <= 128).
+  {
+    static const int env_hp = []() { const char* e = getenv("FM3D_HPATCH"); return e ? atoi(e) : 3; }();
+    int dx0 = 127, dx1 = -127, dy0 = 127, dy1 = -127;
+    for (int i = 0; i < d->ntaps; ++i) {
+      dx0 = d->tap_dx[i] < dx0 ? d->tap_dx[i] : dx0; dx1 = d->tap_dx[i] > dx1 ? d->tap_dx[i] : dx1;
+      dy0 = d->tap_dy[i] < dy0 ? d->tap_dy[i] : dy0; dy1 = d->tap_dy[i] > dy1 ? d->tap_dy[i] : dy1;
+    }
+    const bool plain_x = d->x_pixstride == 0 && d->x_rowstride == 0 && d->x_imgstride == 0;
+    // 0 off | 1 wherever row-patch mode does not apply | 2 always | 3 (default) only N = 256 tiles: with one
+    // accumulator per CTA the weight tile alone (N * 128 B per 2N tensor-pipe cycles) saturates the ~64 B/clk
+    // an SM can take from L2 for N <= 128, so those layers need several accumulators per weight tile first
+    const bool want = env_hp == 2 || (env_hp == 1 && !p.patch) || (env_hp == 3 && !p.patch && bn == 256);
+    if (want && plain_x && sx == 1 && sy == 1 && G == 1 && p.ksplit == 1 && !d->upmode && d->ntaps >= 2 && d->OH >= 12 &&
+        d->OW >= 8 && dx1 - dx0 <= 8 && dy1 - dy0 <= 8 && (!d->tab_bstride || bn <= IG_TAB_ROWS)) {
+      p.hp = 1;
+      p.patch = 0; p.prows = 1;
+      p.tw = 8; p.th = 16; p.tb = 1; p.rows = 128;
+      p.tiles_x = (d->OW + 7) / 8;
+      p.tiles_y = (d->OH + 15) / 16;
+      p.tiles_b = d->B;
+      p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+      p.hp_pw = 8 + dx1 - dx0;
+      p.hp_ph = 16 + dy1 - dy0;
+      p.hp_dx0 = dx0; p.hp_dy0 = dy0;
+      p.hp_bytes = (p.hp_pw * p.hp_ph * 128 + 1023) & ~1023;
+      // The patch of chunk c + D is requested when the weights of chunk c start; its slot was last read by
+      // chunk c + D - NA.  With NA = D + E the producer has by then seen weight stage c*T - S retire, which is at
+      // or after the last tap of chunk c - E when S <= (E - 1) * T + 1: the request never blocks the weight ring.
+      const int T = d->ntaps;
+      const int bbytes = bn * 128;
+      const int st_max = bn == 256 ? 4 : (bn == 128 ? 6 : 8);
+      int D = T >= 5 ? 2 : (T >= 3 ? 3 : 4);
+      const int E = T >= 3 ? 2 : 3;
+      int st = 0;
+      for (; D >= 1; --D) {
+        st = (200 * 1024 - (D + E) * p.hp_bytes) / bbytes;
+        if (st > st_max) st = st_max;
+        if (st > (E - 1) * T + 1) st = (E - 1) * T + 1;
+        if (st >= 3 || (D == 1 && st >= 2)) break;
+      }
+      if (D >= 1 && D + E <= IG_HP_MAXA) {
+        p.hp_dist = D; p.hp_na = D + E; p.hp_stages = st;
+        for (int i = 0; i < d->ntaps; ++i)
+          p.hp_aoff[i] = static_cast<int16_t>(((d->tap_dy[i] - dy0) * p.hp_pw + (d->tap_dx[i] - dx0)) * 8);
+      } else {
+        set_error("fm_conv_igemm: halo-patch ring does not fit (patch %d bytes, block_n %d)", p.hp_bytes, bn);
+        return FM_ERR_INVALID;
+      }
+    }
+  }
   // ---- clusters: CTAs of a cluster work on adjacent m-tiles of the same n-tile and share each weight
   // tile through one multicast TMA load (weights are the dominant L2->SM stream for N <= 128)
   {
@@ -766,7 +912,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
     int cs = env_cluster;
     if (cs != 1 && cs != 2 && cs != 4) cs = 1;
-    while (cs > 1 && (p.m_tiles % cs != 0 || G > 1)) cs >>= 1;   // no padded m-tiles, one weight slab per cluster
+    while (cs > 1 && (p.m_tiles % cs != 0 || G > 1 || p.hp)) cs >>= 1;   // no padded m-tiles, one weight slab per cluster
     p.cluster = cs;
     p.num_super = p.tiles_n * p.ksplit * ((p.m_tiles + cs - 1) / cs);
   }
@@ -778,8 +924,9 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(pixs) * 2, static_cast<cuuint64_t>(rows_) * 2,
                                    static_cast<cuuint64_t>(imgs) * 2};
     // with an element stride s TMA loads ceil(box/s) elements: box = n*s loads n
-    const cuuint32_t box[4] = {IG_BK, static_cast<cuuint32_t>(p.patch ? 130 : tw * sx),
-                               static_cast<cuuint32_t>(p.patch ? p.prows : th * sy), static_cast<cuuint32_t>(tb)};
+    const cuuint32_t box[4] = {IG_BK, static_cast<cuuint32_t>(p.hp ? p.hp_pw : (p.patch ? 130 : tw * sx)),
+                               static_cast<cuuint32_t>(p.hp ? p.hp_ph : (p.patch ? p.prows : th * sy)),
+                               static_cast<cuuint32_t>(p.hp ? 1 : tb)};
     const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(sx), static_cast<cuuint32_t>(sy), 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

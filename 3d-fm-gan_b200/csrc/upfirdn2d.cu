@@ -170,6 +170,73 @@ __device__ __forceinline__ UfsItem ufs_item(int64_t i, const UpfirdnParams& p, i
   return it;
 }
 
+// Row walk of one thread: COLS adjacent output columns, output rows [ty0, ty1).  Relative input row j
+// (iy = ty0 - pad_y0 + j) feeds output row ty0 + j - ky with tap row ky; its partial sum sits in slot
+// (j - ky) & 3 (statically renamed: 4 rows per unrolled step) and tap row 3 closes output row ty0 + j - 3.
+template <typename T, int COLS, bool SEP, bool EDGE>
+__device__ __forceinline__ void ufs_rows(const T* __restrict__ sp, T* __restrict__ op, const float (&w)[4][4],
+                                         const float (&kh1)[4], const float (&kv1)[4], const UpfirdnParams& p, int r_lo, int r_hi,
+                                         int ix0, int ox, int ty0, int ty1) {
+  bool cok[COLS + 3];
+#pragma unroll
+  for (int q = 0; q < COLS + 3; ++q) cok[q] = !EDGE || (ix0 + q >= 0 && ix0 + q < p.in_w);
+  float acc[4][COLS];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) acc[j][c] = 0.f;
+  const int jn = (ty1 - ty0) + 3;
+  const T* rp = sp + static_cast<int64_t>(ty0 - p.pad_y0) * p.in_w + ix0;
+  T* orow = op + static_cast<int64_t>(ty0 - 3) * p.out_w;
+  int iy = ty0 - p.pad_y0;
+  for (int jb = 0; jb < jn; jb += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = jb + u;
+      if (j >= jn) break;
+      if (iy >= r_lo && iy <= r_hi) {           // rows outside the image contribute nothing
+        float v[COLS + 3];
+#pragma unroll
+        for (int q = 0; q < COLS + 3; ++q) v[q] = (!EDGE || cok[q]) ? to_f32<T>(rp[q]) : 0.f;
+        if (SEP) {
+#pragma unroll
+          for (int c = 0; c < COLS; ++c) {
+            const float h = fmaf(v[c + 3], kh1[3], fmaf(v[c + 2], kh1[2], fmaf(v[c + 1], kh1[1], v[c] * kh1[0])));
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) acc[(u - ky) & 3][c] = fmaf(h, kv1[ky], acc[(u - ky) & 3][c]);
+          }
+        } else {
+#pragma unroll
+          for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) {
+              float a = acc[(u - ky) & 3][c];
+#pragma unroll
+              for (int kx = 0; kx < 4; ++kx) a = fmaf(v[c + kx], w[ky][kx], a);
+              acc[(u - ky) & 3][c] = a;
+            }
+        }
+      }
+      float (&done)[COLS] = acc[(u + 1) & 3];
+      if (j >= 3) {
+        if (COLS == 2 && sizeof(T) == 2 && (!EDGE || ox + 1 < p.out_w) && (reinterpret_cast<uintptr_t>(orow) & 3) == 0) {
+          T q2[2] = {from_f32<T>(done[0]), from_f32<T>(done[COLS - 1])};
+          *reinterpret_cast<uint32_t*>(orow) = *reinterpret_cast<uint32_t*>(q2);
+        } else {
+#pragma unroll
+          for (int c = 0; c < COLS; ++c)
+            if (!EDGE || ox + c < p.out_w) orow[c] = from_f32<T>(done[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) done[c] = 0.f;
+      rp += p.in_w;
+      orow += p.out_w;
+      ++iy;
+    }
+  }
+}
+
 template <typename T, int COLS>
 __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __restrict__ out, const T* __restrict__ x,
                                                                        const float* __restrict__ kernel, UpfirdnParams p,
@@ -193,6 +260,21 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
   float w[4][4];
 #pragma unroll
   for (int i = 0; i < 16; ++i) w[i >> 2][i & 3] = s_k[i];
+  // rank-1 test of the (flipped, zero-padded) taps: w == rowsum (x) colsum / total  ->  separable passes
+  float kv1[4], kh1[4], tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    kv1[i] = w[i][0] + w[i][1] + w[i][2] + w[i][3];
+    kh1[i] = w[0][i] + w[1][i] + w[2][i] + w[3][i];
+    tot += kv1[i];
+  }
+  bool sep = fabsf(tot) > 1e-20f;
+  const float inv_tot = sep ? 1.f / tot : 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) kh1[i] *= inv_tot;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    sep = sep && fabsf(kv1[i >> 2] * kh1[i & 3] - w[i >> 2][i & 3]) <= 1e-6f * fabsf(tot);
 
   const int64_t plane_elems = static_cast<int64_t>(p.in_h) * p.in_w;
   const uintptr_t xbase = reinterpret_cast<uintptr_t>(x);
@@ -240,55 +322,16 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
       if (ty0 >= ty1) continue;
       const T* sp = sbuf + static_cast<int64_t>(pl) * plane_elems - static_cast<int64_t>(it.r_lo) * p.in_w;   // row iy at sp + iy*in_w
       const int ix0 = ox - p.pad_x0;
-      bool cok[COLS + 3];
-#pragma unroll
-      for (int q = 0; q < COLS + 3; ++q) cok[q] = ix0 + q >= 0 && ix0 + q < p.in_w;
       T* op = out + ((it.plane0 + pl) * p.out_h) * static_cast<int64_t>(p.out_w) + ox;
-
-      float acc[4][COLS];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int c = 0; c < COLS; ++c) acc[j][c] = 0.f;
-      // relative input row j <-> iy = ty0 - pad_y0 + j feeds output row ty0 + j - ky; slot (j - ky) & 3
-      const int jn = (ty1 - ty0) + 3;
-      for (int jb = 0; jb < jn; jb += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = jb + u;
-          if (j >= jn) break;
-          const int iy = ty0 - p.pad_y0 + j;
-          float v[COLS + 3];
-          const bool rok = iy >= it.r_lo && iy <= it.r_hi;
-          const T* rp = sp + static_cast<int64_t>(rok ? iy : it.r_lo) * p.in_w + ix0;
-#pragma unroll
-          for (int q = 0; q < COLS + 3; ++q) v[q] = (rok && cok[q]) ? to_f32<T>(rp[q]) : 0.f;
-#pragma unroll
-          for (int ky = 0; ky < 4; ++ky)
-#pragma unroll
-            for (int c = 0; c < COLS; ++c) {
-              float a = acc[(u - ky) & 3][c];
-#pragma unroll
-              for (int kx = 0; kx < 4; ++kx) a = fmaf(v[c + kx], w[ky][kx], a);
-              acc[(u - ky) & 3][c] = a;
-            }
-          // tap row 3 closes output row ty0 + j - 3 (slot (u + 1) & 3)
-          float (&done)[COLS] = acc[(u + 1) & 3];
-          const int oy = ty0 + j - 3;
-          if (j >= 3) {
-            T* orow = op + static_cast<int64_t>(oy) * p.out_w;
-            if (COLS == 2 && sizeof(T) == 2 && ox + 1 < p.out_w && (reinterpret_cast<uintptr_t>(orow) & 3) == 0) {
-              T q2[2] = {from_f32<T>(done[0]), from_f32<T>(done[COLS - 1])};
-              *reinterpret_cast<uint32_t*>(orow) = *reinterpret_cast<uint32_t*>(q2);
-            } else {
-#pragma unroll
-              for (int c = 0; c < COLS; ++c)
-                if (ox + c < p.out_w) orow[c] = from_f32<T>(done[c]);
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < COLS; ++c) done[c] = 0.f;
-        }
+      const bool interior = ix0 >= 0 && ix0 + COLS + 3 <= p.in_w && ox + COLS <= p.out_w;
+      // four instantiations of the row walk: rank-1 taps take 8 instead of 16 FMAs per output, interior
+      // columns skip every bounds test (both are warp-uniform almost everywhere)
+      if (sep) {
+        if (interior) ufs_rows<T, COLS, true, false>(sp, op, w, kh1, kv1, p, it.r_lo, it.r_hi, ix0, ox, ty0, ty1);
+        else ufs_rows<T, COLS, true, true>(sp, op, w, kh1, kv1, p, it.r_lo, it.r_hi, ix0, ox, ty0, ty1);
+      } else {
+        if (interior) ufs_rows<T, COLS, false, false>(sp, op, w, kh1, kv1, p, it.r_lo, it.r_hi, ix0, ox, ty0, ty1);
+        else ufs_rows<T, COLS, false, true>(sp, op, w, kh1, kv1, p, it.r_lo, it.r_hi, ix0, ox, ty0, ty1);
       }
     }
     __syncthreads();      // everyone is done with this slot before it is refilled (two items ahead)

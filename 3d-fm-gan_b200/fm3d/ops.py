@@ -236,8 +236,9 @@ def _is_rank1(k):
     return bool(torch.allclose(torch.outer(kk.sum(1), kk.sum(0)) / tot, kk, rtol=1e-6, atol=1e-9))
 
 
-# keyed on the tensor OBJECT (weakly): a data_ptr key would go stale when the allocator re-uses the address
-_RANK1_CACHE = weakref.WeakKeyDictionary()
+# keyed on the tensor OBJECT (id + weak reference): a data_ptr key alone would go stale when the allocator
+# re-uses the address
+_RANK1_CACHE = {}
 
 
 def blur_act_nhwc(t, kernel4x4, tab, noise, noise_per_sample, noise_w, C_, out=None):
@@ -246,10 +247,14 @@ def blur_act_nhwc(t, kernel4x4, tab, noise, noise_per_sample, noise_w, C_, out=N
     OH, OW = IH - 1, IW - 1
     if out is None:
         out = torch.empty(B, OH, OW, cs, device=t.device, dtype=torch.bfloat16)
-    ent = _RANK1_CACHE.get(kernel4x4)
-    if ent is None or ent[0] != (kernel4x4.data_ptr(), kernel4x4._version):   # one host sync per kernel buffer (cached)
-        ent = _RANK1_CACHE[kernel4x4] = ((kernel4x4.data_ptr(), kernel4x4._version), _is_rank1(kernel4x4))
-    sep = ent[1]
+    kid = id(kernel4x4)
+    ent = _RANK1_CACHE.get(kid)
+    if ent is None or ent[0]() is not kernel4x4 or ent[1] != (kernel4x4.data_ptr(), kernel4x4._version):
+        if len(_RANK1_CACHE) > 256:
+            _RANK1_CACHE.clear()
+        # one host sync per kernel buffer (cached)
+        ent = _RANK1_CACHE[kid] = (weakref.ref(kernel4x4), (kernel4x4.data_ptr(), kernel4x4._version), _is_rank1(kernel4x4))
+    sep = ent[2]
     with torch.cuda.device(t.device):
         st = _lib.lib().fm_blur_act_nhwc(_ptr(out), _ptr(t), _ptr(kernel4x4), _ptr(tab), _ptr(noise),
                                          1 if noise_per_sample else 0, _ptr(noise_w), B, OH, OW, C_, cs,
