@@ -136,12 +136,14 @@ __global__ void __launch_bounds__(256) upfirdn2d_tile_kernel(T* __restrict__ out
 // range) into a double-buffered shared-memory ring while the other threads filter the previous item.
 // This is the only way to get wide loads here: rows are W*sizeof(T) bytes with W odd (2h+1), so
 // neither vector loads nor tensor-map TMA (16-byte strides) apply.
-// Compute: a thread owns COLS adjacent output columns and walks down the rows with a rolling window
-// of 4 partial sums (statically renamed, 4 rows per unrolled step): COLS+3 conflict-free LDS and
-// 16*COLS FMAs per row, one coalesced store per row.  fp32 accumulation for every dtype.
+// Compute: a thread owns one output column and walks down the rows with a rolling window of 4 partial
+// sums (statically renamed, 4 rows per unrolled step): 4 conflict-free LDS, 8 FMAs (rank-1 taps) or 16,
+// one coalesced store per row.  In strip mode the rows above / below the image are three zeroed rows in
+// front of / behind the staged range, so the steady-state loop has no bounds test at all (the kernel is
+// instruction-issue bound before it is HBM bound).  fp32 accumulation for every dtype.
 // ------------------------------------------------------------------------------------
-constexpr int UFS_THREADS = 512;
-constexpr int UFS_BUF_BYTES = 48 * 1024;        // per ring slot (2 slots): 2 CTAs of 512 threads per SM
+constexpr int UFS_THREADS = 256;
+constexpr int UFS_BUF_BYTES = 36 * 1024;        // per ring slot (2 slots): 3 CTAs of 256 threads per SM
 constexpr int UFS_CHUNK = 16 * 1024;            // bytes per bulk copy
 
 struct UfsItem {
@@ -173,7 +175,7 @@ __device__ __forceinline__ UfsItem ufs_item(int64_t i, const UpfirdnParams& p, i
 // Row walk of one thread: COLS adjacent output columns, output rows [ty0, ty1).  Relative input row j
 // (iy = ty0 - pad_y0 + j) feeds output row ty0 + j - ky with tap row ky; its partial sum sits in slot
 // (j - ky) & 3 (statically renamed: 4 rows per unrolled step) and tap row 3 closes output row ty0 + j - 3.
-template <typename T, int COLS, bool SEP, bool EDGE>
+template <typename T, int COLS, bool SEP, bool EDGE, bool ROWCHK>
 __device__ __forceinline__ void ufs_rows(const T* __restrict__ sp, T* __restrict__ op, const float (&w)[4][4],
                                          const float (&kh1)[4], const float (&kv1)[4], const UpfirdnParams& p, int r_lo, int r_hi,
                                          int ix0, int ox, int ty0, int ty1) {
@@ -194,7 +196,7 @@ __device__ __forceinline__ void ufs_rows(const T* __restrict__ sp, T* __restrict
     for (int u = 0; u < 4; ++u) {
       const int j = jb + u;
       if (j >= jn) break;
-      if (iy >= r_lo && iy <= r_hi) {           // rows outside the image contribute nothing
+      if (!ROWCHK || (iy >= r_lo && iy <= r_hi)) {   // rows outside the image contribute nothing (or read zeroed rows)
         float v[COLS + 3];
 #pragma unroll
         for (int q = 0; q < COLS + 3; ++q) v[q] = (!EDGE || cok[q]) ? to_f32<T>(rp[q]) : 0.f;
@@ -241,7 +243,9 @@ template <typename T, int COLS>
 __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __restrict__ out, const T* __restrict__ x,
                                                                        const float* __restrict__ kernel, UpfirdnParams p,
                                                                        int64_t planes, int R, int P, int strips,
-                                                                       int64_t n_items) {
+                                                                       int64_t n_items, int head) {
+  // head > 0: strip mode with zero rows -- the staged range starts `head` bytes into the slot, preceded
+  // (top of the image) and followed (bottom) by three zeroed rows
   extern __shared__ __align__(128) uint8_t ufs_smem[];
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ float s_k[16];
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
                                                          static_cast<int64_t>(it.r_hi + 1) * p.in_w) * sizeof(T));
     const uintptr_t lo_a = lo & ~static_cast<uintptr_t>(15);
     const uint32_t bytes = static_cast<uint32_t>(((hi + 15) & ~static_cast<uintptr_t>(15)) - lo_a);
-    uint8_t* dst = ufs_smem + slot * UFS_BUF_BYTES;
+    uint8_t* dst = ufs_smem + slot * UFS_BUF_BYTES + head;
     fence_proxy_async();                       // earlier generic reads of this slot precede the async writes
     mbar_arrive_expect_tx(&s_bar[slot], bytes);
     for (uint32_t off = 0; off < bytes; off += UFS_CHUNK)
@@ -302,10 +306,24 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
     const int slot = k & 1;
     const UfsItem it = ufs_item(item, p, planes, R, P, strips);
     if (tid == 0 && item + gridDim.x < n_items) issue(ufs_item(item + gridDim.x, p, planes, R, P, strips), slot ^ 1);
-    mbar_wait(&s_bar[slot], (k >> 1) & 1);
+    if (tid < 32) mbar_wait(&s_bar[slot], (k >> 1) & 1);      // one warp polls, the rest sleep in the barrier
+    __syncthreads();
 
     const uintptr_t lo = xbase + static_cast<uintptr_t>((it.plane0 * plane_elems + static_cast<int64_t>(it.r_lo) * p.in_w) * sizeof(T));
-    const T* sbuf = reinterpret_cast<const T*>(ufs_smem + slot * UFS_BUF_BYTES + (lo & 15));
+    const T* sbuf = reinterpret_cast<const T*>(ufs_smem + slot * UFS_BUF_BYTES + head + (lo & 15));
+    if (head > 0) {
+      const bool top = it.oy0 - p.pad_y0 < it.r_lo, bottom = it.oy1 - 1 - p.pad_y0 + 3 > it.r_hi;
+      if (top || bottom) {                                    // uniform: only the first / last strip of a plane
+        T* zb = const_cast<T*>(sbuf);
+        const int n3 = 3 * p.in_w;
+        if (top) for (int i = tid; i < n3; i += UFS_THREADS) zb[i - n3] = from_f32<T>(0.f);
+        if (bottom) {
+          T* zt = zb + static_cast<int64_t>(it.r_hi - it.r_lo + 1) * p.in_w;
+          for (int i = tid; i < n3; i += UFS_THREADS) zt[i] = from_f32<T>(0.f);
+        }
+        __syncthreads();
+      }
+    }
     // thread tasks: (plane of the item, column group, row split)
     const int nrows = it.oy1 - it.oy0;
     const int ncg = it.nplanes * colgroups;
@@ -324,15 +342,18 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
       const int ix0 = ox - p.pad_x0;
       T* op = out + ((it.plane0 + pl) * p.out_h) * static_cast<int64_t>(p.out_w) + ox;
       const bool interior = ix0 >= 0 && ix0 + COLS + 3 <= p.in_w && ox + COLS <= p.out_w;
-      // four instantiations of the row walk: rank-1 taps take 8 instead of 16 FMAs per output, interior
-      // columns skip every bounds test (both are warp-uniform almost everywhere)
-      if (sep) {
-        if (interior) ufs_rows<T, COLS, true, false>(sp, op, w, kh1, kv1, p, it.r_lo, it.r_hi, ix0, ox, ty0, ty1);
-        else ufs_rows<T, COLS, true, true>(sp, op, w, kh1, kv1, p, it.r_lo, it.r_hi, ix0, ox, ty0, ty1);
+      // instantiations of the row walk: rank-1 taps take 8 instead of 16 FMAs per output, interior columns
+      // skip every column test, strip mode skips every row test (all warp-uniform almost everywhere)
+#define UFS_CALL(SEP_, EDGE_, RC_) \
+  ufs_rows<T, COLS, SEP_, EDGE_, RC_>(sp, op, w, kh1, kv1, p, it.r_lo, it.r_hi, ix0, ox, ty0, ty1)
+      if (head > 0) {
+        if (sep) { if (interior) UFS_CALL(true, false, false); else UFS_CALL(true, true, false); }
+        else     { if (interior) UFS_CALL(false, false, false); else UFS_CALL(false, true, false); }
       } else {
-        if (interior) ufs_rows<T, COLS, false, false>(sp, op, w, kh1, kv1, p, it.r_lo, it.r_hi, ix0, ox, ty0, ty1);
-        else ufs_rows<T, COLS, false, true>(sp, op, w, kh1, kv1, p, it.r_lo, it.r_hi, ix0, ox, ty0, ty1);
+        if (sep) { if (interior) UFS_CALL(true, false, true); else UFS_CALL(true, true, true); }
+        else     { if (interior) UFS_CALL(false, false, true); else UFS_CALL(false, true, true); }
       }
+#undef UFS_CALL
     }
     __syncthreads();      // everyone is done with this slot before it is refilled (two items ahead)
   }
@@ -343,25 +364,30 @@ static bool stream_eligible(const UpfirdnParams& p, int pad_x1, int pad_y1) {
   if (p.up_x != 1 || p.up_y != 1 || p.down_x != 1 || p.down_y != 1) return false;
   if (p.kh > 4 || p.kw > 4) return false;
   if (p.pad_x0 < 0 || p.pad_y0 < 0 || pad_x1 < 0 || pad_y1 < 0 || p.pad_x0 > 16 || p.pad_y0 > 16) return false;
-  // at least 4 output rows (+3 halo rows) of a full-width strip must fit one ring slot
-  return static_cast<int64_t>(7) * p.in_w * static_cast<int64_t>(sizeof(T)) + 32 <= UFS_BUF_BYTES;
+  // at least 4 output rows (+3 halo rows, +6 zero rows, alignment slack) of a full-width strip must fit one ring slot
+  return static_cast<int64_t>(14) * p.in_w * static_cast<int64_t>(sizeof(T)) + 64 <= UFS_BUF_BYTES;
 }
 
 template <typename T>
-static int launch_stream(void* out, const void* x, const float* kernel, const UpfirdnParams& p, int64_t planes, cudaStream_t st) {
-  constexpr int COLS = sizeof(T) == 4 ? 1 : 2;
+static int launch_stream(void* out, const void* x, const float* kernel, const UpfirdnParams& p, int pad_y1, int64_t planes,
+                         cudaStream_t st) {
+  constexpr int COLS = 1;
   const int64_t row_bytes = static_cast<int64_t>(p.in_w) * sizeof(T);
   const int64_t plane_bytes = row_bytes * p.in_h;
-  int R, P, strips;
+  int R, P, strips, head = 0;
   if (plane_bytes + 32 <= UFS_BUF_BYTES) {
     strips = 1; R = p.out_h;
     P = static_cast<int>((UFS_BUF_BYTES - 32) / plane_bytes);
     // keep enough items to fill the machine
-    const int64_t want_items = static_cast<int64_t>(sm_count()) * 4;
+    const int64_t want_items = static_cast<int64_t>(sm_count()) * 6;
     while (P > 1 && (planes + P - 1) / P < want_items) P >>= 1;
   } else {
     P = 1;
-    R = static_cast<int>((UFS_BUF_BYTES - 32) / row_bytes) - 3;
+    // zero-row layout when the vertical padding fits three rows: [3 zero rows | staged rows | 3 zero rows]
+    // (the walk always spans 4 tap rows: the last output row reads pad_y1 - kh + 4 rows past the image)
+    const bool zrows = p.pad_y0 <= 3 && pad_y1 < p.kh;
+    head = zrows ? static_cast<int>((3 * row_bytes + 15) / 16 * 16 + 16) : 0;
+    R = static_cast<int>((UFS_BUF_BYTES - head - 32) / row_bytes) - 3 - (zrows ? 3 : 0);
     if (R > 40) R = 40;
     strips = (p.out_h + R - 1) / R;
     R = (p.out_h + strips - 1) / strips;          // balance the strips
@@ -373,10 +399,10 @@ static int launch_stream(void* out, const void* x, const float* kernel, const Up
     FM_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * UFS_BUF_BYTES));
     attr_set = true;
   }
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 2;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 3;
   const unsigned grid = static_cast<unsigned>(n_items < cap ? n_items : cap);
   fn<<<grid, UFS_THREADS, 2 * UFS_BUF_BYTES, st>>>(static_cast<T*>(out), static_cast<const T*>(x), kernel, p, planes, R, P, strips,
-                                                   n_items);
+                                                   n_items, head);
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;
@@ -434,7 +460,7 @@ static int upfirdn2d_dispatch(void* out, const void* x, const float* kernel, int
   const int64_t total = planes * p.out_h * p.out_w;
   if (total == 0) return FM_OK;
   static const int env_stream = []() { const char* e = getenv("FM3D_UPFIRDN_STREAM"); return e ? atoi(e) : 1; }();
-  if (env_stream && stream_eligible<T>(p, pad_x1, pad_y1)) return launch_stream<T>(out, x, kernel, p, planes, st);
+  if (env_stream && stream_eligible<T>(p, pad_x1, pad_y1)) return launch_stream<T>(out, x, kernel, p, pad_y1, planes, st);
   const bool sq = p.up_x == p.up_y && p.down_x == p.down_y;
   const int kmax = p.kh > p.kw ? p.kh : p.kw;
   // small images: shorter tiles keep more CTAs busy

@@ -136,7 +136,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -261,11 +261,20 @@ def main():
         e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
 
         # ---------------- roofline of the dominant kernel (per-launch CUDA events)
+        # The profiled steps run the three encoders back to back on ONE stream (FM3D_STREAMS=0) and without
+        # graph replay: with concurrent streams an event pair would also time the wait for SMs another
+        # stream's kernel holds (every igemm CTA owns a whole SM), not the kernel itself.
         prof = []
         ops.PROFILE = prof
+        prev_streams = os.environ.get("FM3D_STREAMS")
+        os.environ["FM3D_STREAMS"] = "0"
         for i in range(2):
             step(*dev_in[i % n_sets])
         torch.cuda.synchronize()
+        if prev_streams is None:
+            del os.environ["FM3D_STREAMS"]
+        else:
+            os.environ["FM3D_STREAMS"] = prev_streams
         ops.PROFILE = None
     flops = sum(f for (_, _, f) in prof)
     ksec = sum(a.elapsed_time(b) for (a, b, _) in prof) * 1e-3
@@ -275,15 +284,20 @@ def main():
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    # dram__bytes_read + dram__bytes_write of the igemm launches of one step / launches, from the committed ncu pass
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "igemm_traffic.json")))
+        traffic, traffic_src = tj["bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     achieved = flops / ksec / 1e12 if ksec > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "igemm_conv_kernel (tcgen05 implicit GEMM, all launches of one step)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "launches_per_step": len(prof) // 2, "kernel_ms_per_step": ksec * 1e3 / 2,
                 "algorithmic_gflop_per_step": flops / 2 / 1e9,
-                # dram__bytes_read+write summed over the igemm launches of one step / launches, from the ncu pass
-                # committed as profiles/r01_step_metrics_v2.csv (5.85 GB read + 2.30 GB write over 103 launches)
-                "traffic": 8.146e9 / 103, "traffic_unit": "bytes per launch (ncu, profiles/r01_step_metrics_v2.csv)"}
+                "traffic": traffic, "traffic_unit": traffic_src}
 
     if rank != 0:
         if world > 1:
