@@ -51,7 +51,7 @@ struct IgemmParams {
   int16_t hp_aoff[FM_MAX_TAPS];    // per-tap start offset of the A descriptor inside the patch (16-byte units)
   int Bg, nslabs;                  // images per group, weight slabs per group
   const float* border_tab;
-  int out_cgroup;
+  int out_cgroup, cg_shrink;
   long long out_gstride;
   void* out;
   int out_H, out_W, out_cstride, out_y0, out_x0, out_ys, out_xs, out_nchw_f32;
@@ -71,7 +71,7 @@ constexpr int IG_EPI_WARPS = 8;                       // two warps per TMEM lane
 constexpr int IG_THREADS2 = 64 + 32 * IG_EPI_WARPS;   // producer + MMA + epilogue warps
 
 // epilogue feature flags (template: dead paths cost nothing)
-constexpr int EPI_RGB = 1, EPI_RES = 2, EPI_BTAB = 4, EPI_SPLIT = 8;
+constexpr int EPI_RGB = 1, EPI_RES = 2, EPI_BTAB = 4, EPI_SPLIT = 8, EPI_IDENT = 16;   // IDENT: out = acc (tab == NULL)
 
 template <int BN> struct IgemmCfg {
   static constexpr int A_BYTES = IG_BM * IG_BK * 2;        // 16 KB
@@ -106,6 +106,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* s_stage = smem;
   float4* s_tab = reinterpret_cast<float4*>(smem + Cfg::RING_BYTES);
   float4* s_rgb = reinterpret_cast<float4*>(smem + Cfg::RING_BYTES + Cfg::TAB_BYTES);
+  // border-correction table [9][BN] of the current n-tile: upper half of the table region + the (unused) RGB
+  // scratch = 10 KB, available when the epilogue tables are shared by the batch and no ToRGB is fused
+  float* s_btab = reinterpret_cast<float*>(smem + Cfg::RING_BYTES + Cfg::TAB_BYTES / 2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES + Cfg::TAB_BYTES + Cfg::RGB_BYTES);
   uint64_t* full_bar = bars;                        // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + Cfg::STAGES;         // [STAGES]  MMA -> TMA
@@ -384,6 +387,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ly = (row / p.tw) % p.th;
     const int lb = row / (p.tw * p.th);
     const float4* trow = s_tab + static_cast<size_t>(p.tab_bstride ? lb : 0) * BN * 2;
+    const bool btab_smem = (EPI & EPI_BTAB) && !(EPI & EPI_RGB) && p.border_tab != nullptr && !p.tab_bstride &&
+                           9 * BN * 4 <= Cfg::TAB_BYTES / 2 + Cfg::RGB_BYTES;
     int tab_key = -1;
     int titer = 0;
     for (int st = cluster_id; st < p.num_super; st += num_clusters, ++titer) {
@@ -402,7 +407,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       // ---- epilogue tables: re-staged only when (sample block | group, n-tile) changes
       const int key = (p.tab_bstride ? bb : grp) * p.tiles_n + nt;
-      if (!(EPI & EPI_SPLIT) && key != tab_key) {
+      if (!(EPI & (EPI_SPLIT | EPI_IDENT)) && key != tab_key) {
         tab_key = key;
         asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done with the old tables
         for (int i = etid; i < tbe * BN; i += 256) {
@@ -417,6 +422,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           s_tab[2 * i] = t0;
           s_tab[2 * i + 1] = t1;
+        }
+        if (btab_smem) {
+          for (int i = etid; i < 9 * BN; i += 256) {
+            const int cls = i / BN, o = n0 + (i - cls * BN);
+            s_btab[i] = o < p.Cout ? __ldg(p.border_tab + static_cast<size_t>(cls) * p.Cout + o) : 0.f;
+          }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
@@ -439,8 +450,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
       const float* btab = nullptr;      // folded-input-BN border correction (per-thread: thread = pixel)
       bool warp_has_border = false;
+      int cls = 0;
       if (EPI & EPI_BTAB) {
-        const int cls = (oy == 0 ? 1 : (oy == p.OH - 1 ? 2 : 0)) * 3 + (ox == 0 ? 1 : (ox == p.OW - 1 ? 2 : 0));
+        cls = (oy == 0 ? 1 : (oy == p.OH - 1 ? 2 : 0)) * 3 + (ox == 0 ? 1 : (ox == p.OW - 1 ? 2 : 0));
         if (cls && p.border_tab) btab = p.border_tab + static_cast<size_t>(cls) * p.Cout;
         warp_has_border = __any_sync(0xffffffffu, btab != nullptr);   // interior warps skip the correction code
       }
@@ -480,7 +492,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float bcor[16];
         if (EPI & EPI_BTAB) {
           // border pixels (one warp in four on a 128-px row tile) fetch their 16 corrections as 4 vector loads
-          if (warp_has_border) {
+          if (warp_has_border && btab_smem) {
+            // class 0 (interior) rows of the table are zero-valued for this purpose: read row `cls` only on the border
+            const float4* bs = reinterpret_cast<const float4*>(s_btab + cls * BN + c * 16);
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const float4 bv = btab != nullptr ? bs[g4] : make_float4(0.f, 0.f, 0.f, 0.f);
+              bcor[4 * g4 + 0] = bv.x; bcor[4 * g4 + 1] = bv.y; bcor[4 * g4 + 2] = bv.z; bcor[4 * g4 + 3] = bv.w;
+            }
+          } else if (warp_has_border) {
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
               float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -501,6 +521,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (o0 >= p.Cout && (p.out_nchw_f32 || p.out_cgroup || ol0 >= p.out_cstride)) continue;
         const float4* tr = trow + 2 * (c * 16);
         float v[16];
+        if (EPI & EPI_IDENT) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+        } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float4 t0 = tr[2 * j];
@@ -521,7 +545,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           v[j] = x * t0.w;
         }
-        if (valid && p.out) {      // out == NULL: only the fused ToRGB sums are wanted (last synthesis layer)
+        }
+        if (valid && p.out && ox < p.OW - og * p.cg_shrink) {   // out == NULL: only the fused ToRGB sums are wanted
           if (p.out_nchw_f32) {
             const size_t plane = static_cast<size_t>(p.out_H) * p.out_W;
             float* op = static_cast<float*>(p.out) + (static_cast<size_t>(b) * p.Cout + o0) * plane +
@@ -685,6 +710,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     FM_LAUNCH_OK();
     return FM_OK;
   }
+  if (!p.tab) return launch_igemm2<BN, EPI_IDENT>(tmA, tmB, p, st);
   const int epi = (p.rgb ? EPI_RGB : 0) | (p.residual ? EPI_RES : 0) | (p.border_tab ? EPI_BTAB : 0);
   switch (epi) {
     case 0: return launch_igemm2<BN, 0>(tmA, tmB, p, st);
@@ -700,7 +726,9 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
 extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   using namespace fm;
   FM_CHECK_ARG(d != nullptr, "fm_conv_igemm: null desc");
-  FM_CHECK_ARG(d->x && d->w && (d->out || d->rgb) && d->tab, "fm_conv_igemm: null tensor");
+  FM_CHECK_ARG(d->x && d->w && (d->out || d->rgb), "fm_conv_igemm: null tensor");
+  FM_CHECK_ARG(d->tab || (!d->rgb && !d->residual && !d->border_tab && !d->noise && d->ksplit <= 1),
+               "fm_conv_igemm: tab == NULL (identity epilogue) excludes rgb / residual / border_tab / noise / split-K");
   FM_CHECK_ARG(d->out || (!d->out_nchw_f32 && !d->out_cgroup && !d->upmode), "fm_conv_igemm: out may be NULL only for a plain NHWC conv with a fused RGB output");
   FM_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "fm_conv_igemm: bad sizes");
   FM_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= FM_MAX_TAPS, "fm_conv_igemm: ntaps %d out of range", d->ntaps);
@@ -755,7 +783,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   int ksplit = 1;
   {
     static const int env_split = []() { const char* e = getenv("FM3D_SPLITK"); return e ? atoi(e) : 1; }();
-    const bool eligible = env_split && d->ksplit != 1 && d->splitk_ws && !d->rgb && !d->border_tab && !d->out_nchw_f32 &&
+    const bool eligible = env_split && d->tab && d->ksplit != 1 && d->splitk_ws && !d->rgb && !d->border_tab && !d->out_nchw_f32 &&
                           !d->out_cgroup && d->block_n <= 0 && !d->upmode;
     if (eligible) {
       const int bn_wide = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
@@ -806,7 +834,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   p.residual = static_cast<const __nv_bfloat16*>(d->residual);
   p.rgb = d->rgb;
   p.border_tab = d->border_tab;
-  p.out_cgroup = d->out_cgroup; p.out_gstride = d->out_gstride;
+  p.out_cgroup = d->out_cgroup; p.out_gstride = d->out_gstride; p.cg_shrink = d->out_cgroup_ow_shrink;
   int max_widx = 0;
   for (int i = 0; i < d->ntaps; ++i) {
     p.tap_dy[i] = d->tap_dy[i]; p.tap_dx[i] = d->tap_dx[i]; p.tap_widx[i] = d->tap_widx[i];

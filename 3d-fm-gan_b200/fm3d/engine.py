@@ -33,6 +33,16 @@ import os
 
 # fused 4-parity launch: correct but not faster than four phase launches yet (weight re-streaming bound)
 _FUSED_UP = os.environ.get("FM3D_UPMODE", "0") == "1"
+# Cout <= 128 up-convs: the two column parities of an output-row parity share one launch as a 2*Cout-wide GEMM
+# (N = 256 tiles instead of N = 128: the tensor pipe is no longer starved by the per-SM L2 fill rate)
+_PAIR_UP = os.environ.get("FM3D_UPPAIR", "1") != "0"
+
+# views (dy, dx) of the input a stride-2 transposed 3x3 conv reads, and for each output-row parity py the
+# (view, tap of column parity 0, tap of column parity 1 or None) triples -- see _up_phase_taps
+_PAIR_VIEWS = {
+    0: [((0, 0), 0, 1), ((0, -1), 2, None), ((-1, 0), 6, 7), ((-1, -1), 8, None)],
+    1: [((0, 0), 3, 4), ((0, -1), 5, None)],
+}
 
 
 def _up_phase_taps(py, px):
@@ -52,7 +62,7 @@ def _up_phase_taps(py, px):
 class _ConvLayer:
     """One modulated 3x3 conv of the plan."""
     __slots__ = ("mod", "act_bias", "noise_w", "cin", "cout", "up", "res_in", "res_out", "latent_idx",
-                 "wq", "wsq", "s", "tab", "rgb_mod", "next_idx", "kernel", "name")
+                 "wq", "wsq", "s", "tab", "rgb_mod", "next_idx", "kernel", "name", "wpair")
 
 
 class SynthesisPlan:
@@ -115,10 +125,11 @@ class SynthesisPlan:
         self.rgb_acc = [torch.zeros(B, L.res_out, L.res_out, 4, **f32) for (_, _, L) in self.rgbs]
         self.ident_tabs = {}
         for L in convs:
-            if L.up and L.cout not in self.ident_tabs:
-                t = torch.zeros(1, L.cout, 8, **f32)
-                t[..., 0] = 1.0; t[..., 2] = 1.0; t[..., 3] = 1.0
-                self.ident_tabs[L.cout] = t
+            for n in ((L.cout, 2 * L.cout) if L.up else ()):
+                if n not in self.ident_tabs:
+                    t = torch.zeros(1, n, 8, **f32)
+                    t[..., 0] = 1.0; t[..., 2] = 1.0; t[..., 3] = 1.0
+                    self.ident_tabs[n] = t
         self._versions = None
         self._desc_keepalive = None
         self._runner = GraphRunner(self._run_flat)
@@ -145,6 +156,17 @@ class SynthesisPlan:
         for L in self.convs:
             w = L.mod.weight.detach()[0]
             L.wq, L.wsq = ops.prep_weight(w, L.mod.scale, want_wsq=True)
+            L.wpair = None
+            if L.up and _PAIR_UP and not _FUSED_UP and L.cout % 32 == 0 and L.cout <= 128 and L.res_in >= 12:
+                # [view][P_x0 rows | P_x1 rows][cin]: zero block where the odd column parity has no tap for the view
+                L.wpair = {}
+                for py, views in _PAIR_VIEWS.items():
+                    wp = torch.zeros(len(views), 2 * L.cout, L.wq.shape[2], device=dev, dtype=torch.bfloat16)
+                    for v, (_, t0, t1) in enumerate(views):
+                        wp[v, :L.cout] = L.wq[t0, :L.cout]
+                        if t1 is not None:
+                            wp[v, L.cout:] = L.wq[t1, :L.cout]
+                    L.wpair[py] = wp
         self.rgb_w = [to_rgb.conv.weight.detach().reshape(3, -1).contiguous().float() for (to_rgb, _, _) in self.rgbs]
         # descriptor arrays (device resident)
         n_style = len(self.convs) + len(self.rgbs)
@@ -226,7 +248,19 @@ class SynthesisPlan:
                 ident = self.ident_tabs[L.cout]
                 tw_ = min(16, _pow2_ge(h + 1))
                 th_ = max(1, min(8, 128 // tw_))
-                if _FUSED_UP:
+                if L.wpair is not None:
+                    # one launch per output-row parity: N = [even columns | odd columns] (2*Cout wide)
+                    up_flops = 2.0 * B * h * h * L.cin * L.cout * 9
+                    cs_t = t.shape[-1]
+                    for py, views in _PAIR_VIEWS.items():
+                        taps = [(dy, dx, v) for v, ((dy, dx), _, _) in enumerate(views)]
+                        ntap = sum(1 + (t1 is not None) for (_, _, t1) in views)
+                        ops.conv_igemm(x, L.wpair[py], taps, t, None, B=B, H=h, W=h, Cin=L.cin,
+                                       Cout=2 * L.cout, OH=h + 1 - py, OW=h + 1, out_H=2 * h + 1, out_W=2 * h + 1,
+                                       out_y0=py, out_x0=0, out_ys=2, out_xs=2, tab_per_sample=False,
+                                       out_cgroup=L.cout, out_gstride=cs_t, out_cstride=cs_t, out_cgroup_ow_shrink=1,
+                                       algo_flops=up_flops * ntap / 9.0)
+                elif _FUSED_UP:
                     # all four output parities in one launch: the input is read once
                     ops.conv_igemm(x, L.wq, ops.conv_taps(3, 3, 1), t, ident, B=B, H=h, W=h, Cin=L.cin, Cout=L.cout,
                                    OH=h + 1, OW=h + 1, out_H=2 * h + 1, out_W=2 * h + 1, out_ys=2, out_xs=2,
@@ -234,7 +268,7 @@ class SynthesisPlan:
                 else:
                     for py in (0, 1):
                         for px in (0, 1):
-                            ops.conv_igemm(x, L.wq, _up_phase_taps(py, px), t, ident, B=B, H=h, W=h, Cin=L.cin,
+                            ops.conv_igemm(x, L.wq, _up_phase_taps(py, px), t, None, B=B, H=h, W=h, Cin=L.cin,
                                            Cout=L.cout, OH=h + 1 - py, OW=h + 1 - px, out_H=2 * h + 1, out_W=2 * h + 1,
                                            out_y0=py, out_x0=px, out_ys=2, out_xs=2, tab_per_sample=False,
                                            tile_w=tw_, tile_h=th_)

@@ -141,7 +141,8 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
                out_H=None, out_W=None, out_y0=0, out_x0=0, out_ys=1, out_xs=1, out_nchw_f32=False,
                tab_per_sample=False, noise=None, noise_per_sample=True, noise_w=None, residual=None,
                rgb=None, block_n=0, tile_w=0, tile_h=0, stride_x=0, stride_y=0, x_pixstride=0, x_rowstride=0,
-               x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None, ksplit=0, upmode=False):
+               x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None, ksplit=0, upmode=False,
+               out_cgroup_ow_shrink=0, algo_flops=None):
     """Launch fm_conv_igemm.  x: bf16 NHWC [B,H,W,cs]; w: bf16 [slabs, w_rows, cin_stride];
     out: bf16 NHWC [B,out_H,out_W,cs_out] or fp32 NCHW; tab: fp32 [B|1, Cout, 8]."""
     d = ConvDesc()
@@ -158,6 +159,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     d.groups = groups
     d.border_tab = _ptr(border_tab)
     d.out_cgroup, d.out_gstride = out_cgroup, out_gstride
+    d.out_cgroup_ow_shrink = out_cgroup_ow_shrink
     d.OH, d.OW = OH, OW
     d.out = out.data_ptr() if out is not None else None
     d.out_H = OH if out_H is None else out_H
@@ -165,7 +167,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     d.out_cstride = out_cstride if out_cstride is not None else (Cout if out_nchw_f32 else (out.shape[-1] if out is not None else (Cout + 7) // 8 * 8))
     d.out_y0, d.out_x0, d.out_ys, d.out_xs = out_y0, out_x0, out_ys, out_xs
     d.out_nchw_f32 = 1 if out_nchw_f32 else 0
-    d.tab = tab.data_ptr(); d.tab_bstride = 1 if tab_per_sample else 0
+    d.tab = tab.data_ptr() if tab is not None else None; d.tab_bstride = 1 if tab_per_sample else 0
     d.noise = _ptr(noise); d.noise_bstride = 1 if noise_per_sample else 0
     d.noise_w = _ptr(noise_w)
     d.residual = _ptr(residual)
@@ -183,7 +185,9 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
         if prof is not None:
             e1.record()
             # up mode: algorithmic FLOPs of the stride-2 transposed conv = 9 taps at the INPUT resolution
-            prof.append((e0, e1, 2.0 * B * (H * W if upmode else OH * OW) * Cin * Cout * len(taps)))
+            # launches that pad their weights with zero blocks pass their algorithmic FLOPs explicitly
+            prof.append((e0, e1, algo_flops if algo_flops is not None else
+                         2.0 * B * (H * W if upmode else OH * OW) * Cin * Cout * len(taps)))
     _lib.check(st, "fm_conv_igemm")
     return out
 

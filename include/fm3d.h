@@ -130,7 +130,9 @@ typedef struct {
   int32_t out_H, out_W, out_cstride, out_y0, out_x0, out_ys, out_xs;
   int32_t out_nchw_f32;
   /* epilogue */
-  const float* tab;         /* [tab_rows][Cout][8] fp32 (see above); tab_bstride = Cout or 0 */
+  const float* tab;         /* [tab_rows][Cout][8] fp32 (see above); tab_bstride = Cout or 0.  NULL = identity epilogue
+                             * (out = acc): the parity phases of the stride-2 transposed conv, whose epilogue runs in
+                             * the blur pass */
   int32_t tab_bstride;      /* 0: one table shared by the batch; 1: per-sample tables */
   const float* noise;       /* fp32 [B or 1][out_H][out_W] or NULL */
   int32_t noise_bstride;    /* 0 shared / 1 per-sample */
@@ -158,6 +160,9 @@ typedef struct {
   /* tiling hints (0 = choose) */
   int32_t block_n;          /* 64, 128 or 256 */
   int32_t tile_w, tile_h;   /* tile_w*tile_h*tile_b = 128 output pixels */
+  /* concatenated-N output: group g only writes columns ox < OW - g*out_cgroup_ow_shrink (the odd-column
+   * parity of a stride-2 transposed conv has one column less than the even one) */
+  int32_t out_cgroup_ow_shrink;
 } fm_conv_desc;
 
 int fm_conv_igemm(const fm_conv_desc* desc, void* stream);
