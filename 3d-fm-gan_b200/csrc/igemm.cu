@@ -39,6 +39,7 @@ struct IgemmParams {
   float* ws;                       // split-K fp32 workspace [B*OH*OW][ws_cs]
   int ws_cs;
   int cluster;                     // CTAs per cluster (1, 2 or 4): weight tiles are TMA-multicast to the cluster
+  int pair;                        // cta_group::2: the 2 CTAs of a cluster run ONE M=256 MMA, each loads half of the weight tile
   int num_super;                   // tiles_n * ksplit * ceil(m_tiles / cluster)
   int m_tiles;
   int upmode;                      // fused stride-2 transposed 3x3 conv: 4 output-parity accumulators share the A tiles
@@ -97,10 +98,15 @@ __constant__ int8_t c_up_acc[4][4] = {{0, 1, 2, 3}, {0, 2, 0, 0}, {0, 1, 0, 0}, 
 __constant__ int8_t c_up_dy[4] = {0, 0, -1, -1};
 __constant__ int8_t c_up_dx[4] = {0, -1, 0, -1};
 
-template <int BN, int EPI>
+// PAIR: cta_group::2 instantiation (a kernel that contains 2-CTA tcgen05 instructions can only be launched with an
+// even cluster size, so the single-CTA paths live in their own instantiation).
+template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(IG_THREADS2, 1)
-igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
+igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p_in) {
   using Cfg = IgemmCfg<BN>;
+  // kPair as a compile-time constant inside the kernel
+  const IgemmParams& p = p_in;
+  constexpr bool kPair = PAIR;
   // SWIZZLE_128B operand tiles need 1024-byte alignment; declaring it keeps the shared address space
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_stage = smem;
@@ -127,7 +133,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], p.cluster);       // every CTA of the cluster releases the slot (multicast commit)
+      mbar_init(&empty_bar[i], kPair ? 1 : p.cluster);   // multicast commit of every CTA (cluster) / of the leader (pair)
     }
     for (int i = 0; i < IG_HP_MAXA; ++i) {
       mbar_init(&afull_bar[i], 1);
@@ -135,13 +141,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], IG_EPI_WARPS);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], IG_EPI_WARPS * (kPair ? 2 : 1));   // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(s_tmem, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc_pair(s_tmem, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(s_tmem, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -165,15 +171,22 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t patch_tx = static_cast<uint32_t>(p.hp_pw) * p.hp_ph * (IG_BK * 2);
     auto hp_prefetch = [&]() {
       if (pst >= p.num_super) return;
-      int m = pst / p.tiles_n;                     // ksplit == cluster == 1 in this mode
+      int m = (pst / p.tiles_n) * p.cluster + crank;   // ksplit == 1 in this mode
       const int bx = m % p.tiles_x; m /= p.tiles_x;
       const int by = m % p.tiles_y;
       const int bb = m / p.tiles_y;
       mbar_wait(&aempty_bar[pslot], pphase ^ 1);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&afull_bar[pslot], patch_tx);
-        tma_load_4d(s_stage + pslot * p.hp_bytes, &tmA, &afull_bar[pslot], pkc * IG_BK,
-                    bx * 8 + p.hp_dx0, by * 16 + p.hp_dy0, bb);
+        if (kPair) {
+          // both CTAs' patches complete on the leader's barrier; the leader announces the bytes of both
+          if (crank == 0) mbar_arrive_expect_tx(&afull_bar[pslot], 2 * patch_tx);
+          tma_load_4d_pair(s_stage + pslot * p.hp_bytes, &tmA, mapa_rank(smem_u32(&afull_bar[pslot]), 0), pkc * IG_BK,
+                           bx * 8 + p.hp_dx0, by * 16 + p.hp_dy0, bb);
+        } else {
+          mbar_arrive_expect_tx(&afull_bar[pslot], patch_tx);
+          tma_load_4d(s_stage + pslot * p.hp_bytes, &tmA, &afull_bar[pslot], pkc * IG_BK,
+                      bx * 8 + p.hp_dx0, by * 16 + p.hp_dy0, bb);
+        }
       }
       __syncwarp();
       if (++pkc == p.kchunks) { pkc = 0; pst += num_clusters; }
@@ -240,8 +253,14 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int tap = 0; tap < p.ntaps; ++tap) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (lane == 0) {
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_BYTES);
-              tma_load_2d(sb0 + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0);
+              if (kPair) {
+                if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_BYTES);       // two halves
+                tma_load_2d_pair(sb0 + stage * Cfg::B_BYTES, &tmB, mapa_rank(smem_u32(&full_bar[stage]), 0), kc * IG_BK,
+                                 (wrow0 + p.tap_widx[tap]) * p.w_rows + n0 + crank * (BN / 2));
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_BYTES);
+                tma_load_2d(sb0 + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0);
+              }
             }
             __syncwarp();
             if (++stage == p.hp_stages) { stage = 0; phase ^= 1; }
@@ -253,7 +272,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int tap = it / p.kchunks;
         const int kc = it - tap * p.kchunks;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (lane == 0) {
+        if (lane == 0 && kPair) {
+          uint8_t* sa = s_stage + stage * Cfg::STAGE_BYTES;
+          const uint32_t lbar = mapa_rank(smem_u32(&full_bar[stage]), 0);
+          if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * static_cast<uint32_t>(p.rows) * (IG_BK * 2) + Cfg::B_BYTES);
+          tma_load_4d_pair(sa, &tmA, lbar, kc * IG_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
+          tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, lbar, kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0 + crank * (BN / 2));
+        } else if (lane == 0) {
           uint8_t* sa = s_stage + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -270,7 +295,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // uniform registers) and one elected lane issues; the four K=16 MMAs of a 64-channel stage go out of one
     // asm block.  At N <= 128 a K=16 MMA lasts only 32-64 tensor-pipe cycles: every instruction between two
     // UTCHMMAs is on the critical path of the kernel.
-    constexpr uint32_t idesc = umma_idesc_bf16(IG_BM, BN);
+    const uint32_t idesc = umma_idesc_bf16(kPair ? 2 * IG_BM : IG_BM, BN);
     constexpr uint32_t dhi = umma_desc_hi_sw128(1024);
     int stage = 0;
     uint32_t phase = 0;
@@ -278,7 +303,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int aslot = 0;
     uint32_t aslot_phase = 0;
     const uint32_t ring = smem_u32(s_stage);
-    for (int st = cluster_id; st < p.num_super; st += num_clusters, ++titer) {
+    // CTA pair: only the leader issues (its MMAs read both CTAs' operands and write both CTAs' TMEM)
+    for (int st = (kPair && crank != 0) ? p.num_super : cluster_id; st < p.num_super; st += num_clusters, ++titer) {
       const int buf = titer % p.nbuf;
       const uint32_t aphase = (titer / p.nbuf) & 1;
       mbar_wait(&tempty_bar[buf], aphase ^ 1);     // epilogue has drained this accumulator
@@ -344,11 +370,20 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t alo = alo0 + static_cast<uint32_t>(p.hp_aoff[tap]);
             const uint32_t blo = umma_desc_lo(sb0 + stage * Cfg::B_BYTES);
             if (elect_one()) {
-              umma_bf16_x4(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tap > 0) ? 1u : 0u);
-              umma_commit(&empty_bar[stage]);
-              if (tap == p.ntaps - 1) {
-                umma_commit(&aempty_bar[aslot]);              // patch slot is free once these MMAs retire
-                if (kc == p.kchunks - 1) umma_commit(&tfull_bar[buf]);
+              if (kPair) {
+                umma_bf16_x4_pair(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tap > 0) ? 1u : 0u);
+                umma_commit_pair(&empty_bar[stage]);
+                if (tap == p.ntaps - 1) {
+                  umma_commit_pair(&aempty_bar[aslot]);
+                  if (kc == p.kchunks - 1) umma_commit_pair(&tfull_bar[buf]);
+                }
+              } else {
+                umma_bf16_x4(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tap > 0) ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);
+                if (tap == p.ntaps - 1) {
+                  umma_commit(&aempty_bar[aslot]);              // patch slot is free once these MMAs retire
+                  if (kc == p.kchunks - 1) umma_commit(&tfull_bar[buf]);
+                }
               }
             }
             __syncwarp();
@@ -367,9 +402,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t alo = umma_desc_lo(sa), blo = umma_desc_lo(sa + Cfg::A_BYTES);
         if (elect_one()) {
           // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
-          umma_bf16_x4(tmem_d, alo, dhi, blo, dhi, idesc, it > it0 ? 1u : 0u);
-          if (p.cluster == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
-          if (it == it1 - 1) umma_commit(&tfull_bar[buf]);
+          if (kPair) {
+            umma_bf16_x4_pair(tmem_d, alo, dhi, blo, dhi, idesc, it > it0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+            if (it == it1 - 1) umma_commit_pair(&tfull_bar[buf]);
+          } else {
+            umma_bf16_x4(tmem_d, alo, dhi, blo, dhi, idesc, it > it0 ? 1u : 0u);
+            if (p.cluster == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
+            if (it == it1 - 1) umma_commit(&tfull_bar[buf]);
+          }
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -592,7 +633,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[buf]), 0));   // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&tempty_bar[buf]);
+      }
     }
   }
 
@@ -601,7 +645,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (p.cluster > 1) cluster_sync_all();           // no CTA exits while a peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (kPair) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -666,12 +710,12 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, int EPI>
-static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
+template <int BN, int EPI, bool PAIR>
+static int launch_igemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
   using Cfg = IgemmCfg<BN>;
   static bool attr_set = false;   // per-process, per-instantiation; benign race
   if (!attr_set) {
-    FM_CUDA_OK(cudaFuncSetAttribute(igemm_conv_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    FM_CUDA_OK(cudaFuncSetAttribute(igemm_conv_kernel<BN, EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int sms = sm_count();
@@ -689,10 +733,20 @@ static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const I
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FM_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_conv_kernel<BN, EPI>, tmA, tmB, p));
+  FM_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_conv_kernel<BN, EPI, PAIR>, tmA, tmB, p));
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;
+}
+
+template <int BN, int EPI>
+static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
+  // pair instantiations exist for the feature sets the N >= 128 layers use
+  if constexpr (BN >= 128 && (EPI == 0 || EPI == EPI_RGB || EPI == EPI_RES || EPI == EPI_BTAB || EPI == EPI_IDENT)) {
+    if (p.pair) return launch_igemm3<BN, EPI, true>(tmA, tmB, p, st);
+  }
+  if (p.pair) { set_error("fm_conv_igemm: internal: no CTA-pair instantiation for block_n %d epilogue %d", BN, EPI); return FM_ERR_INVALID; }
+  return launch_igemm3<BN, EPI, false>(tmA, tmB, p, st);
 }
 
 template <int BN>
@@ -941,6 +995,12 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     int cs = env_cluster;
     if (cs != 1 && cs != 2 && cs != 4) cs = 1;
     while (cs > 1 && (p.m_tiles % cs != 0 || G > 1 || p.hp)) cs >>= 1;   // no padded m-tiles, one weight slab per cluster
+    // CTA pairs (cta_group::2): the two CTAs of a cluster issue ONE M = 256 MMA and each loads only half of the
+    // weight tile -- the weight stream is what saturates the L2 -> SM path of a single-CTA tile (64/R B per clk)
+    static const int env_pair = []() { const char* e = getenv("FM3D_PAIR"); return e ? atoi(e) : 1; }();
+    p.pair = (env_pair && G == 1 && p.ksplit == 1 && !d->upmode && !p.patch && p.m_tiles % 2 == 0 &&
+              bn >= 128 && !((d->rgb != nullptr) + (d->residual != nullptr) + (d->border_tab != nullptr) > 1)) ? 1 : 0;
+    if (p.pair) cs = 2;
     p.cluster = cs;
     p.num_super = p.tiles_n * p.ksplit * ((p.m_tiles + cs - 1) / cs);
   }
@@ -964,7 +1024,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d->Cin), static_cast<cuuint64_t>(G) * p.nslabs * d->w_rows};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d->w_cstride) * 2};
-    const cuuint32_t box[2] = {IG_BK, static_cast<cuuint32_t>(bn)};
+    const cuuint32_t box[2] = {IG_BK, static_cast<cuuint32_t>(p.pair ? bn / 2 : bn)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
