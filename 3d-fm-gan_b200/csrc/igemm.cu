@@ -938,16 +938,17 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   // through a shifted descriptor, so the activation traffic L2 -> SM drops from ntaps x to ~1.4x per chunk
   // (the chip-wide L2 -> SM rate, not the tensor pipe, bounds the per-tap scheme for N <= 128).
   {
-    static const int env_hp = []() { const char* e = getenv("FM3D_HPATCH"); return e ? atoi(e) : 3; }();
+    static const int env_hp = []() { const char* e = getenv("FM3D_HPATCH"); return e ? atoi(e) : 1; }();
     int dx0 = 127, dx1 = -127, dy0 = 127, dy1 = -127;
     for (int i = 0; i < d->ntaps; ++i) {
       dx0 = d->tap_dx[i] < dx0 ? d->tap_dx[i] : dx0; dx1 = d->tap_dx[i] > dx1 ? d->tap_dx[i] : dx1;
       dy0 = d->tap_dy[i] < dy0 ? d->tap_dy[i] : dy0; dy1 = d->tap_dy[i] > dy1 ? d->tap_dy[i] : dy1;
     }
     const bool plain_x = d->x_pixstride == 0 && d->x_rowstride == 0 && d->x_imgstride == 0;
-    // 0 off | 1 wherever row-patch mode does not apply | 2 always | 3 (default) only N = 256 tiles: with one
-    // accumulator per CTA the weight tile alone (N * 128 B per 2N tensor-pipe cycles) saturates the ~64 B/clk
-    // an SM can take from L2 for N <= 128, so those layers need several accumulators per weight tile first
+    // 0 off | 1 (default) wherever row-patch mode does not apply | 2 always | 3 only N = 256 tiles.  The chip-wide
+    // L2 -> SM rate (~6300 B/clk, 42 B/clk per SM) is the budget: a single-CTA tile streams N*128 B of weights
+    // per 2N tensor-pipe cycles (64 B/clk) before any activation byte, which is why the row-patch mode shares a
+    // weight tile between R accumulators and the CTA-pair mode halves it
     const bool want = env_hp == 2 || (env_hp == 1 && !p.patch) || (env_hp == 3 && !p.patch && bn == 256);
     if (want && plain_x && sx == 1 && sy == 1 && G == 1 && p.ksplit == 1 && !d->upmode && d->ntaps >= 2 && d->OH >= 12 &&
         d->OW >= 8 && dx1 - dx0 <= 8 && dy1 - dy0 <= 8 && (!d->tab_bstride || bn <= IG_TAB_ROWS)) {
