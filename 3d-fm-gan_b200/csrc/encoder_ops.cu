@@ -250,6 +250,51 @@ extern "C" int fm_avgpool_nhwc_to_nchw(float* out, const void* x, int B, int H, 
   return FM_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// tensor2im (Evaluation/visual_eval.py:24-38 of the reference): fp32 NCHW [B,3,H,W] in [-1,1] ->
+// uint8 NHWC [B,H,W,3] = trunc((clip(x,-1,1) + cent) * factor), for the whole batch on the device.
+// The reference does this per image on the host (.cpu().float().numpy(), np.clip, transpose, astype):
+// 4x the D2H bytes plus three numpy passes.  A thread owns 4 adjacent pixels: 3 LDG.128, 12 bytes out.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tensor2im_kernel(uint8_t* __restrict__ out, const float* __restrict__ img, int HW,
+                                                        float cent, float factor, int total_quads) {
+  const int qpi = HW >> 2;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total_quads; idx += gridDim.x * blockDim.x) {
+    const int b = idx / qpi, q = idx - b * qpi;
+    const float* ip = img + static_cast<size_t>(b) * 3 * HW + 4 * q;
+    float v[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(ip + static_cast<size_t>(c) * HW));
+      v[c][0] = f.x; v[c][1] = f.y; v[c][2] = f.z; v[c][3] = f.w;
+    }
+    uint32_t w[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {            // byte i of the 12-byte group = pixel i/3, channel i%3
+      const float x = fminf(fmaxf(v[i % 3][i / 3], -1.f), 1.f);
+      // separate rounded add and multiply (never contracted to an FMA): bit-identical to numpy's float32 passes
+      const uint32_t u = static_cast<uint32_t>(static_cast<int>(__fmul_rn(__fadd_rn(x, cent), factor))) & 0xffu;   // astype: truncation
+      w[i >> 2] |= u << (8 * (i & 3));
+    }
+    uint32_t* op = reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * HW + 4 * q) * 3);
+    op[0] = w[0]; op[1] = w[1]; op[2] = w[2];
+  }
+}
+
+extern "C" int fm_tensor2im_u8(void* out_u8, const float* img, int B, int H, int W, float cent, float factor, void* stream) {
+  FM_CHECK_ARG(out_u8 && img && B > 0 && H > 0 && W > 0, "fm_tensor2im_u8: bad args");
+  FM_CHECK_ARG((static_cast<int64_t>(H) * W) % 4 == 0, "fm_tensor2im_u8: H*W must be a multiple of 4");
+  FM_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_u8) & 3) == 0,
+               "fm_tensor2im_u8: image must be 16-byte aligned, output 4-byte aligned");
+  const int64_t total = static_cast<int64_t>(B) * H * W / 4;
+  FM_CHECK_ARG(total < 0x7FFFFFFF, "fm_tensor2im_u8: too many pixels");
+  tensor2im_kernel<<<grid_for2(total), 256, 0, ST>>>(static_cast<uint8_t*>(out_u8), img, H * W, cent, factor,
+                                                     static_cast<int>(total));
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
 extern "C" int fm_channel_sum_nhwc(float* sum_bc, const void* x, int B, int HW, int C, int cs, void* stream) {
   FM_CHECK_ARG(sum_bc && x && B > 0 && HW > 0 && C > 0 && cs >= C && cs % 8 == 0 && cs <= 512 && 256 % (cs / 8) == 0,
                "fm_channel_sum_nhwc: bad args (cs must be 8*2^k <= 512)");

@@ -326,3 +326,18 @@ def bilinear_up_nhwc(x, OH, OW, out):
     with torch.cuda.device(x.device):
         _call("fm_bilinear_up_nhwc", _ptr(out), _ptr(x), B, IH, IW, OH, OW, cs, _stream())
     return out
+
+
+def tensor2im_batch(img, cent=1.0, factor=255.0 / 2.0, out=None):
+    """fp32 NCHW [B,3,H,W] in [-1,1] -> uint8 NHWC [B,H,W,3] on the device (the reference's ``tensor2im``,
+    Evaluation/visual_eval.py:24-38, for the whole batch: clip, shift, scale, truncate, transpose)."""
+    _check_cuda(img, "image")
+    img = img.contiguous().float()
+    B, Cc, H, W = img.shape
+    if Cc != 3:
+        raise RuntimeError(f"tensor2im_batch expects 3 channels, got {Cc}")
+    if out is None:
+        out = torch.empty(B, H, W, 3, device=img.device, dtype=torch.uint8)
+    with torch.cuda.device(img.device):
+        _call("fm_tensor2im_u8", _ptr(out), _ptr(img), B, H, W, float(cent), float(factor), _stream())
+    return out

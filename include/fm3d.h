@@ -237,6 +237,9 @@ int fm_prep_weight(void* wq, float* wsq, const float* w_oikk, int cout, int cin,
 /* fp32 NCHW image with C <= 8 channels -> zero-padded bf16 [B,Hp,Wp,8] (image at (pad_t,pad_l)). */
 int fm_image_to_nhwc8_padded(void* out, const float* x, int B, int C, int H, int W,
                              int pad_t, int pad_l, int Hp, int Wp, void* stream);
+/* tensor2im of the whole batch (replaces Evaluation/visual_eval.py:24-38, which converts one image at a time on
+ * the host): img fp32 NCHW [B,3,H,W] -> out uint8 NHWC [B,H,W,3] = trunc((clip(img,-1,1) + cent) * factor). */
+int fm_tensor2im_u8(void* out_u8, const float* img, int B, int H, int W, float cent, float factor, void* stream);
 /* MaxPool2d(3, stride 2, padding 1): [B,H,W,cs] -> [B,(H-1)/2+1,(W-1)/2+1,cs]. */
 int fm_maxpool3x3s2_nhwc(void* out, const void* x, int B, int H, int W, int cs, void* stream);
 /* Non-overlapping ph x pw average pooling, output fp32 NCHW [B,C,H/ph,W/pw]. */

@@ -53,3 +53,24 @@ def test_rgb_finalize(cuda, B, H, with_skip):
     out = ops.rgb_finalize(acc_d, bias.to(cuda), skip.to(cuda) if with_skip else None, k.to(cuda) if with_skip else None)
     torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-5)
     assert torch.count_nonzero(acc_d) == 0          # the accumulator is handed back zeroed
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 4, 4), (3, 64, 64), (2, 256, 256), (2, 6, 10)])
+def test_tensor2im_bit_exact(cuda, B, H, W):
+    """Device tensor2im vs the reference's numpy recipe (Evaluation/visual_eval.py:24-38): integer output, so the
+    bar is bit-exact -- including values outside [-1,1] and values that land exactly on an integer."""
+    import numpy as np
+    from Evaluation.visual_eval import tensor2im, tensor2im_batch
+    gen = torch.Generator().manual_seed(B * 7 + H)
+    img = torch.randn(B, 3, H, W, generator=gen) * 0.8
+    n = img.numel()
+    img.view(-1)[:min(n, 64)] = torch.linspace(-1.25, 1.25, 64)[:min(n, 64)]                 # clipped on both sides
+    if n >= 320:
+        img.view(-1)[64:320] = (torch.arange(256, dtype=torch.float32) / 127.5) - 1.0    # exact integer preimages
+    ref = np.clip(img.numpy(), -1, 1)
+    ref = ((np.transpose(ref, (0, 2, 3, 1)) + 1.) * (255. / 2.)).astype(np.uint8)
+    out = tensor2im_batch(img.to(cuda))
+    assert out.dtype == torch.uint8 and tuple(out.shape) == (B, H, W, 3)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    one = tensor2im(img.to(cuda))
+    assert one.dtype == np.uint8 and np.array_equal(one, ref[0])
