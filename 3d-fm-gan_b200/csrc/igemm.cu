@@ -25,6 +25,7 @@ namespace fm {
 
 constexpr int IG_BM = 128;     // pixels per tile (UMMA M)
 constexpr int IG_BK = 64;      // channels per k-step (128 B rows, SWIZZLE_128B)
+constexpr int IG_TRACE_N = 64;     // trace slots per CTA (debug)
 constexpr int IG_HP_MAXA = 8;      // halo-patch slots (barrier pairs reserved)
 constexpr int IG_TAB_ROWS = 512;  // staged table rows per tile (tile_b_eff * BLOCK_N <= 512)
 
@@ -49,9 +50,11 @@ struct IgemmParams {
   // halo-patch mode (stride-1 tap sets): tile = 8 x 16 pixels of one image; ONE (16+dy span) x (8+dx span)
   // input patch per channel chunk serves every tap as a shifted UMMA descriptor (group stride = patch row)
   int hp, hp_pw, hp_ph, hp_bytes, hp_dx0, hp_dy0, hp_stages, hp_na, hp_dist;
+  int hpw;                         // halo-patch mode with ALL weight tiles of the (single) n-tile resident in smem
   int16_t hp_aoff[FM_MAX_TAPS];    // per-tap start offset of the A descriptor inside the patch (16-byte units)
   int Bg, nslabs;                  // images per group, weight slabs per group
   const float* border_tab;
+  long long* trace;                // debug (FM3D_TRACE=1): per-CTA event timestamps [grid][IG_TRACE_N]
   int out_cgroup, cg_shrink;
   long long out_gstride;
   void* out;
@@ -159,6 +162,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1);
 
   const int kiters = p.ntaps * p.kchunks;
+  // debug trace: slot i of this CTA <- clock (one writer per slot)
+  long long* trc = p.trace ? p.trace + static_cast<size_t>(blockIdx.x) * IG_TRACE_N : nullptr;
+#define IG_TRACE(slot) do { if (trc && (slot) < IG_TRACE_N) trc[(slot)] = clock64(); } while (0)
+  if (threadIdx.x == 0) IG_TRACE(0);
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
@@ -176,15 +183,16 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int by = m % p.tiles_y;
       const int bb = m / p.tiles_y;
       mbar_wait(&aempty_bar[pslot], pphase ^ 1);
+      const int pkr = pkc;
       if (lane == 0) {
         if (kPair) {
           // both CTAs' patches complete on the leader's barrier; the leader announces the bytes of both
           if (crank == 0) mbar_arrive_expect_tx(&afull_bar[pslot], 2 * patch_tx);
-          tma_load_4d_pair(s_stage + pslot * p.hp_bytes, &tmA, mapa_rank(smem_u32(&afull_bar[pslot]), 0), pkc * IG_BK,
+          tma_load_4d_pair(s_stage + pslot * p.hp_bytes, &tmA, mapa_rank(smem_u32(&afull_bar[pslot]), 0), pkr * IG_BK,
                            bx * 8 + p.hp_dx0, by * 16 + p.hp_dy0, bb);
         } else {
           mbar_arrive_expect_tx(&afull_bar[pslot], patch_tx);
-          tma_load_4d(s_stage + pslot * p.hp_bytes, &tmA, &afull_bar[pslot], pkc * IG_BK,
+          tma_load_4d(s_stage + pslot * p.hp_bytes, &tmA, &afull_bar[pslot], pkr * IG_BK,
                       bx * 8 + p.hp_dx0, by * 16 + p.hp_dy0, bb);
         }
       }
@@ -192,8 +200,29 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (++pkc == p.kchunks) { pkc = 0; pst += num_clusters; }
       if (++pslot == p.hp_na) { pslot = 0; pphase ^= 1; }
     };
+    if (p.hpw) {
+      // weight-resident variant: every (chunk, tap) weight tile of the single n-tile is loaded ONCE per CTA; after
+      // that the producer only streams input patches (a TMA load costs ~5-8 clk per 128-byte row, so for small
+      // channel counts the per-tile weight re-loads -- 64 rows per tap -- were 3/4 of all rows)
+      const uint32_t wb = kPair ? Cfg::B_BYTES / 2 : Cfg::B_BYTES;
+      uint8_t* sw = s_stage + p.hp_na * p.hp_bytes;
+      if (lane == 0) {
+        if (!kPair || crank == 0) mbar_arrive_expect_tx(&full_bar[0], static_cast<uint32_t>(kiters) * Cfg::B_BYTES);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            uint8_t* dst = sw + static_cast<size_t>(kc * p.ntaps + tap) * wb;
+            if (kPair) tma_load_2d_pair(dst, &tmB, mapa_rank(smem_u32(&full_bar[0]), 0), kc * IG_BK, p.tap_widx[tap] * p.w_rows + crank * (BN / 2));
+            else tma_load_2d(dst, &tmB, &full_bar[0], kc * IG_BK, p.tap_widx[tap] * p.w_rows);
+          }
+      }
+      __syncwarp();
+      for (int st = cluster_id; st < p.num_super; st += num_clusters)
+        for (int kc = 0; kc < p.kchunks; ++kc) hp_prefetch();     // blocks on the patch ring only
+    } else {
     if (p.hp)
       for (int i = 0; i < p.hp_dist; ++i) hp_prefetch();
+    if (lane == 0) IG_TRACE(1);
+    int ptile = 0;
     for (int st = cluster_id; st < p.num_super; st += num_clusters) {
       const int nt = st % p.tiles_n;
       int m = st / p.tiles_n;
@@ -266,6 +295,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (++stage == p.hp_stages) { stage = 0; phase ^= 1; }
           }
         }
+        if (lane == 0) IG_TRACE(2 + 4 * ptile);      // producer: all loads of this tile issued
+        ++ptile;
         continue;
       }
       for (int it = it0; it < it1; ++it) {
@@ -289,6 +320,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    }   // !hpw
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     // The whole warp walks the loop in uniform control flow (so ptxas keeps stage indices and descriptors in
@@ -358,29 +390,64 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
+      if (p.hpw) {
+        const uint32_t wb = kPair ? Cfg::B_BYTES / 2 : Cfg::B_BYTES;
+        const uint32_t sw = ring + p.hp_na * p.hp_bytes;
+        const uint32_t ahi = umma_desc_hi_sw128(static_cast<uint32_t>(p.hp_pw) * 128u);
+        if (titer == 0) { mbar_wait(&full_bar[0], 0); tc_fence_after(); }      // resident weights have landed
+        if (lane == 0) IG_TRACE(3 + 4 * titer);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&afull_bar[aslot], aslot_phase);
+          tc_fence_after();
+          if (lane == 0 && kc == 0) IG_TRACE(4 + 4 * titer);
+          const uint32_t alo0 = umma_desc_lo(ring + aslot * p.hp_bytes);
+          const uint32_t blo0 = umma_desc_lo(sw + static_cast<uint32_t>(kc * p.ntaps) * wb);
+          if (elect_one()) {
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              const uint32_t alo = alo0 + static_cast<uint32_t>(p.hp_aoff[tap]);
+              const uint32_t blo = blo0 + static_cast<uint32_t>(tap) * (wb >> 4);
+              if (kPair) umma_bf16_x4_pair(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tap > 0) ? 1u : 0u);
+              else umma_bf16_x4(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tap > 0) ? 1u : 0u);
+            }
+            if (kPair) {
+              umma_commit_pair(&aempty_bar[aslot]);
+              if (kc == p.kchunks - 1) umma_commit_pair(&tfull_bar[buf]);
+            } else {
+              umma_commit(&aempty_bar[aslot]);
+              if (kc == p.kchunks - 1) umma_commit(&tfull_bar[buf]);
+            }
+          }
+          __syncwarp();
+          if (++aslot == p.hp_na) { aslot = 0; aslot_phase ^= 1; }
+        }
+        continue;
+      }
       if (p.hp) {
         const uint32_t sb0 = ring + p.hp_na * p.hp_bytes;
         const uint32_t ahi = umma_desc_hi_sw128(static_cast<uint32_t>(p.hp_pw) * 128u);
+        if (lane == 0) IG_TRACE(3 + 4 * titer);               // MMA: accumulator free
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&afull_bar[aslot], aslot_phase);          // this chunk's input patch has landed
+          if (lane == 0 && kc == 0) IG_TRACE(4 + 4 * titer);  // MMA: first patch landed
           const uint32_t alo0 = umma_desc_lo(ring + aslot * p.hp_bytes);
           for (int tap = 0; tap < p.ntaps; ++tap) {
+            const int tl = tap;
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t alo = alo0 + static_cast<uint32_t>(p.hp_aoff[tap]);
             const uint32_t blo = umma_desc_lo(sb0 + stage * Cfg::B_BYTES);
             if (elect_one()) {
               if (kPair) {
-                umma_bf16_x4_pair(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tap > 0) ? 1u : 0u);
+                umma_bf16_x4_pair(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tl > 0) ? 1u : 0u);
                 umma_commit_pair(&empty_bar[stage]);
-                if (tap == p.ntaps - 1) {
+                if (tl == p.ntaps - 1) {
                   umma_commit_pair(&aempty_bar[aslot]);
                   if (kc == p.kchunks - 1) umma_commit_pair(&tfull_bar[buf]);
                 }
               } else {
-                umma_bf16_x4(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tap > 0) ? 1u : 0u);
+                umma_bf16_x4(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tl > 0) ? 1u : 0u);
                 umma_commit(&empty_bar[stage]);
-                if (tap == p.ntaps - 1) {
+                if (tl == p.ntaps - 1) {
                   umma_commit(&aempty_bar[aslot]);              // patch slot is free once these MMAs retire
                   if (kc == p.kchunks - 1) umma_commit(&tfull_bar[buf]);
                 }
@@ -475,6 +542,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       mbar_wait(&tfull_bar[buf], aphase);
       tc_fence_after();
+      if (threadIdx.x == 64) IG_TRACE(5 + 4 * titer);         // epilogue: accumulator complete
       const int nrows = p.upmode ? 4 : (p.patch ? p.prows : 1);
 #pragma unroll 1
       for (int r = 0; r < nrows; ++r) {
@@ -637,9 +705,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (kPair) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[buf]), 0));   // the leader's MMA warp waits for both CTAs
         else mbar_arrive(&tempty_bar[buf]);
       }
+      if (threadIdx.x == 64 && p.hpw) IG_TRACE(2 + 4 * titer);    // epilogue (warp 2) drained this tile
     }
   }
 
+  if (threadIdx.x == 64) IG_TRACE(IG_TRACE_N - 1);           // epilogue finished its last tile
   tc_fence_before();
   __syncthreads();
   if (p.cluster > 1) cluster_sync_all();           // no CTA exits while a peer may still multicast into it
@@ -698,6 +768,8 @@ __global__ void __launch_bounds__(256) igemm_splitk_finalize_kernel(const IgemmP
 }
 
 // ------------------------------------------------------------------------------------ host
+static long long* g_trace = nullptr;
+
 EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = []() -> EncodeTiledFn {
     void* f = nullptr;
@@ -742,7 +814,7 @@ static int launch_igemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const I
 template <int BN, int EPI>
 static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
   // pair instantiations exist for the feature sets the N >= 128 layers use
-  if constexpr (BN >= 128 && (EPI == 0 || EPI == EPI_RGB || EPI == EPI_RES || EPI == EPI_BTAB || EPI == EPI_IDENT)) {
+  if constexpr (EPI == 0 || EPI == EPI_RGB || EPI == EPI_RES || EPI == EPI_BTAB || EPI == EPI_IDENT) {
     if (p.pair) return launch_igemm3<BN, EPI, true>(tmA, tmB, p, st);
   }
   if (p.pair) { set_error("fm_conv_igemm: internal: no CTA-pair instantiation for block_n %d epilogue %d", BN, EPI); return FM_ERR_INVALID; }
@@ -1000,9 +1072,20 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     // weight tile -- the weight stream is what saturates the L2 -> SM path of a single-CTA tile (64/R B per clk)
     static const int env_pair = []() { const char* e = getenv("FM3D_PAIR"); return e ? atoi(e) : 1; }();
     p.pair = (env_pair && G == 1 && p.ksplit == 1 && !d->upmode && !p.patch && p.m_tiles % 2 == 0 &&
-              bn >= 128 && !((d->rgb != nullptr) + (d->residual != nullptr) + (d->border_tab != nullptr) > 1)) ? 1 : 0;
+              (bn >= 128 || env_pair == 2) && !((d->rgb != nullptr) + (d->residual != nullptr) + (d->border_tab != nullptr) > 1)) ? 1 : 0;
     if (p.pair) cs = 2;
     p.cluster = cs;
+    // weight-resident halo-patch variant: one n-tile and all its (chunk, tap) weight tiles fit beside >= 3 patch slots
+    if (p.hp) {
+      static const int env_hpw = []() { const char* e = getenv("FM3D_HPW"); return e ? atoi(e) : 1; }();
+      const int64_t wbytes = static_cast<int64_t>(kiters_total) * (p.pair ? bn / 2 : bn) * 128;
+      int na = static_cast<int>((200 * 1024 - wbytes) / p.hp_bytes);
+      if (na > IG_HP_MAXA) na = IG_HP_MAXA;
+      if (env_hpw && p.tiles_n == 1 && na >= 3) {
+        p.hpw = 1;
+        p.hp_na = na;
+      }
+    }
     p.num_super = p.tiles_n * p.ksplit * ((p.m_tiles + cs - 1) / cs);
   }
   // ---- tensor maps
@@ -1033,9 +1116,29 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     if (r != CUDA_SUCCESS) { set_error("fm_conv_igemm: cuTensorMapEncodeTiled(B) failed with CUresult %d", (int)r); return FM_ERR_CUDA; }
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    // debug: FM3D_TRACE=1 records per-CTA event clocks of every launch into one device buffer (fm_igemm_trace)
+    static const int env_trace = []() { const char* e = getenv("FM3D_TRACE"); return e ? atoi(e) : 0; }();
+    if (env_trace) {
+      if (!g_trace) cudaMalloc(&g_trace, sizeof(long long) * 1024 * IG_TRACE_N);
+      cudaMemsetAsync(g_trace, 0, sizeof(long long) * 1024 * IG_TRACE_N, st);
+      p.trace = g_trace;
+    }
+  }
   switch (bn) {
     case 64: return launch_igemm<64>(tmA, tmB, p, st);
     case 128: return launch_igemm<128>(tmA, tmB, p, st);
     default: return launch_igemm<256>(tmA, tmB, p, st);
   }
+}
+
+// Debug: copy the event clocks of the last traced launch (FM3D_TRACE=1) to the host: [n_ctas][slots] int64.
+extern "C" int fm_igemm_trace(long long* host_out, int n_ctas, int* slots_out) {
+  using namespace fm;
+  if (slots_out) *slots_out = IG_TRACE_N;
+  FM_CHECK_ARG(host_out && n_ctas > 0 && n_ctas <= 1024, "fm_igemm_trace: bad args");
+  if (!g_trace) { set_error("fm_igemm_trace: tracing is off (set FM3D_TRACE=1)"); return FM_ERR_INVALID; }
+  FM_CUDA_OK(cudaDeviceSynchronize());
+  FM_CUDA_OK(cudaMemcpy(host_out, g_trace, sizeof(long long) * n_ctas * IG_TRACE_N, cudaMemcpyDeviceToHost));
+  return FM_OK;
 }

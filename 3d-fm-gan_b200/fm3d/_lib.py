@@ -60,6 +60,7 @@ _SIGNATURES = {
                                         C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "fm_upfirdn2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int] * 12 + [C.c_int, C.c_void_p]),
     "fm_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "fm_igemm_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "fm_style_affine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fm_build_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fm_tensor2im_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),

@@ -166,6 +166,10 @@ typedef struct {
 } fm_conv_desc;
 
 int fm_conv_igemm(const fm_conv_desc* desc, void* stream);
+/* Debug aid: with FM3D_TRACE=1 every igemm launch records per-CTA event clocks (kernel start, per tile: loads
+ * issued / accumulator free / first operand landed / accumulator complete); this copies the last launch's
+ * [n_ctas][*slots_out] int64 table to the host (synchronises the device). */
+int fm_igemm_trace(long long* host_out, int n_ctas, int* slots_out);
 
 /* ------------------------------------------------------------------------------------
  * Synthesis-path helper kernels (all bandwidth-bound).
