@@ -46,7 +46,7 @@ struct IgemmParams {
   int upmode;                      // fused stride-2 transposed 3x3 conv: 4 output-parity accumulators share the A tiles
   int nbuf;                        // TMEM accumulator buffers (2, or 1 when 4 x BN x 2 columns do not fit)
   int prows;                       // output rows per tile in patch mode (R accumulators share each weight load)
-  int patch_a_bytes, patch_stage_bytes, patch_stages;
+  int patch_a_bytes, patch_stage_bytes, patch_stages, patch_b_bytes;   // patch_b_bytes: stride between the 3 weight tiles of a stage
   // halo-patch mode (stride-1 tap sets): tile = 8 x 16 pixels of one image; ONE (16+dy span) x (8+dx span)
   // input patch per channel chunk serves every tap as a shifted UMMA descriptor (group stride = patch row)
   int hp, hp_pw, hp_ph, hp_bytes, hp_dx0, hp_dy0, hp_stages, hp_na, hp_dist;
@@ -259,7 +259,17 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int ky = it / p.kchunks;
           const int kc = it - ky * p.kchunks;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (lane == 0) {
+          if (lane == 0 && kPair) {
+            // CTA pair: own input rows, half of each of the 3 weight tiles; everything completes on the leader's barrier
+            uint8_t* sa = s_stage + stage * p.patch_stage_bytes;
+            uint8_t* sb = sa + p.patch_a_bytes;
+            const uint32_t lbar = mapa_rank(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(p.prows) * 130u * (IG_BK * 2) + 3u * Cfg::B_BYTES);
+            tma_load_4d_pair(sa, &tmA, lbar, kc * IG_BK, x0 - 1, by * p.prows + ky - 1, b0);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+              tma_load_2d_pair(sb + kx * p.patch_b_bytes, &tmB, lbar, kc * IG_BK, (wrow0 + ky * 3 + kx) * p.w_rows + n0 + crank * (BN / 2));
+          } else if (lane == 0) {
             uint8_t* sa = s_stage + stage * p.patch_stage_bytes;
             uint8_t* sb = sa + p.patch_a_bytes;
             mbar_arrive_expect_tx(&full_bar[stage], ptx);
@@ -378,12 +388,23 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               // 128B swizzle is a function of the smem address, so a shifted start address just works
               const uint32_t alo = umma_desc_lo(sa + r * (130 * 128));
               const uint32_t td = tmem_t + r * BN;
-              umma_bf16_x4(td, alo, dhi, blo, dhi, idesc, it > 0 ? 1u : 0u);
-              umma_bf16_x4(td, alo + (128 >> 4), dhi, blo + (Cfg::B_BYTES >> 4), dhi, idesc, 1u);
-              umma_bf16_x4(td, alo + (256 >> 4), dhi, blo + 2 * (Cfg::B_BYTES >> 4), dhi, idesc, 1u);
+              if (kPair) {
+                umma_bf16_x4_pair(td, alo, dhi, blo, dhi, idesc, it > 0 ? 1u : 0u);
+                umma_bf16_x4_pair(td, alo + (128 >> 4), dhi, blo + (p.patch_b_bytes >> 4), dhi, idesc, 1u);
+                umma_bf16_x4_pair(td, alo + (256 >> 4), dhi, blo + 2 * (p.patch_b_bytes >> 4), dhi, idesc, 1u);
+              } else {
+                umma_bf16_x4(td, alo, dhi, blo, dhi, idesc, it > 0 ? 1u : 0u);
+                umma_bf16_x4(td, alo + (128 >> 4), dhi, blo + (Cfg::B_BYTES >> 4), dhi, idesc, 1u);
+                umma_bf16_x4(td, alo + (256 >> 4), dhi, blo + 2 * (Cfg::B_BYTES >> 4), dhi, idesc, 1u);
+              }
             }
-            if (p.cluster == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
-            if (it == nst - 1) umma_commit(&tfull_bar[buf]);
+            if (kPair) {
+              umma_commit_pair(&empty_bar[stage]);
+              if (it == nst - 1) umma_commit_pair(&tfull_bar[buf]);
+            } else {
+              if (p.cluster == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], cmask);
+              if (it == nst - 1) umma_commit(&tfull_bar[buf]);
+            }
           }
           __syncwarp();
           if (++stage == p.patch_stages) { stage = 0; phase ^= 1; }
@@ -993,6 +1014,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       while (R > 1 && (2 * R * bn > 512 || R > d->OH)) R >>= 1;
       p.prows = R;
       p.patch_a_bytes = (R * 130 * 128 + 1023) & ~1023;
+      p.patch_b_bytes = bn * 128;
       p.patch_stage_bytes = p.patch_a_bytes + 3 * bn * 128;
       p.patch_stages = (200 * 1024) / p.patch_stage_bytes;
       if (p.patch_stages > 8) p.patch_stages = 8;
@@ -1071,10 +1093,17 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     // CTA pairs (cta_group::2): the two CTAs of a cluster issue ONE M = 256 MMA and each loads only half of the
     // weight tile -- the weight stream is what saturates the L2 -> SM path of a single-CTA tile (64/R B per clk)
     static const int env_pair = []() { const char* e = getenv("FM3D_PAIR"); return e ? atoi(e) : 1; }();
-    p.pair = (env_pair && G == 1 && p.ksplit == 1 && !d->upmode && !p.patch && p.m_tiles % 2 == 0 &&
+    static const int env_pair_rp = []() { const char* e = getenv("FM3D_PAIR_RP"); return e ? atoi(e) : 1; }();
+    p.pair = (env_pair && G == 1 && p.ksplit == 1 && !d->upmode && (!p.patch || env_pair_rp) && p.m_tiles % 2 == 0 &&
               (bn >= 128 || env_pair == 2) && !((d->rgb != nullptr) + (d->residual != nullptr) + (d->border_tab != nullptr) > 1)) ? 1 : 0;
     if (p.pair) cs = 2;
     p.cluster = cs;
+    if (p.pair && p.patch) {       // half weight tiles per CTA: smaller stages, deeper ring
+      p.patch_b_bytes = bn * 64;
+      p.patch_stage_bytes = p.patch_a_bytes + 3 * p.patch_b_bytes;
+      p.patch_stages = (200 * 1024) / p.patch_stage_bytes;
+      if (p.patch_stages > 8) p.patch_stages = 8;
+    }
     // weight-resident halo-patch variant: one n-tile and all its (chunk, tap) weight tiles fit beside >= 3 patch slots
     if (p.hp) {
       static const int env_hpw = []() { const char* e = getenv("FM3D_HPW"); return e ? atoi(e) : 1; }();
