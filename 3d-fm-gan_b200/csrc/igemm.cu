@@ -65,6 +65,8 @@ struct IgemmParams {
   int noise_bstride;
   const float* noise_w;
   const __nv_bfloat16* residual;
+  int res_ih, res_iw;              // EPI_RESUP: size of the low-resolution residual source
+  float res_ry, res_rx;            //            source step per output pixel ((ih-1)/(out_H-1), align_corners=True)
   float* rgb;
   int8_t tap_dy[FM_MAX_TAPS];
   int8_t tap_dx[FM_MAX_TAPS];
@@ -76,6 +78,7 @@ constexpr int IG_THREADS2 = 64 + 32 * IG_EPI_WARPS;   // producer + MMA + epilog
 
 // epilogue feature flags (template: dead paths cost nothing)
 constexpr int EPI_RGB = 1, EPI_RES = 2, EPI_BTAB = 4, EPI_SPLIT = 8, EPI_IDENT = 16;   // IDENT: out = acc (tab == NULL)
+constexpr int EPI_RESUP = 32;   // residual = bilinear (align_corners) upsampling of a low-resolution tensor, sampled in the epilogue
 
 template <int BN> struct IgemmCfg {
   static constexpr int A_BYTES = IG_BM * IG_BK * 2;        // 16 KB
@@ -578,6 +581,20 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         nz = nw * __ldg(p.noise + (static_cast<size_t>(p.noise_bstride ? b : 0) * p.out_H + Y) * p.out_W + X);
       const size_t pix = (static_cast<size_t>(b) * p.out_H + Y) * p.out_W + X;
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      // EPI_RESUP: the four source pixels and weights of this thread's output pixel (F.interpolate, bilinear,
+      // align_corners=True: psp_encoders.py:81-98 -- the FPN top-down path, fused here instead of materialised)
+      size_t ru00 = 0, ru01 = 0, ru10 = 0, ru11 = 0;
+      float rw00 = 0.f, rw01 = 0.f, rw10 = 0.f, rw11 = 0.f;
+      if (EPI & EPI_RESUP) {
+        const float fy = p.res_ry * Y, fx = p.res_rx * X;
+        const int y0 = min(static_cast<int>(fy), p.res_ih - 1), x0 = min(static_cast<int>(fx), p.res_iw - 1);
+        const int y1 = min(y0 + 1, p.res_ih - 1), x1 = min(x0 + 1, p.res_iw - 1);
+        const float ly = fy - y0, lx = fx - x0;
+        const size_t ib = static_cast<size_t>(min(b, p.B - 1)) * p.res_ih;
+        ru00 = ((ib + y0) * p.res_iw + x0) * p.out_cstride; ru01 = ((ib + y0) * p.res_iw + x1) * p.out_cstride;
+        ru10 = ((ib + y1) * p.res_iw + x0) * p.out_cstride; ru11 = ((ib + y1) * p.res_iw + x1) * p.out_cstride;
+        rw00 = (1.f - ly) * (1.f - lx); rw01 = (1.f - ly) * lx; rw10 = ly * (1.f - lx); rw11 = ly * lx;
+      }
       const float* btab = nullptr;      // folded-input-BN border correction (per-thread: thread = pixel)
       bool warp_has_border = false;
       int cls = 0;
@@ -618,6 +635,27 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 2; ++g)
             resv[g] = (valid && p.residual && ol0 + 8 * g < p.out_cstride) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
+        }
+        float resf[16];
+        if (EPI & EPI_RESUP) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 qa = make_uint4(0, 0, 0, 0), qb = qa, qc = qa, qd = qa;
+            if (valid && ol0 + 8 * g < p.out_cstride) {
+              const __nv_bfloat16* rb = p.residual + ol0 + 8 * g;
+              qa = __ldg(reinterpret_cast<const uint4*>(rb + ru00)); qb = __ldg(reinterpret_cast<const uint4*>(rb + ru01));
+              qc = __ldg(reinterpret_cast<const uint4*>(rb + ru10)); qd = __ldg(reinterpret_cast<const uint4*>(rb + ru11));
+            }
+            const uint32_t wa[4] = {qa.x, qa.y, qa.z, qa.w}, wb2[4] = {qb.x, qb.y, qb.z, qb.w};
+            const uint32_t wc[4] = {qc.x, qc.y, qc.z, qc.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              resf[8 * g + 2 * k] = rw00 * __uint_as_float(wa[k] << 16) + rw01 * __uint_as_float(wb2[k] << 16) +
+                                    rw10 * __uint_as_float(wc[k] << 16) + rw11 * __uint_as_float(wd[k] << 16);
+              resf[8 * g + 2 * k + 1] = rw00 * __uint_as_float(wa[k] & 0xffff0000u) + rw01 * __uint_as_float(wb2[k] & 0xffff0000u) +
+                                        rw10 * __uint_as_float(wc[k] & 0xffff0000u) + rw11 * __uint_as_float(wd[k] & 0xffff0000u);
+            }
+          }
         }
         float bcor[16];
         if (EPI & EPI_BTAB) {
@@ -666,6 +704,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t w = (&resv[0].x)[j >> 1];
             x += __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
           }
+          if (EPI & EPI_RESUP) x += resf[j];
           x = x > 0.f ? x : x * t0.z;
           if (EPI & EPI_RGB) {
             const float4 t1 = tr[2 * j + 1];
@@ -835,7 +874,7 @@ static int launch_igemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const I
 template <int BN, int EPI>
 static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
   // pair instantiations exist for the feature sets the N >= 128 layers use
-  if constexpr (EPI == 0 || EPI == EPI_RGB || EPI == EPI_RES || EPI == EPI_BTAB || EPI == EPI_IDENT) {
+  if constexpr (EPI == 0 || EPI == EPI_RGB || EPI == EPI_RES || EPI == EPI_BTAB || EPI == EPI_IDENT || EPI == EPI_RESUP) {
     if (p.pair) return launch_igemm3<BN, EPI, true>(tmA, tmB, p, st);
   }
   if (p.pair) { set_error("fm_conv_igemm: internal: no CTA-pair instantiation for block_n %d epilogue %d", BN, EPI); return FM_ERR_INVALID; }
@@ -858,6 +897,10 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     return FM_OK;
   }
   if (!p.tab) return launch_igemm2<BN, EPI_IDENT>(tmA, tmB, p, st);
+  if (p.residual && p.res_ih > 0) {
+    if (p.rgb || p.border_tab) { set_error("fm_conv_igemm: an upsampled residual excludes rgb / border_tab"); return FM_ERR_INVALID; }
+    return launch_igemm2<BN, EPI_RESUP>(tmA, tmB, p, st);
+  }
   const int epi = (p.rgb ? EPI_RGB : 0) | (p.residual ? EPI_RES : 0) | (p.border_tab ? EPI_BTAB : 0);
   switch (epi) {
     case 0: return launch_igemm2<BN, 0>(tmA, tmB, p, st);
@@ -930,7 +973,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   int ksplit = 1;
   {
     static const int env_split = []() { const char* e = getenv("FM3D_SPLITK"); return e ? atoi(e) : 1; }();
-    const bool eligible = env_split && d->tab && d->ksplit != 1 && d->splitk_ws && !d->rgb && !d->border_tab && !d->out_nchw_f32 &&
+    const bool eligible = env_split && d->tab && d->residual_up_h <= 0 && d->ksplit != 1 && d->splitk_ws && !d->rgb && !d->border_tab && !d->out_nchw_f32 &&
                           !d->out_cgroup && d->block_n <= 0 && !d->upmode;
     if (eligible) {
       const int bn_wide = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
@@ -979,6 +1022,13 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   p.tab = d->tab; p.tab_bstride = d->tab_bstride ? 1 : 0;
   p.noise = d->noise; p.noise_bstride = d->noise_bstride ? 1 : 0; p.noise_w = d->noise_w;
   p.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  if (d->residual && d->residual_up_h > 0) {
+    FM_CHECK_ARG(d->residual_up_w > 0 && d->out_ys == 1 && d->out_xs == 1 && d->out_H > 1 && d->out_W > 1,
+                 "fm_conv_igemm: bad upsampled-residual configuration");
+    p.res_ih = d->residual_up_h; p.res_iw = d->residual_up_w;
+    p.res_ry = static_cast<float>(d->residual_up_h - 1) / (d->out_H - 1);
+    p.res_rx = static_cast<float>(d->residual_up_w - 1) / (d->out_W - 1);
+  }
   p.rgb = d->rgb;
   p.border_tab = d->border_tab;
   p.out_cgroup = d->out_cgroup; p.out_gstride = d->out_gstride; p.cg_shrink = d->out_cgroup_ow_shrink;

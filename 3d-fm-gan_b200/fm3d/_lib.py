@@ -33,6 +33,7 @@ class ConvDesc(C.Structure):
         ("border_tab", C.c_void_p), ("out_cgroup", C.c_int32), ("out_gstride", C.c_int64),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64), ("ksplit", C.c_int32), ("upmode", C.c_int32),
         ("block_n", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("out_cgroup_ow_shrink", C.c_int32),
+        ("residual_up_h", C.c_int32), ("residual_up_w", C.c_int32),
     ]
 
 

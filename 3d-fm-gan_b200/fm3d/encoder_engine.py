@@ -16,6 +16,8 @@ Derived tensors are caches keyed on the parameters' version counters, never stat
 """
 import math
 
+import os
+
 import torch
 
 from . import ops
@@ -78,6 +80,9 @@ class _Conv:
 # ======================================================================================
 # ResNet-18
 # ======================================================================================
+_FUSE_UPSAMPLE = os.environ.get("FM3D_FUSE_UPSAMPLE", "1") != "0"
+
+
 class ResNetPlan:
     def __init__(self, model, B, H, W, device):
         self.model, self.B, self.H, self.W, self.device = model, B, H, W, device
@@ -331,13 +336,21 @@ class PspPlan:
 
         nc, nm, nf = len(self.coarse), len(self.middle), len(self.fine)
         first("coarse", self.coarse, c3, h3, lvl8, 0)                                    # 16 -> 8
-        up2 = ops.bilinear_up_nhwc(c3, h2, h2, self._buf("up2", B, h2, h2, 512))
-        p2 = self.lat1.run(c2, self._buf("p2", B, h2, h2, 512), B, h2, h2, residual=up2)
+        # FPN top-down path (psp_encoders.py:81-98,123,127): the bilinear upsampling of the coarser map is sampled
+        # inside the lateral 1x1 conv's epilogue instead of being written out and read back
+        if _FUSE_UPSAMPLE:
+            p2 = self.lat1.run(c2, self._buf("p2", B, h2, h2, 512), B, h2, h2, residual_up=c3)
+        else:
+            up2 = ops.bilinear_up_nhwc(c3, h2, h2, self._buf("up2", B, h2, h2, 512))
+            p2 = self.lat1.run(c2, self._buf("p2", B, h2, h2, 512), B, h2, h2, residual=up2)
         mid16 = self._buf("mid16", nm * B, h2 // 2, h2 // 2, 512)
         first("middle", self.middle, p2, h2, mid16, 0)                                   # 32 -> 16
         grouped(self.mid_l1, mid16, nm, h2 // 2, lvl8[nc * B:])                          # 16 -> 8
-        up1 = ops.bilinear_up_nhwc(p2, h1, h1, self._buf("up1", B, h1, h1, 512))
-        p1 = self.lat2.run(c1, self._buf("p1", B, h1, h1, 512), B, h1, h1, residual=up1)
+        if _FUSE_UPSAMPLE:
+            p1 = self.lat2.run(c1, self._buf("p1", B, h1, h1, 512), B, h1, h1, residual_up=p2)
+        else:
+            up1 = ops.bilinear_up_nhwc(p2, h1, h1, self._buf("up1", B, h1, h1, 512))
+            p1 = self.lat2.run(c1, self._buf("p1", B, h1, h1, 512), B, h1, h1, residual=up1)
         fine32 = self._buf("fine32", nf * B, h1 // 2, h1 // 2, 512)
         first("fine", self.fine, p1, h1, fine32, 0)                                      # 64 -> 32
         fine16 = self._buf("fine16", nf * B, h1 // 4, h1 // 4, 512)

@@ -142,7 +142,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
                tab_per_sample=False, noise=None, noise_per_sample=True, noise_w=None, residual=None,
                rgb=None, block_n=0, tile_w=0, tile_h=0, stride_x=0, stride_y=0, x_pixstride=0, x_rowstride=0,
                x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None, ksplit=0, upmode=False,
-               out_cgroup_ow_shrink=0, algo_flops=None):
+               out_cgroup_ow_shrink=0, algo_flops=None, residual_up=None):
     """Launch fm_conv_igemm.  x: bf16 NHWC [B,H,W,cs]; w: bf16 [slabs, w_rows, cin_stride];
     out: bf16 NHWC [B,out_H,out_W,cs_out] or fp32 NCHW; tab: fp32 [B|1, Cout, 8]."""
     d = ConvDesc()
@@ -171,6 +171,9 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     d.noise = _ptr(noise); d.noise_bstride = 1 if noise_per_sample else 0
     d.noise_w = _ptr(noise_w)
     d.residual = _ptr(residual)
+    if residual_up is not None:          # low-resolution [B,h,w,cs] tensor, bilinearly upsampled in the epilogue
+        d.residual = _ptr(residual_up)
+        d.residual_up_h, d.residual_up_w = residual_up.shape[1], residual_up.shape[2]
     d.rgb = _ptr(rgb)
     d.block_n, d.tile_w, d.tile_h = block_n, tile_w, tile_h
     ws = _splitk_workspace(x.device)

@@ -192,7 +192,7 @@ def main():
         # ---------------- device-resident throughput
         # set-up (not a timed or counted step): the engine plans run eagerly twice and are captured into CUDA
         # graphs on the third call, so the W warm-up steps below already replay the steady-state graphs
-        for i in range(4):
+        for i in range(20):       # also lets clocks / power state settle on a freshly acquired GPU
             step(*dev_in[i % n_sets])
         torch.cuda.synchronize()
         for i in range(warm):

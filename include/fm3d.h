@@ -163,6 +163,10 @@ typedef struct {
   /* concatenated-N output: group g only writes columns ox < OW - g*out_cgroup_ow_shrink (the odd-column
    * parity of a stride-2 transposed conv has one column less than the even one) */
   int32_t out_cgroup_ow_shrink;
+  /* residual_up_h/w > 0: `residual` is a LOW-resolution bf16 NHWC tensor [B, residual_up_h, residual_up_w, out_cstride]
+   * that the epilogue samples bilinearly with align_corners=True (the FPN top-down add of the pSp encoder,
+   * psp_encoders.py:81-98, without materialising the upsampled map) */
+  int32_t residual_up_h, residual_up_w;
 } fm_conv_desc;
 
 int fm_conv_igemm(const fm_conv_desc* desc, void* stream);
