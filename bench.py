@@ -23,7 +23,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 import types
 
@@ -63,35 +62,71 @@ def synthetic_batch(batch, seed):
     return p, r
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), read through NVML from a
+    background thread (ctypes releases the GIL) a few times per second.  Forking `nvidia-smi` per sample, or
+    letting `nvidia-smi -lms` poll at 10 Hz, cost up to 10 % of the device-resident number (driver lock /
+    child start-up inside the timed region); the NVML calls here are microseconds each."""
 
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.stop_flag = threading.Event()
+    def __init__(self, index, period=0.1):
+        self.index, self.period = index, period
         self.rows = []
+        self.stop_flag = None
+        self.thread = None
+        self.nvml = None
+        self.handle = None
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    def start(self):
+        import threading
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+            return
+        self.stop_flag = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        n = self.nvml
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((sm, mx, rs))
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(self.period)
+
+    def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        n = self.nvml
+        names = {"hw_slowdown": "nvmlClocksThrottleReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksThrottleReasonHwThermalSlowdown",
+                 "sw_thermal_slowdown": "nvmlClocksThrottleReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksThrottleReasonSwPowerCap"}
+        reasons = set()
+        for (_, _, rs) in self.rows:
+            for k, attr in names.items():
+                bit = getattr(n, attr, None)
+                if bit is not None and (rs & bit):
+                    reasons.add(k)
+        sm = sorted(r[0] for r in self.rows)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in self.rows), "reasons": sorted(reasons),
+                "samples": len(self.rows), "source": "NVML"}
 
 
 def cpu_port_rate(batch, iters, warm):
@@ -198,8 +233,9 @@ def main():
         for i in range(warm):
             step(*dev_in[i % n_sets])
         sampler = ClockSampler(local_rank)
+        if os.environ.get("FM3D_BENCH_SAMPLER", "nvml") != "none":
+            sampler.start()
         barrier()
-        sampler.start()
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -208,7 +244,7 @@ def main():
         e1.record()
         barrier()
         launches = _lib.launch_count() - l0
-        sampler.stop_flag.set()
+        sampler.stop()
         ms = max_over_ranks(e0.elapsed_time(e1))
         value = B * world * args.steps / (ms * 1e-3)
 
