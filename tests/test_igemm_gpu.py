@@ -287,3 +287,59 @@ def test_conv_fused_upsample_mode(cuda, B, h, Cin, Cout):
                    tile_w=tw, tile_h=max(1, min(8, 128 // tw)), upmode=True)
     torch.cuda.synchronize()
     torch.testing.assert_close(out[..., :Cout].float().permute(0, 3, 1, 2).cpu(), ref, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 32, 64, 64), (2, 16, 64, 64, 128), (1, 48, 40, 128, 64), (4, 64, 64, 64, 64)])
+def test_conv_halo_patch_resident_weights(cuda, B, H, W, Cin, Cout):
+    """Halo-patch mode with the whole weight set resident in shared memory (single n-tile, small Cin*Cout):
+    8x16-pixel tiles, one (18 x 10)-pixel input patch per channel chunk, taps as shifted descriptors; N = 128
+    additionally runs as a CTA pair (cta_group::2)."""
+    got, ref = _run_conv(cuda, B, H, W, Cin, Cout, 3, seed=H * 3 + Cout, out_nchw=True)
+    torch.testing.assert_close(got, ref, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("B,h,Cin,Cout", [(2, 16, 64, 128), (1, 24, 128, 64), (3, 12, 72, 32)])
+def test_conv_paired_parity_upsample(cuda, B, h, Cin, Cout):
+    """Stride-2 transposed 3x3 conv as TWO launches (one per output-row parity) whose N dimension concatenates
+    the even- and odd-column parities (zero weight blocks where the odd parity has no tap): the engine's
+    Cout <= 128 up-conv path, against F.conv_transpose2d (stylegan2.py:276)."""
+    from fm3d import engine, ops
+    gen = torch.Generator().manual_seed(h * 7 + Cin)
+    x = torch.randn(B, Cin, h, h, generator=gen)
+    w = torch.randn(Cout, Cin, 3, 3, generator=gen) / (Cin * 9) ** 0.5
+    ref = F.conv_transpose2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float().transpose(0, 1), stride=2)
+    wq, _ = ops.prep_weight(w.to(cuda), 1.0, want_wsq=False)          # [9][Cout][cin_stride]
+    cs = (Cout + 7) // 8 * 8
+    out = torch.full((B, 2 * h + 1, 2 * h + 1, cs), 7.0, device=cuda, dtype=torch.bfloat16)
+    xg = ops.nchw_to_nhwc_bf16(x.to(cuda))
+    for py, views in engine._PAIR_VIEWS.items():
+        wp = torch.zeros(len(views), 2 * Cout, wq.shape[2], device=cuda, dtype=torch.bfloat16)
+        for v, (_, t0, t1) in enumerate(views):
+            wp[v, :Cout] = wq[t0, :Cout]
+            if t1 is not None:
+                wp[v, Cout:] = wq[t1, :Cout]
+        taps = [(dy, dx, v) for v, ((dy, dx), _, _) in enumerate(views)]
+        ops.conv_igemm(xg, wp, taps, out, None, B=B, H=h, W=h, Cin=Cin, Cout=2 * Cout, OH=h + 1 - py, OW=h + 1,
+                       out_H=2 * h + 1, out_W=2 * h + 1, out_y0=py, out_x0=0, out_ys=2, out_xs=2, tab_per_sample=False,
+                       out_cgroup=Cout, out_gstride=cs, out_cstride=cs, out_cgroup_ow_shrink=1)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out[..., :Cout].float().permute(0, 3, 1, 2).cpu(), ref, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("B,h,Cin,Cout", [(2, 16, 128, 512), (1, 8, 64, 64)])
+def test_conv_upsampled_residual(cuda, B, h, Cin, Cout):
+    """1x1 lateral conv + bilinear (align_corners=True) upsampling of a half-resolution map sampled in the
+    epilogue: the FPN top-down add of the pSp encoder (psp_encoders.py:81-98) without the intermediate tensor."""
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(h + Cout)
+    x = torch.randn(B, Cin, 2 * h, 2 * h, generator=gen)
+    low = torch.randn(B, Cout, h, h, generator=gen)
+    w = torch.randn(Cout, Cin, 1, 1, generator=gen) / Cin ** 0.5
+    ref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()) + \
+        F.interpolate(low.to(torch.bfloat16).float(), size=(2 * h, 2 * h), mode="bilinear", align_corners=True)
+    wq, _ = ops.prep_weight(w.to(cuda), 1.0, want_wsq=False)
+    out = torch.zeros(B, 2 * h, 2 * h, Cout, device=cuda, dtype=torch.bfloat16)
+    ops.conv_igemm(ops.nchw_to_nhwc_bf16(x.to(cuda)), wq, [(0, 0, 0)], out, _tab(Cout, cuda), B=B, H=2 * h, W=2 * h, Cin=Cin,
+                   Cout=Cout, OH=2 * h, OW=2 * h, residual_up=ops.nchw_to_nhwc_bf16(low.to(cuda)))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.float().permute(0, 3, 1, 2).cpu(), ref, rtol=1e-2, atol=2e-2)
