@@ -50,6 +50,11 @@ struct IgemmParams {
   // halo-patch mode (stride-1 tap sets): tile = 8 x 16 pixels of one image; ONE (16+dy span) x (8+dx span)
   // input patch per channel chunk serves every tap as a shifted UMMA descriptor (group stride = patch row)
   int hp, hp_pw, hp_ph, hp_bytes, hp_dx0, hp_dy0, hp_stages, hp_na, hp_dist;
+  // strided convs: the taps split into parity planes of the input (iy = s*oy + dy -> plane dy mod s, row (dy - plane)/s of
+  // the subsampled grid); each (chunk, plane) is one patch load (TMA element stride s) shared by the plane's taps
+  int hp_np, hp_sx, hp_sy;
+  int8_t hp_pl_first[5];           // taps [first[pl], first[pl+1]) belong to plane pl (taps are sorted by plane)
+  int16_t hp_pl_x[4], hp_pl_y[4];  // input-space offset of a plane's patch origin relative to (sx*x0, sy*y0)
   int hpw;                         // halo-patch mode with ALL weight tiles of the (single) n-tile resident in smem
   int16_t hp_aoff[FM_MAX_TAPS];    // per-tap start offset of the A descriptor inside the patch (16-byte units)
   int Bg, nslabs;                  // images per group, weight slabs per group
@@ -179,6 +184,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int pst = cluster_id, pkc = 0, pslot = 0;
     uint32_t pphase = 0;
     const uint32_t patch_tx = static_cast<uint32_t>(p.hp_pw) * p.hp_ph * (IG_BK * 2);
+    const int nvc = p.kchunks * p.hp_np;          // virtual chunks: (channel chunk, parity plane)
     auto hp_prefetch = [&]() {
       if (pst >= p.num_super) return;
       int m = (pst / p.tiles_n) * p.cluster + crank;   // ksplit == 1 in this mode
@@ -186,21 +192,20 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int by = m % p.tiles_y;
       const int bb = m / p.tiles_y;
       mbar_wait(&aempty_bar[pslot], pphase ^ 1);
-      const int pkr = pkc;
+      const int pkr = pkc / p.hp_np, ppl = pkc - pkr * p.hp_np;
+      const int cx = bx * 8 * p.hp_sx + p.hp_pl_x[ppl], cy = by * 16 * p.hp_sy + p.hp_pl_y[ppl];
       if (lane == 0) {
         if (kPair) {
           // both CTAs' patches complete on the leader's barrier; the leader announces the bytes of both
           if (crank == 0) mbar_arrive_expect_tx(&afull_bar[pslot], 2 * patch_tx);
-          tma_load_4d_pair(s_stage + pslot * p.hp_bytes, &tmA, mapa_rank(smem_u32(&afull_bar[pslot]), 0), pkr * IG_BK,
-                           bx * 8 + p.hp_dx0, by * 16 + p.hp_dy0, bb);
+          tma_load_4d_pair(s_stage + pslot * p.hp_bytes, &tmA, mapa_rank(smem_u32(&afull_bar[pslot]), 0), pkr * IG_BK, cx, cy, bb);
         } else {
           mbar_arrive_expect_tx(&afull_bar[pslot], patch_tx);
-          tma_load_4d(s_stage + pslot * p.hp_bytes, &tmA, &afull_bar[pslot], pkr * IG_BK,
-                      bx * 8 + p.hp_dx0, by * 16 + p.hp_dy0, bb);
+          tma_load_4d(s_stage + pslot * p.hp_bytes, &tmA, &afull_bar[pslot], pkr * IG_BK, cx, cy, bb);
         }
       }
       __syncwarp();
-      if (++pkc == p.kchunks) { pkc = 0; pst += num_clusters; }
+      if (++pkc == nvc) { pkc = 0; pst += num_clusters; }
       if (++pslot == p.hp_na) { pslot = 0; pphase ^= 1; }
     };
     if (p.hpw) {
@@ -220,7 +225,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       __syncwarp();
       for (int st = cluster_id; st < p.num_super; st += num_clusters)
-        for (int kc = 0; kc < p.kchunks; ++kc) hp_prefetch();     // blocks on the patch ring only
+        for (int vc = 0; vc < nvc; ++vc) hp_prefetch();           // blocks on the patch ring only
     } else {
     if (p.hp)
       for (int i = 0; i < p.hp_dist; ++i) hp_prefetch();
@@ -290,9 +295,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // chunk-major weight stages; the input patch of chunk c + hp_dist is requested when chunk c starts
         // (its slot was last read hp_na - hp_dist >= 2 chunks ago, so the wait below never blocks the weights)
         uint8_t* sb0 = s_stage + p.hp_na * p.hp_bytes;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int vc = 0; vc < nvc; ++vc) {
           hp_prefetch();
-          for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int kc = vc / p.hp_np, pl = vc - kc * p.hp_np;
+          for (int tap = p.hp_pl_first[pl]; tap < p.hp_pl_first[pl + 1]; ++tap) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (lane == 0) {
               if (kPair) {
@@ -420,25 +426,28 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t ahi = umma_desc_hi_sw128(static_cast<uint32_t>(p.hp_pw) * 128u);
         if (titer == 0) { mbar_wait(&full_bar[0], 0); tc_fence_after(); }      // resident weights have landed
         if (lane == 0) IG_TRACE(3 + 4 * titer);
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+        const int nvc = p.kchunks * p.hp_np;
+        for (int vc = 0; vc < nvc; ++vc) {
           mbar_wait(&afull_bar[aslot], aslot_phase);
           tc_fence_after();
-          if (lane == 0 && kc == 0) IG_TRACE(4 + 4 * titer);
+          if (lane == 0 && vc == 0) IG_TRACE(4 + 4 * titer);
+          const int kc = vc / p.hp_np, pl = vc - kc * p.hp_np;
           const uint32_t alo0 = umma_desc_lo(ring + aslot * p.hp_bytes);
           const uint32_t blo0 = umma_desc_lo(sw + static_cast<uint32_t>(kc * p.ntaps) * wb);
           if (elect_one()) {
-            for (int tap = 0; tap < p.ntaps; ++tap) {
+            for (int tap = p.hp_pl_first[pl]; tap < p.hp_pl_first[pl + 1]; ++tap) {
               const uint32_t alo = alo0 + static_cast<uint32_t>(p.hp_aoff[tap]);
               const uint32_t blo = blo0 + static_cast<uint32_t>(tap) * (wb >> 4);
-              if (kPair) umma_bf16_x4_pair(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tap > 0) ? 1u : 0u);
-              else umma_bf16_x4(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tap > 0) ? 1u : 0u);
+              const uint32_t accf = (vc > 0 || tap > p.hp_pl_first[pl]) ? 1u : 0u;
+              if (kPair) umma_bf16_x4_pair(tmem_d, alo, ahi, blo, dhi, idesc, accf);
+              else umma_bf16_x4(tmem_d, alo, ahi, blo, dhi, idesc, accf);
             }
             if (kPair) {
               umma_commit_pair(&aempty_bar[aslot]);
-              if (kc == p.kchunks - 1) umma_commit_pair(&tfull_bar[buf]);
+              if (vc == nvc - 1) umma_commit_pair(&tfull_bar[buf]);
             } else {
               umma_commit(&aempty_bar[aslot]);
-              if (kc == p.kchunks - 1) umma_commit(&tfull_bar[buf]);
+              if (vc == nvc - 1) umma_commit(&tfull_bar[buf]);
             }
           }
           __syncwarp();
@@ -450,30 +459,33 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t sb0 = ring + p.hp_na * p.hp_bytes;
         const uint32_t ahi = umma_desc_hi_sw128(static_cast<uint32_t>(p.hp_pw) * 128u);
         if (lane == 0) IG_TRACE(3 + 4 * titer);               // MMA: accumulator free
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&afull_bar[aslot], aslot_phase);          // this chunk's input patch has landed
-          if (lane == 0 && kc == 0) IG_TRACE(4 + 4 * titer);  // MMA: first patch landed
+        const int nvc = p.kchunks * p.hp_np;
+        for (int vc = 0; vc < nvc; ++vc) {
+          mbar_wait(&afull_bar[aslot], aslot_phase);          // this (chunk, plane)'s input patch has landed
+          if (lane == 0 && vc == 0) IG_TRACE(4 + 4 * titer);  // MMA: first patch landed
+          const int pl = vc % p.hp_np;
           const uint32_t alo0 = umma_desc_lo(ring + aslot * p.hp_bytes);
-          for (int tap = 0; tap < p.ntaps; ++tap) {
-            const int tl = tap;
+          const int t0 = p.hp_pl_first[pl], t1 = p.hp_pl_first[pl + 1];
+          for (int tap = t0; tap < t1; ++tap) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t alo = alo0 + static_cast<uint32_t>(p.hp_aoff[tap]);
             const uint32_t blo = umma_desc_lo(sb0 + stage * Cfg::B_BYTES);
+            const uint32_t accf = (vc > 0 || tap > t0) ? 1u : 0u;
             if (elect_one()) {
               if (kPair) {
-                umma_bf16_x4_pair(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tl > 0) ? 1u : 0u);
+                umma_bf16_x4_pair(tmem_d, alo, ahi, blo, dhi, idesc, accf);
                 umma_commit_pair(&empty_bar[stage]);
-                if (tl == p.ntaps - 1) {
+                if (tap == t1 - 1) {
                   umma_commit_pair(&aempty_bar[aslot]);
-                  if (kc == p.kchunks - 1) umma_commit_pair(&tfull_bar[buf]);
+                  if (vc == nvc - 1) umma_commit_pair(&tfull_bar[buf]);
                 }
               } else {
-                umma_bf16_x4(tmem_d, alo, ahi, blo, dhi, idesc, (kc > 0 || tl > 0) ? 1u : 0u);
+                umma_bf16_x4(tmem_d, alo, ahi, blo, dhi, idesc, accf);
                 umma_commit(&empty_bar[stage]);
-                if (tl == p.ntaps - 1) {
+                if (tap == t1 - 1) {
                   umma_commit(&aempty_bar[aslot]);              // patch slot is free once these MMAs retire
-                  if (kc == p.kchunks - 1) umma_commit(&tfull_bar[buf]);
+                  if (vc == nvc - 1) umma_commit(&tfull_bar[buf]);
                 }
               }
             }
@@ -1077,25 +1089,39 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       p.prows = 1;
     }
   }
-  // ---- halo-patch mode: any stride-1 tap set on images at least 16 rows tall.  Tile = 8 x 16 output pixels;
-  // the (16 + dy span) x (8 + dx span) input patch of a channel chunk is loaded ONCE and every tap reads it
-  // through a shifted descriptor, so the activation traffic L2 -> SM drops from ntaps x to ~1.4x per chunk
-  // (the chip-wide L2 -> SM rate, not the tensor pipe, bounds the per-tap scheme for N <= 128).
+  // ---- halo-patch mode: plain tap sets (stride 1 or 2) on outputs at least 12 rows tall.  Tile = 8 x 16 output
+  // pixels; per channel chunk the input patch the tile's taps touch is loaded ONCE and every tap reads it through a
+  // shifted descriptor, so the activation traffic L2 -> SM drops from ntaps x to ~1.4x per chunk.  A strided conv
+  // splits its taps by the parity plane of the input they read (iy = s*oy + dy: plane dy mod s, subsampled row
+  // oy + (dy - plane)/s); each (chunk, plane) is one patch, fetched with TMA element stride s.
   {
     static const int env_hp = []() { const char* e = getenv("FM3D_HPATCH"); return e ? atoi(e) : 1; }();
-    int dx0 = 127, dx1 = -127, dy0 = 127, dy1 = -127;
-    for (int i = 0; i < d->ntaps; ++i) {
-      dx0 = d->tap_dx[i] < dx0 ? d->tap_dx[i] : dx0; dx1 = d->tap_dx[i] > dx1 ? d->tap_dx[i] : dx1;
-      dy0 = d->tap_dy[i] < dy0 ? d->tap_dy[i] : dy0; dy1 = d->tap_dy[i] > dy1 ? d->tap_dy[i] : dy1;
-    }
+    static const int env_hp_s2 = []() { const char* e = getenv("FM3D_HPATCH_S2"); return e ? atoi(e) : 1; }();
     const bool plain_x = d->x_pixstride == 0 && d->x_rowstride == 0 && d->x_imgstride == 0;
     // 0 off | 1 (default) wherever row-patch mode does not apply | 2 always | 3 only N = 256 tiles.  The chip-wide
     // L2 -> SM rate (~6300 B/clk, 42 B/clk per SM) is the budget: a single-CTA tile streams N*128 B of weights
     // per 2N tensor-pipe cycles (64 B/clk) before any activation byte, which is why the row-patch mode shares a
     // weight tile between R accumulators and the CTA-pair mode halves it
     const bool want = env_hp == 2 || (env_hp == 1 && !p.patch) || (env_hp == 3 && !p.patch && bn == 256);
-    if (want && plain_x && sx == 1 && sy == 1 && G == 1 && p.ksplit == 1 && !d->upmode && d->ntaps >= 2 && d->OH >= 12 &&
-        d->OW >= 8 && dx1 - dx0 <= 8 && dy1 - dy0 <= 8 && (!d->tab_bstride || bn <= IG_TAB_ROWS)) {
+    // stride 2: measured slower than the per-tap scheme for the wide layers (512 -> 3584: 723 -> 959 us; one patch
+    // per (chunk, plane) makes 1-tap virtual chunks), faster where the weights stay resident (64 -> 64 at 256^2:
+    // 119 -> 97 us) -- so only there (env 2 forces it everywhere)
+    const bool s2_resident = bn == 64 && d->Cout <= 64 &&
+                             static_cast<int64_t>(kiters_total) * bn * 128 + 3 * 21 * 1024 <= 200 * 1024;
+    const bool stride_ok = (sx == 1 && sy == 1) || (sx == 2 && sy == 2 && (env_hp_s2 == 2 || (env_hp_s2 == 1 && s2_resident)));
+    // plane / subsampled offset of every tap
+    int pl_of[FM_MAX_TAPS], du[FM_MAX_TAPS], dv[FM_MAX_TAPS];
+    int du0 = 127, du1 = -127, dv0 = 127, dv1 = -127;
+    for (int i = 0; i < d->ntaps; ++i) {
+      const int py = ((d->tap_dy[i] % sy) + sy) % sy, px = ((d->tap_dx[i] % sx) + sx) % sx;
+      pl_of[i] = py * sx + px;
+      du[i] = (d->tap_dy[i] - py) / sy;
+      dv[i] = (d->tap_dx[i] - px) / sx;
+      du0 = du[i] < du0 ? du[i] : du0; du1 = du[i] > du1 ? du[i] : du1;
+      dv0 = dv[i] < dv0 ? dv[i] : dv0; dv1 = dv[i] > dv1 ? dv[i] : dv1;
+    }
+    if (want && stride_ok && plain_x && G == 1 && p.ksplit == 1 && !d->upmode && d->ntaps >= 2 && d->OH >= 12 &&
+        d->OW >= 8 && dv1 - dv0 <= 8 && du1 - du0 <= 8 && sx * sy <= 4 && (!d->tab_bstride || bn <= IG_TAB_ROWS)) {
       p.hp = 1;
       p.patch = 0; p.prows = 1;
       p.tw = 8; p.th = 16; p.tb = 1; p.rows = 128;
@@ -1103,14 +1129,35 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       p.tiles_y = (d->OH + 15) / 16;
       p.tiles_b = d->B;
       p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
-      p.hp_pw = 8 + dx1 - dx0;
-      p.hp_ph = 16 + dy1 - dy0;
-      p.hp_dx0 = dx0; p.hp_dy0 = dy0;
+      p.hp_pw = 8 + dv1 - dv0;
+      p.hp_ph = 16 + du1 - du0;
+      p.hp_dx0 = dv0; p.hp_dy0 = du0;
+      p.hp_sx = sx; p.hp_sy = sy;
       p.hp_bytes = (p.hp_pw * p.hp_ph * 128 + 1023) & ~1023;
-      // The patch of chunk c + D is requested when the weights of chunk c start; its slot was last read by
-      // chunk c + D - NA.  With NA = D + E the producer has by then seen weight stage c*T - S retire, which is at
-      // or after the last tap of chunk c - E when S <= (E - 1) * T + 1: the request never blocks the weight ring.
-      const int T = d->ntaps;
+      // sort the taps by plane (stable) and record each plane's tap range and patch origin
+      int order[FM_MAX_TAPS], n = 0, np = 0;
+      for (int pl = 0; pl < sx * sy; ++pl) {
+        const int first = n;
+        for (int i = 0; i < d->ntaps; ++i)
+          if (pl_of[i] == pl) order[n++] = i;
+        if (n > first) {
+          p.hp_pl_first[np] = static_cast<int8_t>(first);
+          p.hp_pl_x[np] = static_cast<int16_t>(sx * dv0 + pl % sx);
+          p.hp_pl_y[np] = static_cast<int16_t>(sy * du0 + pl / sx);
+          ++np;
+        }
+      }
+      p.hp_pl_first[np] = static_cast<int8_t>(n);
+      p.hp_np = np;
+      for (int k = 0; k < d->ntaps; ++k) {
+        const int i = order[k];
+        p.tap_dy[k] = d->tap_dy[i]; p.tap_dx[k] = d->tap_dx[i]; p.tap_widx[k] = d->tap_widx[i];
+        p.hp_aoff[k] = static_cast<int16_t>(((du[i] - du0) * p.hp_pw + (dv[i] - dv0)) * 8);
+      }
+      // The patch of virtual chunk c + D is requested when the weights of chunk c start; its slot was last read
+      // by chunk c + D - NA (NA = D + E, E >= 2), whose MMAs only need loads issued earlier: no deadlock, and with
+      // S <= (E - 1) * T + 1 weight stages (T = taps per virtual chunk) the request does not even block.
+      const int T = (d->ntaps + np - 1) / np;
       const int bbytes = bn * 128;
       const int st_max = bn == 256 ? 4 : (bn == 128 ? 6 : 8);
       int D = T >= 5 ? 2 : (T >= 3 ? 3 : 4);
@@ -1119,13 +1166,11 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       for (; D >= 1; --D) {
         st = (200 * 1024 - (D + E) * p.hp_bytes) / bbytes;
         if (st > st_max) st = st_max;
-        if (st > (E - 1) * T + 1) st = (E - 1) * T + 1;
+        if (np == 1 && st > (E - 1) * T + 1) st = (E - 1) * T + 1;
         if (st >= 3 || (D == 1 && st >= 2)) break;
       }
       if (D >= 1 && D + E <= IG_HP_MAXA) {
         p.hp_dist = D; p.hp_na = D + E; p.hp_stages = st;
-        for (int i = 0; i < d->ntaps; ++i)
-          p.hp_aoff[i] = static_cast<int16_t>(((d->tap_dy[i] - dy0) * p.hp_pw + (d->tap_dx[i] - dx0)) * 8);
       } else {
         set_error("fm_conv_igemm: halo-patch ring does not fit (patch %d bytes, block_n %d)", p.hp_bytes, bn);
         return FM_ERR_INVALID;
@@ -1175,8 +1220,8 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(pixs) * 2, static_cast<cuuint64_t>(rows_) * 2,
                                    static_cast<cuuint64_t>(imgs) * 2};
     // with an element stride s TMA loads ceil(box/s) elements: box = n*s loads n
-    const cuuint32_t box[4] = {IG_BK, static_cast<cuuint32_t>(p.hp ? p.hp_pw : (p.patch ? 130 : tw * sx)),
-                               static_cast<cuuint32_t>(p.hp ? p.hp_ph : (p.patch ? p.prows : th * sy)),
+    const cuuint32_t box[4] = {IG_BK, static_cast<cuuint32_t>(p.hp ? p.hp_pw * sx : (p.patch ? 130 : tw * sx)),
+                               static_cast<cuuint32_t>(p.hp ? p.hp_ph * sy : (p.patch ? p.prows : th * sy)),
                                static_cast<cuuint32_t>(p.hp ? 1 : tb)};
     const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(sx), static_cast<cuuint32_t>(sy), 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
