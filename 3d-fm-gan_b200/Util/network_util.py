@@ -14,10 +14,27 @@ _SIDE_STREAMS = {}
 
 
 def _side_streams(device):
-    st = _SIDE_STREAMS.get(device)
+    """Two side streams per (device, calling stream): forwards in flight on different streams do not share them."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    st = _SIDE_STREAMS.get(key)
     if st is None:
-        st = _SIDE_STREAMS[device] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+        st = _SIDE_STREAMS[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
     return st
+
+
+_GATES = {}
+
+
+def _gate(mask, device, dtype):
+    """[1,n,1] 0/1 mask of the sliced layers, cached on the device: building it from a Python list every call is a
+    pageable host->device copy, i.e. a host-side wait for everything queued on the stream (the encoders)."""
+    key = (mask, device, dtype)
+    g = _GATES.get(key)
+    if g is None:
+        if len(_GATES) > 64:
+            _GATES.clear()
+        g = _GATES[key] = torch.tensor(mask, device=device, dtype=dtype).view(1, len(mask), 1)
+    return g
 
 
 def _n_latent(g_ema):
@@ -62,8 +79,7 @@ def Forward_Inference_3_Encoder(p_input, r_input, E_Tsr, E_W, E_W_Plus, g_ema, t
     n = encoded_W_plus.shape[1]
     if sliced_layer is None:
         sliced_layer = range(_n_latent(g_ema))
-    gate = torch.tensor([1.0 if i in sliced_layer else 0.0 for i in range(n)], device=encoded_W.device,
-                        dtype=encoded_W.dtype).view(1, n, 1)
+    gate = _gate(tuple(1.0 if i in sliced_layer else 0.0 for i in range(n)), encoded_W.device, encoded_W.dtype)
     w = encoded_W.unsqueeze(1)
     encoded_latent = w * encoded_W_plus * gate + w * (1.0 - gate)
 

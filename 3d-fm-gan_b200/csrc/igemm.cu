@@ -157,14 +157,23 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) {
-    if (kPair) { tmem_alloc_pair(s_tmem, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
-    else { tmem_alloc(s_tmem, Cfg::TMEM_COLS); tmem_relinquish(); }
+    // Every CTA manages its own TMEM with cta_group::1 instructions, also under a cta_group::2 MMA (which only needs
+    // the same column range in both CTAs: each allocates all 512 columns, base 0).  The cta_group::2 alloc / dealloc
+    // couple the allocator state of the two SMs of the pair; with other streams' single-CTA kernels landing on one SM of
+    // a TPC between two pair kernels that left a later pair's peer CTA blocked in tcgen05.alloc forever (observed with
+    // cuda-gdb: one CTA at the cluster barrier, its peer's warp 1 polling in the alloc).
+    tmem_alloc(s_tmem, Cfg::TMEM_COLS);
+    tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   if (p.cluster > 1) cluster_sync_all();           // barriers of every CTA are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; the
+  // next kernel may start taking SMs as soon as every CTA of this grid got here
+  pdl_wait();
+  pdl_launch_dependents();
   const int crank = p.cluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int cluster_id = blockIdx.x / p.cluster, num_clusters = gridDim.x / p.cluster;
   const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1);
@@ -576,9 +585,6 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
 
-      mbar_wait(&tfull_bar[buf], aphase);
-      tc_fence_after();
-      if (threadIdx.x == 64) IG_TRACE(5 + 4 * titer);         // epilogue: accumulator complete
       const int nrows = p.upmode ? 4 : (p.patch ? p.prows : 1);
 #pragma unroll 1
       for (int r = 0; r < nrows; ++r) {
@@ -616,6 +622,24 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         warp_has_border = __any_sync(0xffffffffu, btab != nullptr);   // interior warps skip the correction code
       }
 
+      // residual of this thread's first chunk: requested before the accumulator wait, later chunks one iteration ahead
+      uint4 resn[2];
+      auto res_fetch = [&](int c) {
+        const int o0 = n0 + c * 16;
+        const int ol0 = o0 - (p.out_cgroup ? o0 / p.out_cgroup : 0) * p.out_cgroup;
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.out_cstride + ol0);
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          resn[g] = (valid && p.residual && c < BN / 16 && ol0 + 8 * g < p.out_cstride) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
+      };
+      if (EPI & EPI_RES) res_fetch(half);
+      if (r == 0) {
+        // everything above (noise, residual, bilinear taps) is in flight while the MMAs of this tile finish
+        mbar_wait(&tfull_bar[buf], aphase);
+        tc_fence_after();
+        if (threadIdx.x == 64) IG_TRACE(5 + 4 * titer);         // epilogue: accumulator complete
+      }
+
 #pragma unroll 1
       for (int c = half; c < BN / 16; c += 2) {     // 16-column chunks, alternating between the two warps
         uint32_t acc[16];
@@ -643,10 +667,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int ol0 = o0 - og * p.out_cgroup;
         uint4 resv[2];
         if (EPI & EPI_RES) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.out_cstride + ol0);
-#pragma unroll
-          for (int g = 0; g < 2; ++g)
-            resv[g] = (valid && p.residual && ol0 + 8 * g < p.out_cstride) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
+          resv[0] = resn[0]; resv[1] = resn[1];
+          res_fetch(c + 2);
         }
         float resf[16];
         if (EPI & EPI_RESUP) {
@@ -787,13 +809,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (p.cluster > 1) cluster_sync_all();           // no CTA exits while a peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    if (kPair) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
 // Split-K tail: workspace (fp32 sums) -> epilogue -> bf16 NHWC, and re-zero the workspace.
 // All loads of a thread (2 workspace vectors, 8 table rows, residual, noise) are issued up front.
 __global__ void __launch_bounds__(256) igemm_splitk_finalize_kernel(const IgemmParams p, int64_t total) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int groups8 = p.ws_cs / 8;
   const float nw = p.noise ? (p.noise_w ? __ldg(p.noise_w) : 1.f) : 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -870,13 +894,15 @@ static int launch_igemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const I
   cfg.blockDim = dim3(IG_THREADS2);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(p.cluster);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   FM_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_conv_kernel<BN, EPI, PAIR>, tmA, tmB, p));
   count_launch();
   FM_LAUNCH_OK();
@@ -903,9 +929,8 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
     if (blocks > cap) blocks = cap;
-    igemm_splitk_finalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(p, total);
+    FM_CUDA_OK(launch_pdl(igemm_splitk_finalize_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, p, total));
     count_launch();
-    FM_LAUNCH_OK();
     return FM_OK;
   }
   if (!p.tab) return launch_igemm2<BN, EPI_IDENT>(tmA, tmB, p, st);

@@ -1,5 +1,6 @@
 // libfm3d runtime glue: error text, launch counter, device queries.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -26,6 +27,11 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("FM3D_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
 }
 
 }  // namespace fm

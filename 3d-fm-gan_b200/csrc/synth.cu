@@ -220,6 +220,8 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
   __shared__ __align__(8) uint64_t s_full[BL_NST];
   __shared__ float s_k[16];
   __shared__ float s_kv[4], s_kh[4];
+  pdl_wait();
+  pdl_launch_dependents();
   int bid = blockIdx.x;
   const int cb = bid % cblocks; bid /= cblocks;
   const int tx = bid % tiles_x; bid /= tiles_x;
@@ -575,16 +577,10 @@ extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4
     FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_SMEM));
     attr_set = true;
   }
-  if (separable)
-    blur_act_nhwc_kernel<true><<<static_cast<unsigned>(blocks), 256, BL_SMEM, st>>>(
-        tmT, static_cast<__nv_bfloat16*>(out), kernel4x4, tab, noise, noise_bstride, noise_w, OH, OW, C, cstride, tiles_x, tiles_y,
-        cblocks);
-  else
-    blur_act_nhwc_kernel<false><<<static_cast<unsigned>(blocks), 256, BL_SMEM, st>>>(
-        tmT, static_cast<__nv_bfloat16*>(out), kernel4x4, tab, noise, noise_bstride, noise_w, OH, OW, C, cstride, tiles_x, tiles_y,
-        cblocks);
+  FM_CUDA_OK(launch_pdl(separable ? blur_act_nhwc_kernel<true> : blur_act_nhwc_kernel<false>, dim3(static_cast<unsigned>(blocks)),
+                        dim3(256), BL_SMEM, st, tmT, static_cast<__nv_bfloat16*>(out), kernel4x4, tab, noise, noise_bstride, noise_w,
+                        OH, OW, C, cstride, tiles_x, tiles_y, cblocks));
   count_launch();
-  FM_LAUNCH_OK();
   return FM_OK;
 }
 

@@ -164,7 +164,7 @@ def run_resnet(model, x):
             type(model.layer1[0]).__name__ != "BasicBlock":
         return None
     plans = model.__dict__.setdefault("_fm3d_plans", {})
-    key = (tuple(x.shape), x.device.index)
+    key = (tuple(x.shape), x.device.index, ops.current_slot())
     plan = plans.get(key)
     if plan is None:
         plan = plans[key] = ResNetPlan(model, x.shape[0], x.shape[2], x.shape[3], x.device)
@@ -375,7 +375,7 @@ def run_psp(model, x):
     if m.style_count < m.middle_ind + 1 or m.coarse_ind != 3 or m.middle_ind != 7:
         return None
     plans = m.__dict__.setdefault("_fm3d_plans", {})
-    key = (x.shape[0], x.device.index)
+    key = (x.shape[0], x.device.index, ops.current_slot())
     plan = plans.get(key)
     if plan is None:
         plan = plans[key] = PspPlan(m, x.shape[0], x.device)

@@ -303,7 +303,7 @@ def _pow2_ge(n):
 
 def run_synthesis(gen, latent, start, noise):
     """Entry used by ``stylegan2.Generator.forward``: cached plan per (batch, device)."""
-    key = (latent.shape[0], latent.device.index)
+    key = (latent.shape[0], latent.device.index, ops.current_slot())
     plan = gen._engine_plans.get(key)
     if plan is None:
         plan = SynthesisPlan(gen, latent.shape[0], latent.device)

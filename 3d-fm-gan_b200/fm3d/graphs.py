@@ -27,6 +27,11 @@ class GraphRunner:
         return tuple(None if a is None else (tuple(a.shape), a.dtype, a.device.index) for a in args)
 
     def __call__(self, *args):
+        from . import ops
+        with ops.splitk_scope(self):
+            return self._call(*args)
+
+    def _call(self, *args):
         from . import _lib, ops
         if not _ENABLED or ops.PROFILE is not None or torch.cuda.is_current_stream_capturing():
             return self.fn(*args)

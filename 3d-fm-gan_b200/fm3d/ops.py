@@ -3,14 +3,39 @@ current stream), allocate outputs, call libfm3d.  Mirrors what the reference's p
 shims do (op/fused_bias_act.cpp:11-17, op/upfirdn2d.cpp:12-19): CUDA checks, contiguity,
 ``torch.empty`` outputs, current-stream semantics.  No CPU path.
 """
+import contextlib
 import ctypes as C
-
+import threading
 import weakref
 
 import torch
 
 from . import _lib
 from ._lib import ConvDesc, FM_BF16, FM_F16, FM_F32
+
+# ---- engine slots: plans own their activation buffers and CUDA graphs, so two forwards of the same model that
+# are in flight at once (different streams) must use different plans.  ``with engine_slot(k):`` selects plan set k
+# for the calling thread (default 0).
+class _Slot(threading.local):
+    value = 0
+
+
+_SLOT = _Slot()
+
+
+@contextlib.contextmanager
+def engine_slot(k):
+    prev = _SLOT.value
+    _SLOT.value = int(k)
+    try:
+        yield
+    finally:
+        _SLOT.value = prev
+
+
+def current_slot():
+    return _SLOT.value
+
 
 # bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops) per conv launch
 PROFILE = None
@@ -122,13 +147,39 @@ _SPLITK_WS = {}
 SPLITK_WS_BYTES = 64 << 20
 
 
+class _Scope(threading.local):
+    owner = None
+
+
+_SCOPE = _Scope()
+
+
+@contextlib.contextmanager
+def splitk_scope(owner):
+    """Convs issued inside the scope reduce their split-K partial sums in a workspace owned by ``owner`` (an engine
+    plan's GraphRunner).  The stream alone is not a safe key: every plan is captured on torch's one shared
+    graph-capture stream and the captured graphs are then replayed concurrently on different streams."""
+    prev = _SCOPE.owner
+    _SCOPE.owner = owner
+    try:
+        yield
+    finally:
+        _SCOPE.owner = prev
+
+
 def _splitk_workspace(device):
-    """fp32 zero workspace per (device, stream): convs on one stream run in order and each user
-    re-zeroes what it touched; concurrent streams (the three encoders) get their own buffer."""
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
-    ws = _SPLITK_WS.get(key)
+    """fp32 zero workspace: convs that share one run in stream order and each user re-zeroes what it touched.
+    One per engine plan (see splitk_scope); outside a plan, one per (device, stream)."""
+    owner = _SCOPE.owner
+    if owner is not None:
+        store = owner.__dict__.setdefault("_splitk_ws", {})
+        key = device
+    else:
+        store = _SPLITK_WS
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = store.get(key)
     if ws is None:
-        ws = _SPLITK_WS[key] = torch.zeros(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32)
+        ws = store[key] = torch.zeros(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32)
     return ws
 
 

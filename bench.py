@@ -169,6 +169,10 @@ def run_reference(args, rank):
 
 
 def main():
+    wd = int(os.environ.get("FM3D_BENCH_WATCHDOG", "0"))
+    if wd > 0:      # debugging aid: dump every thread's Python stack and exit if the run takes longer than wd seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -176,6 +180,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("FM3D_BENCH_INFLIGHT", "2")),
+                    help="batches in flight per GPU: consecutive steps alternate between this many streams (each with "
+                         "its own engine plan), so one batch's large kernels fill the SMs another batch's small ones leave idle")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -227,11 +234,26 @@ def main():
         # ---------------- device-resident throughput
         # set-up (not a timed or counted step): the engine plans run eagerly twice and are captured into CUDA
         # graphs on the third call, so the W warm-up steps below already replay the steady-state graphs
-        for i in range(20):       # also lets clocks / power state settle on a freshly acquired GPU
-            step(*dev_in[i % n_sets])
+        NS = max(1, args.inflight)
+        main = torch.cuda.current_stream()
+        streams = [torch.cuda.Stream(device) for _ in range(NS)]
+
+        def run_steps(n):
+            """n steps; step i runs on stream i % NS with engine slot i % NS (its own buffers and CUDA graphs)."""
+            out = None
+            for s_ in streams:
+                s_.wait_stream(main)
+            for i in range(n):
+                k = i % NS
+                with torch.cuda.stream(streams[k]), ops.engine_slot(k):
+                    out = step(*dev_in[i % n_sets])
+            for s_ in streams:
+                main.wait_stream(s_)
+            return out
+
+        run_steps(20 * NS)        # also lets clocks / power state settle on a freshly acquired GPU
         torch.cuda.synchronize()
-        for i in range(warm):
-            step(*dev_in[i % n_sets])
+        run_steps(max(warm, NS))
         sampler = ClockSampler(local_rank)
         if os.environ.get("FM3D_BENCH_SAMPLER", "nvml") != "none":
             sampler.start()
@@ -239,8 +261,7 @@ def main():
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
-            out = step(*dev_in[i % n_sets])
+        out = run_steps(args.steps)
         e1.record()
         barrier()
         launches = _lib.launch_count() - l0
@@ -252,46 +273,52 @@ def main():
         # Every step's photo+render batch is copied from pinned host memory and its fp32 image is
         # copied back, all inside the timed region.  Copies run on a side stream and are double
         # buffered, so the H2D of step i+1 and the D2H of step i-1 overlap the compute of step i.
-        copy_stream = torch.cuda.Stream()
-        main = torch.cuda.current_stream()
-        in_bufs = [(torch.empty_like(dev_in[0][0]), torch.empty_like(dev_in[0][1])) for _ in range(2)]
-        out_bufs = [torch.empty(B, 3, 256, 256, device=device) for _ in range(2)]
-        out_hosts = [torch.empty(B, 3, 256, 256).pin_memory() for _ in range(2)]
+        h2d, d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        NB = 2 * NS
+        in_bufs = [(torch.empty_like(dev_in[0][0]), torch.empty_like(dev_in[0][1])) for _ in range(NB)]
+        out_bufs = [torch.empty(B, 3, 256, 256, device=device) for _ in range(NB)]
+        out_hosts = [torch.empty(B, 3, 256, 256).pin_memory() for _ in range(NB)]
 
         def e2e_loop(n):
-            in_ready = [torch.cuda.Event() for _ in range(2)]
-            in_free = [torch.cuda.Event() for _ in range(2)]
-            out_ready = [torch.cuda.Event() for _ in range(2)]
-            out_free = [torch.cuda.Event() for _ in range(2)]
+            in_ready = [torch.cuda.Event() for _ in range(NB)]
+            in_free = [torch.cuda.Event() for _ in range(NB)]
+            out_ready = [torch.cuda.Event() for _ in range(NB)]
+            out_free = [torch.cuda.Event() for _ in range(NB)]
             for ev in in_free + out_free:
                 ev.record(main)
+            for s_ in streams + [h2d, d2h]:
+                s_.wait_stream(main)
 
             def fetch(i):
-                s = i % 2
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(in_free[s])
+                j = i % NB
+                with torch.cuda.stream(h2d):
+                    h2d.wait_event(in_free[j])
                     p, r = host[i % n_sets]
-                    in_bufs[s][0].copy_(p, non_blocking=True)
-                    in_bufs[s][1].copy_(r, non_blocking=True)
-                    in_ready[s].record(copy_stream)
-            fetch(0)
+                    in_bufs[j][0].copy_(p, non_blocking=True)
+                    in_bufs[j][1].copy_(r, non_blocking=True)
+                    in_ready[j].record(h2d)
+            for i in range(min(NS, n)):
+                fetch(i)
             for i in range(n):
-                s = i % 2
-                if i + 1 < n:
-                    fetch(i + 1)
-                main.wait_event(in_ready[s])
-                main.wait_event(out_free[s])
-                img = step(in_bufs[s][0], in_bufs[s][1])
-                out_bufs[s].copy_(img)
-                in_free[s].record(main)
-                out_ready[s].record(main)
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(out_ready[s])
-                    out_hosts[s].copy_(out_bufs[s], non_blocking=True)
-                    out_free[s].record(copy_stream)
-            main.wait_stream(copy_stream)
+                if i + NS < n:
+                    fetch(i + NS)
+                k, j = i % NS, i % NB
+                cs = streams[k]
+                with torch.cuda.stream(cs), ops.engine_slot(k):
+                    cs.wait_event(in_ready[j])
+                    cs.wait_event(out_free[j])
+                    img = step(in_bufs[j][0], in_bufs[j][1])
+                    out_bufs[j].copy_(img)
+                    in_free[j].record(cs)
+                    out_ready[j].record(cs)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(out_ready[j])
+                    out_hosts[j].copy_(out_bufs[j], non_blocking=True)
+                    out_free[j].record(d2h)
+            for s_ in streams + [h2d, d2h]:
+                main.wait_stream(s_)
 
-        e2e_loop(3)
+        e2e_loop(3 * NS)
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
@@ -359,6 +386,7 @@ def main():
         "config": {"workload": "3-encoder (E_Tsr+E_W resnet18, E_W_Plus pSp ir_se-18, StyleGAN2 G cm=2) forward 256x256, "
                                f"batch {B} per GPU, random-init weights, eval mode",
                    "global_batch": B * world, "parallelism": f"batch-sharded replicas x{world} (no collective)",
+                   "batches_in_flight": f"{NS} per GPU (consecutive steps alternate between {NS} streams, each with its own plan)",
                    "l2": f"{n_sets} distinct input batches rotate ({n_sets * 2 * img_bytes / 1e6:.0f} MB > L2); "
                          "a step streams > 2 GB of activations"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * img_bytes, "d2h_bytes_per_step": img_bytes,
