@@ -64,6 +64,7 @@ struct IgemmParams {
   long long out_gstride;
   void* out;
   int out_H, out_W, out_cstride, out_y0, out_x0, out_ys, out_xs, out_nchw_f32;
+  int out_PH, out_PW;              // physical pitch of the NHWC output (rows per image, pixels per row) >= out_H, out_W
   const float* tab;
   int tab_bstride;
   const float* noise;
@@ -597,7 +598,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float nz = 0.f;
       if (valid && p.noise)
         nz = nw * __ldg(p.noise + (static_cast<size_t>(p.noise_bstride ? b : 0) * p.out_H + Y) * p.out_W + X);
-      const size_t pix = (static_cast<size_t>(b) * p.out_H + Y) * p.out_W + X;
+      const size_t pix = (static_cast<size_t>(b) * p.out_H + Y) * p.out_W + X;        // logical: noise, residual, rgb
+      const size_t opix = (static_cast<size_t>(b) * p.out_PH + Y) * p.out_PW + X;     // physical: the NHWC output
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
       // EPI_RESUP: the four source pixels and weights of this thread's output pixel (F.interpolate, bilinear,
       // align_corners=True: psp_encoders.py:81-98 -- the FPN top-down path, fused here instead of materialised)
@@ -759,7 +761,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (o0 + j < p.Cout) op[j * plane] = v[j];
           } else {
             uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + og * p.out_gstride +
-                                                 pix * p.out_cstride + ol0);
+                                                 opix * p.out_cstride + ol0);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               if (ol0 + 8 * g < p.out_cstride) {
@@ -832,6 +834,7 @@ __global__ void __launch_bounds__(256) igemm_splitk_finalize_kernel(const IgemmP
     const float4 a0 = wp[0], a1 = wp[1];
     const int Y = oy * p.out_ys + p.out_y0, X = ox * p.out_xs + p.out_x0;
     const size_t pix = (static_cast<size_t>(b) * p.out_H + Y) * p.out_W + X;
+    const size_t opix = (static_cast<size_t>(b) * p.out_PH + Y) * p.out_PW + X;
     const bool store = o0 < p.out_cstride;
     const int trow = p.tab_bstride ? b : b / p.Bg;
     const float4* tp = reinterpret_cast<const float4*>(p.tab + static_cast<size_t>(trow) * p.Cout * 8);
@@ -859,7 +862,7 @@ __global__ void __launch_bounds__(256) igemm_splitk_finalize_kernel(const IgemmP
     uint4 w;
     w.x = pack_bf16x2(v0, v1); w.y = pack_bf16x2(v2, v3);
     w.z = pack_bf16x2(v4, v5); w.w = pack_bf16x2(v6, v7);
-    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.out_cstride + o0) = w;
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + opix * p.out_cstride + o0) = w;
   }
 }
 
@@ -1056,6 +1059,11 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   p.out = d->out; p.out_H = d->out_H; p.out_W = d->out_W; p.out_cstride = d->out_cstride;
   p.out_y0 = d->out_y0; p.out_x0 = d->out_x0; p.out_ys = d->out_ys; p.out_xs = d->out_xs;
   p.out_nchw_f32 = d->out_nchw_f32;
+  FM_CHECK_ARG((d->out_pitch_h == 0 || d->out_pitch_h >= d->out_H) && (d->out_pitch_w == 0 || d->out_pitch_w >= d->out_W) &&
+                   (!(d->out_pitch_h || d->out_pitch_w) || !d->out_nchw_f32),
+               "fm_conv_igemm: out_pitch_h / out_pitch_w must be >= out_H / out_W (bf16 NHWC outputs only)");
+  p.out_PH = d->out_pitch_h > 0 ? d->out_pitch_h : d->out_H;
+  p.out_PW = d->out_pitch_w > 0 ? d->out_pitch_w : d->out_W;
   p.tab = d->tab; p.tab_bstride = d->tab_bstride ? 1 : 0;
   p.noise = d->noise; p.noise_bstride = d->noise_bstride ? 1 : 0; p.noise_w = d->noise_w;
   p.residual = static_cast<const __nv_bfloat16*>(d->residual);

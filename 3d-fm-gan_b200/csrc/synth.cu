@@ -547,9 +547,11 @@ extern "C" int fm_nhwc_bf16_to_nchw(float* out, const void* x, const float* inv_
 
 extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4, const float* tab, const float* noise,
                                 int noise_bstride, const float* noise_w, int B, int OH, int OW, int C, int cstride,
-                                int separable, void* stream) {
+                                int separable, int t_pitch_h, int t_pitch_w, void* stream) {
   FM_CHECK_ARG(out && t && kernel4x4 && tab && B > 0 && OH > 0 && OW > 0 && C > 0, "fm_blur_act_nhwc: bad args");
   FM_CHECK_ARG(cstride % 8 == 0 && cstride >= C, "fm_blur_act_nhwc: cstride must be a multiple of 8 >= C");
+  FM_CHECK_ARG((t_pitch_h == 0 || t_pitch_h >= OH + 1) && (t_pitch_w == 0 || t_pitch_w >= OW + 1),
+               "fm_blur_act_nhwc: t_pitch_h / t_pitch_w must be >= OH+1 / OW+1");
   FM_CHECK_ARG((reinterpret_cast<uintptr_t>(t) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "fm_blur_act_nhwc: tensors must be 16-byte aligned");
   const int tiles_x = (OW + BL_TW - 1) / BL_TW, tiles_y = (OH + BL_ROWS - 1) / BL_ROWS, cblocks = (cstride + 63) / 64;
@@ -561,8 +563,9 @@ extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4
   {
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(cstride), static_cast<cuuint64_t>(OW + 1), static_cast<cuuint64_t>(OH + 1),
                                 static_cast<cuuint64_t>(B)};
-    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(cstride) * 2, static_cast<cuuint64_t>(cstride) * 2 * (OW + 1),
-                                   static_cast<cuuint64_t>(cstride) * 2 * (OW + 1) * (OH + 1)};
+    const cuuint64_t pw = t_pitch_w > 0 ? t_pitch_w : OW + 1, ph = t_pitch_h > 0 ? t_pitch_h : OH + 1;
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(cstride) * 2, static_cast<cuuint64_t>(cstride) * 2 * pw,
+                                   static_cast<cuuint64_t>(cstride) * 2 * pw * ph};
     const cuuint32_t box[4] = {64, BL_IW, BL_SR, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(t), dims, strides, box, estr,

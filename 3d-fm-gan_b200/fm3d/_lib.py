@@ -34,6 +34,7 @@ class ConvDesc(C.Structure):
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64), ("ksplit", C.c_int32), ("upmode", C.c_int32),
         ("block_n", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("out_cgroup_ow_shrink", C.c_int32),
         ("residual_up_h", C.c_int32), ("residual_up_w", C.c_int32),
+        ("out_pitch_h", C.c_int32), ("out_pitch_w", C.c_int32),
     ]
 
 
@@ -68,7 +69,7 @@ _SIGNATURES = {
     "fm_nchw_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "fm_nhwc_bf16_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "fm_blur_act_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
-                         + [C.c_int] * 6 + [C.c_void_p]),
+                         + [C.c_int] * 8 + [C.c_void_p]),
     "fm_rgb_finalize": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p]),
     "fm_prep_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                  C.c_int, C.c_int, C.c_void_p]),

@@ -9,7 +9,10 @@ Dataflow per forward (B samples, activations NHWC bf16, never NCHW fp32 in betwe
   conv1          igemm 3x3 (+noise +bias +lrelu*sqrt2, *s_next, RGB)  -> x, rgb_acc
   per resolution:
      up-conv     stride-2 transposed conv as 4 output-parity phases (4/2/2/1 taps: exactly the
-                 algorithmic FLOPs, no zero-stuffing work) -> T[(2h+1)^2] bf16
+                 algorithmic FLOPs, no zero-stuffing work) -> T[(2h+1)^2] bf16.  Its input is stored
+                 with one zero row + column per image, so the batch is ONE tall [B*(h+1), h+1] image
+                 whose separator rows are the conv's zero padding: the (h+1)^2 phase grids tile
+                 without per-image tile tails (65 = 64+1 rows cost 9 tiles of 8 per image otherwise)
      blur_act    4x4 FIR + demod + noise + bias + lrelu, *s_next      -> x
      conv        igemm 3x3 with fused epilogue and fused ToRGB        -> x, rgb_acc
      rgb_finalize  rgb_acc + bias + Upsample(skip)                    -> skip (fp32 NCHW)
@@ -31,8 +34,6 @@ from ._lib import StyleLayer, TableLayer
 
 import os
 
-# fused 4-parity launch: correct but not faster than four phase launches yet (weight re-streaming bound)
-_FUSED_UP = os.environ.get("FM3D_UPMODE", "0") == "1"
 # Cout <= 128 up-convs: the two column parities of an output-row parity share one launch as a 2*Cout-wide GEMM
 # (N = 256 tiles instead of N = 128: the tensor pipe is no longer starved by the per-SM L2 fill rate)
 _PAIR_UP = os.environ.get("FM3D_UPPAIR", "1") != "0"
@@ -117,19 +118,17 @@ class SynthesisPlan:
             L.tab = torch.empty(B, L.cout, 8, **f32)
         self.rgb_s = [torch.empty(B, L.cout, **f32) for (_, _, L) in self.rgbs]
         # the last layer's activations feed nothing but its fused ToRGB: they are never stored
-        self.acts = [torch.empty(B, L.res_out, L.res_out, cs(L.cout), **bf16) if i + 1 < len(convs) else None
+        # a plain conv's output feeds the next up-conv: [B, h+1, h+1, cs] with a zero last row / column per image
+        # (written once here, never by the conv); an up-conv's (blurred) output is dense
+        self.acts = [None if i + 1 == len(convs) else
+                     (torch.empty(B, L.res_out, L.res_out, cs(L.cout), **bf16) if L.up else
+                      torch.zeros(B, L.res_out + 1, L.res_out + 1, cs(L.cout), **bf16))
                      for i, L in enumerate(convs)]
-        self.tbuf = {i: torch.empty(B, L.res_out + 1, L.res_out + 1, cs(L.cout), **bf16)
+        # interleaved phase outputs, one spare row / column per image (the phases write exact zeros there)
+        self.tbuf = {i: torch.empty(B, L.res_out + 2, L.res_out + 2, cs(L.cout), **bf16)
                      for i, L in enumerate(convs) if L.up}
         self.x0 = torch.empty(B, 4, 4, cs(convs[0].cin), **bf16)
         self.rgb_acc = [torch.zeros(B, L.res_out, L.res_out, 4, **f32) for (_, _, L) in self.rgbs]
-        self.ident_tabs = {}
-        for L in convs:
-            for n in ((L.cout, 2 * L.cout) if L.up else ()):
-                if n not in self.ident_tabs:
-                    t = torch.zeros(1, n, 8, **f32)
-                    t[..., 0] = 1.0; t[..., 2] = 1.0; t[..., 3] = 1.0
-                    self.ident_tabs[n] = t
         self._versions = None
         self._desc_keepalive = None
         self._runner = GraphRunner(self._run_flat)
@@ -157,7 +156,7 @@ class SynthesisPlan:
             w = L.mod.weight.detach()[0]
             L.wq, L.wsq = ops.prep_weight(w, L.mod.scale, want_wsq=True)
             L.wpair = None
-            if L.up and _PAIR_UP and not _FUSED_UP and L.cout % 32 == 0 and L.cout <= 128 and L.res_in >= 12:
+            if L.up and _PAIR_UP and L.cout % 32 == 0 and L.cout <= 128 and L.res_in >= 12:
                 # [view][P_x0 rows | P_x1 rows][cin]: zero block where the odd column parity has no tap for the view
                 L.wpair = {}
                 for py, views in _PAIR_VIEWS.items():
@@ -214,32 +213,31 @@ class SynthesisPlan:
         noise = [None if n is None else n.contiguous().float() for n in noise]
         return self._runner(latent.contiguous().float(), start.contiguous().float(), *noise)
 
-    def _up_conv(self, L, x, t, B, h, tw_, th_):
-        """Stride-2 transposed 3x3 conv of B samples into the interleaved (2h+1)^2 tensor t (no epilogue)."""
+    def _up_conv(self, L, x, t, B, h):
+        """Stride-2 transposed 3x3 conv (no epilogue) of the tall image x [B*(h+1), h+1] (zero separator row / column
+        per image) into the interleaved tensor t [B*(2h+2), 2h+2]: phase (py,px) of input pixel (y,x) lands on
+        (2y+py, 2x+px); the separator inputs produce the last row / column of T and exact zeros in the spare ones."""
+        Ht, Wt = B * (h + 1), h + 1
+        up_flops = 2.0 * B * h * h * L.cin * L.cout           # per tap, at the input resolution (SURVEY 8d)
+        # generic-mode tile (1-tap phase, narrow images): the width that wastes the fewest columns
+        tw_ = min((8, 16, 32, 64, 128), key=lambda w: ((Wt + w - 1) // w * w, -w))
+        th_ = 128 // tw_
+        kw = dict(B=1, H=Ht, W=Wt, Cin=L.cin, OH=Ht, OW=Wt, out_H=B * (2 * h + 2), out_W=2 * h + 2, out_ys=2, out_xs=2,
+                  tab_per_sample=False, tile_w=tw_, tile_h=th_)
         if L.wpair is not None:
             # one launch per output-row parity: N = [even columns | odd columns] (2*Cout wide)
-            up_flops = 2.0 * B * h * h * L.cin * L.cout * 9
             cs_t = t.shape[-1]
             for py, views in _PAIR_VIEWS.items():
                 taps = [(dy, dx, v) for v, ((dy, dx), _, _) in enumerate(views)]
                 ntap = sum(1 + (t1 is not None) for (_, _, t1) in views)
-                ops.conv_igemm(x, L.wpair[py], taps, t, None, B=B, H=h, W=h, Cin=L.cin,
-                               Cout=2 * L.cout, OH=h + 1 - py, OW=h + 1, out_H=2 * h + 1, out_W=2 * h + 1,
-                               out_y0=py, out_x0=0, out_ys=2, out_xs=2, tab_per_sample=False,
-                               out_cgroup=L.cout, out_gstride=cs_t, out_cstride=cs_t, out_cgroup_ow_shrink=1,
-                               algo_flops=up_flops * ntap / 9.0)
-        elif _FUSED_UP:
-            # all four output parities in one launch: the input is read once
-            ops.conv_igemm(x, L.wq, ops.conv_taps(3, 3, 1), t, self.ident_tabs[L.cout], B=B, H=h, W=h, Cin=L.cin, Cout=L.cout,
-                           OH=h + 1, OW=h + 1, out_H=2 * h + 1, out_W=2 * h + 1, out_ys=2, out_xs=2,
-                           tab_per_sample=False, tile_w=tw_, tile_h=th_, upmode=True)
+                ops.conv_igemm(x, L.wpair[py], taps, t, None, Cout=2 * L.cout, out_y0=py, out_x0=0,
+                               out_cgroup=L.cout, out_gstride=cs_t, out_cstride=cs_t, algo_flops=up_flops * ntap, **kw)
         else:
             for py in (0, 1):
                 for px in (0, 1):
-                    ops.conv_igemm(x, L.wq, _up_phase_taps(py, px), t, None, B=B, H=h, W=h, Cin=L.cin,
-                                   Cout=L.cout, OH=h + 1 - py, OW=h + 1 - px, out_H=2 * h + 1, out_W=2 * h + 1,
-                                   out_y0=py, out_x0=px, out_ys=2, out_xs=2, tab_per_sample=False,
-                                   tile_w=tw_, tile_h=th_)
+                    taps = _up_phase_taps(py, px)
+                    ops.conv_igemm(x, L.wq, taps, t, None, Cout=L.cout, out_y0=py, out_x0=px,
+                                   algo_flops=up_flops * len(taps), **kw)
 
     def _run_flat(self, latent, start, *noise):
         lib = _lib.lib()
@@ -272,18 +270,16 @@ class SynthesisPlan:
             h = L.res_in
             if L.up:
                 t = self.tbuf[i]
-                ident = self.ident_tabs[L.cout]
-                tw_ = min(16, _pow2_ge(h + 1))
-                th_ = max(1, min(8, 128 // tw_))
                 # (Tried: producing and blurring the intermediate a few samples at a time so it stays in L2 -- the extra
                 # launches and tile tails cost more than the DRAM round trip saves: 3.8k -> 3.1-3.6k img/s.)
-                self._up_conv(L, x, t, B, h, tw_, th_)
-                ops.blur_act_nhwc(t, L.kernel, L.tab, nz, per_sample, L.noise_w, L.cout, out=y)
+                self._up_conv(L, x, t, B, h)
+                ops.blur_act_nhwc(t, L.kernel, L.tab, nz, per_sample, L.noise_w, L.cout, out=y, padded=True)
             else:
                 rgb = self.rgb_acc[rgb_i] if L.rgb_mod is not None else None
                 ops.conv_igemm(x, L.wq, ops.conv_taps(3, 3, 1), y, L.tab, B=B, H=h, W=h, Cin=L.cin, Cout=L.cout,
                                OH=h, OW=h, tab_per_sample=True, noise=nz, noise_per_sample=per_sample,
-                               noise_w=L.noise_w, rgb=rgb)
+                               noise_w=L.noise_w, rgb=rgb, out_pitch_h=h + 1 if y is not None else 0,
+                               out_pitch_w=h + 1 if y is not None else 0)
                 if L.rgb_mod is not None:
                     to_rgb = L.rgb_mod[0]
                     kern = to_rgb.upsample.kernel if skip is not None else None
@@ -292,13 +288,6 @@ class SynthesisPlan:
                     rgb_i += 1
             x = y
         return outs
-
-
-def _pow2_ge(n):
-    p = 1
-    while p < n:
-        p <<= 1
-    return p
 
 
 def run_synthesis(gen, latent, start, noise):

@@ -193,7 +193,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
                tab_per_sample=False, noise=None, noise_per_sample=True, noise_w=None, residual=None,
                rgb=None, block_n=0, tile_w=0, tile_h=0, stride_x=0, stride_y=0, x_pixstride=0, x_rowstride=0,
                x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None, ksplit=0, upmode=False,
-               out_cgroup_ow_shrink=0, algo_flops=None, residual_up=None):
+               out_cgroup_ow_shrink=0, algo_flops=None, residual_up=None, out_pitch_h=0, out_pitch_w=0):
     """Launch fm_conv_igemm.  x: bf16 NHWC [B,H,W,cs]; w: bf16 [slabs, w_rows, cin_stride];
     out: bf16 NHWC [B,out_H,out_W,cs_out] or fp32 NCHW; tab: fp32 [B|1, Cout, 8]."""
     d = ConvDesc()
@@ -218,6 +218,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     d.out_cstride = out_cstride if out_cstride is not None else (Cout if out_nchw_f32 else (out.shape[-1] if out is not None else (Cout + 7) // 8 * 8))
     d.out_y0, d.out_x0, d.out_ys, d.out_xs = out_y0, out_x0, out_ys, out_xs
     d.out_nchw_f32 = 1 if out_nchw_f32 else 0
+    d.out_pitch_h, d.out_pitch_w = out_pitch_h, out_pitch_w
     d.tab = tab.data_ptr() if tab is not None else None; d.tab_bstride = 1 if tab_per_sample else 0
     d.noise = _ptr(noise); d.noise_bstride = 1 if noise_per_sample else 0
     d.noise_w = _ptr(noise_w)
@@ -299,9 +300,13 @@ def _is_rank1(k):
 _RANK1_CACHE = {}
 
 
-def blur_act_nhwc(t, kernel4x4, tab, noise, noise_per_sample, noise_w, C_, out=None):
-    """t bf16 [B,OH+1,OW+1,cs] -> bf16 [B,OH,OW,cs] (see fm_blur_act_nhwc)."""
+def blur_act_nhwc(t, kernel4x4, tab, noise, noise_per_sample, noise_w, C_, out=None, padded=False):
+    """t bf16 [B,OH+1,OW+1,cs] -> bf16 [B,OH,OW,cs] (see fm_blur_act_nhwc).  padded: t is [B,OH+2,OW+2,cs] with one
+    spare row / column per image (pitch only; the spare entries are never read)."""
     B, IH, IW, cs = t.shape
+    ph, pw = (IH, IW) if padded else (0, 0)
+    if padded:
+        IH, IW = IH - 1, IW - 1
     OH, OW = IH - 1, IW - 1
     if out is None:
         out = torch.empty(B, OH, OW, cs, device=t.device, dtype=torch.bfloat16)
@@ -316,7 +321,7 @@ def blur_act_nhwc(t, kernel4x4, tab, noise, noise_per_sample, noise_w, C_, out=N
     with torch.cuda.device(t.device):
         st = _lib.lib().fm_blur_act_nhwc(_ptr(out), _ptr(t), _ptr(kernel4x4), _ptr(tab), _ptr(noise),
                                          1 if noise_per_sample else 0, _ptr(noise_w), B, OH, OW, C_, cs,
-                                         1 if sep else 0, _stream())
+                                         1 if sep else 0, ph, pw, _stream())
     _lib.check(st, "fm_blur_act_nhwc")
     return out
 

@@ -167,6 +167,11 @@ typedef struct {
    * that the epilogue samples bilinearly with align_corners=True (the FPN top-down add of the pSp encoder,
    * psp_encoders.py:81-98, without materialising the upsampled map) */
   int32_t residual_up_h, residual_up_w;
+  /* physical pitch of the bf16 NHWC output tensor when it is larger than its logical size: rows per image and pixels
+   * per row (0 = out_H / out_W).  noise, residual and rgb stay indexed on the logical [out_H][out_W] grid.  The
+   * synthesis engine stores every activation that feeds a stride-2 transposed conv with one zero row and column of
+   * padding, so that the batch is ONE tall image whose separator rows are the conv's zero padding. */
+  int32_t out_pitch_h, out_pitch_w;
 } fm_conv_desc;
 
 int fm_conv_igemm(const fm_conv_desc* desc, void* stream);
@@ -222,7 +227,9 @@ int fm_nhwc_bf16_to_nchw(float* out, const void* x, const float* inv_scale_bc,
  * separable != 0 asserts that kernel4x4 is rank-1 (outer product): half the FMAs. */
 int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4,
                      const float* tab, const float* noise, int noise_bstride, const float* noise_w,
-                     int B, int OH, int OW, int C, int cstride, int separable, void* stream);
+                     int B, int OH, int OW, int C, int cstride, int separable,
+                     int t_pitch_h, int t_pitch_w, void* stream);
+/* t_pitch_h / t_pitch_w: physical rows per image / pixels per row of t when larger than OH+1 / OW+1 (0 = dense). */
 
 /* ToRGB tail (stylegan2.py:394-399): rgb_out[b,:,y,x] = acc[b,y,x,:] + bias + up2(skip).
  * acc fp32 [B][H][W][4] (from the fused epilogue), skip fp32 NCHW [B,3,H/2,W/2] or NULL,

@@ -237,4 +237,4 @@ def test_concurrent_graph_replay_matches_eager(cuda):
                 # flipped bf16 rounding (0.4 %) then travels down the layers; a workspace race gives O(1) garbage
                 d = (o - ref).abs()
                 assert d.max().item() <= 3e-2 * ref.abs().max().item(), (it, d.max().item())
-                assert d.mean().item() <= 2e-3 * ref.abs().max().item(), (it, d.mean().item())
+                assert d.mean().item() <= 5e-3 * ref.abs().max().item(), (it, d.mean().item())

@@ -343,3 +343,63 @@ def test_conv_upsampled_residual(cuda, B, h, Cin, Cout):
                    Cout=Cout, OH=2 * h, OW=2 * h, residual_up=ops.nchw_to_nhwc_bf16(low.to(cuda)))
     torch.cuda.synchronize()
     torch.testing.assert_close(out.float().permute(0, 3, 1, 2).cpu(), ref, rtol=1e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("B,h,Cin,Cout,pair", [(2, 16, 64, 128, True), (3, 12, 72, 32, True), (2, 16, 128, 256, False),
+                                                (5, 4, 64, 64, False), (1, 33, 64, 64, False), (4, 8, 512, 512, False)])
+def test_conv_tall_image_upsample(cuda, B, h, Cin, Cout, pair):
+    """The engine's stride-2 transposed conv: the batch as ONE tall image [B*(h+1), h+1] whose zero separator row /
+    column per image is the conv's padding, phases written into [B, 2h+2, 2h+2] (spare row / column = exact zeros),
+    against F.conv_transpose2d (stylegan2.py:276)."""
+    import types
+    from fm3d import engine, ops
+    gen = torch.Generator().manual_seed(h * 11 + Cin + B)
+    x = torch.randn(B, Cin, h, h, generator=gen)
+    w = torch.randn(Cout, Cin, 3, 3, generator=gen) / (Cin * 9) ** 0.5
+    ref = F.conv_transpose2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float().transpose(0, 1), stride=2)
+    wq, _ = ops.prep_weight(w.to(cuda), 1.0, want_wsq=False)
+    L = types.SimpleNamespace(cin=Cin, cout=Cout, wq=wq, wpair=None)
+    if pair:
+        L.wpair = {}
+        for py, views in engine._PAIR_VIEWS.items():
+            wp = torch.zeros(len(views), 2 * Cout, wq.shape[2], device=cuda, dtype=torch.bfloat16)
+            for v, (_, t0, t1) in enumerate(views):
+                wp[v, :Cout] = wq[t0, :Cout]
+                if t1 is not None:
+                    wp[v, Cout:] = wq[t1, :Cout]
+            L.wpair[py] = wp
+    cs_in, cs = (Cin + 7) // 8 * 8, (Cout + 7) // 8 * 8
+    xp = torch.zeros(B, h + 1, h + 1, cs_in, device=cuda, dtype=torch.bfloat16)
+    xp[:, :h, :h] = ops.nchw_to_nhwc_bf16(x.to(cuda))
+    t = torch.full((B, 2 * h + 2, 2 * h + 2, cs), 7.0, device=cuda, dtype=torch.bfloat16)
+    engine.SynthesisPlan._up_conv(None, L, xp, t, B, h)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(t[:, :2 * h + 1, :2 * h + 1, :Cout].float().permute(0, 3, 1, 2).cpu(), ref, rtol=1e-2, atol=1e-2)
+    assert float(t[:, 2 * h + 1].abs().max()) == 0.0 and float(t[:, :, 2 * h + 1].abs().max()) == 0.0
+
+
+def test_conv_output_pitch(cuda):
+    """out_pitch_h / out_pitch_w: the NHWC output lives in a larger zero-initialised tensor (one spare row / column
+    per image) while noise and the fused RGB sums stay on the logical grid."""
+    from fm3d import ops
+    B, H, Cin, Cout = 3, 16, 64, 128
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(B, Cin, H, H, generator=gen)
+    w = torch.randn(Cout, Cin, 3, 3, generator=gen) / (Cin * 9) ** 0.5
+    noise = torch.randn(B, H, H, generator=gen)
+    tab = torch.zeros(B, Cout, 8)
+    tab[..., 0] = 1.0; tab[..., 2] = 0.2; tab[..., 3] = 1.0; tab[..., 4:7] = torch.randn(B, Cout, 3, generator=gen) * 0.1
+    wg, _ = ops.prep_weight(w.to(cuda), 1.0)
+    xg = ops.nchw_to_nhwc_bf16(x.to(cuda))
+    outs, rgbs = [], []
+    for pitch in (0, H + 1):
+        out = torch.zeros(B, H + (1 if pitch else 0), H + (1 if pitch else 0), Cout, device=cuda, dtype=torch.bfloat16)
+        rgb = torch.zeros(B, H, H, 4, device=cuda)
+        ops.conv_igemm(xg, wg, ops.conv_taps(3, 3, 1), out, tab.to(cuda), B=B, H=H, W=H, Cin=Cin, Cout=Cout, OH=H, OW=H,
+                       tab_per_sample=True, noise=noise.to(cuda), noise_per_sample=True, rgb=rgb,
+                       out_pitch_h=pitch, out_pitch_w=pitch)
+        torch.cuda.synchronize()
+        outs.append(out); rgbs.append(rgb)
+    assert torch.equal(outs[1][:, :H, :H], outs[0])
+    assert float(outs[1][:, H].abs().max()) == 0.0 and float(outs[1][:, :, H].abs().max()) == 0.0
+    torch.testing.assert_close(rgbs[1], rgbs[0], rtol=1e-5, atol=1e-5)

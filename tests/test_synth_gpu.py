@@ -35,6 +35,12 @@ def test_blur_act_nhwc(cuda, B, OH, OW, C, rank1, per_sample_noise):
     got = out[..., :C].float().permute(0, 3, 1, 2).cpu()
     # bf16 output rounding (2^-8 relative) on fp32-accumulated values
     torch.testing.assert_close(got, v, rtol=1e-2, atol=1e-2)
+    # the engine's layout: one spare row / column per image (pitch only, poisoned here: they must never be read)
+    tp = torch.full((B, OH + 2, OW + 2, cs), float("nan")).to(torch.bfloat16)
+    tp[:, :OH + 1, :OW + 1] = t
+    out_p = ops.blur_act_nhwc(tp.to(cuda), k.to(cuda), tab.to(cuda), noise.to(cuda), per_sample_noise, nw.to(cuda), C,
+                              padded=True)
+    assert torch.equal(out_p, out)
 
 
 @pytest.mark.parametrize("B,H", [(2, 4), (3, 8), (2, 64), (1, 256)])

@@ -53,34 +53,46 @@ def bench_synth(res):
 
 
 def bench_upconv(res):
-    """Stride-2 transposed 3x3 conv: four parity-phase launches vs the fused 4-accumulator launch."""
+    """Stride-2 transposed 3x3 conv: per-image parity-phase launches vs the engine's tall-image launches."""
+    import types
     sys.path.insert(0, os.path.join(ROOT, "3d-fm-gan_b200"))
     from fm3d import engine
     B = 32
-    for (h, Cin, Cout) in [(128, 256, 128), (64, 512, 256), (32, 512, 512), (16, 512, 512)]:
+    for (h, Cin, Cout) in [(128, 256, 128), (64, 512, 256), (32, 512, 512), (16, 512, 512), (8, 512, 512)]:
         x = torch.randn(B, h, h, Cin, device=dev).to(torch.bfloat16)
         w = (torch.randn(9, Cout, Cin, device=dev) / (Cin * 9) ** 0.5).to(torch.bfloat16)
-        tab = torch.zeros(1, Cout, 8, device=dev); tab[..., 0] = 1; tab[..., 2] = 1; tab[..., 3] = 1
         t_out = torch.empty(B, 2 * h + 1, 2 * h + 1, Cout, device=dev, dtype=torch.bfloat16)
-        tw_ = min(16, engine._pow2_ge(h + 1)); th_ = max(1, min(8, 128 // tw_))
+        tw_ = 16 if h + 1 > 8 else 8
+        th_ = 128 // tw_ if h + 1 > 8 else 8
 
         def phases():
             for py in (0, 1):
                 for px in (0, 1):
-                    ops.conv_igemm(x, w, engine._up_phase_taps(py, px), t_out, tab, B=B, H=h, W=h, Cin=Cin, Cout=Cout,
+                    ops.conv_igemm(x, w, engine._up_phase_taps(py, px), t_out, None, B=B, H=h, W=h, Cin=Cin, Cout=Cout,
                                    OH=h + 1 - py, OW=h + 1 - px, out_H=2 * h + 1, out_W=2 * h + 1, out_y0=py, out_x0=px,
                                    out_ys=2, out_xs=2, tab_per_sample=False, tile_w=tw_, tile_h=th_)
 
-        def fused():
-            ops.conv_igemm(x, w, ops.conv_taps(3, 3, 1), t_out, tab, B=B, H=h, W=h, Cin=Cin, Cout=Cout, OH=h + 1, OW=h + 1,
-                           out_H=2 * h + 1, out_W=2 * h + 1, out_ys=2, out_xs=2, tab_per_sample=False, tile_w=tw_, tile_h=th_,
-                           upmode=True)
+        xp = torch.zeros(B, h + 1, h + 1, Cin, device=dev, dtype=torch.bfloat16)
+        xp[:, :h, :h] = x
+        tp = torch.empty(B, 2 * h + 2, 2 * h + 2, Cout, device=dev, dtype=torch.bfloat16)
+        L = types.SimpleNamespace(cin=Cin, cout=Cout, wq=w, wpair=None)
+        if Cout <= 128:
+            L.wpair = {}
+            for py, views in engine._PAIR_VIEWS.items():
+                wp = torch.zeros(len(views), 2 * Cout, Cin, device=dev, dtype=torch.bfloat16)
+                for v, (_, t0, t1) in enumerate(views):
+                    wp[v, :Cout] = w[t0]
+                    if t1 is not None:
+                        wp[v, Cout:] = w[t1]
+                L.wpair[py] = wp
+
+        def tall():
+            engine.SynthesisPlan._up_conv(None, L, xp, tp, B, h)
         fl = 2.0 * B * h * h * Cin * Cout * 9
-        for name, fn in (("upconv_phases", phases), ("upconv_fused", fused)):
+        for name, fn in (("upconv_phases_per_image", phases), ("upconv_tall_image", tall)):
             t = timeit(fn)
-            res.append(dict(kernel=name, h=h, Cin=Cin, Cout=Cout, ms=t * 1e3, TFLOPs=fl / t / 1e12,
-                            cluster=os.environ.get("FM3D_CLUSTER", "default")))
-        del x, t_out
+            res.append(dict(kernel=name, h=h, Cin=Cin, Cout=Cout, ms=t * 1e3, TFLOPs=fl / t / 1e12))
+        del x, t_out, xp, tp
 
 
 def main():
