@@ -143,8 +143,23 @@ __global__ void __launch_bounds__(256) upfirdn2d_tile_kernel(T* __restrict__ out
 // instruction-issue bound before it is HBM bound).  fp32 accumulation for every dtype.
 // ------------------------------------------------------------------------------------
 constexpr int UFS_THREADS = 256;
-constexpr int UFS_BUF_BYTES = 36 * 1024;        // per ring slot (2 slots): 3 CTAs of 256 threads per SM
+constexpr int UFS_MAX_SLOTS = 4;
 constexpr int UFS_CHUNK = 16 * 1024;            // bytes per bulk copy
+// ring geometry (slots x bytes per slot), tunable for experiments: FM3D_UFS_SLOTS / FM3D_UFS_SLOT_KB.
+struct UfsRing { int slots, bytes; };
+template <typename T>
+static UfsRing ufs_ring(const UpfirdnParams& p) {
+  static const int env_slots = []() { const char* e = getenv("FM3D_UFS_SLOTS"); return e ? atoi(e) : 0; }();
+  static const int env_kb = []() { const char* e = getenv("FM3D_UFS_SLOT_KB"); return e ? atoi(e) : 0; }();
+  // Measured on the largest generator blur (fp32 [4096,257,257], B200): 2 x 36 KB 534 us, 3 x 24 KB 698, 4 x 18 KB 924,
+  // 3 x 36 KB (2 CTAs/SM) 670: a strip costs ~3.5k cycles of fixed work (halo rows, hand-over) on top of ~290 per
+  // row, so fewer, taller strips beat a deeper ring.
+  UfsRing r{2, 36 * 1024};
+  (void)p;
+  if (env_slots >= 2 && env_slots <= UFS_MAX_SLOTS) r.slots = env_slots;
+  if (env_kb >= 8 && env_kb <= 100) r.bytes = env_kb * 1024;
+  return r;
+}
 
 struct UfsItem {
   int64_t plane0;      // first plane
@@ -224,6 +239,8 @@ __device__ __forceinline__ void ufs_rows(const T* __restrict__ sp, T* __restrict
         if (COLS == 2 && sizeof(T) == 2 && (!EDGE || ox + 1 < p.out_w) && (reinterpret_cast<uintptr_t>(orow) & 3) == 0) {
           T q2[2] = {from_f32<T>(done[0]), from_f32<T>(done[COLS - 1])};
           *reinterpret_cast<uint32_t*>(orow) = *reinterpret_cast<uint32_t*>(q2);
+        } else if (COLS == 2 && sizeof(T) == 4 && (!EDGE || ox + 1 < p.out_w) && (reinterpret_cast<uintptr_t>(orow) & 7) == 0) {
+          *reinterpret_cast<float2*>(orow) = make_float2(done[0], done[COLS - 1]);
         } else {
 #pragma unroll
           for (int c = 0; c < COLS; ++c)
@@ -243,11 +260,11 @@ template <typename T, int COLS>
 __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __restrict__ out, const T* __restrict__ x,
                                                                        const float* __restrict__ kernel, UpfirdnParams p,
                                                                        int64_t planes, int R, int P, int strips,
-                                                                       int64_t n_items, int head) {
+                                                                       int64_t n_items, int head, int nslots, int buf_bytes) {
   // head > 0: strip mode with zero rows -- the staged range starts `head` bytes into the slot, preceded
   // (top of the image) and followed (bottom) by three zeroed rows
   extern __shared__ __align__(128) uint8_t ufs_smem[];
-  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ __align__(8) uint64_t s_bar[UFS_MAX_SLOTS];
   __shared__ float s_k[16];
   const int tid = threadIdx.x;
   if (tid < 16) {
@@ -256,8 +273,7 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
     s_k[tid] = (ky < p.kh && kx < p.kw) ? kernel[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)] : 0.f;
   }
   if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
+    for (int i = 0; i < nslots; ++i) mbar_init(&s_bar[i], 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -291,7 +307,7 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
                                                          static_cast<int64_t>(it.r_hi + 1) * p.in_w) * sizeof(T));
     const uintptr_t lo_a = lo & ~static_cast<uintptr_t>(15);
     const uint32_t bytes = static_cast<uint32_t>(((hi + 15) & ~static_cast<uintptr_t>(15)) - lo_a);
-    uint8_t* dst = ufs_smem + slot * UFS_BUF_BYTES + head;
+    uint8_t* dst = ufs_smem + slot * buf_bytes + head;
     fence_proxy_async();                       // earlier generic reads of this slot precede the async writes
     mbar_arrive_expect_tx(&s_bar[slot], bytes);
     for (uint32_t off = 0; off < bytes; off += UFS_CHUNK)
@@ -301,16 +317,22 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
 
   const int colgroups = (p.out_w + COLS - 1) / COLS;
   int64_t item = blockIdx.x;
-  if (item < n_items && tid == 0) issue(ufs_item(item, p, planes, R, P, strips), 0);
+  if (tid == 0)
+    for (int a = 0; a < nslots - 1; ++a)
+      if (item + static_cast<int64_t>(a) * gridDim.x < n_items)
+        issue(ufs_item(item + static_cast<int64_t>(a) * gridDim.x, p, planes, R, P, strips), a);
+  int slot = 0, ahead_slot = nslots - 1;
+  uint32_t parity = 0;
   for (int k = 0; item < n_items; item += gridDim.x, ++k) {
-    const int slot = k & 1;
     const UfsItem it = ufs_item(item, p, planes, R, P, strips);
-    if (tid == 0 && item + gridDim.x < n_items) issue(ufs_item(item + gridDim.x, p, planes, R, P, strips), slot ^ 1);
-    if (tid < 32) mbar_wait(&s_bar[slot], (k >> 1) & 1);      // one warp polls, the rest sleep in the barrier
+    // the slot refilled now was drained by the previous iteration (its closing __syncthreads)
+    const int64_t ahead = item + static_cast<int64_t>(nslots - 1) * gridDim.x;
+    if (tid == 0 && ahead < n_items) issue(ufs_item(ahead, p, planes, R, P, strips), ahead_slot);
+    if (tid < 32) mbar_wait(&s_bar[slot], parity);            // one warp polls, the rest sleep in the barrier
     __syncthreads();
 
     const uintptr_t lo = xbase + static_cast<uintptr_t>((it.plane0 * plane_elems + static_cast<int64_t>(it.r_lo) * p.in_w) * sizeof(T));
-    const T* sbuf = reinterpret_cast<const T*>(ufs_smem + slot * UFS_BUF_BYTES + head + (lo & 15));
+    const T* sbuf = reinterpret_cast<const T*>(ufs_smem + slot * buf_bytes + head + (lo & 15));
     if (head > 0) {
       const bool top = it.oy0 - p.pad_y0 < it.r_lo, bottom = it.oy1 - 1 - p.pad_y0 + 3 > it.r_hi;
       if (top || bottom) {                                    // uniform: only the first / last strip of a plane
@@ -355,7 +377,9 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
       }
 #undef UFS_CALL
     }
-    __syncthreads();      // everyone is done with this slot before it is refilled (two items ahead)
+    __syncthreads();      // everyone is done with this slot before it is refilled (next iteration)
+    ahead_slot = slot;
+    if (++slot == nslots) { slot = 0; parity ^= 1; }
   }
 }
 
@@ -365,16 +389,17 @@ static bool stream_eligible(const UpfirdnParams& p, int pad_x1, int pad_y1) {
   if (p.kh > 4 || p.kw > 4) return false;
   if (p.pad_x0 < 0 || p.pad_y0 < 0 || pad_x1 < 0 || pad_y1 < 0 || p.pad_x0 > 16 || p.pad_y0 > 16) return false;
   // at least 4 output rows (+3 halo rows, +6 zero rows, alignment slack) of a full-width strip must fit one ring slot
-  return static_cast<int64_t>(14) * p.in_w * static_cast<int64_t>(sizeof(T)) + 64 <= UFS_BUF_BYTES;
+  return static_cast<int64_t>(14) * p.in_w * static_cast<int64_t>(sizeof(T)) + 64 <= ufs_ring<T>(p).bytes;
 }
 
-template <typename T>
-static int launch_stream(void* out, const void* x, const float* kernel, const UpfirdnParams& p, int pad_y1, int64_t planes,
-                         cudaStream_t st) {
-  constexpr int COLS = 1;
+template <typename T, int COLS>
+static int launch_stream_c(void* out, const void* x, const float* kernel, const UpfirdnParams& p, int pad_y1, int64_t planes,
+                           cudaStream_t st) {
   const int64_t row_bytes = static_cast<int64_t>(p.in_w) * sizeof(T);
   const int64_t plane_bytes = row_bytes * p.in_h;
   int R, P, strips, head = 0;
+  const UfsRing ring = ufs_ring<T>(p);
+  const int UFS_BUF_BYTES = ring.bytes, nslots = ring.slots;
   if (plane_bytes + 32 <= UFS_BUF_BYTES) {
     strips = 1; R = p.out_h;
     P = static_cast<int>((UFS_BUF_BYTES - 32) / plane_bytes);
@@ -395,17 +420,30 @@ static int launch_stream(void* out, const void* x, const float* kernel, const Up
   const int64_t n_items = strips > 1 ? planes * strips : (planes + P - 1) / P;
   static bool attr_set = false;
   auto fn = upfirdn2d_stream_kernel<T, COLS>;
+  const int smem = nslots * UFS_BUF_BYTES;
   if (!attr_set) {
-    FM_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * UFS_BUF_BYTES));
+    FM_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 3;
+  int cps = (227 * 1024) / (smem + 2048);          // CTAs per SM that fit (persistent grid)
+  cps = cps < 1 ? 1 : (cps > 4 ? 4 : cps);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * cps;
   const unsigned grid = static_cast<unsigned>(n_items < cap ? n_items : cap);
-  fn<<<grid, UFS_THREADS, 2 * UFS_BUF_BYTES, st>>>(static_cast<T*>(out), static_cast<const T*>(x), kernel, p, planes, R, P, strips,
-                                                   n_items, head);
+  fn<<<grid, UFS_THREADS, smem, st>>>(static_cast<T*>(out), static_cast<const T*>(x), kernel, p, planes, R, P, strips,
+                                      n_items, head, nslots, UFS_BUF_BYTES);
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;
+}
+
+// columns per thread: 1 = one thread per output column; 2 = column pairs (5 LDS + 16 FMA + one 8-byte store per two
+// outputs) with the strip's rows split between two thread groups (FM3D_UFS_COLS)
+template <typename T>
+static int launch_stream(void* out, const void* x, const float* kernel, const UpfirdnParams& p, int pad_y1, int64_t planes,
+                         cudaStream_t st) {
+  static const int cols = []() { const char* e = getenv("FM3D_UFS_COLS"); return e ? atoi(e) : 1; }();
+  if (cols == 2) return launch_stream_c<T, 2>(out, x, kernel, p, pad_y1, planes, st);
+  return launch_stream_c<T, 1>(out, x, kernel, p, pad_y1, planes, st);
 }
 
 // Generic kernel: any up/down (per axis), any kernel size, one thread per output.

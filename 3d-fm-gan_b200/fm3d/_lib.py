@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfm3d.so")
+LIB_PATH = os.environ.get("FM3D_LIB") or os.path.join(_HERE, "libfm3d.so")   # FM3D_LIB: A/B-test another build
 
 FM_F32, FM_F16, FM_BF16 = 0, 1, 2
 FM_MAX_TAPS = 49
