@@ -206,7 +206,7 @@ constexpr int BL_IW = BL_TW + 3;                 // staged input columns
 constexpr int BL_SR = 2;                         // input rows per stage
 constexpr int BL_NST = 4;                        // ring stages
 constexpr int BL_STAGE_BYTES = BL_SR * BL_IW * 128;
-constexpr int BL_ROWS = 64;                      // output rows per strip
+constexpr int BL_ROWS = 64;                      // default output rows per strip (see fm_blur_act_nhwc)
 constexpr int BL_SMEM = BL_NST * BL_STAGE_BYTES;
 
 template <bool SEP>
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
                                                                const float* __restrict__ kernel, const float* __restrict__ tab,
                                                                const float* __restrict__ noise, int noise_bstride,
                                                                const float* __restrict__ noise_w, int OH, int OW, int C, int cs,
-                                                               int tiles_x, int tiles_y, int cblocks) {
+                                                               int tiles_x, int tiles_y, int cblocks, int strip_rows) {
   extern __shared__ __align__(128) uint8_t bl_smem[];
   __shared__ __align__(8) uint64_t s_full[BL_NST];
   __shared__ float s_k[16];
@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
   const int ty = bid % tiles_y;
   const int b = bid / tiles_y;
   const int c0 = cb * 64, x0 = tx * BL_TW;
-  const int Y0 = ty * BL_ROWS;
-  const int Y1 = min(OH, Y0 + BL_ROWS);
+  const int Y0 = ty * strip_rows;
+  const int Y1 = min(OH, Y0 + strip_rows);
   const int tid = threadIdx.x;
   if (tid < 16) {
     const int a = tid >> 2, bb = tid & 3;
@@ -554,7 +554,25 @@ extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4
                "fm_blur_act_nhwc: t_pitch_h / t_pitch_w must be >= OH+1 / OW+1");
   FM_CHECK_ARG((reinterpret_cast<uintptr_t>(t) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "fm_blur_act_nhwc: tensors must be 16-byte aligned");
-  const int tiles_x = (OW + BL_TW - 1) / BL_TW, tiles_y = (OH + BL_ROWS - 1) / BL_ROWS, cblocks = (cstride + 63) / 64;
+  // strip height: the grid is not persistent, so pick the height whose CTA count wastes the least of the last wave
+  // (2 CTAs per SM); shorter strips re-read 3 halo rows more often, but those hit L2 (neighbouring strips run together)
+  static const int env_rows = []() { const char* e = getenv("FM3D_BLUR_ROWS"); return e ? atoi(e) : 0; }();
+  const int tiles_x = (OW + BL_TW - 1) / BL_TW, cblocks = (cstride + 63) / 64;
+  int strip_rows = BL_ROWS;
+  if (env_rows > 0) {
+    strip_rows = env_rows;
+  } else {
+    const int64_t slots = static_cast<int64_t>(sm_count()) * 2;
+    double best = -1.0;
+    for (int r : {128, 64, 32, 16}) {
+      const int64_t n = static_cast<int64_t>(B) * tiles_x * ((OH + r - 1) / r) * cblocks;
+      const int64_t waves = (n + slots - 1) / slots;
+      // useful fraction: wave fill x (1 - halo overhead)
+      const double eff = static_cast<double>(n) / (waves * slots) * r / (r + 3.0);
+      if (eff > best + 1e-9) { best = eff; strip_rows = r; }
+    }
+  }
+  const int tiles_y = (OH + strip_rows - 1) / strip_rows;
   const int64_t blocks = static_cast<int64_t>(B) * tiles_x * tiles_y * cblocks;
   FM_CHECK_ARG(blocks < 0x7FFFFFFF, "fm_blur_act_nhwc: too many blocks");
   EncodeTiledFn encode = get_encode_fn();
@@ -582,7 +600,7 @@ extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4
   }
   FM_CUDA_OK(launch_pdl(separable ? blur_act_nhwc_kernel<true> : blur_act_nhwc_kernel<false>, dim3(static_cast<unsigned>(blocks)),
                         dim3(256), BL_SMEM, st, tmT, static_cast<__nv_bfloat16*>(out), kernel4x4, tab, noise, noise_bstride, noise_w,
-                        OH, OW, C, cstride, tiles_x, tiles_y, cblocks));
+                        OH, OW, C, cstride, tiles_x, tiles_y, cblocks, strip_rows));
   count_launch();
   return FM_OK;
 }

@@ -149,6 +149,28 @@ def cpu_port_rate(batch, iters, warm):
     return batch * len(times) / total, cores, total / len(times)
 
 
+WORKLOAD = ("3-encoder (E_Tsr+E_W resnet18, E_W_Plus pSp ir_se-18, StyleGAN2 G cm=2) forward 256x256, "
+            "batch {B} per GPU, random-init weights, eval mode")
+
+# The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner on fd 1 when
+# NCCL_DEBUG is set): keep a private handle on the real stdout for the result line and point fd 1 at stderr.
+_RESULT_OUT = None
+
+
+def _protect_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -158,14 +180,15 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "3-encoder (E_Tsr+E_W resnet18, E_W_Plus pSp ir_se-18, StyleGAN2 G) forward 256x256, CPU "
-                               "port of the reference op path, batch 2 per step", "batch_per_step": batch},
+        "config": {"workload": WORKLOAD.format(B=args.batch),
+                   "sample": "CPU port of the reference op path (fp32), a bounded sample of the workload: "
+                             f"{batch} images per step", "batch_per_step": batch},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps x {batch} images, fp32, torch CPU threads={cores}"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def main():
@@ -184,6 +207,7 @@ def main():
                     help="batches in flight per GPU: consecutive steps alternate between this many streams (each with "
                          "its own engine plan), so one batch's large kernels fill the SMs another batch's small ones leave idle")
     args = ap.parse_args()
+    _protect_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -383,8 +407,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "3-encoder (E_Tsr+E_W resnet18, E_W_Plus pSp ir_se-18, StyleGAN2 G cm=2) forward 256x256, "
-                               f"batch {B} per GPU, random-init weights, eval mode",
+        "config": {"workload": WORKLOAD.format(B=B),
                    "global_batch": B * world, "parallelism": f"batch-sharded replicas x{world} (no collective)",
                    "batches_in_flight": f"{NS} per GPU (consecutive steps alternate between {NS} streams, each with its own plan)",
                    "l2": f"{n_sets} distinct input batches rotate ({n_sets * 2 * img_bytes / 1e6:.0f} MB > L2); "
@@ -397,7 +420,7 @@ def main():
         "cpu_baseline": cpu,
         "tflops_algorithmic": value * GFLOP_PER_IMAGE / 1e3,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
