@@ -56,6 +56,7 @@ struct IgemmParams {
   int8_t hp_pl_first[5];           // taps [first[pl], first[pl+1]) belong to plane pl (taps are sorted by plane)
   int16_t hp_pl_x[4], hp_pl_y[4];  // input-space offset of a plane's patch origin relative to (sx*x0, sy*y0)
   int hpw;                         // halo-patch mode with ALL weight tiles of the (single) n-tile resident in smem
+  int wres, wres_stages;           // generic mode with all (tap, chunk) weight tiles of the single n-tile resident: only A tiles stream
   int16_t hp_aoff[FM_MAX_TAPS];    // per-tap start offset of the A descriptor inside the patch (16-byte units)
   int Bg, nslabs;                  // images per group, weight slabs per group
   const float* border_tab;
@@ -239,6 +240,16 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
     if (p.hp)
       for (int i = 0; i < p.hp_dist; ++i) hp_prefetch();
+    if (p.wres && lane == 0 && cluster_id < p.num_super) {
+      // resident weights: every (tap, chunk) tile once per CTA (a TMA load costs ~5-6 clk per 128-byte row, and the
+      // 3- and 7-tap stem convs spent a third of their rows re-loading the same 64 weight rows per tap for every tile)
+      mbar_arrive_expect_tx(&afull_bar[0], static_cast<uint32_t>(kiters) * Cfg::B_BYTES);
+      for (int it = 0; it < kiters; ++it) {
+        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+        tma_load_2d(s_stage + static_cast<size_t>(it) * Cfg::B_BYTES, &tmB, &afull_bar[0], kc * IG_BK, p.tap_widx[tap] * p.w_rows);
+      }
+    }
+    __syncwarp();
     if (lane == 0) IG_TRACE(1);
     int ptile = 0;
     for (int st = cluster_id; st < p.num_super; st += num_clusters) {
@@ -326,6 +337,22 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (lane == 0) IG_TRACE(2 + 4 * ptile);      // producer: all loads of this tile issued
         ++ptile;
+        continue;
+      }
+      if (p.wres) {
+        // weights were loaded once (below the tile loop); a stage holds one A tile
+        uint8_t* sa0 = s_stage + static_cast<size_t>(kiters) * Cfg::B_BYTES;
+        for (int it = 0; it < kiters; ++it) {
+          const int tap = it / p.kchunks;
+          const int kc = it - tap * p.kchunks;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.rows) * (IG_BK * 2));
+            tma_load_4d(sa0 + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kc * IG_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
+          }
+          __syncwarp();
+          if (++stage == p.wres_stages) { stage = 0; phase ^= 1; }
+        }
         continue;
       }
       for (int it = it0; it < it1; ++it) {
@@ -503,6 +530,23 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (++stage == p.hp_stages) { stage = 0; phase ^= 1; }
           }
           if (++aslot == p.hp_na) { aslot = 0; aslot_phase ^= 1; }
+        }
+        continue;
+      }
+      if (p.wres) {
+        if (titer == 0) { mbar_wait(&afull_bar[0], 0); tc_fence_after(); }      // resident weights have landed
+        const uint32_t sa0 = ring + static_cast<uint32_t>(kiters) * Cfg::B_BYTES;
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t alo = umma_desc_lo(sa0 + stage * Cfg::A_BYTES), blo = umma_desc_lo(ring + static_cast<uint32_t>(it) * Cfg::B_BYTES);
+          if (elect_one()) {
+            umma_bf16_x4(tmem_d, alo, dhi, blo, dhi, idesc, it > 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (it == kiters - 1) umma_commit(&tfull_bar[buf]);
+          }
+          __syncwarp();
+          if (++stage == p.wres_stages) { stage = 0; phase ^= 1; }
         }
         continue;
       }
@@ -1241,6 +1285,21 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       if (env_hpw && p.tiles_n == 1 && na >= 3) {
         p.hpw = 1;
         p.hp_na = na;
+      }
+    }
+    // weight-resident generic mode (stems with overlapping-window inputs, 1x1 convs): single n-tile, single CTA,
+    // all weight tiles + at least 3 A stages fit the ring
+    {
+      static const int env_wres = []() { const char* e = getenv("FM3D_WRES"); return e ? atoi(e) : 1; }();
+      const int64_t wbytes = static_cast<int64_t>(kiters_total) * bn * 128;
+      int nst = static_cast<int>((200 * 1024 - wbytes) / (IG_BM * IG_BK * 2));
+      const int st_max = bn == 256 ? 4 : (bn == 128 ? 6 : 8);
+      if (nst > st_max) nst = st_max;
+      if (env_wres && !p.hp && !p.patch && !p.upmode && !p.pair && p.ksplit == 1 && G == 1 && p.tiles_n == 1 && nst >= 3 &&
+          kiters_total >= 2) {
+        p.wres = 1;
+        p.wres_stages = nst;
+        p.cluster = cs = 1;
       }
     }
     p.num_super = p.tiles_n * p.ksplit * ((p.m_tiles + cs - 1) / cs);
