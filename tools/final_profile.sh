@@ -1,0 +1,14 @@
+#!/bin/bash
+# Round-end evidence pass (one B200): bench lines, launch list, per-launch metrics, full capture of the top kernel, timeline, microbench.
+set -x
+O=gpurun_out/v5; mkdir -p $O
+python bench.py > $O/bench.json 2> $O/bench.err
+python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
+FM3D_GRAPH=0 FM3D_STREAMS=0 python tools/timeline.py -v > $O/timeline.txt 2>&1
+python tools/microbench.py > $O/microbench.jsonl 2> $O/microbench.err
+export FM3D_GRAPH=0 FM3D_STREAMS=0
+python tools/profile_step.py && ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_step.csv python tools/profile_step.py > $O/ncu_launches.log 2>&1
+ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none --csv --log-file $O/step_metrics.csv python tools/profile_step.py > $O/ncu_metrics.log 2>&1
+unset FM3D_GRAPH FM3D_STREAMS
+python tools/prof_conv.py 64 512 512 rgb && ncu --set full --clock-control none --import-source on -k regex:igemm_conv -s 4 -c 1 -o $O/igemm64_pair_full -f python tools/prof_conv.py 64 512 512 rgb > $O/ncu_full.log 2>&1
+ls -la $O
