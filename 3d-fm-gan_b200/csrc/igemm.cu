@@ -391,10 +391,19 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int aslot = 0;
     uint32_t aslot_phase = 0;
     const uint32_t ring = smem_u32(s_stage);
+    // Between the last MMA of a tile and the first of the next one this single warp runs a chain of dependent scalar
+    // instructions while the tensor pipe idles (per-CTA traces: ~1100 clk per tile, a third of a 64-channel layer's
+    // tile): everything loop-invariant is hoisted, and the accumulator buffer / phase are counters, not divisions.
+    int buf = 0;
+    uint32_t aphase = 0;
+    auto next_acc = [&]() { if (++buf == p.nbuf) { buf = 0; aphase ^= 1; } };
+    const uint32_t hp_wb = kPair ? Cfg::B_BYTES / 2 : Cfg::B_BYTES;
+    const uint32_t hp_sw = ring + p.hp_na * p.hp_bytes;
+    const uint32_t hp_ahi = umma_desc_hi_sw128(static_cast<uint32_t>(p.hp_pw) * 128u);
+    const int hp_nvc = p.kchunks * p.hp_np;
+    const bool hp_np1 = p.hp_np == 1;
     // CTA pair: only the leader issues (its MMAs read both CTAs' operands and write both CTAs' TMEM)
-    for (int st = (kPair && crank != 0) ? p.num_super : cluster_id; st < p.num_super; st += num_clusters, ++titer) {
-      const int buf = titer % p.nbuf;
-      const uint32_t aphase = (titer / p.nbuf) & 1;
+    for (int st = (kPair && crank != 0) ? p.num_super : cluster_id; st < p.num_super; st += num_clusters, ++titer, next_acc()) {
       mbar_wait(&tempty_bar[buf], aphase ^ 1);     // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * BN;
@@ -458,17 +467,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         continue;
       }
       if (p.hpw) {
-        const uint32_t wb = kPair ? Cfg::B_BYTES / 2 : Cfg::B_BYTES;
-        const uint32_t sw = ring + p.hp_na * p.hp_bytes;
-        const uint32_t ahi = umma_desc_hi_sw128(static_cast<uint32_t>(p.hp_pw) * 128u);
+        const uint32_t wb = hp_wb, sw = hp_sw, ahi = hp_ahi;
         if (titer == 0) { mbar_wait(&full_bar[0], 0); tc_fence_after(); }      // resident weights have landed
         if (lane == 0) IG_TRACE(3 + 4 * titer);
-        const int nvc = p.kchunks * p.hp_np;
+        const int nvc = hp_nvc;
         for (int vc = 0; vc < nvc; ++vc) {
           mbar_wait(&afull_bar[aslot], aslot_phase);
           tc_fence_after();
           if (lane == 0 && vc == 0) IG_TRACE(4 + 4 * titer);
-          const int kc = vc / p.hp_np, pl = vc - kc * p.hp_np;
+          const int kc = hp_np1 ? vc : vc / p.hp_np, pl = hp_np1 ? 0 : vc - kc * p.hp_np;
           const uint32_t alo0 = umma_desc_lo(ring + aslot * p.hp_bytes);
           const uint32_t blo0 = umma_desc_lo(sw + static_cast<uint32_t>(kc * p.ntaps) * wb);
           if (elect_one()) {
@@ -493,14 +500,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         continue;
       }
       if (p.hp) {
-        const uint32_t sb0 = ring + p.hp_na * p.hp_bytes;
-        const uint32_t ahi = umma_desc_hi_sw128(static_cast<uint32_t>(p.hp_pw) * 128u);
+        const uint32_t sb0 = hp_sw, ahi = hp_ahi;
         if (lane == 0) IG_TRACE(3 + 4 * titer);               // MMA: accumulator free
-        const int nvc = p.kchunks * p.hp_np;
+        const int nvc = hp_nvc;
         for (int vc = 0; vc < nvc; ++vc) {
           mbar_wait(&afull_bar[aslot], aslot_phase);          // this (chunk, plane)'s input patch has landed
           if (lane == 0 && vc == 0) IG_TRACE(4 + 4 * titer);  // MMA: first patch landed
-          const int pl = vc % p.hp_np;
+          const int pl = hp_np1 ? 0 : vc % p.hp_np;
           const uint32_t alo0 = umma_desc_lo(ring + aslot * p.hp_bytes);
           const int t0 = p.hp_pl_first[pl], t1 = p.hp_pl_first[pl + 1];
           for (int tap = t0; tap < t1; ++tap) {
@@ -550,7 +556,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
-      const int ks = (st / p.tiles_n) % p.ksplit;
+      const int ks = p.ksplit == 1 ? 0 : (st / p.tiles_n) % p.ksplit;
       const int it0 = ks * p.kper, it1 = min(kiters, it0 + p.kper);
       for (int it = it0; it < it1; ++it) {
         mbar_wait(&full_bar[stage], phase);        // TMA bytes have landed
@@ -589,19 +595,24 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                            9 * BN * 4 <= Cfg::TAB_BYTES / 2 + Cfg::RGB_BYTES;
     int tab_key = -1;
     int titer = 0;
-    for (int st = cluster_id; st < p.num_super; st += num_clusters, ++titer) {
-      const int buf = titer % p.nbuf;
-      const uint32_t aphase = (titer / p.nbuf) & 1;
-      const int nt = st % p.tiles_n;
-      int m = st / p.tiles_n;
-      m /= p.ksplit;
+    const bool e_tn1 = p.tiles_n == 1, e_ty1 = p.tiles_y == 1, e_g1 = p.Bg == p.B;
+    int buf = 0;
+    uint32_t aphase = 0;
+    auto next_acc = [&]() { if (++buf == p.nbuf) { buf = 0; aphase ^= 1; } };
+    for (int st = cluster_id; st < p.num_super; st += num_clusters, ++titer, next_acc()) {
+      // tile coordinates: the common single-n-tile / unsplit / ungrouped cases skip their integer divisions (each costs
+      // ~25 dependent instructions, and a 64-channel tile's whole epilogue is only ~300 per warp)
+      const int nt = e_tn1 ? 0 : st % p.tiles_n;
+      int m = e_tn1 ? st : st / p.tiles_n;
+      if (p.ksplit > 1) m /= p.ksplit;
       m = m * p.cluster + crank;
-      const int bx = m % p.tiles_x; m /= p.tiles_x;
-      const int by = m % p.tiles_y;
-      const int bb = m / p.tiles_y;
+      const int m2 = m / p.tiles_x;
+      const int bx = m - m2 * p.tiles_x;
+      const int bb = e_ty1 ? m2 : m2 / p.tiles_y;
+      const int by = e_ty1 ? 0 : m2 - bb * p.tiles_y;
       const int n0 = nt * BN;
       const int ox = bx * p.tw + lx, b = bb * p.tb + lb;
-      const int grp = min((bb * p.tb) / p.Bg, p.B / p.Bg - 1);   // padded cluster tiles clamp to the last group
+      const int grp = e_g1 ? 0 : min((bb * p.tb) / p.Bg, p.B / p.Bg - 1);   // padded cluster tiles clamp to the last group
 
       // ---- epilogue tables: re-staged only when (sample block | group, n-tile) changes
       const int key = (p.tab_bstride ? bb : grp) * p.tiles_n + nt;
