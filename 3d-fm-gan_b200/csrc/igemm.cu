@@ -27,6 +27,7 @@ constexpr int IG_BM = 128;     // pixels per tile (UMMA M)
 constexpr int IG_BK = 64;      // channels per k-step (128 B rows, SWIZZLE_128B)
 constexpr int IG_TRACE_N = 64;     // trace slots per CTA (debug)
 constexpr int IG_HP_MAXA = 8;      // halo-patch slots (barrier pairs reserved)
+constexpr int IG_MAX_STAGES = 12;  // operand-ring barrier pairs reserved (generic ring: Cfg::STAGES; halo-patch weight ring: hp_stages)
 constexpr int IG_TAB_ROWS = 512;  // staged table rows per tile (tile_b_eff * BLOCK_N <= 512)
 
 struct IgemmParams {
@@ -50,6 +51,8 @@ struct IgemmParams {
   // halo-patch mode (stride-1 tap sets): tile = 8 x 16 pixels of one image; ONE (16+dy span) x (8+dx span)
   // input patch per channel chunk serves every tap as a shifted UMMA descriptor (group stride = patch row)
   int hp, hp_pw, hp_ph, hp_bytes, hp_dx0, hp_dy0, hp_stages, hp_na, hp_dist;
+  int gen_sbytes, gen_stages;      // generic ring: bytes per (A tile + weight tile) stage and stage count
+  int hp_bstride;                  // bytes between weight stages of the halo-patch ring (half a tile per CTA of a pair)
   // strided convs: the taps split into parity planes of the input (iy = s*oy + dy -> plane dy mod s, row (dy - plane)/s of
   // the subsampled grid); each (chunk, plane) is one patch load (TMA element stride s) shared by the plane's taps
   int hp_np, hp_sx, hp_sy;
@@ -130,11 +133,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   float* s_btab = reinterpret_cast<float*>(smem + Cfg::RING_BYTES + Cfg::TAB_BYTES / 2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES + Cfg::TAB_BYTES + Cfg::RGB_BYTES);
   uint64_t* full_bar = bars;                        // [STAGES]  TMA -> MMA
-  uint64_t* empty_bar = bars + Cfg::STAGES;         // [STAGES]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;     // [2]       MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]     epilogue -> MMA
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
-  uint64_t* afull_bar = bars + 2 * Cfg::STAGES + 5;   // [IG_HP_MAXA] halo-patch slots: TMA -> MMA
+  uint64_t* empty_bar = bars + IG_MAX_STAGES;       // [STAGES]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * IG_MAX_STAGES;   // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * IG_MAX_STAGES + 2;  // [2]   epilogue -> MMA
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * IG_MAX_STAGES + 4);
+  uint64_t* afull_bar = bars + 2 * IG_MAX_STAGES + 5;   // [IG_HP_MAXA] halo-patch slots: TMA -> MMA
+  static_assert((2 * IG_MAX_STAGES + 5 + 2 * IG_HP_MAXA) * 8 <= 512, "barrier region");
   uint64_t* aempty_bar = afull_bar + IG_HP_MAXA;      // [IG_HP_MAXA] MMA -> TMA
 
   const int warp = threadIdx.x >> 5;
@@ -144,7 +148,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if ((smem_u32(smem) & 1023u) != 0) { printf("fm3d: dynamic smem base not 1024-aligned\n"); __trap(); }
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < Cfg::STAGES; ++i) {
+    for (int i = 0; i < IG_MAX_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], kPair ? 1 : p.cluster);   // multicast commit of every CTA (cluster) / of the leader (pair)
     }
@@ -324,11 +328,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (lane == 0) {
               if (kPair) {
                 if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_BYTES);       // two halves
-                tma_load_2d_pair(sb0 + stage * Cfg::B_BYTES, &tmB, mapa_rank(smem_u32(&full_bar[stage]), 0), kc * IG_BK,
+                tma_load_2d_pair(sb0 + stage * p.hp_bstride, &tmB, mapa_rank(smem_u32(&full_bar[stage]), 0), kc * IG_BK,
                                  (wrow0 + p.tap_widx[tap]) * p.w_rows + n0 + crank * (BN / 2));
               } else {
                 mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_BYTES);
-                tma_load_2d(sb0 + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0);
+                tma_load_2d(sb0 + stage * p.hp_bstride, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0);
               }
             }
             __syncwarp();
@@ -360,20 +364,20 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int kc = it - tap * p.kchunks;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0 && kPair) {
-          uint8_t* sa = s_stage + stage * Cfg::STAGE_BYTES;
+          uint8_t* sa = s_stage + stage * p.gen_sbytes;
           const uint32_t lbar = mapa_rank(smem_u32(&full_bar[stage]), 0);
           if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * static_cast<uint32_t>(p.rows) * (IG_BK * 2) + Cfg::B_BYTES);
           tma_load_4d_pair(sa, &tmA, lbar, kc * IG_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
           tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, lbar, kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0 + crank * (BN / 2));
         } else if (lane == 0) {
-          uint8_t* sa = s_stage + stage * Cfg::STAGE_BYTES;
+          uint8_t* sa = s_stage + stage * p.gen_sbytes;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_4d(sa, &tmA, &full_bar[stage], kc * IG_BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
           { if (p.cluster == 1) tma_load_2d(sb, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0); else if (crank == 0) tma_load_2d_mcast(sb, &tmB, &full_bar[stage], kc * IG_BK, (wrow0 + p.tap_widx[tap]) * p.w_rows + n0, cmask); }
         }
         __syncwarp();
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.gen_stages) { stage = 0; phase ^= 1; }
       }
     }
     }   // !hpw
@@ -513,7 +517,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t alo = alo0 + static_cast<uint32_t>(p.hp_aoff[tap]);
-            const uint32_t blo = umma_desc_lo(sb0 + stage * Cfg::B_BYTES);
+            const uint32_t blo = umma_desc_lo(sb0 + stage * p.hp_bstride);
             const uint32_t accf = (vc > 0 || tap > t0) ? 1u : 0u;
             if (elect_one()) {
               if (kPair) {
@@ -561,7 +565,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int it = it0; it < it1; ++it) {
         mbar_wait(&full_bar[stage], phase);        // TMA bytes have landed
         tc_fence_after();
-        const uint32_t sa = ring + stage * Cfg::STAGE_BYTES;
+        const uint32_t sa = ring + stage * p.gen_sbytes;
         const uint32_t alo = umma_desc_lo(sa), blo = umma_desc_lo(sa + Cfg::A_BYTES);
         if (elect_one()) {
           // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
@@ -576,7 +580,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         __syncwarp();
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.gen_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -1258,7 +1262,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
         if (st >= 3 || (D == 1 && st >= 2)) break;
       }
       if (D >= 1 && D + E <= IG_HP_MAXA) {
-        p.hp_dist = D; p.hp_na = D + E; p.hp_stages = st;
+        p.hp_dist = D; p.hp_na = D + E; p.hp_stages = st; p.hp_bstride = bbytes;
       } else {
         set_error("fm_conv_igemm: halo-patch ring does not fit (patch %d bytes, block_n %d)", p.hp_bytes, bn);
         return FM_ERR_INVALID;
@@ -1286,6 +1290,27 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       p.patch_stage_bytes = p.patch_a_bytes + 3 * p.patch_b_bytes;
       p.patch_stages = (200 * 1024) / p.patch_stage_bytes;
       if (p.patch_stages > 8) p.patch_stages = 8;
+    }
+    // generic ring: a CTA of a pair stages half a weight tile, so its stages are smaller and the ring deeper
+    {
+      const int sb = IG_BM * IG_BK * 2 + (p.pair ? bn * 64 : bn * 128);
+      int st = (200 * 1024) / sb;
+      const int st_cfg = bn == 256 ? 4 : (bn == 128 ? 6 : 8);
+      if (st > IG_MAX_STAGES) st = IG_MAX_STAGES;
+      p.gen_sbytes = p.pair ? sb : IG_BM * IG_BK * 2 + bn * 128;
+      p.gen_stages = p.pair ? st : st_cfg;
+    }
+    // halo-patch weight ring, now that the pair decision is known: a CTA of a pair stages only its half of each weight
+    // tile, so the same smem holds twice as many stages.  Per-CTA traces of the 64x64 128->128 layer showed the MMA phase
+    // of a tile at 2x its tensor-pipe time with ~470 clk per TMA box: the ring depth over the load latency was the limit.
+    if (p.hp) {
+      static const int env_deep = []() { const char* e = getenv("FM3D_HP_DEEP"); return e ? atoi(e) : 1; }();
+      const int np = p.hp_np, T = (d->ntaps + np - 1) / np, E = p.hp_na - p.hp_dist;
+      const int bstride = p.pair ? bn * 64 : bn * 128;
+      int st = (200 * 1024 - p.hp_na * p.hp_bytes) / bstride;
+      if (st > IG_MAX_STAGES) st = IG_MAX_STAGES;
+      if (np == 1 && st > (E - 1) * T + 1) st = (E - 1) * T + 1;      // weights never run further ahead than the patches
+      if (env_deep && st > p.hp_stages) { p.hp_stages = st; p.hp_bstride = bstride; }
     }
     // weight-resident halo-patch variant: one n-tile and all its (chunk, tap) weight tiles fit beside >= 3 patch slots
     if (p.hp) {
