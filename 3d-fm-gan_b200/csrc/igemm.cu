@@ -1318,7 +1318,10 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       const int64_t wbytes = static_cast<int64_t>(kiters_total) * (p.pair ? bn / 2 : bn) * 128;
       int na = static_cast<int>((200 * 1024 - wbytes) / p.hp_bytes);
       if (na > IG_HP_MAXA) na = IG_HP_MAXA;
-      if (env_hpw && p.tiles_n == 1 && na >= 3) {
+      static const int env_hpw_min = []() { const char* e = getenv("FM3D_HPW_MIN"); return e ? atoi(e) : 2; }();
+      // two patch slots are enough to keep the weights resident (128 -> 128 pair layers: 144 KB of weights + 2 x 23 KB):
+      // the next chunk's patch loads while the current chunk's 36 MMAs run
+      if (env_hpw && p.tiles_n == 1 && na >= env_hpw_min) {
         p.hpw = 1;
         p.hp_na = na;
       }

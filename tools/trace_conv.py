@@ -35,4 +35,8 @@ for cta in (0, 1, 73, 147):
         if s[3] == 0 and s[1] == 0:
             break
         print(f"   tile {t}: epi done {s[0] - r[0]:7d}  acc free {s[1] - r[0]:7d}  patch landed {s[2] - r[0]:7d}  acc complete {s[3] - r[0]:7d}")
+r = buf[0]
+if r[32] > 0:
+    print("CTA 0, tile 1, chunk 0, per tap: weights landed / MMAs issued (clk since kernel start):")
+    print("   " + "  ".join(f"{r[32 + 2 * i] - r[0]}/{r[33 + 2 * i] - r[0]}" for i in range(9) if r[32 + 2 * i] > 0))
 print("kernel span (clk):", buf[:, 63].max() - t0)
