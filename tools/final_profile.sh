@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence pass (one B200): bench lines, launch list, per-launch metrics, full capture of the top kernel, timeline, microbench.
 set -x
-O=gpurun_out/v5; mkdir -p $O
+O=gpurun_out/v6; mkdir -p $O
 python bench.py > $O/bench.json 2> $O/bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
 FM3D_GRAPH=0 FM3D_STREAMS=0 python tools/timeline.py -v > $O/timeline.txt 2>&1
