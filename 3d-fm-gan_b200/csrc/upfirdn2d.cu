@@ -10,6 +10,8 @@
 // Algorithmic bytes: (planes*in_h*in_w + planes*out_h*out_w) * sizeof(T); roofline = HBM.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace fm {
@@ -206,52 +208,101 @@ __device__ __forceinline__ void ufs_rows(const T* __restrict__ sp, T* __restrict
   const T* rp = sp + static_cast<int64_t>(ty0 - p.pad_y0) * p.in_w + ix0;
   T* orow = op + static_cast<int64_t>(ty0 - 3) * p.out_w;
   int iy = ty0 - p.pad_y0;
-  for (int jb = 0; jb < jn; jb += 4) {
+  // one input row: horizontal taps, then its contribution to the 4 open output rows; u = j & 3 is static
+  auto row_math = [&](auto uc, const float (&v)[COLS + 3]) {
+    constexpr int u = decltype(uc)::value;
+    if (SEP) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = jb + u;
-      if (j >= jn) break;
-      if (!ROWCHK || (iy >= r_lo && iy <= r_hi)) {   // rows outside the image contribute nothing (or read zeroed rows)
-        float v[COLS + 3];
+      for (int c = 0; c < COLS; ++c) {
+        const float h = fmaf(v[c + 3], kh1[3], fmaf(v[c + 2], kh1[2], fmaf(v[c + 1], kh1[1], v[c] * kh1[0])));
 #pragma unroll
-        for (int q = 0; q < COLS + 3; ++q) v[q] = (!EDGE || cok[q]) ? to_f32<T>(rp[q]) : 0.f;
-        if (SEP) {
-#pragma unroll
-          for (int c = 0; c < COLS; ++c) {
-            const float h = fmaf(v[c + 3], kh1[3], fmaf(v[c + 2], kh1[2], fmaf(v[c + 1], kh1[1], v[c] * kh1[0])));
-#pragma unroll
-            for (int ky = 0; ky < 4; ++ky) acc[(u - ky) & 3][c] = fmaf(h, kv1[ky], acc[(u - ky) & 3][c]);
-          }
-        } else {
-#pragma unroll
-          for (int ky = 0; ky < 4; ++ky)
-#pragma unroll
-            for (int c = 0; c < COLS; ++c) {
-              float a = acc[(u - ky) & 3][c];
-#pragma unroll
-              for (int kx = 0; kx < 4; ++kx) a = fmaf(v[c + kx], w[ky][kx], a);
-              acc[(u - ky) & 3][c] = a;
-            }
-        }
+        for (int ky = 0; ky < 4; ++ky) acc[(u - ky) & 3][c] = fmaf(h, kv1[ky], acc[(u - ky) & 3][c]);
       }
-      float (&done)[COLS] = acc[(u + 1) & 3];
-      if (j >= 3) {
-        if (COLS == 2 && sizeof(T) == 2 && (!EDGE || ox + 1 < p.out_w) && (reinterpret_cast<uintptr_t>(orow) & 3) == 0) {
-          T q2[2] = {from_f32<T>(done[0]), from_f32<T>(done[COLS - 1])};
-          *reinterpret_cast<uint32_t*>(orow) = *reinterpret_cast<uint32_t*>(q2);
-        } else if (COLS == 2 && sizeof(T) == 4 && (!EDGE || ox + 1 < p.out_w) && (reinterpret_cast<uintptr_t>(orow) & 7) == 0) {
-          *reinterpret_cast<float2*>(orow) = make_float2(done[0], done[COLS - 1]);
-        } else {
+    } else {
 #pragma unroll
-          for (int c = 0; c < COLS; ++c)
-            if (!EDGE || ox + c < p.out_w) orow[c] = from_f32<T>(done[c]);
+      for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+          float a = acc[(u - ky) & 3][c];
+#pragma unroll
+          for (int kx = 0; kx < 4; ++kx) a = fmaf(v[c + kx], w[ky][kx], a);
+          acc[(u - ky) & 3][c] = a;
         }
-      }
+    }
+  };
+  // tap row 3 closed output row j - 3 (slot (u + 1) & 3): store it and re-open the slot
+  auto row_store = [&](auto uc, T* o) {
+    constexpr int u = decltype(uc)::value;
+    float (&done)[COLS] = acc[(u + 1) & 3];
+    if (COLS == 2 && sizeof(T) == 2 && (!EDGE || ox + 1 < p.out_w) && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+      T q2[2] = {from_f32<T>(done[0]), from_f32<T>(done[COLS - 1])};
+      *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<uint32_t*>(q2);
+    } else if (COLS == 2 && sizeof(T) == 4 && (!EDGE || ox + 1 < p.out_w) && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+      *reinterpret_cast<float2*>(o) = make_float2(done[0], done[COLS - 1]);
+    } else {
 #pragma unroll
-      for (int c = 0; c < COLS; ++c) done[c] = 0.f;
-      rp += p.in_w;
-      orow += p.out_w;
-      ++iy;
+      for (int c = 0; c < COLS; ++c)
+        if (!EDGE || ox + c < p.out_w) o[c] = from_f32<T>(done[c]);
+    }
+  };
+  auto row_load = [&](const T* r, int y, float (&v)[COLS + 3]) {
+    const bool rok = !ROWCHK || (y >= r_lo && y <= r_hi);   // rows outside the image contribute nothing (or read zeroed rows)
+#pragma unroll
+    for (int q = 0; q < COLS + 3; ++q) v[q] = (rok && (!EDGE || cok[q])) ? to_f32<T>(r[q]) : 0.f;
+  };
+  int jb = 0;
+  // steady state: 4 input rows per step with all their loads issued up front (no loop-carried branch between rows, so
+  // the LDS latency of rows 1-3 hides behind the arithmetic of the rows before them)
+  for (; jb + 4 <= jn; jb += 4) {
+    float v0[COLS + 3], v1[COLS + 3], v2[COLS + 3], v3[COLS + 3];
+    row_load(rp, iy, v0);
+    row_load(rp + p.in_w, iy + 1, v1);
+    row_load(rp + 2 * p.in_w, iy + 2, v2);
+    row_load(rp + 3 * static_cast<int64_t>(p.in_w), iy + 3, v3);
+    const bool st012 = jb >= 4;                               // the first step only closes a row at u = 3
+    row_math(std::integral_constant<int, 0>{}, v0);
+    if (st012) row_store(std::integral_constant<int, 0>{}, orow);
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) acc[1][c] = 0.f;
+    row_math(std::integral_constant<int, 1>{}, v1);
+    if (st012) row_store(std::integral_constant<int, 1>{}, orow + p.out_w);
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) acc[2][c] = 0.f;
+    row_math(std::integral_constant<int, 2>{}, v2);
+    if (st012) row_store(std::integral_constant<int, 2>{}, orow + 2 * p.out_w);
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) acc[3][c] = 0.f;
+    row_math(std::integral_constant<int, 3>{}, v3);
+    row_store(std::integral_constant<int, 3>{}, orow + 3 * static_cast<int64_t>(p.out_w));
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) acc[0][c] = 0.f;
+    rp += 4 * static_cast<int64_t>(p.in_w);
+    orow += 4 * static_cast<int64_t>(p.out_w);
+    iy += 4;
+  }
+  // tail: up to 3 rows (u = 0, 1, 2)
+  {
+    float v[COLS + 3];
+    if (jb < jn) {
+      row_load(rp, iy, v);
+      row_math(std::integral_constant<int, 0>{}, v);
+      if (jb >= 3) row_store(std::integral_constant<int, 0>{}, orow);
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) acc[1][c] = 0.f;
+    }
+    if (jb + 1 < jn) {
+      row_load(rp + p.in_w, iy + 1, v);
+      row_math(std::integral_constant<int, 1>{}, v);
+      if (jb + 1 >= 3) row_store(std::integral_constant<int, 1>{}, orow + p.out_w);
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) acc[2][c] = 0.f;
+    }
+    if (jb + 2 < jn) {
+      row_load(rp + 2 * p.in_w, iy + 2, v);
+      row_math(std::integral_constant<int, 2>{}, v);
+      if (jb + 2 >= 3) row_store(std::integral_constant<int, 2>{}, orow + 2 * p.out_w);
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) acc[3][c] = 0.f;
     }
   }
 }
