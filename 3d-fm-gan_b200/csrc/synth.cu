@@ -201,7 +201,17 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(float* __restrict__ o
 // Rank-1 kernels (the default [1,3,3,1] outer product) take the separable path.
 // Algorithmic bytes per output pixel-channel: 2 B read ((OH+1)(OW+1)/(OH*OW) ~ 1) + 2 B write.
 // ------------------------------------------------------------------------------------
-constexpr int BL_TW = 64;                        // output columns per CTA
+// A CTA owns CB channels x TW columns with CB * TW = 4096: CB = 128 when the tensor has at least 128 channels, so a
+// staged pixel is 256 contiguous bytes (two CTAs no longer split every 256-byte pixel of the 128-channel layers between
+// them -- DRAM sees whole rows of the strip), else CB = 64.
+template <int CB> struct BlurCfg {
+  static constexpr int TW = 4096 / CB;             // output columns per CTA
+  static constexpr int IW = TW + 3;                // staged input columns
+  static constexpr int PIX = CB * 2;               // bytes per staged pixel
+  static constexpr int STAGE_BYTES = 2 * IW * PIX; // BL_SR rows
+  static constexpr int SMEM = 4 * STAGE_BYTES;     // BL_NST stages
+};
+constexpr int BL_TW = 64;                        // (CB = 64) output columns per CTA
 constexpr int BL_IW = BL_TW + 3;                 // staged input columns
 constexpr int BL_SR = 2;                         // input rows per stage
 constexpr int BL_NST = 4;                        // ring stages
@@ -209,7 +219,7 @@ constexpr int BL_STAGE_BYTES = BL_SR * BL_IW * 128;
 constexpr int BL_ROWS = 64;                      // default output rows per strip (see fm_blur_act_nhwc)
 constexpr int BL_SMEM = BL_NST * BL_STAGE_BYTES;
 
-template <bool SEP>
+template <bool SEP, int CB>
 __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_constant__ CUtensorMap tmT,
                                                                __nv_bfloat16* __restrict__ out,
                                                                const float* __restrict__ kernel, const float* __restrict__ tab,
@@ -227,7 +237,8 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
   const int tx = bid % tiles_x; bid /= tiles_x;
   const int ty = bid % tiles_y;
   const int b = bid / tiles_y;
-  const int c0 = cb * 64, x0 = tx * BL_TW;
+  using BC = BlurCfg<CB>;
+  const int c0 = cb * CB, x0 = tx * BC::TW;
   const int Y0 = ty * strip_rows;
   const int Y1 = min(OH, Y0 + strip_rows);
   const int tid = threadIdx.x;
@@ -249,8 +260,8 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
   auto issue = [&](int s) {                                  // thread 0 only
     const int slot = s % BL_NST;
     fence_proxy_async();                                     // generic reads of this slot precede the async refill
-    mbar_arrive_expect_tx(&s_full[slot], BL_STAGE_BYTES);
-    tma_load_4d(bl_smem + slot * BL_STAGE_BYTES, &tmT, &s_full[slot], c0, x0 - 1, Y0 - 1 + s * BL_SR, b);
+    mbar_arrive_expect_tx(&s_full[slot], BC::STAGE_BYTES);
+    tma_load_4d(bl_smem + slot * BC::STAGE_BYTES, &tmT, &s_full[slot], c0, x0 - 1, Y0 - 1 + s * BL_SR, b);
   };
   if (tid == 0) {
     tma_prefetch_desc(&tmT);
@@ -260,8 +271,8 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
   }
   __syncthreads();
 
-  const int g = tid & 15;                 // 4-channel group inside the 64-channel block
-  const int cg = tid >> 4;                // 4-column group inside the 64-column tile
+  const int g = tid & (CB / 4 - 1);       // 4-channel group inside the channel block
+  const int cg = tid / (CB / 4);          // 4-column group inside the column tile
   const int X = x0 + 4 * cg;
   const int ch = c0 + g * 4;
   const bool active = X < OW && ch < cs;
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[i][c][0] = acc[i][c][1] = 0ull;
 
-  const uint8_t* my = bl_smem + (4 * cg) * 128 + g * 8;
+  const uint8_t* my = bl_smem + (4 * cg) * BC::PIX + g * 8;
   __nv_bfloat16* orow0 = out + (static_cast<size_t>(b) * OH * OW + X) * cs + ch;
 
   auto do_row = [&](auto uc, int j, const uint8_t* rowp) {
@@ -298,7 +309,7 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
     f32x2 v[7][2];
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
-      const uint2 w = *reinterpret_cast<const uint2*>(rowp + i * 128);
+      const uint2 w = *reinterpret_cast<const uint2*>(rowp + i * BC::PIX);
       v[i][0] = f2_from_bf16x2(w.x);
       v[i][1] = f2_from_bf16x2(w.y);
     }
@@ -373,14 +384,14 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
       const int slot = sc % BL_NST;
       mbar_wait(&s_full[slot], (sc / BL_NST) & 1);
       if (active) {
-        const uint8_t* base = my + slot * BL_STAGE_BYTES;
+        const uint8_t* base = my + slot * BC::STAGE_BYTES;
         const int j0 = sc * BL_SR;
         if (h2 == 0) {
           do_row(std::integral_constant<int, 0>{}, j0, base);
-          if (j0 + 1 < nrows_in) do_row(std::integral_constant<int, 1>{}, j0 + 1, base + BL_IW * 128);
+          if (j0 + 1 < nrows_in) do_row(std::integral_constant<int, 1>{}, j0 + 1, base + BC::IW * BC::PIX);
         } else {
           do_row(std::integral_constant<int, 2>{}, j0, base);
-          if (j0 + 1 < nrows_in) do_row(std::integral_constant<int, 3>{}, j0 + 1, base + BL_IW * 128);
+          if (j0 + 1 < nrows_in) do_row(std::integral_constant<int, 3>{}, j0 + 1, base + BC::IW * BC::PIX);
         }
       }
       __syncthreads();                                   // the slot is drained
@@ -557,7 +568,10 @@ extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4
   // strip height: the grid is not persistent, so pick the height whose CTA count wastes the least of the last wave
   // (2 CTAs per SM); shorter strips re-read 3 halo rows more often, but those hit L2 (neighbouring strips run together)
   static const int env_rows = []() { const char* e = getenv("FM3D_BLUR_ROWS"); return e ? atoi(e) : 0; }();
-  const int tiles_x = (OW + BL_TW - 1) / BL_TW, cblocks = (cstride + 63) / 64;
+  static const int env_cb = []() { const char* e = getenv("FM3D_BLUR_CB"); return e ? atoi(e) : 0; }();
+  const int CBv = env_cb == 64 || env_cb == 128 ? env_cb : (cstride % 128 == 0 ? 128 : 64);
+  const int TWv = 4096 / CBv;
+  const int tiles_x = (OW + TWv - 1) / TWv, cblocks = (cstride + CBv - 1) / CBv;
   int strip_rows = BL_ROWS;
   if (env_rows > 0) {
     strip_rows = env_rows;
@@ -584,7 +598,7 @@ extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4
     const cuuint64_t pw = t_pitch_w > 0 ? t_pitch_w : OW + 1, ph = t_pitch_h > 0 ? t_pitch_h : OH + 1;
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(cstride) * 2, static_cast<cuuint64_t>(cstride) * 2 * pw,
                                    static_cast<cuuint64_t>(cstride) * 2 * pw * ph};
-    const cuuint32_t box[4] = {64, BL_IW, BL_SR, 1};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(CBv), static_cast<cuuint32_t>(TWv + 3), BL_SR, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(t), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -594,12 +608,16 @@ extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static bool attr_set = false;
   if (!attr_set) {
-    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_SMEM));
-    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL_SMEM));
+    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlurCfg<64>::SMEM));
+    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlurCfg<64>::SMEM));
+    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlurCfg<128>::SMEM));
+    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlurCfg<128>::SMEM));
     attr_set = true;
   }
-  FM_CUDA_OK(launch_pdl(separable ? blur_act_nhwc_kernel<true> : blur_act_nhwc_kernel<false>, dim3(static_cast<unsigned>(blocks)),
-                        dim3(256), BL_SMEM, st, tmT, static_cast<__nv_bfloat16*>(out), kernel4x4, tab, noise, noise_bstride, noise_w,
+  auto fn = CBv == 128 ? (separable ? blur_act_nhwc_kernel<true, 128> : blur_act_nhwc_kernel<false, 128>)
+                       : (separable ? blur_act_nhwc_kernel<true, 64> : blur_act_nhwc_kernel<false, 64>);
+  FM_CUDA_OK(launch_pdl(fn, dim3(static_cast<unsigned>(blocks)), dim3(256), CBv == 128 ? BlurCfg<128>::SMEM : BlurCfg<64>::SMEM, st,
+                        tmT, static_cast<__nv_bfloat16*>(out), kernel4x4, tab, noise, noise_bstride, noise_w,
                         OH, OW, C, cstride, tiles_x, tiles_y, cblocks, strip_rows));
   count_launch();
   return FM_OK;
