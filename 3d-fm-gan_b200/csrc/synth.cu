@@ -304,6 +304,22 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
   const uint8_t* my = bl_smem + (4 * cg) * BC::PIX + g * 8;
   __nv_bfloat16* orow0 = out + (static_cast<size_t>(b) * OH * OW + X) * cs + ch;
 
+  auto load_noise = [&](int Y) -> float4 {
+    float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nzp && active) {
+      const float* np = nzp + static_cast<size_t>(Y) * OW;
+      if (nz_vec) {
+        n4 = __ldg(reinterpret_cast<const float4*>(np));
+      } else {
+        if (X + 0 < OW) n4.x = __ldg(np + 0);
+        if (X + 1 < OW) n4.y = __ldg(np + 1);
+        if (X + 2 < OW) n4.z = __ldg(np + 2);
+        if (X + 3 < OW) n4.w = __ldg(np + 3);
+      }
+    }
+    return n4;
+  };
+  float4 npre = load_noise(Y0);
   auto do_row = [&](auto uc, int j, const uint8_t* rowp) {
     constexpr int u = decltype(uc)::value;
     f32x2 v[7][2];
@@ -342,17 +358,10 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
     }
     const int Y = Y0 + j - 3;
     if (j >= 3 && Y < Y1) {
-      float nz[4] = {0.f, 0.f, 0.f, 0.f};
-      if (nzp) {
-        const float* np = nzp + static_cast<size_t>(Y) * OW;
-        if (nz_vec) {
-          const float4 n4 = __ldg(reinterpret_cast<const float4*>(np));
-          nz[0] = n4.x * nw; nz[1] = n4.y * nw; nz[2] = n4.z * nw; nz[3] = n4.w * nw;
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) nz[c] = X + c < OW ? nw * __ldg(np + c) : 0.f;
-        }
-      }
+      // the noise of this row was requested one row ago (a load issued here would sit on the row's critical path; two rows
+      // ahead measured the same)
+      const float nz[4] = {npre.x * nw, npre.y * nw, npre.z * nw, npre.w * nw};
+      if (Y + 1 < Y1) npre = load_noise(Y + 1);
       __nv_bfloat16* orow = orow0 + static_cast<size_t>(Y) * OW * cs;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
