@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence pass (one B200): bench lines, launch list, per-launch metrics, full capture of the top kernel, timeline, microbench.
 set -x
-O=gpurun_out/v6; mkdir -p $O
+O=gpurun_out/v7; mkdir -p $O
 python bench.py > $O/bench.json 2> $O/bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
 FM3D_GRAPH=0 FM3D_STREAMS=0 python tools/timeline.py -v > $O/timeline.txt 2>&1
@@ -11,4 +11,6 @@ python tools/profile_step.py && ncu --profile-from-start off --metrics gpu__time
 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none --csv --log-file $O/step_metrics.csv python tools/profile_step.py > $O/ncu_metrics.log 2>&1
 unset FM3D_GRAPH FM3D_STREAMS
 python tools/prof_conv.py 64 512 512 rgb && ncu --set full --clock-control none --import-source on -k regex:igemm_conv -s 4 -c 1 -o $O/igemm64_pair_full -f python tools/prof_conv.py 64 512 512 rgb > $O/ncu_full.log 2>&1
+python tools/prof_upfirdn.py && ncu --set full --clock-control none --import-source on -k regex:upfirdn2d_stream -s 4 -c 1 -o $O/upfirdn2d_stream_full -f python tools/prof_upfirdn.py > $O/ncu_full_upfirdn.log 2>&1
+python tools/kernel_sweep.py > $O/kernel_sweep.jsonl 2> $O/kernel_sweep.err
 ls -la $O
