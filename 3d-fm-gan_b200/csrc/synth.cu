@@ -34,14 +34,36 @@ __device__ __forceinline__ void stage_rows(float* s_a, const float* __restrict__
 __device__ __forceinline__ void dot4x4(const float* s_row, const float* __restrict__ w, int K, int o_valid, float (&acc)[4]) {
   // acc[c] = sum_k s_row[k] * w[c*K + k], c < o_valid (rows beyond are clamped by the caller)
   if ((K & 3) == 0) {
-#pragma unroll 8
-    for (int k = 0; k < K; k += 4) {      // unrolled: 32 independent broadcast loads in flight per thread
-      const float4 av = *reinterpret_cast<const float4*>(s_row + k);
+    // The W rows are warp-uniform.  Loading them as uniform (broadcast) LDG.128s fetched 16 bytes per instruction and
+    // kept only a few hundred bytes in flight per warp: the kernels ran at 260 GB/s, bound by load latency.  Now
+    // lane l fetches quad l of a 128-element k-block of each row (512 coalesced bytes per instruction, the next block
+    // already in flight) and the quads are handed round with shuffles.
+    const int lane = threadIdx.x & 31;
+    const float* wr[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(min(c, o_valid - 1)) * K + k));
-        acc[c] = fmaf(av.x, wv.x, fmaf(av.y, wv.y, fmaf(av.z, wv.z, fmaf(av.w, wv.w, acc[c]))));
+    for (int c = 0; c < 4; ++c) wr[c] = w + static_cast<size_t>(min(c, o_valid - 1)) * K;
+    auto fetch = [&](int kb, float4 (&dst)[4]) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        dst[c] = kb + 4 * lane < K ? __ldg(reinterpret_cast<const float4*>(wr[c] + kb + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 cur[4], nxt[4] = {};
+    fetch(0, cur);
+    for (int kb = 0; kb < K; kb += 128) {
+      if (kb + 128 < K) fetch(kb + 128, nxt);
+      const int nq = min(32, (K - kb) >> 2);
+#pragma unroll 4
+      for (int q = 0; q < nq; ++q) {
+        const float4 av = *reinterpret_cast<const float4*>(s_row + kb + 4 * q);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float wx = __shfl_sync(0xffffffffu, cur[c].x, q), wy = __shfl_sync(0xffffffffu, cur[c].y, q);
+          const float wz = __shfl_sync(0xffffffffu, cur[c].z, q), ww = __shfl_sync(0xffffffffu, cur[c].w, q);
+          acc[c] = fmaf(av.x, wx, fmaf(av.y, wy, fmaf(av.z, wz, fmaf(av.w, ww, acc[c]))));
+        }
       }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
     }
   } else {
     for (int k = 0; k < K; ++k) {
