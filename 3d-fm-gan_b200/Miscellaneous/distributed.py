@@ -116,14 +116,22 @@ class GradBucketReducer:
 
     Parameters are packed into ~``bucket_mb`` MB flat buckets in reverse registration order.  A
     post-accumulate-grad hook counts arrivals; when the last gradient of a bucket lands, the
-    bucket is flattened and all-reduced asynchronously (on NCCL's own stream, ordered after the
-    producing kernels through an event), while autograd keeps computing earlier layers.
-    ``finish()`` waits for the outstanding collectives, divides by the world size and scatters
-    the averages back into ``.grad``.  Two independent reducers are used for the two parameter
-    groups that step at different times (G + encoders, D), train_3_encoder.py:476-477,557-558.
+    bucket's gradients are copied into its persistent flat buffer and all-reduced asynchronously
+    (on NCCL's own stream, ordered after the producing kernels through an event), while autograd
+    keeps computing earlier layers.  ``finish()`` waits for the outstanding collectives, divides by
+    the world size and scatters the averages back into ``.grad``.  Two independent reducers are used
+    for the two parameter groups that step at different times (G + encoders, D),
+    train_3_encoder.py:476-477,557-558.
 
-    Double-backward passes (R1, path-length) only produce parameter gradients in the final
-    backward, so the hooks fire there -- nothing special is needed.
+    Contract:
+      * exactly ONE parameter-gradient-producing backward between two ``finish()`` calls (no gradient
+        accumulation over micro-batches: a second arrival for a parameter raises).  Double-backward
+        passes (R1, path length) are fine -- ``autograd.grad(create_graph=True)`` does not accumulate into
+        ``.grad``, so the hooks fire only in the final backward;
+      * every collective has the same size on every rank: a bucket always carries all of its parameters,
+        zero-filled where a parameter received no gradient on this rank.  Such a parameter keeps
+        ``grad = None`` locally, so the set of parameters that receive gradients must still be the same on
+        every rank (as with DistributedDataParallel without ``find_unused_parameters``).
     """
 
     def __init__(self, params, bucket_mb=32):
@@ -131,46 +139,87 @@ class GradBucketReducer:
         self.buckets = _bucketize(params, int(bucket_mb * (1 << 20)))
         self.index = {}
         self.hooks = []
+        self.flat = [None] * len(self.buckets)          # persistent flat buffers, allocated on first use
+        self.slots = []
         for bi, bucket in enumerate(self.buckets):
+            off, sl = 0, []
             for p in bucket:
                 self.index[p] = bi
+                sl.append((off, p.numel()))
+                off += p.numel()
                 if self.world > 1:
                     self.hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+            self.slots.append(sl)
+        self.exposed_ms = []                             # per finish(): time the step waited for communication
+        self._timing = False
         self._reset()
+
+    def bucket_bytes(self):
+        return [sum(p.numel() * p.element_size() for p in b) for b in self.buckets]
+
+    def enable_timing(self, on=True):
+        """Record, per ``finish()``, how long the compute stream had to wait for the collectives that were still
+        running when backward ended (the part of the all-reduce that backward did NOT hide)."""
+        self._timing = on
+        self.exposed_ms = []
 
     def _reset(self):
         self.pending = [len(b) for b in self.buckets]
+        self.launched = [False] * len(self.buckets)
         self.inflight = []
 
     def _on_grad(self, p):
         bi = self.index[p]
+        if self.pending[bi] <= 0 or self.launched[bi]:
+            raise RuntimeError("GradBucketReducer: a parameter received a second gradient before finish() -- gradient "
+                               "accumulation over several backward() calls is not supported; call finish() after each")
         self.pending[bi] -= 1
         if self.pending[bi] == 0:
             self._launch(bi)
 
     def _launch(self, bi):
-        grads = [p.grad for p in self.buckets[bi] if p.grad is not None]
-        if not grads:
-            return
-        flat = torch.cat([g.reshape(-1) for g in grads])
+        bucket = self.buckets[bi]
+        flat = self.flat[bi]
+        if flat is None:
+            n = self.slots[bi][-1][0] + self.slots[bi][-1][1]
+            flat = self.flat[bi] = torch.zeros(n, device=bucket[0].device, dtype=bucket[0].dtype)
+        for p, (off, n) in zip(bucket, self.slots[bi]):
+            if p.grad is not None:
+                flat[off:off + n].copy_(p.grad.reshape(-1))
+            else:
+                flat[off:off + n].zero_()                # rank-invariant message size
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
-        self.inflight.append((work, flat, grads))
+        self.launched[bi] = True
+        self.inflight.append((work, bi))
 
     def finish(self):
         """Call after ``loss.backward()`` and before ``optimizer.step()``."""
         if self.world > 1:
-            for bi, left in enumerate(self.pending):      # parameters that received no gradient
-                if 0 < left < len(self.buckets[bi]) or (left == len(self.buckets[bi]) and
-                                                        any(p.grad is not None for p in self.buckets[bi])):
+            for bi in range(len(self.buckets)):           # buckets some of whose parameters received no gradient
+                if not self.launched[bi] and any(p.grad is not None for p in self.buckets[bi]):
                     self._launch(bi)
-            for work, flat, grads in self.inflight:
+            timed = self._timing and self.inflight and self.flat[self.inflight[0][1]].is_cuda
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            for work, bi in self.inflight:
                 work.wait()
+                flat = self.flat[bi]
                 flat.div_(self.world)
-                off = 0
-                for g in grads:
-                    g.copy_(flat[off:off + g.numel()].view_as(g))
-                    off += g.numel()
+                for p, (off, n) in zip(self.buckets[bi], self.slots[bi]):
+                    if p.grad is not None:
+                        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            if timed:
+                e1.record()
+                self.exposed_ms.append((e0, e1))
         self._reset()
+
+    def exposed_times_ms(self):
+        """Milliseconds per finish() between the end of backward and the last averaged gradient (needs a device sync)."""
+        out = []
+        for e in self.exposed_ms:
+            out.append(e[0].elapsed_time(e[1]) if isinstance(e, tuple) else e)
+        return out
 
     def remove(self):
         for h in self.hooks:

@@ -49,6 +49,21 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 int sm_count();
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: one process that drives several
+// GPUs (the worker threads of nn.DataParallel, train_3_encoder.py:355-362) must opt in on each of them.  ``done`` is
+// the caller's per-kernel table indexed by device ordinal.
+struct SmemOptIn { std::atomic<unsigned char> done[64]; };
+template <typename F>
+inline cudaError_t smem_opt_in(SmemOptIn& t, F* fn, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && t.done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) t.done[dev].store(1, std::memory_order_release);
+  return e;
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency); NULL if unavailable.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -943,11 +943,8 @@ EncodeTiledFn get_encode_fn() {
 template <int BN, int EPI, bool PAIR>
 static int launch_igemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
   using Cfg = IgemmCfg<BN>;
-  static bool attr_set = false;   // per-process, per-instantiation; benign race
-  if (!attr_set) {
-    FM_CUDA_OK(cudaFuncSetAttribute(igemm_conv_kernel<BN, EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in;        // per instantiation, per device
+  FM_CUDA_OK(smem_opt_in(opt_in, igemm_conv_kernel<BN, EPI, PAIR>, Cfg::SMEM_BYTES));
   const int sms = sm_count();
   const int max_clusters = sms / p.cluster;
   const int nclusters = p.num_super < max_clusters ? p.num_super : max_clusters;

@@ -637,14 +637,11 @@ extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4
     if (r != CUDA_SUCCESS) { set_error("fm_blur_act_nhwc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return FM_ERR_CUDA; }
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlurCfg<64>::SMEM));
-    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlurCfg<64>::SMEM));
-    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlurCfg<128>::SMEM));
-    FM_CUDA_OK(cudaFuncSetAttribute(blur_act_nhwc_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlurCfg<128>::SMEM));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in[4];     // per kernel instantiation, per device
+  FM_CUDA_OK(smem_opt_in(opt_in[0], blur_act_nhwc_kernel<true, 64>, BlurCfg<64>::SMEM));
+  FM_CUDA_OK(smem_opt_in(opt_in[1], blur_act_nhwc_kernel<false, 64>, BlurCfg<64>::SMEM));
+  FM_CUDA_OK(smem_opt_in(opt_in[2], blur_act_nhwc_kernel<true, 128>, BlurCfg<128>::SMEM));
+  FM_CUDA_OK(smem_opt_in(opt_in[3], blur_act_nhwc_kernel<false, 128>, BlurCfg<128>::SMEM));
   auto fn = CBv == 128 ? (separable ? blur_act_nhwc_kernel<true, 128> : blur_act_nhwc_kernel<false, 128>)
                        : (separable ? blur_act_nhwc_kernel<true, 64> : blur_act_nhwc_kernel<false, 64>);
   FM_CUDA_OK(launch_pdl(fn, dim3(static_cast<unsigned>(blocks)), dim3(256), CBv == 128 ? BlurCfg<128>::SMEM : BlurCfg<64>::SMEM, st,

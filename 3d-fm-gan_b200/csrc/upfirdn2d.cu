@@ -469,13 +469,10 @@ static int launch_stream_c(void* out, const void* x, const float* kernel, const 
     R = (p.out_h + strips - 1) / strips;          // balance the strips
   }
   const int64_t n_items = strips > 1 ? planes * strips : (planes + P - 1) / P;
-  static bool attr_set = false;
+  static SmemOptIn opt_in;        // per instantiation (T, COLS), per device
   auto fn = upfirdn2d_stream_kernel<T, COLS>;
   const int smem = nslots * UFS_BUF_BYTES;
-  if (!attr_set) {
-    FM_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  FM_CUDA_OK(smem_opt_in(opt_in, fn, 200 * 1024));
   int cps = (227 * 1024) / (smem + 2048);          // CTAs per SM that fit (persistent grid)
   cps = cps < 1 ? 1 : (cps > 4 ? 4 : cps);
   const int64_t cap = static_cast<int64_t>(sm_count()) * cps;

@@ -63,6 +63,22 @@ def _worker(rank, world, port, ret):
             exp.append([p.grad.clone() for p in ref.parameters()])
         for g, a, b in zip(mine, exp[0], exp[1]):
             assert torch.allclose(g, (a + b) / 2, atol=1e-6)
+    # contract: a second parameter-gradient backward before finish() raises instead of silently dropping gradients
+    model.zero_grad(set_to_none=True)
+    model(x).pow(2).sum().backward()
+    try:
+        model(x).pow(2).sum().backward()
+        raise AssertionError("second backward before finish() did not raise")
+    except RuntimeError as e:
+        assert "finish()" in str(e)
+    red.finish()
+    # a parameter without a gradient keeps its zero-filled slot: equal message sizes on every rank, no hang
+    model.zero_grad(set_to_none=True)
+    model[0](x).pow(2).sum().backward()               # only the first Linear receives gradients
+    red.finish()
+    assert model[2].weight.grad is None and model[0].weight.grad is not None
+    g0 = D.all_gather(model[0].weight.grad.clone())
+    assert torch.allclose(g0[0], g0[1])
     red.remove()
     # loss dict: rank 0 holds the mean
     out = D.reduce_loss_dict({"b": torch.tensor(float(rank)), "a": torch.tensor(2.0 * rank)})
