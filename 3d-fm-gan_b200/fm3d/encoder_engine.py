@@ -18,14 +18,19 @@ import math
 
 import os
 
+import weakref
+
 import torch
 
 from . import ops
+from .engine import epoch_of, plans_of
 from .graphs import GraphRunner
 
 
 def _versions(module):
-    return [(t._version, t.data_ptr()) for t in module.state_dict(keep_vars=True).values()]
+    """Cache key of everything derived from ``module``: version counter and address of every parameter / buffer, plus
+    the module's engine epoch (``fm3d.engine.invalidate(module)`` for value changes the counters do not show)."""
+    return [epoch_of(module)] + [(t._version, t.data_ptr()) for t in module.state_dict(keep_vars=True).values()]
 
 
 def _fold_bn(bn):
@@ -84,8 +89,10 @@ _FUSE_UPSAMPLE = os.environ.get("FM3D_FUSE_UPSAMPLE", "1") != "0"
 
 
 class ResNetPlan:
+    model = property(lambda self: self._model())      # weak: the plan cache is keyed weakly on the module
+
     def __init__(self, model, B, H, W, device):
-        self.model, self.B, self.H, self.W, self.device = model, B, H, W, device
+        self._model, self.B, self.H, self.W, self.device = weakref.ref(model), B, H, W, device
         self.versions = None
         bf = dict(device=device, dtype=torch.bfloat16)
         # stem geometry: 7x7 stride 2 pad 3; a window of 8 padded pixels x 8 channels per (ky, out x)
@@ -137,9 +144,11 @@ class ResNetPlan:
     def _run(self, x):
         B = self.B
         ops.image_to_nhwc8_padded(x, 3, 3, self.Hp, self.Wp, out=self.packed)
+        # algorithmic FLOPs of the 7x7 conv on 3 channels (the K dimension is padded to 7 x 64 for the tensor core)
         ops.conv_igemm(self.packed, self.stem_w, [(ky, 0, ky) for ky in range(7)], self.stem_out, self.stem_tab,
                        B=B, H=self.Hp, W=self.ow, Cin=64, Cout=64, OH=self.oh, OW=self.ow, stride_x=1, stride_y=2,
-                       x_pixstride=16, x_rowstride=self.Wp * 8, x_imgstride=self.Hp * self.Wp * 8)
+                       x_pixstride=16, x_rowstride=self.Wp * 8, x_imgstride=self.Hp * self.Wp * 8,
+                       algo_flops=2.0 * B * self.oh * self.ow * 3 * 64 * 49)
         ops.maxpool3x3s2_nhwc(self.stem_out, self.pool_out)
         cur = self.pool_out
         h, w = cur.shape[1], cur.shape[2]
@@ -163,7 +172,7 @@ def run_resnet(model, x):
     if [len(l) for l in (model.layer1, model.layer2, model.layer3, model.layer4)] != [2, 2, 2, 2] or \
             type(model.layer1[0]).__name__ != "BasicBlock":
         return None
-    plans = model.__dict__.setdefault("_fm3d_plans", {})
+    plans = plans_of(model)
     key = (tuple(x.shape), x.device.index, ops.current_slot())
     plan = plans.get(key)
     if plan is None:
@@ -196,8 +205,10 @@ class _Unit:
 
 
 class PspPlan:
+    model = property(lambda self: self._model())
+
     def __init__(self, model, B, device):
-        self.model, self.B, self.device = model, B, device
+        self._model, self.B, self.device = weakref.ref(model), B, device
         self.versions = None
         bf = dict(device=device, dtype=torch.bfloat16)
         S = 256
@@ -301,7 +312,8 @@ class PspPlan:
         cur = self._buf("in", B, S, S, 64)
         ops.conv_igemm(self.packed, self.in_w, [(ky, 0, ky) for ky in range(3)], cur, self.in_tab,
                        B=B, H=self.Hp, W=S, Cin=64, Cout=64, OH=S, OW=S, stride_x=1, stride_y=1,
-                       x_pixstride=8, x_rowstride=self.Wp * 8, x_imgstride=self.Hp * self.Wp * 8)
+                       x_pixstride=8, x_rowstride=self.Wp * 8, x_imgstride=self.Hp * self.Wp * 8,
+                       algo_flops=2.0 * B * S * S * 3 * 64 * 9)          # 3x3 conv on 3 channels, not the padded K
         h = S
         feats = {}
         for i, u in enumerate(self.units):
@@ -374,7 +386,7 @@ def run_psp(model, x):
         return None
     if m.style_count < m.middle_ind + 1 or m.coarse_ind != 3 or m.middle_ind != 7:
         return None
-    plans = m.__dict__.setdefault("_fm3d_plans", {})
+    plans = plans_of(m)
     key = (x.shape[0], x.device.index, ops.current_slot())
     plan = plans.get(key)
     if plan is None:

@@ -24,6 +24,7 @@ the parameters' version counters -- they are never part of the state dict.
 """
 import ctypes as C
 import math
+import weakref
 
 import torch
 
@@ -68,7 +69,7 @@ class _ConvLayer:
 
 class SynthesisPlan:
     def __init__(self, gen, batch, device):
-        self.gen = gen
+        self._gen = weakref.ref(gen)        # the plan cache is keyed weakly on the generator: no strong reference back
         self.B = batch
         self.device = device
         self.style_dim = gen.style_dim
@@ -129,44 +130,79 @@ class SynthesisPlan:
                      for i, L in enumerate(convs) if L.up}
         self.x0 = torch.empty(B, 4, 4, cs(convs[0].cin), **bf16)
         self.rgb_acc = [torch.zeros(B, L.res_out, L.res_out, 4, **f32) for (_, _, L) in self.rgbs]
+        self._ptrs = None
         self._versions = None
+        self._epoch = None
         self._desc_keepalive = None
         self._runner = GraphRunner(self._run_flat)
         self._refresh_weights()
 
     # ------------------------------------------------------------------ derived caches
-    def _param_versions(self):
+    # Two levels of staleness:
+    #   * a parameter tensor was REPLACED (``.to()``, ``load_state_dict(assign=True)``, a new device): the descriptor
+    #     arrays hold raw pointers -> rebuild everything and drop the captured graphs;
+    #   * a parameter's VALUES changed: its version counter moved (optimizer step, ``copy_`` under ``no_grad``), or the
+    #     generator's engine epoch moved -- ``Generator.named_parameters()`` / ``parameters()`` bump it, because whoever
+    #     holds parameter handles may write through ``.data`` without touching the version counter (the reference's EMA
+    #     does exactly that every iteration: ``accumulate``, train_3_encoder.py:195-200).  The derived tensors are then
+    #     re-computed IN PLACE, so captured graphs stay valid.
+    # ``Generator.invalidate_engine()`` forces the second kind for writers this cannot see.
+    def _param_ptrs(self):
         v = []
         for L in self.convs:
-            v += [L.mod.weight._version, L.mod.weight.data_ptr(), L.mod.modulation.weight.data_ptr(),
-                  L.mod.modulation.bias.data_ptr(), L.act_bias.data_ptr(), L.noise_w.data_ptr()]
+            v += [L.mod.weight.data_ptr(), L.mod.modulation.weight.data_ptr(), L.mod.modulation.bias.data_ptr(),
+                  L.act_bias.data_ptr(), L.noise_w.data_ptr()]
         for (to_rgb, _, _) in self.rgbs:
-            v += [to_rgb.conv.weight._version, to_rgb.conv.weight.data_ptr(), to_rgb.bias.data_ptr(),
-                  to_rgb.conv.modulation.weight.data_ptr(), to_rgb.conv.modulation.bias.data_ptr()]
+            v += [to_rgb.conv.weight.data_ptr(), to_rgb.bias.data_ptr(), to_rgb.conv.modulation.weight.data_ptr(),
+                  to_rgb.conv.modulation.bias.data_ptr()]
         return v
 
-    def _refresh_weights(self):
-        vers = self._param_versions()
-        if vers == self._versions:
-            return
-        self._versions = vers
-        self._runner.invalidate()          # derived buffers are re-created: captured graphs are stale
+    def _param_versions(self):
+        return [L.mod.weight._version for L in self.convs] + [t[0].conv.weight._version for t in self.rgbs]
+
+    def _derive(self, rebuild):
+        """(Re-)compute bf16 K-major conv weights, sum-of-squares tables, paired-parity up-conv weights and the fp32
+        ToRGB weights from the live parameters; ``rebuild=False`` writes into the existing buffers.  (Modulation
+        weights, biases, noise weights, blur kernels and ToRGB biases are read live through their pointers.)"""
         dev = self.device
         for L in self.convs:
             w = L.mod.weight.detach()[0]
-            L.wq, L.wsq = ops.prep_weight(w, L.mod.scale, want_wsq=True)
-            L.wpair = None
+            if rebuild:
+                L.wq, L.wsq = ops.prep_weight(w, L.mod.scale, want_wsq=True)
+                L.wpair = None
+            else:
+                ops.prep_weight(w, L.mod.scale, want_wsq=True, out=(L.wq, L.wsq))
             if L.up and _PAIR_UP and L.cout % 32 == 0 and L.cout <= 128 and L.res_in >= 12:
                 # [view][P_x0 rows | P_x1 rows][cin]: zero block where the odd column parity has no tap for the view
-                L.wpair = {}
+                if rebuild:
+                    L.wpair = {py: torch.zeros(len(views), 2 * L.cout, L.wq.shape[2], device=dev, dtype=torch.bfloat16)
+                               for py, views in _PAIR_VIEWS.items()}
                 for py, views in _PAIR_VIEWS.items():
-                    wp = torch.zeros(len(views), 2 * L.cout, L.wq.shape[2], device=dev, dtype=torch.bfloat16)
+                    wp = L.wpair[py]
                     for v, (_, t0, t1) in enumerate(views):
-                        wp[v, :L.cout] = L.wq[t0, :L.cout]
+                        wp[v, :L.cout].copy_(L.wq[t0, :L.cout])
                         if t1 is not None:
-                            wp[v, L.cout:] = L.wq[t1, :L.cout]
-                    L.wpair[py] = wp
-        self.rgb_w = [to_rgb.conv.weight.detach().reshape(3, -1).contiguous().float() for (to_rgb, _, _) in self.rgbs]
+                            wp[v, L.cout:].copy_(L.wq[t1, :L.cout])
+        if rebuild:
+            self.rgb_w = [to_rgb.conv.weight.detach().reshape(3, -1).contiguous().float() for (to_rgb, _, _) in self.rgbs]
+        else:
+            for dst, (to_rgb, _, _) in zip(self.rgb_w, self.rgbs):
+                dst.copy_(to_rgb.conv.weight.detach().reshape(3, -1))
+
+    def _refresh_weights(self):
+        gen = self._gen()
+        epoch = gen._engine_epoch if gen is not None else 0
+        ptrs = self._param_ptrs()
+        if ptrs == self._ptrs:
+            vers = self._param_versions()
+            if vers != self._versions or epoch != self._epoch:
+                self._versions, self._epoch = vers, epoch
+                self._derive(rebuild=False)
+            return
+        self._ptrs, self._versions, self._epoch = ptrs, self._param_versions(), epoch
+        self._runner.invalidate()          # derived buffers are re-created: captured graphs are stale
+        dev = self.device
+        self._derive(rebuild=True)
         # descriptor arrays (device resident)
         n_style = len(self.convs) + len(self.rgbs)
         sl = (StyleLayer * n_style)()
@@ -283,18 +319,72 @@ class SynthesisPlan:
                 if L.rgb_mod is not None:
                     to_rgb = L.rgb_mod[0]
                     kern = to_rgb.upsample.kernel if skip is not None else None
-                    skip = ops.rgb_finalize(rgb, to_rgb.bias.detach().reshape(3).contiguous(), skip, kern)
+                    skip = ops.rgb_finalize(rgb, to_rgb.bias.detach().reshape(3), skip, kern)     # live view of the parameter
                     outs.append(skip)
                     rgb_i += 1
             x = y
         return outs
 
 
+# plans live OUTSIDE the module, keyed weakly on it: ``nn.DataParallel.replicate`` shallow-copies ``__dict__`` (replicas
+# would share -- and keep alive -- the first replica's plans), and a plan holds ctypes arrays and CUDA graphs that
+# ``copy.deepcopy`` / ``torch.save`` of the generator must not meet
+_PLANS = weakref.WeakKeyDictionary()
+
+
+_EPOCHS = weakref.WeakKeyDictionary()
+
+
+def plans_of(module):
+    d = _PLANS.get(module)
+    if d is None:
+        d = _PLANS[module] = {}
+    return d
+
+
+def epoch_of(module):
+    e = getattr(module, "_engine_epoch", None)
+    return _EPOCHS.get(module, 0) if e is None else e
+
+
+def invalidate(module):
+    """Mark the engine's derived tensors of ``module`` (a Generator or an encoder) stale: parameter or buffer VALUES
+    were changed in a way version counters do not show (``.data`` writes).  ``Generator.invalidate_engine()`` is
+    the same thing as a method."""
+    if hasattr(module, "_engine_epoch"):
+        module._engine_epoch += 1
+    else:
+        _EPOCHS[module] = _EPOCHS.get(module, 0) + 1
+
+
+def check_inputs(gen, latent, start, noise):
+    """Shape contract of the engine (the reference raises a shape error inside the first mismatching op; the engine
+    passes raw pointers to kernels, so it has to check up front).  Returns False for valid inputs the engine does not
+    cover (the caller then takes the differentiable composition), raises on invalid ones."""
+    B = latent.shape[0]
+    if latent.ndim != 3 or latent.shape[1] < gen.n_latent or latent.shape[2] != gen.style_dim:
+        raise RuntimeError(f"Generator: latent must be [B, >={gen.n_latent}, {gen.style_dim}], got {tuple(latent.shape)}")
+    c0 = gen.conv1.conv.in_channel
+    if start.ndim != 4 or start.shape[0] != B or start.shape[1] != c0:
+        raise RuntimeError(f"Generator: start tensor must be [{B}, {c0}, 4, 4], got {tuple(start.shape)}")
+    if tuple(start.shape[2:]) != (4, 4):
+        return False                     # other start resolutions: valid for the module composition, not planned here
+    if len(noise) != gen.num_layers:
+        raise RuntimeError(f"Generator: {gen.num_layers} noise maps expected, got {len(noise)}")
+    for i, n in enumerate(noise):
+        if n is None:
+            continue
+        res = 2 ** ((i + 5) // 2)
+        if n.ndim != 4 or n.shape[0] not in (1, B) or tuple(n.shape[1:]) != (1, res, res):
+            raise RuntimeError(f"Generator: noise[{i}] must be [1|{B}, 1, {res}, {res}], got {tuple(n.shape)}")
+    return True
+
+
 def run_synthesis(gen, latent, start, noise):
-    """Entry used by ``stylegan2.Generator.forward``: cached plan per (batch, device)."""
+    """Entry used by ``stylegan2.Generator.forward``: cached plan per (batch, device, engine slot)."""
+    plans = plans_of(gen)
     key = (latent.shape[0], latent.device.index, ops.current_slot())
-    plan = gen._engine_plans.get(key)
+    plan = plans.get(key)
     if plan is None:
-        plan = SynthesisPlan(gen, latent.shape[0], latent.device)
-        gen._engine_plans[key] = plan
+        plan = plans[key] = SynthesisPlan(gen, latent.shape[0], latent.device)
     return plan.run(latent, start, noise)

@@ -247,15 +247,21 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     return out
 
 
-def prep_weight(w_oikk, scale, cout_rows=None, cin_stride=None, want_wsq=True):
-    """fp32 [O,I,kh,kw] -> (bf16 [kh*kw, rows, cin_stride], fp32 wsq [O,I] or None)."""
+def prep_weight(w_oikk, scale, cout_rows=None, cin_stride=None, want_wsq=True, out=None):
+    """fp32 [O,I,kh,kw] -> (bf16 [kh*kw, rows, cin_stride], fp32 wsq [O,I] or None).
+    ``out=(wq, wsq)``: refresh existing buffers in place (their addresses are baked into captured CUDA graphs)."""
     _check_cuda(w_oikk, "weight")
     w = w_oikk.contiguous().to(torch.float32)
     O, I, kh, kw = w.shape
     rows = O if cout_rows is None else cout_rows
     cs = (I + 7) // 8 * 8 if cin_stride is None else cin_stride
-    wq = torch.empty(kh * kw, rows, cs, device=w.device, dtype=torch.bfloat16)
-    wsq = torch.empty(O, I, device=w.device, dtype=torch.float32) if want_wsq else None
+    if out is not None:
+        wq, wsq = out
+        if tuple(wq.shape) != (kh * kw, rows, cs) or (wsq is not None and tuple(wsq.shape) != (O, I)):
+            raise RuntimeError("prep_weight: out buffers do not match the weight's shape")
+    else:
+        wq = torch.empty(kh * kw, rows, cs, device=w.device, dtype=torch.bfloat16)
+        wsq = torch.empty(O, I, device=w.device, dtype=torch.float32) if want_wsq else None
     with torch.cuda.device(w.device):
         st = _lib.lib().fm_prep_weight(_ptr(wq), _ptr(wsq), _ptr(w), O, I, kh, kw, float(scale), rows, cs, _stream())
     _lib.check(st, "fm_prep_weight")

@@ -299,7 +299,20 @@ class Generator(nn.Module):
             self.to_rgbs.append(ToRGB(c_out, style_dim))
 
         self.n_latent = self.log_size * 2 - 2
-        self._engine_plans = {}
+        self._engine_epoch = 0
+
+    # -- engine cache control (fm3d/engine.py: SynthesisPlan._refresh_weights)
+    def invalidate_engine(self):
+        """Tell the fused engine that parameter VALUES may have changed behind autograd's back (writes through
+        ``.data`` / ``.detach()`` views do not move the version counters the engine watches).  Cheap: the derived bf16
+        weights are recomputed in place on the next gradient-free forward; captured CUDA graphs stay valid."""
+        self._engine_epoch += 1
+
+    def named_parameters(self, *args, **kwargs):
+        # whoever asks for parameter handles may write through ``.data`` (the reference's EMA does, every iteration:
+        # ``accumulate``, train_3_encoder.py:195-200): treat the derived weights as stale from here on
+        self._engine_epoch += 1
+        return super().named_parameters(*args, **kwargs)
 
     # -- helpers also present on the reference class
     def make_noise(self):
@@ -334,11 +347,12 @@ class Generator(nn.Module):
         if not (latent.is_cuda and latent.dtype == torch.float32):
             return False
         if torch.is_grad_enabled() and (latent.requires_grad or start.requires_grad or
-                                        any(p.requires_grad for p in self.parameters())):
+                                        any(p.requires_grad for _, p in nn.Module.named_parameters(self))):
             return False
         if noise is not None and any(n is not None and n.requires_grad for n in noise):
             return False
-        return True
+        from fm3d.engine import check_inputs
+        return check_inputs(self, latent, start, noise)      # raises on shapes the reference would reject too
 
     def forward(self, noise_z, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
                 latent_styles=None, input_is_latent=False, noise=None, randomize_noise=True,

@@ -281,16 +281,23 @@ def main():
         sampler = ClockSampler(local_rank)
         if os.environ.get("FM3D_BENCH_SAMPLER", "nvml") != "none":
             sampler.start()
-        barrier()
-        l0 = _lib.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = run_steps(args.steps)
-        e1.record()
-        barrier()
-        launches = _lib.launch_count() - l0
+        # The timed region is EXACTLY --steps steps between two barriers.  It is measured REPEATS times back to back
+        # (a 20-step region lasts ~0.15 s, and run-to-run noise at that length is +-3 %): `value` is the median
+        # repeat, the others are reported as `repeats` so the spread is visible.
+        REPEATS = 3
+        rep_ms, launches = [], 0
+        for rep in range(REPEATS):
+            barrier()
+            l0 = _lib.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = run_steps(args.steps)
+            e1.record()
+            barrier()
+            launches = _lib.launch_count() - l0
+            rep_ms.append(max_over_ranks(e0.elapsed_time(e1)))
         sampler.stop()
-        ms = max_over_ranks(e0.elapsed_time(e1))
+        ms = sorted(rep_ms)[REPEATS // 2]
         value = B * world * args.steps / (ms * 1e-3)
 
         # ---------------- end to end: pinned host inputs -> device -> image back on the host
@@ -376,6 +383,7 @@ def main():
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_burst = peaks.get("bf16_tflops", 1650.0)
     # dram__bytes_read + dram__bytes_write of the igemm launches of one step / launches, from the committed ncu pass
     traffic, traffic_src = None, None
     try:
@@ -387,6 +395,11 @@ def main():
     roofline = {"bound": "tensor", "kernel": "igemm_conv_kernel (tcgen05 implicit GEMM, all launches of one step)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
+                # the launches are event-timed one by one (each alone on the GPU), so the burst figure is the stricter
+                # denominator; the sustained one is what a long step can hold under the power cap
+                "peak_burst": peak_burst, "frac_burst": achieved / peak_burst,
+                "flops_counted": "algorithmic: 3-channel stems counted with Cin=3 (not their padded K), transposed convs "
+                                 "with 9 taps at the input resolution, zero weight blocks not credited",
                 "launches_per_step": len(prof) // 2, "kernel_ms_per_step": ksec * 1e3 / 2,
                 "algorithmic_gflop_per_step": flops / 2 / 1e9,
                 "traffic": traffic, "traffic_unit": traffic_src}
@@ -414,6 +427,9 @@ def main():
                          "a step streams > 2 GB of activations"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * img_bytes, "d2h_bytes_per_step": img_bytes,
                 "ms_per_step": ms_e2e / args.steps},
+        "repeats": {"values": [B * world * args.steps / (m * 1e-3) for m in rep_ms], "unit": UNIT,
+                    "spread": (max(rep_ms) - min(rep_ms)) / ms,
+                    "note": f"{REPEATS} back-to-back timed regions of exactly {args.steps} steps; value = median"},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": roofline,

@@ -339,10 +339,60 @@ def gen_encoders(sg, rn, psp, nu):
     print("three_encoder: img stats", out["img.stats"])
 
 
+def gen_encoders_big(sg, rn, psp, nu, B, fname):
+    """The 3-encoder forward at the batch sizes that are BENCHMARKED (BASELINE config 2: B=32; config 5: B=64 per GPU).
+    Batch size picks block_n, tile shape, split-K and the pair / halo-patch / resident-weight modes of the conv kernel,
+    so parity at B=2 does not cover them.  Same models as gen_encoders (same seeds); inputs from their own seeds."""
+    out = {}
+    torch.manual_seed(600)
+    e_tsr = rn.resnet18(tensor_encoding=True).eval()
+    e_w = rn.resnet18(tensor_encoding=False).eval()
+    e_wp = psp.GradualStyleEncoder(18, 'ir_se', types.SimpleNamespace(input_nc=3, n_styles=14)).eval()
+    g = sg.Generator(256, 512, 8, channel_multiplier=2).eval()
+    randomize_fused_terms(g, 601)
+    gen = torch.Generator().manual_seed(602)
+    with torch.no_grad():
+        for m in list(e_tsr.modules()) + list(e_w.modules()) + list(e_wp.modules()):
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen) * 0.1)
+                m.running_var.copy_(1.0 + 0.2 * torch.rand(m.running_var.shape, generator=gen))
+                m.weight.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=gen))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=gen))
+    out["cs.g"] = checksum(g.state_dict())
+    out["cs.e_wp"] = checksum(e_wp.state_dict())
+    gin = torch.Generator().manual_seed(700 + B)
+    p = (torch.rand(B, 3, 256, 256, generator=gin) * 2 - 1)
+    r = (torch.rand(B, 3, 256, 256, generator=gin) * 2 - 1)
+    gn = torch.Generator().manual_seed(800 + B)
+    noise = [torch.randn(B, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), generator=gn) for i in range(13)]
+
+    class _G(torch.nn.Module):
+        def __init__(s, m):
+            super().__init__(); s.module = m
+        def forward(s, *a, **k):
+            k["noise"] = noise
+            return s.module(*a, **k)
+    with torch.no_grad():
+        w = e_w(r); wp = e_wp(p)
+        img = nu.Forward_Inference_3_Encoder(p, r, e_tsr, e_w, e_wp, _G(g), tsr_encode='Render Image')
+    out["e_w"] = w.numpy()
+    out["e_wp.sel"] = wp[:, [0, 7, 13]].numpy()
+    out["img.stats"] = np.array([float(img.mean()), float(img.std())])
+    out["img.absmax"] = np.array([float(img.abs().max())])
+    out["img.ds8"] = img[:, :, ::8, ::8].numpy().astype(np.float16 if B > 32 else np.float32)
+    out["img.last"] = img[B - 1].numpy().astype(np.float16)
+    np.savez_compressed(os.path.join(OUT, fname), **out)
+    print(fname, "img stats", out["img.stats"], "absmax", out["img.absmax"])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sg, rn, psp, nu, op = import_reference()
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "big":        # only the benchmarked-batch fixtures (minutes of CPU)
+        gen_encoders_big(sg, rn, psp, nu, 32, "three_encoder_b32.npz")
+        gen_encoders_big(sg, rn, psp, nu, 64, "three_encoder_b64.npz")
+        return
     gen_upfirdn2d(op)
     gen_bias_act(op)
     gen_modconv(sg)
@@ -350,6 +400,8 @@ def main():
     gen_discriminator(sg)
     gen_generator_cfg1(sg)
     gen_encoders(sg, rn, psp, nu)
+    gen_encoders_big(sg, rn, psp, nu, 32, "three_encoder_b32.npz")
+    gen_encoders_big(sg, rn, psp, nu, 64, "three_encoder_b64.npz")
 
 
 if __name__ == "__main__":

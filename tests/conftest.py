@@ -29,9 +29,10 @@ def cuda():
     return torch.device("cuda:0")
 
 
-def build_three_encoder_models(device="cpu"):
-    """Re-create the models of tests/golden/three_encoder.npz (same seeds and RNG order as
-    oracle/make_golden.py:gen_encoders) from the product mirror classes."""
+def build_three_encoder_models(device="cpu", B=2):
+    """Re-create the models of tests/golden/three_encoder*.npz (same seeds and RNG order as
+    oracle/make_golden.py:gen_encoders / gen_encoders_big) from the product mirror classes.  B=2 reproduces the inputs
+    of three_encoder.npz, any other B those of three_encoder_b<B>.npz."""
     import types
     import torch
     import resnet_encoder as rn
@@ -56,10 +57,11 @@ def build_three_encoder_models(device="cpu"):
                 m.running_var.copy_(1.0 + 0.2 * torch.rand(m.running_var.shape, generator=gen))
                 m.weight.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=gen))
                 m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=gen))
-    B = 2
+    if B != 2:
+        gen = torch.Generator().manual_seed(700 + B)
     p = torch.rand(B, 3, 256, 256, generator=gen) * 2 - 1
     r = torch.rand(B, 3, 256, 256, generator=gen) * 2 - 1
-    gen3 = torch.Generator().manual_seed(603)
+    gen3 = torch.Generator().manual_seed(603 if B == 2 else 800 + B)
     noise = [torch.randn(B, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), generator=gen3) for i in range(13)]
     models = [m.to(device) for m in (e_tsr, e_w, e_wp, g)]
     return models, p, r, noise

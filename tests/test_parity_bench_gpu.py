@@ -1,0 +1,319 @@
+"""Parity at the configurations that are BENCHMARKED (BASELINE configs 2 and 5) and at the generator's real layer
+shapes, plus gradient parity of the generator against autograd of the oracle.
+
+Batch size picks block_n, tile shape, split-K and the pair / halo-patch / row-patch / resident-weight modes of the
+implicit-GEMM kernel (igemm.cu: fm_conv_igemm), so parity at B = 2..4 says nothing about the kernels a bench step
+launches.  Here:
+
+  * the 3-encoder forward at B = 32 and B = 64 against goldens made by the unmodified reference on CPU
+    (oracle/make_golden.py:gen_encoders_big);
+  * every conv mode at the real layer shapes, B = 32, against fp32 ``F.conv2d`` / ``F.conv_transpose2d`` (TF32 off) on
+    the same bf16-rounded operands, on a sample of output channels from every n-tile;
+  * dL/dW, dL/dlatent, dL/dnoise_weight, dL/dbias of ``Generator`` against autograd of ``oracle.modulated_conv2d_ref``
+    (the reference's per-sample formulation, stylegan2.py:250-298).
+
+Tolerances: bf16 operands / fp32 accumulate -> 1e-2 relative to the tensor's max for one conv; 3e-2 for encoder outputs,
+5e-2 of max for the final image through encoders + 13 modulated layers (measured 1-2 %); fp32 gradients 2e-3 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, build_three_encoder_models
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fm_oracle as orc  # noqa: E402  (checker only)
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max())
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+# ------------------------------------------------------------------ the benchmarked workloads vs the reference
+@pytest.mark.parametrize("B", [32, 64])
+def test_three_encoder_forward_benchmarked_batch(cuda, B):
+    """BASELINE config 2 (B=32, bench.py's workload) and config 5 (64 per GPU) against the reference's own output."""
+    from Util.network_util import Forward_Inference_3_Encoder
+    g = load_golden(f"three_encoder_b{B}.npz")
+    (e_tsr, e_w, e_wp, gen), p, r, noise = build_three_encoder_models(cuda, B=B)
+
+    class _G(torch.nn.Module):
+        def __init__(s, m):
+            super().__init__(); s.module = m
+        def forward(s, *a, **k):
+            k["noise"] = noise
+            return s.module(*a, **k)
+    p, r = p.to(cuda), r.to(cuda)
+    noise = [n.to(cuda) for n in noise]
+    G = _G(gen)
+    with torch.no_grad():
+        # three calls: eager, eager, CUDA-graph capture + replay -- the replayed result is what a bench step produces
+        for _ in range(3):
+            img = Forward_Inference_3_Encoder(p, r, e_tsr, e_w, e_wp, G, tsr_encode='Render Image')
+        w = e_w(r); wp = e_wp(p)
+    assert img.shape == (B, 3, 256, 256)
+    e1, e2 = _rel(w.cpu(), torch.from_numpy(g["e_w"])), _rel(wp[:, [0, 7, 13]].cpu(), torch.from_numpy(g["e_wp.sel"]))
+    e3 = _rel(img[:, :, ::8, ::8].cpu(), torch.from_numpy(g["img.ds8"].astype(np.float32)))
+    e4 = _rel(img[B - 1].cpu(), torch.from_numpy(g["img.last"].astype(np.float32)))
+    print(f"B={B}: e_w {e1:.4f} e_wp {e2:.4f} image ds8 {e3:.4f} last image {e4:.4f}")
+    assert e1 < 3e-2 and e2 < 3e-2, (e1, e2)
+    assert e3 < 5e-2 and e4 < 5e-2, (e3, e4)
+    np.testing.assert_allclose([float(img.mean()), float(img.std())], g["img.stats"], rtol=0, atol=2e-2)
+
+
+def test_generator_b32_engine_vs_fp32_composition(cuda, monkeypatch):
+    """All 13 modulated layers + 7 ToRGBs at B=32 on the engine vs the differentiable fp32 composition (cuDNN fp32,
+    TF32 off), every resolution's RGB: localises a wrong layer to its resolution."""
+    import stylegan2
+    torch.manual_seed(0)
+    gen = stylegan2.Generator(256, 512, 8, channel_multiplier=2)
+    rg = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p in gen.named_parameters():
+            if name.endswith("noise.weight") or name.endswith("activate.bias") or \
+               (name.endswith(".bias") and "to_rgb" in name and p.ndim == 4):
+                p.copy_(torch.randn(p.shape, generator=rg) * 0.1)
+    gen = gen.to(cuda).eval()
+    B = 32
+    rg = torch.Generator().manual_seed(2)
+    lat = torch.randn(B, 14, 512, generator=rg).to(cuda)
+    ext = torch.randn(B, 512, 4, 4, generator=rg).to(cuda)
+    noise = [torch.randn(B, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), generator=rg).to(cuda) for i in range(13)]
+    kw = dict(latent_styles=[lat], input_is_latent=True, noise=noise, use_external_input_tensor=True,
+              external_input_tensor=ext, return_rgb_list=True)
+    with torch.no_grad():
+        for _ in range(3):                      # third call replays the captured graph
+            got = gen(None, **kw)
+        monkeypatch.setenv("FM3D_ENGINE", "0")
+        ref = []
+        for b0 in range(0, B, 8):               # fp32 composition in slices of 8 (memory)
+            kws = dict(kw, latent_styles=[lat[b0:b0 + 8]], noise=[n[b0:b0 + 8] for n in noise], external_input_tensor=ext[b0:b0 + 8])
+            ref.append(gen(None, **kws))
+        ref = [torch.cat([r[i] for r in ref], 0) for i in range(len(got))]
+    for i, (a, b) in enumerate(zip(got, ref)):
+        e = _rel(a, b)
+        print(f"rgb[{i}] {tuple(a.shape)} rel err {e:.4f}")
+        assert e < 3e-2, (i, e)
+
+
+# ------------------------------------------------------------------ conv modes at real layer shapes
+def _sel_channels(cout, bn=64, per_tile=4):
+    """A few output channels from every 64-wide n-tile (first, last and two inside)."""
+    sel = []
+    for n0 in range(0, cout, bn):
+        hi = min(n0 + bn, cout) - 1
+        sel += sorted({n0, n0 + 1 if n0 + 1 <= hi else n0, (n0 + hi) // 2, hi})
+    return torch.tensor(sorted(set(sel)))
+
+
+def _conv_case(cuda, B, H, Cin, Cout, k=3, stride=1, residual=False, seed=0, **conv_kw):
+    from fm3d import ops
+    pad = k // 2
+    gen = torch.Generator(device=cuda).manual_seed(seed)
+    x = torch.randn(B, Cin, H, H, generator=gen, device=cuda)
+    w = torch.randn(Cout, Cin, k, k, generator=gen, device=cuda) / (Cin * k * k) ** 0.5
+    sel = _sel_channels(Cout).to(cuda)
+    xq, wq = x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()
+    ref = torch.cat([F.conv2d(xq[b0:b0 + 8], wq[sel], stride=stride, padding=pad) for b0 in range(0, B, 8)], 0)
+    OH = ref.shape[2]
+    tab = torch.zeros(1, Cout, 8, device=cuda); tab[..., 0] = 1; tab[..., 2] = 1; tab[..., 3] = 1
+    out = torch.zeros(B, OH, OH, Cout, device=cuda, dtype=torch.bfloat16)
+    res = None
+    if residual:
+        res = torch.randn(B, OH, OH, Cout, generator=gen, device=cuda).to(torch.bfloat16)
+        ref = ref + res[..., sel].float().permute(0, 3, 1, 2)
+    wg, _ = ops.prep_weight(w, 1.0)
+    ops.conv_igemm(ops.nchw_to_nhwc_bf16(x), wg, ops.conv_taps(k, k, pad), out, tab, B=B, H=H, W=H, Cin=Cin, Cout=Cout,
+                   OH=OH, OW=OH, stride=stride, residual=res, **conv_kw)
+    torch.cuda.synchronize()
+    got = out[..., sel].float().permute(0, 3, 1, 2)
+    return got, ref
+
+
+@pytest.mark.parametrize("name,H,Cin,Cout,k,stride,residual", [
+    ("g64  pair + halo patch N=256", 64, 512, 512, 3, 1, False),
+    ("g128 pair + halo patch N=256", 128, 256, 256, 3, 1, False),
+    ("g256 row-patch pair N=128", 256, 128, 128, 3, 1, False),
+    ("g32", 32, 512, 512, 3, 1, False),
+    ("g16", 16, 512, 512, 3, 1, False),
+    ("g8 split-K", 8, 512, 512, 3, 1, False),
+    ("g4", 4, 512, 512, 3, 1, False),
+    ("cm1 256^2 64->64 row-patch R=4 / hpw", 256, 64, 64, 3, 1, False),
+    ("resnet 64^2 64->64 hpw + residual", 64, 64, 64, 3, 1, True),
+    ("resnet 8^2 512->512 split-K + residual", 8, 512, 512, 3, 1, True),
+    ("resnet 64->128 stride 2", 64, 64, 128, 3, 2, False),
+    ("psp 128->128 stride 2", 128, 128, 128, 3, 2, False),
+    ("psp 64^2 128->128 hpw two slots", 64, 128, 128, 3, 1, False),
+    ("psp lateral 1x1 128->512", 64, 128, 512, 1, 1, False),
+    ("psp 1x1 stride-2 shortcut", 64, 128, 256, 1, 2, False),
+    ("psp heads 512->3584 stride 2 (7 heads share the input)", 64, 512, 3584, 3, 2, False),
+])
+def test_conv_modes_at_real_layer_shapes(cuda, name, H, Cin, Cout, k, stride, residual):
+    got, ref = _conv_case(cuda, 32, H, Cin, Cout, k, stride, residual, seed=H + Cout)
+    e = _rel(got, ref)
+    print(f"{name}: rel err {e:.5f}")
+    assert e < 1e-2, (name, e)
+
+
+@pytest.mark.parametrize("idx,h", [(7, 32), (9, 64), (11, 128)])
+def test_up_conv_tall_image_at_real_shapes(cuda, idx, h):
+    """The stride-2 transposed conv of convs.6 / convs.8 / convs.10 (32->64, 64->128, 128->256) exactly as the engine
+    issues it at B=32 (tall image, parity phases, paired-parity weights for Cout <= 128) vs F.conv_transpose2d."""
+    import stylegan2
+    from fm3d.engine import SynthesisPlan
+    torch.manual_seed(0)
+    gen = stylegan2.Generator(256, 512, 8, channel_multiplier=2).to(cuda).eval()
+    B = 32
+    plan = SynthesisPlan(gen, B, cuda)
+    L = plan.convs[idx]
+    assert L.up and L.res_in == h
+    g = torch.Generator(device=cuda).manual_seed(idx)
+    x = torch.zeros(B, h + 1, h + 1, L.cin, device=cuda, dtype=torch.bfloat16)
+    x[:, :h, :h] = torch.randn(B, h, h, L.cin, generator=g, device=cuda).to(torch.bfloat16)
+    t = plan.tbuf[idx]
+    t.fill_(float("nan"))
+    plan._up_conv(L, x, t, B, h)
+    torch.cuda.synchronize()
+    w = (L.mod.weight.detach()[0] * L.mod.scale).to(torch.bfloat16).float()          # [O, I, 3, 3]
+    sel = _sel_channels(L.cout).to(cuda)
+    xin = x[:, :h, :h].float().permute(0, 3, 1, 2)
+    ref = torch.cat([F.conv_transpose2d(xin[b0:b0 + 8], w[sel].transpose(0, 1), stride=2) for b0 in range(0, B, 8)], 0)
+    got = t[:, :2 * h + 1, :2 * h + 1][..., sel].float().permute(0, 3, 1, 2)
+    assert torch.isfinite(got).all()
+    e = _rel(got, ref)
+    print(f"up-conv {h}->{2 * h} {L.cin}->{L.cout}: rel err {e:.5f}")
+    assert e < 1e-2, e
+    # the spare row / column of the interleaved tensor hold exact zeros (the blur pass relies on the pitch only)
+    assert float(t[:, 2 * h + 1].float().abs().max()) == 0.0 and float(t[:, :, 2 * h + 1].float().abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ gradient parity
+def test_generator_gradients_vs_oracle_autograd(cuda):
+    """dL/dW (plain, up-conv and ToRGB weights), dL/dlatent, dL/dnoise_weight, dL/dbias, dL/d(modulation) of the
+    shared-weight composition against autograd of the reference's per-sample formulation (oracle, CPU fp32)."""
+    import stylegan2
+    g = load_golden("generator_small.npz")
+    gen = stylegan2.Generator(32, 64, 2, generator_net_shape=[int(v) for v in g["shape"]])
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    gen.load_state_dict(sd)
+    gen = gen.to(cuda)
+    noise = [torch.from_numpy(g[f"noise.{i}"]) for i in range(7)]
+    lat0, ext = torch.from_numpy(g["latent"]), torch.from_numpy(g["ext"])
+    probe = torch.randn(lat0.shape[0], 3, 32, 32, generator=torch.Generator().manual_seed(9))
+
+    lat = lat0.clone().to(cuda).requires_grad_(True)
+    for p in gen.parameters():
+        p.requires_grad_(True)
+    img = gen(None, latent_styles=[lat], input_is_latent=True, noise=[n.to(cuda) for n in noise],
+              use_external_input_tensor=True, external_input_tensor=ext.to(cuda))
+    (img * probe.to(cuda)).sum().backward()
+
+    sd_r = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    lat_r = lat0.clone().requires_grad_(True)
+    img_r = orc.generator_forward_ref(sd_r, latent_styles=[lat_r], input_is_latent=True, noise=noise,
+                                      external_input_tensor=ext)
+    (img_r * probe).sum().backward()
+    np.testing.assert_allclose(img.detach().cpu().numpy(), img_r.detach().numpy(), rtol=1e-4, atol=1e-4)
+
+    checked = 0
+    worst = ("", 0.0)
+    for name, p in gen.named_parameters():
+        ref = sd_r[name].grad
+        if ref is None or float(ref.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) < 1e-6, name     # mapping MLP / constant input: unused
+            continue
+        e = _rel(p.grad.cpu(), ref)
+        if e > worst[1]:
+            worst = (name, e)
+        assert e < 2e-3, (name, e)
+        checked += 1
+    e_lat = _rel(lat.grad.cpu(), lat_r.grad)
+    print(f"gradient parity: {checked} parameter tensors, worst {worst[0]} {worst[1]:.2e}; latent {e_lat:.2e}")
+    assert e_lat < 2e-3
+    kinds = [n for n, _ in gen.named_parameters() if sd_r[n].grad is not None and float(sd_r[n].grad.abs().max()) > 0]
+    for frag in ("conv.weight", "modulation.weight", "modulation.bias", "noise.weight", "activate.bias", "to_rgb1.bias"):
+        assert any(frag in n for n in kinds), frag
+
+
+def test_engine_sees_data_writes_and_survives_deepcopy(cuda):
+    """the reference's EMA writes weights through ``.data`` (train_3_encoder.py:195-200), which does
+    not move version counters; the engine must not keep serving the old derived weights.  And a generator that has run
+    on the engine can still be deep-copied."""
+    import copy
+    import stylegan2
+    g = load_golden("generator_small.npz")
+    gen = stylegan2.Generator(32, 64, 2, generator_net_shape=[int(v) for v in g["shape"]])
+    gen.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")})
+    gen = gen.to(cuda).eval()
+    other = copy.deepcopy(gen)
+    with torch.no_grad():
+        for p in other.parameters():
+            p.add_(torch.randn_like(p) * 0.5)
+    noise = [torch.from_numpy(g[f"noise.{i}"]).to(cuda) for i in range(7)]
+    lat, ext = torch.from_numpy(g["latent"]).to(cuda), torch.from_numpy(g["ext"]).to(cuda)
+    kw = dict(latent_styles=[lat], input_is_latent=True, noise=noise, use_external_input_tensor=True, external_input_tensor=ext)
+
+    def accumulate(model1, model2, decay):                      # the reference's EMA, verbatim semantics
+        par1, par2 = dict(model1.named_parameters()), dict(model2.named_parameters())
+        for k in par1.keys():
+            par1[k].data.mul_(decay).add_(par2[k].data, alpha=1 - decay)
+
+    with torch.no_grad():
+        for _ in range(4):                                      # plan exists and its graph is captured
+            a0 = gen(None, **kw)
+        accumulate(gen, other, 0.5)
+        a1 = gen(None, **kw)                                    # must reflect the new weights
+        os.environ["FM3D_ENGINE"] = "0"
+        try:
+            ref = gen(None, **kw)
+        finally:
+            del os.environ["FM3D_ENGINE"]
+    assert _rel(a1, ref) < 3e-2, _rel(a1, ref)
+    assert _rel(a0, ref) > 5e-2                                 # the test would not notice stale weights otherwise
+    g2 = copy.deepcopy(gen)                                     # plans live outside the module
+    with torch.no_grad():
+        assert _rel(g2(None, **kw), ref) < 3e-2
+    # writers the module cannot see: explicit invalidation
+    with torch.no_grad():
+        w = gen.convs[1].conv.weight
+        w.data.mul_(1.5)
+        gen.invalidate_engine()
+        a2 = gen(None, **kw)
+        os.environ["FM3D_ENGINE"] = "0"
+        try:
+            ref2 = gen(None, **kw)
+        finally:
+            del os.environ["FM3D_ENGINE"]
+    assert _rel(a2, ref2) < 3e-2
+
+
+def test_engine_rejects_bad_shapes(cuda):
+    import stylegan2
+    gen = stylegan2.Generator(32, 64, 2).to(cuda).eval()
+    lat = torch.randn(2, gen.n_latent, 64, device=cuda)
+    ext = torch.randn(2, 512, 4, 4, device=cuda)
+    kw = dict(input_is_latent=True, use_external_input_tensor=True)
+    with torch.no_grad():
+        with pytest.raises(RuntimeError):
+            gen(None, latent_styles=[lat[:, :3]], external_input_tensor=ext, **kw)            # short W+
+        with pytest.raises(RuntimeError):
+            gen(None, latent_styles=[lat], external_input_tensor=ext[:, :100], **kw)          # wrong start width
+        bad_noise = [torch.randn(2, 1, 5, 5, device=cuda)] * gen.num_layers
+        with pytest.raises(RuntimeError):
+            gen(None, latent_styles=[lat], external_input_tensor=ext, noise=bad_noise, **kw)  # wrong-resolution noise
+        # a valid but unplanned start resolution takes the module composition, as the reference would
+        y = gen(None, latent_styles=[lat], external_input_tensor=torch.randn(2, 512, 8, 8, device=cuda), **kw)
+        assert y.shape == (2, 3, 64, 64)

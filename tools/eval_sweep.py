@@ -76,6 +76,31 @@ def main():
         for _ in range(4):                       # plans: two eager calls, capture, replay
             sweep(False)
         sweep(True)
+        # ---- correctness before timing: the replayed bf16 engine vs the fp32 composition of the same modules
+        # (FM3D_ENGINE=0: cuDNN fp32, TF32 off) on the first 8 pairs, and the uint8 conversion vs the numpy recipe
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.manual_seed(7)
+        img = Forward_Inference_3_Encoder(*dev_in[0], e_tsr, e_w, e_wp, g, tsr_encode='Render Image')
+        os.environ["FM3D_ENGINE"] = "0"
+        try:
+            torch.manual_seed(7)                 # same per-layer noise draws (NoiseInjection order, stylegan2.py:308-310)
+            lat_t = e_tsr(dev_in[0][1][:8]); lat_w = e_w(dev_in[0][1][:8]); lat_wp = e_wp(dev_in[0][0][:8])
+        finally:
+            del os.environ["FM3D_ENGINE"]
+        import numpy as np
+        u8 = tensor2im_batch(img[:2]).cpu().numpy()
+        ref8 = ((np.transpose(np.clip(img[:2].cpu().float().numpy(), -1, 1), (0, 2, 3, 1)) + 1.0) * (255.0 / 2.0)).astype(np.uint8)
+        if not np.array_equal(u8, ref8):
+            raise SystemExit("eval_sweep: tensor2im_batch differs from the numpy recipe of visual_eval.py:24-38")
+        with ops.engine_slot(5):
+            e_t2, e_w2, e_wp2 = e_tsr(dev_in[0][1][:8]), e_w(dev_in[0][1][:8]), e_wp(dev_in[0][0][:8])
+        for nm, a, b in (("E_Tsr", e_t2, lat_t), ("E_W", e_w2, lat_w), ("E_W_Plus", e_wp2, lat_wp)):
+            err = float((a - b).abs().max() / b.abs().max())
+            if not err < 3e-2:
+                raise SystemExit(f"eval_sweep: {nm} engine output differs from the fp32 modules (rel err {err:.3e})")
+        if not bool(torch.isfinite(img).all()):
+            raise SystemExit("eval_sweep: non-finite image")
         ms_dev = timed(False)
         ms_e2e = timed(True)
     n = world * nb * B * args.reps
