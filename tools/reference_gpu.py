@@ -9,6 +9,7 @@ The reference cannot be imported next to the mirror (same module names), so the 
   python tools/reference_gpu.py ref   [--batch 32]   # sys.path = baseline/_ref only; writes gpurun_out/ref_gpu.pt
   python tools/reference_gpu.py ours  [--batch 32]   # mirror; reads that file, writes gpurun_out/r02_reference_gpu.json
   python tools/reference_gpu.py both                 # runs the two as subprocesses
+  python tools/reference_gpu.py jit                  # (container, no GPU) pre-build the reference's two extensions
 
 Needs the staged reference (tools/stage_reference.sh -> baseline/_ref, git-ignored).  Measurement tool: not on the
 product path, not used by tests / bench.py / smoke().
@@ -138,6 +139,9 @@ def small_inputs(device):
 def main_ref(args):
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
     os.environ.setdefault("MAX_JOBS", "8")
+    # build directory inside the staged (git-ignored) tree: a build made in the container (``reference_gpu.py jit``)
+    # travels to the GPU box with the snapshot, and ninja finds nothing to do there
+    os.environ.setdefault("TORCH_EXTENSIONS_DIR", os.path.join(REF, "_torch_ext"))
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import ref_env
     ref_env.install_shims()
@@ -146,6 +150,9 @@ def main_ref(args):
     t0 = time.time()
     import op                                   # JIT-builds op/fused_bias_act*.{cpp,cu}, op/upfirdn2d*.{cpp,cu} for sm_100a
     jit_s = time.time() - t0
+    if args.mode == "jit":
+        print(f"reference extensions built in {jit_s:.0f} s under {os.environ['TORCH_EXTENSIONS_DIR']}")
+        return
     import stylegan2 as sg
     import resnet_encoder as rn
     from psp_encoder_model.encoders import psp_encoders as psp
@@ -292,7 +299,7 @@ def main_ours(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["ref", "ours", "both"])
+    ap.add_argument("mode", choices=["ref", "ours", "both", "jit"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--iters", type=int, default=10)
@@ -304,7 +311,7 @@ def main():
             subprocess.check_call([sys.executable, os.path.abspath(__file__), m, "--batch", str(args.batch),
                                    "--warmup", str(args.warmup), "--iters", str(args.iters)])
         return
-    (main_ref if args.mode == "ref" else main_ours)(args)
+    (main_ours if args.mode == "ours" else main_ref)(args)
 
 
 if __name__ == "__main__":

@@ -8,8 +8,12 @@ ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 SRC="${1:-/root/reference}"
 DST="$ROOT/baseline/_ref"
 [ -f "$SRC/stylegan2.py" ] || { echo "no reference checkout at $SRC" >&2; exit 1; }
+# keep a pre-built extension directory (tools/reference_gpu.py jit) across re-staging
+KEEP=""
+if [ -d "$DST/_torch_ext" ]; then KEEP="$(mktemp -d)"; mv "$DST/_torch_ext" "$KEEP/"; fi
 rm -rf "$DST"
 mkdir -p "$DST"
+if [ -n "$KEEP" ]; then mv "$KEEP/_torch_ext" "$DST/"; rmdir "$KEEP"; fi
 # code only: python sources, the two op extensions, the small LPIPS linear-layer weights; no docs / env files
 ( cd "$SRC" && tar cf - --exclude='doc' --exclude='Conda_Env_Setup' --exclude='DiscoFaceGAN_related_scripts' \
       --exclude='.git' --exclude='__pycache__' . ) | ( cd "$DST" && tar xf - )
