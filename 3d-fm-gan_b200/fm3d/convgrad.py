@@ -1,0 +1,254 @@
+"""Differentiable convolutions on the tcgen05 kernels: the training path of BASELINE config 4.
+
+The reference differentiates ``F.conv2d`` / ``F.conv_transpose2d`` through ATen (cuDNN dgrad / wgrad:
+stylegan2.py:129,276,285,291 under ``loss.backward()``, train_3_encoder.py:476,492,557,593).  Here the three maps a
+convolution is made of are ``autograd.Function``s over ``libfm3d.so``:
+
+    ConvFwd(x, w)        y[b,o,oy,ox]  = sum w[o,i,ky,kx] * x[b,i,oy*s+ky-p,ox*s+kx-p]     fm_conv_igemm
+    ConvBwdData(g, w)    gx[b,i,y,x]   = sum w[o,i,ky,kx] * g[b,o,oy,ox]  (y = oy*s+ky-p)   fm_conv_igemm, one launch per
+                                                                                           output phase (y+p mod s)
+    ConvBwdWeight(x, g)  gw[o,i,ky,kx] = sum x[b,i,oy*s+ky-p,ox*s+kx-p] * g[b,o,oy,ox]     fm_wgrad_gemm (GEMM over pixels)
+
+Each is bilinear and the derivative of each is again one of the three ("gradfix" pattern), so
+second-order passes -- R1 through the discriminator (Util/training_util.py:46-52) and path-length regularisation
+through the generator (stylegan2.py:683-688) -- fall out of autograd with no further kernels:
+
+    d ConvFwd       : dx = ConvBwdData(gy, w)      dw = ConvBwdWeight(x, gy)
+    d ConvBwdData   : dg = ConvFwd(ggx, w)         dw = ConvBwdWeight(ggx, g)
+    d ConvBwdWeight : dx = ConvBwdData(g, ggw)     dg = ConvFwd(x, ggw)
+
+``conv_transpose2d(x, w)`` (the generator's stride-2 up-conv, stylegan2.py:276) IS ConvBwdData(x, w).
+
+Tensors at this boundary are NCHW fp32 (the autograd graph of the mirrored modules); operands are rounded to bf16,
+products accumulate in fp32 in TMEM (the precision of the whole B200 path).  CUDA only.
+"""
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+
+from . import _lib, ops
+from ._lib import WgradDesc
+
+_IDENT_TABS = {}
+
+
+def _ident_tab(cout, device):
+    key = (cout, device)
+    t = _IDENT_TABS.get(key)
+    if t is None:
+        t = torch.zeros(1, cout, 8, device=device, dtype=torch.float32)
+        t[..., 0] = 1.0
+        t[..., 2] = 1.0
+        t[..., 3] = 1.0
+        _IDENT_TABS[key] = t
+    return t
+
+
+def _out_size(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+# ---------------------------------------------------------------------------------------------- kernels
+def conv_forward(x, w, stride, pad):
+    """x [B,I,H,W] fp32, w [O,I,k,k] fp32 -> [B,O,OH,OW] fp32."""
+    B, I, H, W = x.shape
+    O, _, k, _ = w.shape
+    OH, OW = _out_size(H, k, stride, pad), _out_size(W, k, stride, pad)
+    out = torch.empty(B, O, OH, OW, device=x.device, dtype=torch.float32)
+    if out.numel() == 0:
+        return out
+    xq = ops.nchw_to_nhwc_bf16(x)
+    wq, _ = ops.prep_weight(w, 1.0, want_wsq=False)
+    ops.conv_igemm(xq, wq, ops.conv_taps(k, k, pad), out, _ident_tab(O, x.device), B=B, H=H, W=W, Cin=I, Cout=O,
+                   OH=OH, OW=OW, stride=stride, out_nchw_f32=True)
+    return out
+
+
+def conv_backward_data(g, w, stride, pad, in_hw):
+    """g [B,O,OH,OW], w [O,I,k,k] -> gx [B,I,H,W] (H,W = in_hw): the adjoint of conv_forward w.r.t. x, i.e. the
+    transposed convolution.  Phase r = (y + pad) mod stride of the output takes the taps ky = r (mod stride); each
+    phase is one plain conv over the grid q (y = stride*q' + y0) written with output stride ``stride``."""
+    B, O, OH, OW = g.shape
+    _, I, k, _ = w.shape
+    H, W = in_hw
+    s = stride
+    multi = s > 1
+    out = (torch.zeros if multi else torch.empty)(B, I, H, W, device=g.device, dtype=torch.float32)
+    if out.numel() == 0 or g.numel() == 0:
+        return out.zero_()
+    gq = ops.nchw_to_nhwc_bf16(g)
+    wq, _ = ops.prep_weight(w.transpose(0, 1), 1.0, want_wsq=False)        # [k*k][I rows][O]: K dimension = g's channels
+    tab = _ident_tab(I, g.device)
+
+    def phase_1d(r, n_in, n_out):
+        """-> (y0, rows, [(d, kidx)]) for residue r: outputs y = s*q' + y0, q' in [0, rows); tap j reads g[q' + d]."""
+        y0 = (r - pad) % s
+        qshift = (y0 - (r - pad)) // s
+        rows = (n_out - y0 + s - 1) // s if n_out > y0 else 0
+        taps = [(qshift - j, r + s * j) for j in range((k - r + s - 1) // s)] if r < k else []
+        return y0, rows, taps
+    for ry in range(s):
+        y0, rows, ty = phase_1d(ry, OH, H)
+        for rx in range(s):
+            x0, cols, tx = phase_1d(rx, OW, W)
+            if rows <= 0 or cols <= 0:
+                continue
+            taps = [(dy, dx, ky * k + kx) for (dy, ky) in ty for (dx, kx) in tx]
+            if not taps:
+                continue                                  # this phase receives no contribution: stays zero
+            ops.conv_igemm(gq, wq, taps, out, tab, B=B, H=OH, W=OW, Cin=O, Cout=I, OH=rows, OW=cols, out_H=H, out_W=W,
+                           out_y0=y0, out_x0=x0, out_ys=s, out_xs=s, out_nchw_f32=True,
+                           algo_flops=2.0 * B * OH * OW * O * I * len(taps))
+    return out
+
+
+def to_cpl(x, s, y0, x0, Hq, Wq, scale_bc=None):
+    """fp32 NCHW -> bf16 [s*s*C, B*Hq*Wq] (fm_nchw_to_cpl_bf16)."""
+    x = x.contiguous().float()
+    B, Cc, H, W = x.shape
+    out = torch.empty(s * s * Cc, B * Hq * Wq, device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().fm_nchw_to_cpl_bf16(out.data_ptr(), x.data_ptr(), None if scale_bc is None else scale_bc.data_ptr(),
+                                                  B, Cc, H, W, s, y0, x0, Hq, Wq, torch.cuda.current_stream().cuda_stream),
+                   "fm_nchw_to_cpl_bf16")
+    return out
+
+
+def wgrad_gemm(a, b, Ca, Cb, nslabs_a, nslabs_b, L, taps, ksplit=0):
+    """dw[t][a][b] = sum_l A[slab_a*Ca + a][l + off_a] * Bm[slab_b*Cb + b][l + off_b]; taps = [(slab_a, off_a, slab_b, off_b)]."""
+    dw = torch.zeros(len(taps), Ca, (Cb + 3) // 4 * 4, device=a.device, dtype=torch.float32)
+    d = WgradDesc()
+    d.a, d.b = a.data_ptr(), b.data_ptr()
+    d.Ca, d.Cb, d.nslabs_a, d.nslabs_b = Ca, Cb, nslabs_a, nslabs_b
+    d.La, d.Lb, d.L = a.shape[1], b.shape[1], L
+    d.ntaps = len(taps)
+    for i, (sa, oa, sb, ob) in enumerate(taps):
+        d.tap_slab_a[i], d.tap_off_a[i], d.tap_slab_b[i], d.tap_off_b[i] = sa, oa, sb, ob
+    d.dw, d.dw_tap_stride, d.dw_row_stride, d.ksplit = dw.data_ptr(), dw.shape[1] * dw.shape[2], dw.shape[2], ksplit
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().fm_wgrad_gemm(C.byref(d), torch.cuda.current_stream().cuda_stream), "fm_wgrad_gemm")
+    return dw[..., :Cb]
+
+
+def conv_backward_weight(x, g, stride, pad, k):
+    """x [B,I,H,W], g [B,O,OH,OW] -> gw [O,I,k,k].  Geometry (see csrc/wgrad.cu): both operands live on one pixel grid
+    [B][Hq][Wq]; g sits at its own coordinates, x is split into the stride^2 parity planes the conv reads, shifted by a
+    margin m = ceil(pad/stride) so that every tap is a non-negative linear offset (dyq+m)*Wq + (dxq+m)."""
+    B, I, H, W = x.shape
+    _, O, OH, OW = g.shape
+    s = stride
+    m = (pad + s - 1) // s
+    dmax = ((k - 1 - pad) - ((k - 1 - pad) % s)) // s
+    Hq = OH + dmax + m                                    # last row a tap reads: (OH-1) + dmax + m
+    Wq = (OW + dmax + m + 7) // 8 * 8                     # no wrap into the next row: (OW-1) + dmax + m < Wq
+    xp = to_cpl(x, s, s * m, s * m, Hq, Wq)               # [s*s*I, L]
+    gp = to_cpl(g, 1, 0, 0, Hq, Wq)                       # [O, L]
+    L = B * Hq * Wq
+    taps = []
+    for ky in range(k):
+        py, dyq = (ky - pad) % s, ((ky - pad) - (ky - pad) % s) // s
+        for kx in range(k):
+            px, dxq = (kx - pad) % s, ((kx - pad) - (kx - pad) % s) // s
+            taps.append((py * s + px, (dyq + m) * Wq + (dxq + m)))
+    if O >= I:          # the larger channel count takes the 128-row M side, the smaller one the N side (>= 16 wide)
+        dw = wgrad_gemm(gp, xp, O, I, 1, s * s, L, [(0, 0, sl, off) for (sl, off) in taps])         # [t][o][i]
+        return dw.permute(1, 2, 0).reshape(O, I, k, k).contiguous()
+    dw = wgrad_gemm(xp, gp, I, O, s * s, 1, L, [(sl, off, 0, 0) for (sl, off) in taps])             # [t][i][o]
+    return dw.permute(2, 1, 0).reshape(O, I, k, k).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------- autograd
+class ConvFwd(Function):
+    @staticmethod
+    def forward(ctx, x, w, stride, pad):
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, pad)
+        return conv_forward(x.detach(), w.detach(), stride, pad)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, pad = ctx.cfg
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvBwdData.apply(gy, w, stride, pad, (x.shape[2], x.shape[3]))
+        if ctx.needs_input_grad[1]:
+            gw = ConvBwdWeight.apply(x, gy, stride, pad, w.shape[2])
+        return gx, gw, None, None
+
+
+class ConvBwdData(Function):
+    @staticmethod
+    def forward(ctx, g, w, stride, pad, in_hw):
+        ctx.save_for_backward(g, w)
+        ctx.cfg = (stride, pad)
+        return conv_backward_data(g.detach(), w.detach(), stride, pad, tuple(in_hw))
+
+    @staticmethod
+    def backward(ctx, ggx):
+        g, w = ctx.saved_tensors
+        stride, pad = ctx.cfg
+        gg = gw = None
+        if ctx.needs_input_grad[0]:
+            gg = ConvFwd.apply(ggx, w, stride, pad)
+            if gg.shape != g.shape:
+                # rows / columns of g the strided window never reached (H not = (OH-1)*s + k - 2p): zero gradient there
+                full = gg.new_zeros(g.shape)
+                full[:, :, :gg.shape[2], :gg.shape[3]] = gg[:, :, :g.shape[2], :g.shape[3]]
+                gg = full
+        if ctx.needs_input_grad[1]:
+            gw = ConvBwdWeight.apply(ggx, g, stride, pad, w.shape[2])
+        return gg, gw, None, None, None
+
+
+class ConvBwdWeight(Function):
+    @staticmethod
+    def forward(ctx, x, g, stride, pad, k):
+        ctx.save_for_backward(x, g)
+        ctx.cfg = (stride, pad)
+        return conv_backward_weight(x.detach(), g.detach(), stride, pad, k)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, g = ctx.saved_tensors
+        stride, pad = ctx.cfg
+        gx = gg = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvBwdData.apply(g, ggw, stride, pad, (x.shape[2], x.shape[3]))
+        if ctx.needs_input_grad[1]:
+            gg = ConvFwd.apply(x, ggw, stride, pad)
+            if gg.shape != g.shape:
+                full = gg.new_zeros(g.shape)
+                full[:, :, :gg.shape[2], :gg.shape[3]] = gg[:, :, :g.shape[2], :g.shape[3]]
+                gg = full
+        return gx, gg, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------- public
+def _check(x, w):
+    if not (x.is_cuda and w.is_cuda):
+        raise RuntimeError("fm3d.convgrad: CUDA tensors required (the B200 path has no CPU fallback)")
+    if x.ndim != 4 or w.ndim != 4 or w.shape[2] != w.shape[3]:
+        raise RuntimeError(f"fm3d.convgrad: expected x [B,I,H,W] and a square kernel, got {tuple(x.shape)} / {tuple(w.shape)}")
+
+
+def conv2d(x, w, bias=None, stride=1, padding=0):
+    """``F.conv2d(x, w, bias, stride, padding)`` (square kernels, symmetric stride / padding, groups = 1)."""
+    _check(x, w)
+    if x.shape[1] != w.shape[1]:
+        raise RuntimeError(f"conv2d: input has {x.shape[1]} channels, weight expects {w.shape[1]}")
+    y = ConvFwd.apply(x.float(), w.float(), int(stride), int(padding))
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1)
+    return y
+
+
+def conv_transpose2d(x, w, stride=1, padding=0):
+    """``F.conv_transpose2d(x, w, stride=stride, padding=padding)`` with w [I,O,k,k]."""
+    _check(x, w)
+    if x.shape[1] != w.shape[0]:
+        raise RuntimeError(f"conv_transpose2d: input has {x.shape[1]} channels, weight expects {w.shape[0]}")
+    k, s, p = w.shape[2], int(stride), int(padding)
+    out_hw = ((x.shape[2] - 1) * s + k - 2 * p, (x.shape[3] - 1) * s + k - 2 * p)
+    return ConvBwdData.apply(x.float(), w.float(), s, p, out_hw)

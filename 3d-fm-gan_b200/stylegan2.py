@@ -31,6 +31,27 @@ from op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
 _SQRT2 = math.sqrt(2.0)
 
 
+def _native_grad(x):
+    """Differentiable convolutions run on the tcgen05 kernels (fm3d/convgrad.py: forward, dgrad and wgrad, all closed
+    under double backward).  ``FM3D_NATIVE_GRAD=0`` keeps ATen's convolutions instead -- the fp32 cross-check of the
+    tests, not a product path."""
+    return x.is_cuda and os.environ.get("FM3D_NATIVE_GRAD", "1") != "0"
+
+
+def _conv2d(x, w, bias=None, stride=1, padding=0):
+    if _native_grad(x):
+        from fm3d import convgrad
+        return convgrad.conv2d(x, w, bias, stride, padding)
+    return F.conv2d(x, w, bias=bias, stride=stride, padding=padding)
+
+
+def _conv_transpose2d(x, w, stride):
+    if _native_grad(x):
+        from fm3d import convgrad
+        return convgrad.conv_transpose2d(x, w, stride=stride)
+    return F.conv_transpose2d(x, w, padding=0, stride=stride)
+
+
 # --------------------------------------------------------------------------- small layers
 class PixelNorm(nn.Module):
     """x / sqrt(mean_c(x^2) + 1e-8) over dim 1 (vectors [N,D] or maps [N,D,H,W])."""
@@ -102,7 +123,7 @@ class EqualConv2d(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
     def forward(self, input):
-        return F.conv2d(input, self.weight * self.scale, bias=self.bias, stride=self.stride, padding=self.padding)
+        return _conv2d(input, self.weight * self.scale, bias=self.bias, stride=self.stride, padding=self.padding)
 
     def __repr__(self):
         o, i, k, _ = self.weight.shape
@@ -177,12 +198,12 @@ class ModulatedConv2d(nn.Module):
         x = input * s.view(batch, self.in_channel, 1, 1)
 
         if self.upsample:
-            out = F.conv_transpose2d(x, w.transpose(0, 1), padding=0, stride=2)
+            out = _conv_transpose2d(x, w.transpose(0, 1), stride=2)
             out = self.blur(out)
         elif self.downsample:
-            out = F.conv2d(self.blur(x), w, padding=0, stride=2)
+            out = _conv2d(self.blur(x), w, padding=0, stride=2)
         else:
-            out = F.conv2d(x, w, padding=self.padding)
+            out = _conv2d(x, w, padding=self.padding)
 
         if self.demodulate:
             wsq = w.square().sum(dim=(2, 3))                              # [O, I]

@@ -244,6 +244,46 @@ int fm_prep_weight(void* wq, float* wsq, const float* w_oikk, int cout, int cin,
                    float scale, int cout_rows, int cin_stride, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Weight gradient of a convolution (training, BASELINE config 4).
+ * Replaces the wgrad half of ATen autograd over F.conv2d / F.conv_transpose2d
+ * (stylegan2.py:129,276,285,291; cuDNN in the reference).  With activations x and the
+ * upstream gradient g stored channel-major / pixel-linear ("CPL", bf16 [channels][B*Hq*Wq],
+ * made by fm_nchw_to_cpl_bf16), dL/dW is one GEMM over pixels on the tcgen05 tensor cores:
+ *
+ *   dw[t*dw_tap_stride + a*dw_row_stride + b] +=
+ *       sum_{l in [0,L)}  A[(tap_slab_a[t]*Ca + a)][l + tap_off_a[t]] * Bm[(tap_slab_b[t]*Cb + b)][l + tap_off_b[t]]
+ *
+ * (fp32 atomics: dw must be zero-initialised by the caller; positions outside a row read as 0).
+ * A conv tap (ky,kx) is the linear offset ky*Wq + kx into a zero-haloed pixel grid, a stride-2
+ * conv reads one of the 4 parity planes (slabs) of its input.  dL/dW of the modulated conv in
+ * its shared-weight form (one wgrad GEMM over M = B*HW on d*g and s*x) is this
+ * call with the two scalings folded into the layout pass.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  const void* a;            /* bf16 [nslabs_a*Ca][La] */
+  const void* b;            /* bf16 [nslabs_b*Cb][Lb] */
+  int32_t Ca, Cb, nslabs_a, nslabs_b;
+  int64_t La, Lb;           /* row lengths in elements (multiples of 8) */
+  int64_t L;                /* contraction length */
+  int32_t ntaps;
+  int32_t tap_off_a[FM_MAX_TAPS], tap_off_b[FM_MAX_TAPS];
+  int8_t tap_slab_a[FM_MAX_TAPS], tap_slab_b[FM_MAX_TAPS];
+  float* dw;                /* fp32, accumulated into */
+  int64_t dw_tap_stride;
+  int32_t dw_row_stride;
+  int32_t ksplit;           /* 0 = choose (split-K over pixels so that every SM has work) */
+} fm_wgrad_desc;
+int fm_wgrad_gemm(const fm_wgrad_desc* desc, void* stream);
+
+/* fp32 NCHW [B,C,H,W] -> bf16 CPL [s*s][C][B][Hq][Wq] (Wq a multiple of 8):
+ *   dst[py*s+px][c][b][yq][xq] = scale_bc[b*C+c] * src[b][c][yq*s + py - y0][xq*s + px - x0]   (0 outside the image)
+ * s = 1: zero-haloed copy (y0 = x0 = conv padding); s = 2: the four parity planes a stride-2 conv
+ * (or the gradient of a stride-2 transposed conv) reads.  scale_bc may be NULL; it carries the
+ * style modulation s[b,i] of x or the demodulation d[b,o] of g (stylegan2.py:257-262). */
+int fm_nchw_to_cpl_bf16(void* dst, const float* src, const float* scale_bc, int B, int C, int H, int W,
+                        int s, int y0, int x0, int Hq, int Wq, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Encoder-path helpers (NHWC bf16, bandwidth-bound).  They replace the ATen kernels behind
  * resnet_encoder.py:258-280 (stem, MaxPool2d, AvgPool2d / AdaptiveAvgPool2d),
  * psp_encoder_model/encoders/helpers.py:76-139 (SEModule, residual add, MaxPool2d(1,s)

@@ -1,0 +1,145 @@
+"""Differentiable convolutions on the tcgen05 kernels (fm3d/convgrad.py: fm_conv_igemm for forward and dgrad,
+fm_wgrad_gemm for the weight gradient) against ATen autograd in strict fp32: forward, first-order gradients and the
+second-order passes R1 / path-length regularisation need.  Operands are rounded to bf16, so the tolerance is 2e-2 of
+each tensor's max magnitude (measured ~4e-3)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+def _inputs(cuda, B, I, O, H, k, seed, transpose=False):
+    g = torch.Generator(device=cuda).manual_seed(seed)
+    x = torch.randn(B, I, H, H, generator=g, device=cuda)
+    wshape = (I, O, k, k) if transpose else (O, I, k, k)
+    w = torch.randn(*wshape, generator=g, device=cuda) / (I * k * k) ** 0.5
+    return x, w, g
+
+
+CONV_CASES = [
+    # B, I, O, H, k, stride, pad
+    (2, 64, 64, 16, 3, 1, 1),
+    (2, 96, 40, 9, 3, 1, 1),          # ragged channels, odd size
+    (2, 64, 128, 17, 3, 2, 0),        # discriminator conv2: blur pad(2,2) then 3x3 stride 2 (stylegan2.py:705-716)
+    (2, 64, 128, 15, 1, 2, 0),        # discriminator skip: blur pad(1,1) then 1x1 stride 2 (:748-750)
+    (3, 512, 512, 4, 3, 1, 1),        # 4x4 layers (conv1)
+    (2, 513, 512, 4, 3, 1, 1),        # final_conv after the minibatch-stddev channel (:816)
+    (2, 3, 64, 32, 1, 1, 0),          # discriminator stem (from RGB)
+    (2, 128, 3, 32, 1, 1, 0),         # ToRGB
+    (4, 128, 128, 64, 3, 1, 1),
+    (2, 64, 64, 32, 3, 2, 1),         # encoders' stride-2 3x3 pad 1
+    (2, 256, 256, 33, 3, 1, 1),       # K loop over several chunks, 33-wide rows
+]
+
+
+@pytest.mark.parametrize("B,I,O,H,k,s,p", CONV_CASES)
+def test_conv2d_forward_backward(cuda, B, I, O, H, k, s, p):
+    from fm3d import convgrad
+    x, w, g = _inputs(cuda, B, I, O, H, k, seed=H * 7 + I)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    xn, wn = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, stride=s, padding=p)
+    yn = convgrad.conv2d(xn, wn, stride=s, padding=p)
+    assert yn.shape == yr.shape
+    gy = torch.randn(yr.shape, generator=g, device=cuda)
+    gxr, gwr = torch.autograd.grad(yr, [xr, wr], gy)
+    gxn, gwn = torch.autograd.grad(yn, [xn, wn], gy)
+    e = (_rel(yn, yr), _rel(gxn, gxr), _rel(gwn, gwr))
+    print(f"conv2d B{B} {I}->{O} {H}^2 k{k} s{s} p{p}: fwd {e[0]:.4f} dgrad {e[1]:.4f} wgrad {e[2]:.4f}")
+    assert max(e) < 2e-2, e
+
+
+@pytest.mark.parametrize("B,I,O,H,k,s", [(2, 64, 48, 8, 3, 2), (3, 512, 512, 4, 3, 2), (2, 128, 64, 32, 3, 2), (2, 256, 128, 17, 3, 2)])
+def test_conv_transpose2d_forward_backward(cuda, B, I, O, H, k, s):
+    """The generator's up-conv (stylegan2.py:276): stride-2 transposed 3x3, h -> 2h+1."""
+    from fm3d import convgrad
+    x, w, g = _inputs(cuda, B, I, O, H, k, seed=H + O, transpose=True)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    xn, wn = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = F.conv_transpose2d(xr, wr, stride=s)
+    yn = convgrad.conv_transpose2d(xn, wn, stride=s)
+    assert yn.shape == yr.shape == (B, O, (H - 1) * s + k, (H - 1) * s + k)
+    gy = torch.randn(yr.shape, generator=g, device=cuda)
+    gxr, gwr = torch.autograd.grad(yr, [xr, wr], gy)
+    gxn, gwn = torch.autograd.grad(yn, [xn, wn], gy)
+    e = (_rel(yn, yr), _rel(gxn, gxr), _rel(gwn, gwr))
+    print(f"conv_transpose2d B{B} {I}->{O} {H}^2: fwd {e[0]:.4f} dgrad {e[1]:.4f} wgrad {e[2]:.4f}")
+    assert max(e) < 2e-2, e
+
+
+@pytest.mark.parametrize("kind,B,I,O,H,k,s,p", [("conv", 2, 32, 48, 12, 3, 1, 1), ("conv", 2, 32, 64, 13, 3, 2, 0),
+                                                ("conv", 2, 16, 32, 11, 1, 2, 0), ("convT", 2, 48, 32, 6, 3, 2, 0)])
+def test_double_backward(cuda, kind, B, I, O, H, k, s, p):
+    """R1 / path-length pattern: differentiate a function of the first-order gradient w.r.t. the weight and the input.
+    Every second-order term is again ConvFwd / ConvBwdData / ConvBwdWeight."""
+    from fm3d import convgrad
+    x, w, g = _inputs(cuda, B, I, O, H, k, seed=H * 3 + O, transpose=(kind == "convT"))
+
+    def run(native):
+        xv, wv = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        if kind == "conv":
+            y = convgrad.conv2d(xv, wv, stride=s, padding=p) if native else F.conv2d(xv, wv, stride=s, padding=p)
+        else:
+            y = convgrad.conv_transpose2d(xv, wv, stride=s) if native else F.conv_transpose2d(xv, wv, stride=s)
+        probe = torch.randn(y.shape, generator=torch.Generator(device=cuda).manual_seed(1), device=cuda)
+        gx, gw = torch.autograd.grad((y.tanh() * probe).sum(), [xv, wv], create_graph=True)
+        loss = gx.pow(2).sum() + gw.pow(2).sum()
+        ggx, ggw = torch.autograd.grad(loss, [xv, wv])
+        return y.detach(), gx.detach(), gw.detach(), ggx, ggw
+    ref, got = run(False), run(True)
+    errs = [_rel(a, b) for a, b in zip(got, ref)]
+    print(f"{kind} double backward: " + " ".join(f"{e:.4f}" for e in errs))
+    assert max(errs[:3]) < 2e-2 and max(errs[3:]) < 4e-2, errs
+
+
+def test_wgrad_gemm_direct(cuda):
+    """fm_wgrad_gemm on hand-made CPL operands: slabs, positive / negative offsets, ragged channel counts, split-K."""
+    from fm3d import convgrad
+    g = torch.Generator(device=cuda).manual_seed(3)
+    Ca, Cb, L = 136, 40, 1000
+    a = torch.randn(2 * Ca, 1008, generator=g, device=cuda).to(torch.bfloat16)
+    b = torch.randn(3 * Cb, 1040, generator=g, device=cuda).to(torch.bfloat16)
+    taps = [(0, 0, 0, 0), (1, 0, 2, 5), (0, 3, 1, 0), (1, -2, 0, 7)]
+    for ksplit in (0, 1, 5):
+        dw = convgrad.wgrad_gemm(a, b, Ca, Cb, 2, 3, L, taps, ksplit=ksplit)
+        for t, (sa, oa, sb, ob) in enumerate(taps):
+            A = torch.zeros(Ca, L, device=cuda); Bm = torch.zeros(Cb, L, device=cuda)
+            la = torch.arange(L, device=cuda) + oa
+            lb = torch.arange(L, device=cuda) + ob
+            ma, mb = (la >= 0) & (la < a.shape[1]), (lb >= 0) & (lb < b.shape[1])
+            A[:, ma] = a[sa * Ca:(sa + 1) * Ca][:, la[ma]].float()
+            Bm[:, mb] = b[sb * Cb:(sb + 1) * Cb][:, lb[mb]].float()
+            ref = A @ Bm.t()
+            assert _rel(dw[t], ref) < 2e-3, (ksplit, t, _rel(dw[t], ref))
+
+
+def test_cpl_layout(cuda):
+    from fm3d import convgrad
+    x = torch.randn(2, 5, 7, 9, device=cuda)
+    sc = torch.rand(2, 5, device=cuda) + 0.5
+    out = convgrad.to_cpl(x, 2, 2, 2, 6, 8, sc)          # parity planes with one margin row / column
+    assert out.shape == (4 * 5, 2 * 6 * 8)
+    ref = torch.zeros(2, 2, 5, 2, 6, 8)
+    xs = (x * sc[:, :, None, None]).cpu()
+    for py in range(2):
+        for px in range(2):
+            for yq in range(6):
+                for xq in range(8):
+                    y, xx = yq * 2 + py - 2, xq * 2 + px - 2
+                    if 0 <= y < 7 and 0 <= xx < 9:
+                        ref[py, px, :, :, yq, xq] = xs[:, :, y, xx].t()
+    assert torch.equal(out.float().cpu().view(2, 2, 5, 2, 6, 8), ref.to(torch.bfloat16).float())

@@ -98,6 +98,7 @@ def test_generator_b32_engine_vs_fp32_composition(cuda, monkeypatch):
         for _ in range(3):                      # third call replays the captured graph
             got = gen(None, **kw)
         monkeypatch.setenv("FM3D_ENGINE", "0")
+        monkeypatch.setenv("FM3D_NATIVE_GRAD", "0")         # the reference side: ATen convolutions, strict fp32
         ref = []
         for b0 in range(0, B, 8):               # fp32 composition in slices of 8 (memory)
             kws = dict(kw, latent_styles=[lat[b0:b0 + 8]], noise=[n[b0:b0 + 8] for n in noise], external_input_tensor=ext[b0:b0 + 8])
@@ -201,10 +202,15 @@ def test_up_conv_tall_image_at_real_shapes(cuda, idx, h):
 
 
 # ------------------------------------------------------------------ gradient parity
-def test_generator_gradients_vs_oracle_autograd(cuda):
+@pytest.mark.parametrize("native", [0, 1])
+def test_generator_gradients_vs_oracle_autograd(cuda, monkeypatch, native):
     """dL/dW (plain, up-conv and ToRGB weights), dL/dlatent, dL/dnoise_weight, dL/dbias, dL/d(modulation) of the
-    shared-weight composition against autograd of the reference's per-sample formulation (oracle, CPU fp32)."""
+    shared-weight composition against autograd of the reference's per-sample formulation (oracle, CPU fp32).
+    native=1: forward, dgrad and wgrad on the tcgen05 kernels (bf16 operands -> 3e-2 of each gradient's max);
+    native=0: the same composition on ATen convolutions in strict fp32 (2e-3), which pins the algebra itself."""
     import stylegan2
+    monkeypatch.setenv("FM3D_NATIVE_GRAD", str(native))
+    tol = 3e-2 if native else 2e-3
     g = load_golden("generator_small.npz")
     gen = stylegan2.Generator(32, 64, 2, generator_net_shape=[int(v) for v in g["shape"]])
     sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
@@ -226,7 +232,10 @@ def test_generator_gradients_vs_oracle_autograd(cuda):
     img_r = orc.generator_forward_ref(sd_r, latent_styles=[lat_r], input_is_latent=True, noise=noise,
                                       external_input_tensor=ext)
     (img_r * probe).sum().backward()
-    np.testing.assert_allclose(img.detach().cpu().numpy(), img_r.detach().numpy(), rtol=1e-4, atol=1e-4)
+    if native:
+        assert _rel(img.detach().cpu(), img_r.detach()) < 3e-2
+    else:
+        np.testing.assert_allclose(img.detach().cpu().numpy(), img_r.detach().numpy(), rtol=1e-4, atol=1e-4)
 
     checked = 0
     worst = ("", 0.0)
@@ -238,11 +247,11 @@ def test_generator_gradients_vs_oracle_autograd(cuda):
         e = _rel(p.grad.cpu(), ref)
         if e > worst[1]:
             worst = (name, e)
-        assert e < 2e-3, (name, e)
+        assert e < tol, (name, e)
         checked += 1
     e_lat = _rel(lat.grad.cpu(), lat_r.grad)
     print(f"gradient parity: {checked} parameter tensors, worst {worst[0]} {worst[1]:.2e}; latent {e_lat:.2e}")
-    assert e_lat < 2e-3
+    assert e_lat < tol
     kinds = [n for n, _ in gen.named_parameters() if sd_r[n].grad is not None and float(sd_r[n].grad.abs().max()) > 0]
     for frag in ("conv.weight", "modulation.weight", "modulation.bias", "noise.weight", "activate.bias", "to_rgb1.bias"):
         assert any(frag in n for n in kinds), frag

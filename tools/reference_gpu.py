@@ -6,7 +6,7 @@ this repo's kernels against the reference's CUDA ops and layers.
 
 The reference cannot be imported next to the mirror (same module names), so the work is split over two processes:
 
-  python tools/reference_gpu.py ref   [--batch 32]   # sys.path = baseline/_ref only; writes gpurun_out/ref_gpu.pt
+  python tools/reference_gpu.py ref   [--batch 32]   # sys.path = baseline/_ref only; writes /tmp/fm3d_ref_gpu.pt
   python tools/reference_gpu.py ours  [--batch 32]   # mirror; reads that file, writes gpurun_out/r02_reference_gpu.json
   python tools/reference_gpu.py both                 # runs the two as subprocesses
   python tools/reference_gpu.py jit                  # (container, no GPU) pre-build the reference's two extensions
@@ -25,7 +25,7 @@ import types
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "baseline", "_ref")
 OUT_DIR = os.path.join(ROOT, "gpurun_out")
-PT = os.path.join(OUT_DIR, "ref_gpu.pt")
+PT = os.path.join(os.environ.get("TMPDIR", "/tmp"), "fm3d_ref_gpu.pt")      # hand-over file between the two processes (large)
 
 
 def build_models(rn, sg, psp, device, seed=0):

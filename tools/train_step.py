@@ -1,52 +1,49 @@
 #!/usr/bin/env python
-"""BASELINE config 4: the four update functions of the reference's training iteration
-(train_3_encoder.py: D_Loss_BackProp :448-477, D_Reg_BackProp :479-493, G_Loss_BackProp :495-558,
-G_Reg_BackProp :561-596) run on the mirrored modules, one process per GPU, gradients averaged with the
-bucketed overlapped all-reduce of Miscellaneous/distributed.py (replaces nn.DataParallel,
-train_3_encoder.py:355-362).
+"""BASELINE config 4: the reference's OWN training-step functions, loaded from its source (train_3_encoder.py lines
+1-879, the valid prefix: SURVEY 0.6) and run unchanged on the mirrored modules, one process per GPU:
 
-  python tools/train_step.py [--batch 8] [--iters 16]
+    Module_To_Train_Setup :311-364      Optimizer_Initilization :405-445
+    D_Loss_BackProp :448-477            D_Reg_BackProp :479-493 (R1, double backward)
+    G_Loss_BackProp :495-558            G_Reg_BackProp :561-596 (path length, double backward)
+    accumulate :195-200 (EMA through .data)
+
+The iteration below is the body of ``train()`` (:786-815) without its data loaders, logging and checkpointing.
+``nn.DataParallel`` (:355-362) is replaced by one process per GPU: the optimizers the reference's functions call
+``.step()`` on are wrapped so that the bucketed, overlapped all-reduce of Miscellaneous/distributed.py completes first.
+
+  python tools/train_step.py [--batch 32] [--iters 16]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_step.py
 
-Losses: GAN (non-saturating / logistic), R1 (every d_reg_every), path length (every g_reg_every), L1;
-LPIPS / face-identity / heat-map terms need pretrained blobs that are not in the tree and are 0.
-Synthetic data, random-init weights.  Prints one JSON line (iterations/s averaged over a cycle that
-contains both regularisers).  The gradient-free generator forward inside the D step runs on the fused
-bf16 engine; everything under autograd runs the fp32 differentiable composition on the libfm3d ops."""
+Needs the reference source: /root/reference in the build container, baseline/_ref (tools/stage_reference.sh) on a GPU
+box.  Losses that need pretrained blobs which are not in the tree (LPIPS-VGG weights, ArcFace, face_alignment)
+are fed stub networks that return zeros; the GAN, R1, path-length, L1 and face-regional terms are the reference's code.
+Synthetic data, random-init weights.  Every convolution of G and D -- forward, dgrad, wgrad, and the second-order passes
+of R1 / path length -- runs on the tcgen05 kernels (fm3d/convgrad.py); ``FM3D_NATIVE_GRAD=0`` runs them on ATen.
+Prints one JSON line."""
 import argparse
 import json
 import os
 import sys
-import types
+import warnings
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "3d-fm-gan_b200"))
-import torch  # noqa: E402
-import torch.nn.functional as F  # noqa: E402
-
-import resnet_encoder as rn  # noqa: E402
-import stylegan2  # noqa: E402
-from Miscellaneous import distributed as D_  # noqa: E402
-from psp_encoder_model.encoders import psp_encoders as psp  # noqa: E402
-from Util.network_util import Forward_Inference_3_Encoder  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import ref_env  # noqa: E402
 
 
-def requires_grad(model, flag=True):          # train_3_encoder.py:190-193
-    for p in model.parameters():
-        p.requires_grad = flag
+class SteppedOptimizer:
+    """What the reference's step functions see as ``*_optim``: ``step()`` first completes the gradient all-reduce of
+    this parameter group (hooks launched it bucket by bucket during backward), then steps the real optimizer."""
 
+    def __init__(self, optim, reducer):
+        self.optim, self.reducer = optim, reducer
 
-def d_logistic_loss(real_pred, fake_pred):    # Util/training_util.py:38-43
-    return F.softplus(-real_pred).mean() + F.softplus(fake_pred).mean()
+    def step(self, *a, **k):
+        self.reducer.finish()
+        return self.optim.step(*a, **k)
 
-
-def d_r1_loss(real_pred, real_img):           # Util/training_util.py:46-52
-    grad_real, = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
-    return grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
-
-
-def g_nonsaturating_loss(fake_pred):          # Util/training_util.py:55-58
-    return F.softplus(-fake_pred).mean()
+    def __getattr__(self, name):
+        return getattr(self.optim, name)
 
 
 def main():
@@ -58,96 +55,95 @@ def main():
     ap.add_argument("--d-reg-every", type=int, default=16)
     ap.add_argument("--g-reg-every", type=int, default=4)
     ap.add_argument("--path-batch-shrink", type=int, default=2)
-    args = ap.parse_args()
+    ap.add_argument("--bucket-mb", type=int, default=32)
+    args_cli = ap.parse_args()
+
+    ts = ref_env.load_train_script()                 # the reference's functions, bound to the mirrored classes
+    import numpy as np
+    import torch
+    import stylegan2
+    import train_3_encoder_hyperparams as hp          # the reference's config module
+    from Miscellaneous import distributed as D_
+    assert ts.Generator is stylegan2.Generator and ts.D_Loss_BackProp.__code__.co_filename.endswith("train_3_encoder.py")
 
     rank, world, local_rank = D_.init_distributed()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    torch.manual_seed(0)                         # identical initial weights on every rank
-    G = stylegan2.Generator(args.size, 512, 8, channel_multiplier=2).to(dev)
-    Dn = stylegan2.Discriminator(args.size, channel_multiplier=2).to(dev)
-    E_Tsr = rn.resnet18(tensor_encoding=True).to(dev)
-    E_W = rn.resnet18(tensor_encoding=False).to(dev)
-    E_WP = psp.GradualStyleEncoder(18, 'ir_se', types.SimpleNamespace(input_nc=3, n_styles=G.n_latent)).to(dev)
-    for m in (E_Tsr, E_W, E_WP):
-        m.eval()                                 # frozen BN statistics, as the reference ends up with
+    torch.manual_seed(0)                              # identical initial weights on every rank
+    np.random.seed(0)
+    warnings.filterwarnings("ignore", message=".*add_.*deprecated.*")     # accumulate(): add_(scalar, tensor) overload (:200)
 
-    g_ratio = args.g_reg_every / (args.g_reg_every + 1)
-    d_ratio = args.d_reg_every / (args.d_reg_every + 1)
-    g_params = list(G.parameters()) + list(E_Tsr.parameters()) + list(E_W.parameters()) + list(E_WP.parameters())
-    g_optim = torch.optim.Adam(g_params, lr=0.002 * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio))      # :405-433
-    d_optim = torch.optim.Adam(Dn.parameters(), lr=0.002 * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio))
-    g_red = D_.GradBucketReducer(g_params)
-    d_red = D_.GradBucketReducer(list(Dn.parameters()))
+    args = argparse.Namespace(
+        device=str(dev), size=args_cli.size, latent=hp.latent, n_mlp=hp.n_mlp, channel_multiplier=hp.channel_multiplier,
+        w_plus_encoder_layer_num=hp.w_plus_encoder_layer_num, rec_dataset_type=hp.rec_dataset_type,
+        ds_dataset_type=hp.ds_dataset_type, use_separate_D=False, ckpt=None, load_train_state=False,
+        distributed=False, gpu_device_ids=[local_rank],          # no nn.DataParallel: one process per GPU
+        lr=hp.init_lr, g_reg_every=args_cli.g_reg_every, d_reg_every=args_cli.d_reg_every, use_g_reg=hp.use_g_reg,
+        tsr_train=hp.tsr_train, w_train=hp.w_train, w_plus_train=hp.w_plus_train,
+        tsr_encode='Render Image', w_plus_sliced_layer=hp.w_plus_sliced_layer, use_tanh=hp.use_tanh,
+        r1=hp.discriminator_r1, generator_path_reg_weight=hp.generator_path_reg_weight,
+        path_reg_batch_shrink=args_cli.path_batch_shrink, rec_batch=args_cli.batch,
+        lpips_loss_lambda=hp.lpips_loss_lambda, l1_loss_lambda=hp.l1_loss_lambda,
+        ep_lpips_l1_weight_shrink=hp.ep_lpips_l1_weight_shrink, face_id_loss_lambda=hp.face_id_loss_lambda,
+        face_id_loss_type=hp.face_id_loss_type, hmap_loss_lambda=hp.hmap_loss_lambda, hmap_iter_thres=hp.hmap_iter_thres,
+        rec_face_reg_loss_lambda=hp.rec_face_reg_loss_lambda, ds_face_reg_loss_lambda=hp.ds_face_reg_loss_lambda,
+        ep_face_reg_loss_lambda=hp.ep_face_reg_loss_lambda, ds_freq=hp.ds_freq, ex_ds_freq=hp.ex_ds_freq)
 
-    B = args.batch
+    G, E_Tsr, E_W, E_W_Plus, D, D_edit, g_ema, ckpt = ts.Module_To_Train_Setup(args)         # reference :311-364
+    for m in (E_Tsr, E_W, E_W_Plus):
+        m.eval()          # what the reference ends up with from its first sampling step on (:678-683)
+    g_enc_optim, d_optim, _ = ts.Optimizer_Initilization(args, G, E_Tsr, E_W, E_W_Plus, D, D_edit, ckpt)   # :405-445
+    g_params = [p for grp in g_enc_optim.param_groups for p in grp["params"]]
+    g_red = D_.GradBucketReducer(g_params, bucket_mb=args_cli.bucket_mb)
+    d_red = D_.GradBucketReducer(list(D.parameters()), bucket_mb=args_cli.bucket_mb)
+    g_red.enable_timing(); d_red.enable_timing()
+    g_step, d_step = SteppedOptimizer(g_enc_optim, g_red), SteppedOptimizer(d_optim, d_red)
+
+    class ZeroLPIPS(torch.nn.Module):                 # lpips.PerceptualLoss needs VGG weights from the network
+        def forward(self, a, b):
+            return (a[:, :1, :1, :1] * 0).flatten()
+
+    class ZeroFaceNet(torch.nn.Module):               # ArcFace weights are not in the tree (.MISSING_LARGE_BLOBS)
+        def forward(self, x):
+            return x.mean(dim=(1, 2, 3), keepdim=False)[:, None] * 0
+    lpips_model, face_rec_model, fa_model = ZeroLPIPS(), ZeroFaceNet(), None
+
+    B = args_cli.batch
     gen = torch.Generator(device="cpu").manual_seed(100 + rank)
     batches = [tuple((torch.rand(B, 3, args.size, args.size, generator=gen) * 2 - 1).to(dev) for _ in range(3)) for _ in range(2)]
-    mean_path_length = torch.zeros((), device=dev)
-    losses = {}
+    state = dict(r1=torch.tensor(0.0, device=dev), path=torch.tensor(0.0, device=dev), mean_path_length=0, ds_count=0)
+    loss_dict = {}
+    accum = 0.5 ** (32 / (10 * 1000))
 
-    def fwd(p, r, **kw):
-        return Forward_Inference_3_Encoder(p, r, E_Tsr, E_W, E_WP, G, 'Render Image', None, False, **kw)
+    def iteration(iter_idx):                          # body of train(), reference :786-815
+        if (iter_idx % args.ds_freq) == (args.ds_freq - 1):
+            ds_flag = True
+            extreme_ds_flag = ((state["ds_count"] % args.ex_ds_freq) == (args.ex_ds_freq - 1))
+            state["ds_count"] += 1
+        else:
+            ds_flag, extreme_ds_flag = False, False
+        g_input, r_input, g_ref = (t.clone() for t in batches[iter_idx % 2])       # stands in for Data_Loading (:361-413)
+        ts.D_Loss_BackProp(G, E_Tsr, E_W, E_W_Plus, D, g_input, r_input, g_ref, args, loss_dict, d_step)
+        if iter_idx % args.d_reg_every == 0:
+            state["r1"] = ts.D_Reg_BackProp(g_ref, D, args, d_step)
+        loss_dict['r1'] = state["r1"]
+        ts.G_Loss_BackProp(G, E_Tsr, E_W, E_W_Plus, D, g_input, r_input, g_ref, args, loss_dict, g_step, lpips_model,
+                           face_rec_model, fa_model, iter_idx, extreme_ds_flag, ds_flag)
+        if (iter_idx % args.g_reg_every) == 0 and args.use_g_reg:
+            state["path"], _, state["mean_path_length"] = ts.G_Reg_BackProp(G, E_Tsr, E_W, E_W_Plus, g_input, r_input, args,
+                                                                            state["mean_path_length"], g_step)
+        loss_dict['g_reg'] = state["path"]
+        ts.accumulate(g_ema, G, accum)
 
-    def iteration(i):
-        nonlocal mean_path_length
-        g_input, r_input, g_ref = batches[i % 2]
-        # ---- D step (:448-477): generator + encoders frozen -> fused bf16 engine forward
-        for m in (G, E_Tsr, E_W, E_WP):
-            requires_grad(m, False)
-        requires_grad(Dn, True)
-        with torch.no_grad():
-            fake = fwd(g_input, r_input)
-        d_loss = d_logistic_loss(Dn(g_ref), Dn(fake))
-        Dn.zero_grad(set_to_none=True)
-        d_loss.backward()
-        d_red.finish()
-        d_optim.step()
-        losses["d"] = d_loss.detach()
-        # ---- D regularisation (:479-493)
-        if i % args.d_reg_every == 0:
-            real = g_ref.detach().clone().requires_grad_(True)
-            real_pred = Dn(real)
-            r1 = d_r1_loss(real_pred, real)
-            Dn.zero_grad(set_to_none=True)
-            (10.0 / 2 * r1 * args.d_reg_every + 0 * real_pred[0]).backward()
-            d_red.finish()
-            d_optim.step()
-            losses["r1"] = r1.detach()
-        # ---- G step (:495-558)
-        for m in (G, E_Tsr, E_W, E_WP):
-            requires_grad(m, True)
-        requires_grad(Dn, False)
-        out = fwd(g_input, r_input)
-        g_loss = g_nonsaturating_loss(Dn(out))
-        l1 = F.l1_loss(out, g_ref)
-        for m in (G, E_Tsr, E_W, E_WP):
-            m.zero_grad(set_to_none=True)
-        (g_loss + l1).backward()
-        g_red.finish()
-        g_optim.step()
-        losses["g"], losses["l1"] = g_loss.detach(), l1.detach()
-        # ---- G regularisation (:561-596)
-        if i % args.g_reg_every == 0:
-            pb = max(1, B // args.path_batch_shrink)
-            out, path_lengths = fwd(g_input[:pb], r_input[:pb], PPL_regularize=True)
-            path_mean = mean_path_length + 0.01 * (path_lengths.mean() - mean_path_length)
-            path_loss = (path_lengths - path_mean).pow(2).mean()
-            mean_path_length = path_mean.detach()
-            for m in (G, E_Tsr, E_W, E_WP):
-                m.zero_grad(set_to_none=True)
-            (2.0 * args.g_reg_every * path_loss + 0 * out[0, 0, 0, 0]).backward()
-            g_red.finish()
-            g_optim.step()
-            losses["path"] = path_loss.detach()
-
-    for i in range(args.warmup):
+    for i in range(args_cli.warmup):
         iteration(i)
+    g_red.enable_timing(); d_red.enable_timing()
     D_.synchronize()
     torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.iters):
+    for i in range(args_cli.iters):
         iteration(i)
     e1.record()
     D_.synchronize()
@@ -155,17 +151,34 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-    red = D_.reduce_loss_dict(dict(losses))
+    # the EMA generator is what evaluation samples from: it must run on the engine with the weights accumulate() wrote
+    with torch.no_grad():
+        sample = ts.Forward_Inference_3_Encoder(batches[0][0][:2], batches[0][1][:2], E_Tsr, E_W, E_W_Plus, g_ema,
+                                                args.tsr_encode, args.w_plus_sliced_layer, args.use_tanh)
+    keys = sorted(k for k, v in loss_dict.items() if torch.is_tensor(v))
+    red = D_.reduce_loss_dict({k: loss_dict[k].detach().float().reshape(()) for k in keys})
+    exposed = {"g_enc": g_red.exposed_times_ms(), "d": d_red.exposed_times_ms()}
     if rank == 0:
         sec = float(ms.item()) * 1e-3
-        finite = all(bool(torch.isfinite(v).all()) for v in red.values())
+        finite = all(bool(torch.isfinite(v).all()) for v in red.values()) and bool(torch.isfinite(sample).all())
+        ex_total = sum(sum(v) for v in exposed.values())
         print(json.dumps({
-            "metric": "train_3_encoder iterations/s (D + R1/16 + G + path-length/4)", "value": args.iters / sec, "unit": "it/s",
-            "images_per_s": args.iters * B * world / sec, "n_gpus": world, "batch_per_gpu": B, "iters": args.iters,
-            "ms_per_iter": sec * 1e3 / args.iters, "size": args.size, "losses_finite": finite,
-            "losses": {k: float(v) / (world if world > 1 else 1) for k, v in red.items()},
+            "metric": "train_3_encoder iterations/s (D + R1/%d + G + path-length/%d; the reference's own step functions)"
+                      % (args.d_reg_every, args.g_reg_every),
+            "value": args_cli.iters / sec, "unit": "it/s",
+            "images_per_s": args_cli.iters * B * world / sec, "n_gpus": world, "batch_per_gpu": B, "iters": args_cli.iters,
+            "ms_per_iter": sec * 1e3 / args_cli.iters, "size": args.size, "losses_finite": finite,
+            "losses": {k: float(v) for k, v in red.items()},
+            "native_grad": os.environ.get("FM3D_NATIVE_GRAD", "1") != "0",
+            "allreduce": {"world": world, "bucket_mb": args_cli.bucket_mb,
+                          "bytes_per_step": {"g_enc": sum(g_red.bucket_bytes()), "d": sum(d_red.bucket_bytes())},
+                          "buckets": {"g_enc": len(g_red.buckets), "d": len(d_red.buckets)},
+                          "exposed_ms_per_iter": ex_total / args_cli.iters if world > 1 else 0.0,
+                          "exposed_fraction_of_iteration": (ex_total / args_cli.iters) / (sec * 1e3 / args_cli.iters) if world > 1 else 0.0,
+                          "note": "exposed = time the compute stream waited in finish() for collectives still running when "
+                                  "backward ended; the rest of the all-reduce overlapped backward"},
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
-            "note": "fp32 autograd composition on libfm3d ops + bf16 engine for the frozen-generator forward; LPIPS/face-id/heat-map = 0"}))
+            "source": ts.D_Loss_BackProp.__code__.co_filename}))
     if world > 1:
         torch.distributed.destroy_process_group()
 
