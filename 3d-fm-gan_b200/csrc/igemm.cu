@@ -58,6 +58,11 @@ struct IgemmParams {
   int hp_np, hp_sx, hp_sy;
   int8_t hp_pl_first[5];           // taps [first[pl], first[pl+1]) belong to plane pl (taps are sorted by plane)
   int16_t hp_pl_x[4], hp_pl_y[4];  // input-space offset of a plane's patch origin relative to (sx*x0, sy*y0)
+  // several output phases of a stride-2 transposed conv in one launch: super tile st -> (phase = st / nsup1, tile = st % nsup1);
+  // taps [ph_first[ph], ph_first[ph+1]) and the output offset (ph_oy0, ph_ox0) belong to the phase
+  int nph, nsup1;
+  int8_t ph_first[5];
+  int16_t ph_oy0[4], ph_ox0[4];
   int hpw;                         // halo-patch mode with ALL weight tiles of the (single) n-tile resident in smem
   int wres, wres_stages;           // generic mode with all (tap, chunk) weight tiles of the single n-tile resident: only A tiles stream
   int16_t hp_aoff[FM_MAX_TAPS];    // per-tap start offset of the A descriptor inside the patch (16-byte units)
@@ -202,7 +207,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int nvc = p.kchunks * p.hp_np;          // virtual chunks: (channel chunk, parity plane)
     auto hp_prefetch = [&]() {
       if (pst >= p.num_super) return;
-      int m = (pst / p.tiles_n) * p.cluster + crank;   // ksplit == 1 in this mode
+      const int pstl = p.nph > 1 ? pst % p.nsup1 : pst;   // the patch depends on the tile position only, not on the phase
+      int m = (pstl / p.tiles_n) * p.cluster + crank;   // ksplit == 1 in this mode
       const int bx = m % p.tiles_x; m /= p.tiles_x;
       const int by = m % p.tiles_y;
       const int bb = m / p.tiles_y;
@@ -257,8 +263,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) IG_TRACE(1);
     int ptile = 0;
     for (int st = cluster_id; st < p.num_super; st += num_clusters) {
-      const int nt = st % p.tiles_n;
-      int m = st / p.tiles_n;
+      const int ph = p.nph > 1 ? st / p.nsup1 : 0;
+      const int stl = st - ph * p.nsup1;
+      const int nt = stl % p.tiles_n;
+      int m = stl / p.tiles_n;
       const int ks = m % p.ksplit; m /= p.ksplit;
       m = m * p.cluster + crank;                  // CTAs of a cluster take adjacent m-tiles of the same n-tile
       const int bx = m % p.tiles_x; m /= p.tiles_x;
@@ -323,7 +331,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int vc = 0; vc < nvc; ++vc) {
           hp_prefetch();
           const int kc = vc / p.hp_np, pl = vc - kc * p.hp_np;
-          for (int tap = p.hp_pl_first[pl]; tap < p.hp_pl_first[pl + 1]; ++tap) {
+          const int tp0 = p.nph > 1 ? p.ph_first[ph] : p.hp_pl_first[pl], tp1 = p.nph > 1 ? p.ph_first[ph + 1] : p.hp_pl_first[pl + 1];
+          for (int tap = tp0; tap < tp1; ++tap) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (lane == 0) {
               if (kPair) {
@@ -512,7 +521,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (lane == 0 && vc == 0) IG_TRACE(4 + 4 * titer);  // MMA: first patch landed
           const int pl = hp_np1 ? 0 : vc % p.hp_np;
           const uint32_t alo0 = umma_desc_lo(ring + aslot * p.hp_bytes);
-          const int t0 = p.hp_pl_first[pl], t1 = p.hp_pl_first[pl + 1];
+          const int mph = p.nph > 1 ? st / p.nsup1 : 0;
+          const int t0 = p.nph > 1 ? p.ph_first[mph] : p.hp_pl_first[pl], t1 = p.nph > 1 ? p.ph_first[mph + 1] : p.hp_pl_first[pl + 1];
           for (int tap = t0; tap < t1; ++tap) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
@@ -606,8 +616,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int st = cluster_id; st < p.num_super; st += num_clusters, ++titer, next_acc()) {
       // tile coordinates: the common single-n-tile / unsplit / ungrouped cases skip their integer divisions (each costs
       // ~25 dependent instructions, and a 64-channel tile's whole epilogue is only ~300 per warp)
-      const int nt = e_tn1 ? 0 : st % p.tiles_n;
-      int m = e_tn1 ? st : st / p.tiles_n;
+      const int eph = p.nph > 1 ? st / p.nsup1 : 0;
+      const int stl = st - eph * p.nsup1;
+      const int nt = e_tn1 ? 0 : stl % p.tiles_n;
+      int m = e_tn1 ? stl : stl / p.tiles_n;
       if (p.ksplit > 1) m /= p.ksplit;
       m = m * p.cluster + crank;
       const int m2 = m / p.tiles_x;
@@ -653,7 +665,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int upy = p.upmode ? (r >> 1) : 0, upx = p.upmode ? (r & 1) : 0;
       const bool valid = row < p.rows && ox < p.OW - upx && oy < p.OH - upy && b < p.B;
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (nrows * BN) + r * BN;
-      const int Y = oy * p.out_ys + p.out_y0 + upy, X = ox * p.out_xs + p.out_x0 + upx;
+      const int Y = oy * p.out_ys + (p.nph > 1 ? p.ph_oy0[eph] : p.out_y0) + upy, X = ox * p.out_xs + (p.nph > 1 ? p.ph_ox0[eph] : p.out_x0) + upx;
       float nz = 0.f;
       if (valid && p.noise)
         nz = nw * __ldg(p.noise + (static_cast<size_t>(p.noise_bstride ? b : 0) * p.out_H + Y) * p.out_W + X);

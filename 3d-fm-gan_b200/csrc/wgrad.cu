@@ -1,22 +1,23 @@
-// Weight-gradient GEMM on tcgen05 / TMEM, fed by TMA (sm_100a), and the layout pass that feeds it.
+// Weight gradient of a convolution on tcgen05 / TMEM, fed by TMA (sm_100a).
 //
 // The reference gets dL/dW of every convolution from ATen autograd over F.conv2d / F.conv_transpose2d
-// (stylegan2.py:129,276,285,291 -> cuDNN wgrad).  Here the gradient of a conv weight is a plain GEMM whose
-// contraction runs over PIXELS:
+// (stylegan2.py:129,276,285,291 -> cuDNN wgrad).  Here it is one GEMM whose contraction runs over PIXELS:
 //
-//   dW[t][a][b] += sum_{l < L}  A[slab_a(t)*Ca + a][l + off_a(t)] * Bm[slab_b(t)*Cb + b][l + off_b(t)]
+//   dW[t][a][b] += sum_{(n,oy,ox)}  A[n, oy*sa + dya(t), ox*sa + dxa(t), a] * Bm[n, oy*sb + dyb(t), ox*sb + dxb(t), b]
 //
-// with both operands stored channel-major / pixel-linear ("CPL": [channels][B*Hq*Wq] bf16, rows 16-byte aligned), so a
-// K chunk of 64 pixels of 128 (or N) channels is one 2-D TMA box that lands as a K-major SWIZZLE_128B UMMA operand.
-// All geometry lives in the layout pass: the conv's zero padding is a zero halo in the pixel grid, a conv tap is a
-// linear offset (ky*Wq + kx) into that grid, a stride-2 conv reads one of four parity planes (slabs) of its input, and
-// out-of-range coordinates are TMA zero fill.  One kernel therefore serves conv2d (stride 1/2) and conv_transpose2d.
+// with both operands in the layout the forward / dgrad kernels already use: NHWC bf16.  A K chunk is 64 grid pixels
+// (tw x th x tb, like an igemm tile); for every 64 channels of an operand ONE 4-D TMA box (64 ch x tw x th x tb, the
+// tap's shift in the pixel coordinates, the conv stride as TMA element stride, zero padding = out-of-bounds fill) lands
+// as 64 rows (pixels = K) of 128 bytes (channels = M or N): the canonical **MN-major** SWIZZLE_128B UMMA operand
+// (cute::UMMA Layout_MN_SW128_Atom: 8 K-rows of 64 MN-elements per 1024-byte atom; stride between 8-row groups along
+// K = SBO = 1024 B; stride between 64-channel boxes along M/N = LBO = 8192 B).  So the operands need no transposed copy:
+// the instruction descriptor just marks A and B as MN-major.
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (TMEM lane quarter =
 // warp % 4).  Persistent CTAs over work items (m-tile, n-tile, tap, k-slice); the fp32 accumulator of an item is added to
-// dW with vector atomics (split-K over pixels: a 128 x 256 tile of one tap would otherwise be the whole job of one SM).
+// dW with vector atomics (split-K over pixels: a 128 x 256 tile of one tap would otherwise be one SM's whole job).
 //
-// Algorithmic FLOPs per launch: 2 * L_valid * Ca * Cb * ntaps.
+// Algorithmic FLOPs per launch: 2 * B*GH*GW * Ca * Cb * ntaps.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -24,30 +25,58 @@
 namespace fm {
 
 constexpr int WG_BM = 128;
-constexpr int WG_BK = 64;
+constexpr int WG_BK = 64;                 // pixels per K chunk
+constexpr int WG_BOX_BYTES = 64 * 128;    // one TMA box: 64 pixels x 64 channels bf16
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_STAGES = 8;
 
 struct WgradParams {
   int Ca, Cb;
   int m_tiles, n_tiles, ntaps, ksplit, kper, nchunks, num_items;
-  int stages;
+  int tw, th, tb, tiles_x, tiles_y;
+  int sa, sb;
   float* dw;
   long long dw_tap_stride;
   int dw_row_stride;
-  int32_t off_a[FM_MAX_TAPS], off_b[FM_MAX_TAPS];
-  int8_t slab_a[FM_MAX_TAPS], slab_b[FM_MAX_TAPS];
+  int8_t dya[FM_MAX_TAPS], dxa[FM_MAX_TAPS], dyb[FM_MAX_TAPS], dxb[FM_MAX_TAPS];
 };
 
 template <int BN>
 struct WgradCfg {
-  static constexpr int A_BYTES = WG_BM * WG_BK * 2;     // 16 KB
-  static constexpr int B_BYTES = BN * WG_BK * 2;
+  static constexpr int NB_BOXES = BN >= 64 ? BN / 64 : 1;
+  static constexpr int A_BYTES = 2 * WG_BOX_BYTES;                 // 128 channels
+  static constexpr int B_BYTES = NB_BOXES * WG_BOX_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (192 * 1024 / STAGE_BYTES) > WG_MAX_STAGES ? WG_MAX_STAGES : (192 * 1024 / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
+
+// Instruction descriptor: D = f32, A = B = bf16, both MN-major (bits 15, 16), dense, M x N.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {
+  return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
+}
+// MN-major SWIZZLE_128B operand descriptor halves: LBO = 8192 B between 64-channel boxes, SBO = 1024 B between 8-pixel groups.
+__device__ __forceinline__ uint32_t umma_desc_lo_mn(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | ((8192u >> 4) << 16); }
+
+// The four K=16 steps of one 64-pixel chunk: both start addresses advance 16 pixel rows = 2048 bytes (+128 in the >>4 field).
+__device__ __forceinline__ void umma_bf16_x4_mn(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.u32 q, 0, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "add.u32 al, %1, 128;\n\tadd.u32 bl, %3, 128;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u32 al, %1, 256;\n\tadd.u32 bl, %3, 256;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t"
+      "add.u32 al, %1, 384;\n\tadd.u32 bl, %3, 384;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 template <int BN>
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -95,24 +124,33 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       int mt, nt, tap, c0, c1;
       decode(it, mt, nt, tap, c0, c1);
-      const int ra = p.slab_a[tap] * p.Ca + mt * WG_BM, rb = p.slab_b[tap] * p.Cb + nt * BN;
-      const int oa = p.off_a[tap], ob = p.off_b[tap];
+      const int dya = p.dya[tap], dxa = p.dxa[tap], dyb = p.dyb[tap], dxb = p.dxb[tap];
+      // chunk c -> tile (bx, by, bb) of the contraction grid
+      int bx = c0 % p.tiles_x, t = c0 / p.tiles_x;
+      int by = t % p.tiles_y, bb = t / p.tiles_y;
       for (int c = c0; c < c1; ++c) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          const int gx = bx * p.tw, gy = by * p.th, gb = bb * p.tb;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], c * WG_BK + oa, ra);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], c * WG_BK + ob, rb);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_4d(sa + j * WG_BOX_BYTES, &tmA, &full_bar[stage], mt * WG_BM + j * 64, gx * p.sa + dxa, gy * p.sa + dya, gb);
+#pragma unroll
+          for (int j = 0; j < Cfg::NB_BOXES; ++j)
+            tma_load_4d(sb + j * WG_BOX_BYTES, &tmB, &full_bar[stage], nt * BN + j * 64, gx * p.sb + dxb, gy * p.sb + dyb, gb);
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (++bx == p.tiles_x) { bx = 0; if (++by == p.tiles_y) { by = 0; ++bb; } }
       }
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    const uint32_t idesc = umma_idesc_bf16(WG_BM, BN);
-    constexpr uint32_t dhi = umma_desc_hi_sw128(1024);
+    const uint32_t idesc = umma_idesc_bf16_mn(WG_BM, BN);
+    constexpr uint32_t dhi = umma_desc_hi_sw128(1024);      // SBO = 1024 B
     const uint32_t ring = smem_u32(smem);
     int stage = 0, buf = 0;
     uint32_t phase = 0, aphase = 0;
@@ -127,7 +165,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_after();
         const uint32_t sa = ring + stage * Cfg::STAGE_BYTES;
         if (elect_one()) {
-          umma_bf16_x4(tmem_d, umma_desc_lo(sa), dhi, umma_desc_lo(sa + Cfg::A_BYTES), dhi, idesc, c > c0 ? 1u : 0u);
+          umma_bf16_x4_mn(tmem_d, umma_desc_lo_mn(sa), dhi, umma_desc_lo_mn(sa + Cfg::A_BYTES), dhi, idesc, c > c0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (c == c1 - 1) umma_commit(&tfull_bar[buf]);
         }
@@ -156,7 +194,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t acc[16];
         tmem_ld_32x16(tmem_acc + cb, acc);
         tmem_ld_wait();
-        if (c1 > c0 && a < p.Ca) {
+        if (a < p.Ca) {
           const int b0 = nt * BN + cb;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
@@ -199,86 +237,59 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Wg
   return FM_OK;
 }
 
-// dst[(slab*C + c)][b*Hq*Wq + yq*Wq + xq] = scale[b,c] * src[b, c, yq*s + py - y0, xq*s + px - x0]   (0 outside the image),
-// slab = py*s + px.  One thread per 8 consecutive xq (one 16-byte store).
-__global__ void __launch_bounds__(256) nchw_to_cpl_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src,
-                                                         const float* __restrict__ scale, int B, int C, int H, int W, int s,
-                                                         int y0, int x0, int Hq, int Wq, int64_t total8) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const int wq8 = Wq >> 3;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total8; idx += stride) {
-    int64_t t = idx;
-    const int xg = static_cast<int>(t % wq8); t /= wq8;
-    const int yq = static_cast<int>(t % Hq); t /= Hq;
-    const int b = static_cast<int>(t % B); t /= B;
-    const int c = static_cast<int>(t % C);
-    const int slab = static_cast<int>(t / C);
-    const int py = slab / s, px = slab - py * s;
-    const int y = yq * s + py - y0;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (y >= 0 && y < H) {
-      const float sc = scale ? __ldg(scale + static_cast<int64_t>(b) * C + c) : 1.f;
-      const float* row = src + ((static_cast<int64_t>(b) * C + c) * H + y) * W;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int x = (xg * 8 + j) * s + px - x0;
-        if (x >= 0 && x < W) v[j] = __ldg(row + x) * sc;
-      }
-    }
-    uint4 w;
-    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
-    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(dst + idx * 8) = w;
-  }
+static int encode_operand(EncodeTiledFn encode, CUtensorMap* tm, const fm_wgrad_operand& o, int B, int tw, int th, int tb, int s,
+                          const char* which) {
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(o.C), static_cast<cuuint64_t>(o.W), static_cast<cuuint64_t>(o.H),
+                              static_cast<cuuint64_t>(B)};
+  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(o.cstride) * 2, static_cast<cuuint64_t>(o.cstride) * o.W * 2,
+                                 static_cast<cuuint64_t>(o.cstride) * o.W * o.H * 2};
+  // with an element stride s TMA loads ceil(box/s) elements: box = n*s loads n
+  const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tw * s), static_cast<cuuint32_t>(th * s), static_cast<cuuint32_t>(tb)};
+  const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(s), static_cast<cuuint32_t>(s), 1};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(o.ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("fm_conv_wgrad: cuTensorMapEncodeTiled(%s) failed with CUresult %d", which, (int)r); return FM_ERR_CUDA; }
+  return FM_OK;
 }
 
 }  // namespace fm
 
 using namespace fm;
 
-extern "C" int fm_nchw_to_cpl_bf16(void* dst, const float* src, const float* scale_bc, int B, int C, int H, int W, int s, int y0,
-                                   int x0, int Hq, int Wq, void* stream) {
-  FM_CHECK_ARG(dst && src && B > 0 && C > 0 && H > 0 && W > 0, "fm_nchw_to_cpl_bf16: bad args");
-  FM_CHECK_ARG((s == 1 || s == 2) && Hq > 0 && Wq > 0 && Wq % 8 == 0, "fm_nchw_to_cpl_bf16: s must be 1 or 2, Wq a multiple of 8");
-  FM_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "fm_nchw_to_cpl_bf16: dst must be 16-byte aligned");
-  const int64_t total8 = static_cast<int64_t>(s) * s * C * B * Hq * (Wq / 8);
-  int64_t blocks = (total8 + 255) / 256;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
-  if (blocks > cap) blocks = cap;
-  FM_CUDA_OK(launch_pdl(nchw_to_cpl_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream),
-                        static_cast<__nv_bfloat16*>(dst), src, scale_bc, B, C, H, W, s, y0, x0, Hq, Wq, total8));
-  count_launch();
-  FM_LAUNCH_OK();
-  return FM_OK;
-}
-
-extern "C" int fm_wgrad_gemm(const fm_wgrad_desc* d, void* stream) {
-  FM_CHECK_ARG(d != nullptr && d->a && d->b && d->dw, "fm_wgrad_gemm: null pointer");
-  FM_CHECK_ARG(d->Ca > 0 && d->Cb > 0 && d->L > 0 && d->ntaps >= 1 && d->ntaps <= FM_MAX_TAPS, "fm_wgrad_gemm: bad sizes");
-  FM_CHECK_ARG(d->La % 8 == 0 && d->Lb % 8 == 0 && d->La > 0 && d->Lb > 0, "fm_wgrad_gemm: row lengths must be multiples of 8 elements");
-  FM_CHECK_ARG(d->La < 0x7FFFFF00LL && d->Lb < 0x7FFFFF00LL, "fm_wgrad_gemm: row length exceeds the TMA coordinate range");
-  FM_CHECK_ARG((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->b) & 15) == 0,
-               "fm_wgrad_gemm: operands must be 16-byte aligned");
-  FM_CHECK_ARG(d->nslabs_a >= 1 && d->nslabs_b >= 1 && d->dw_row_stride >= d->Cb, "fm_wgrad_gemm: bad slab counts / dw_row_stride");
+extern "C" int fm_conv_wgrad(const fm_wgrad_desc* d, void* stream) {
+  FM_CHECK_ARG(d != nullptr && d->a.ptr && d->b.ptr && d->dw, "fm_conv_wgrad: null pointer");
+  FM_CHECK_ARG(d->B > 0 && d->GH > 0 && d->GW > 0 && d->ntaps >= 1 && d->ntaps <= FM_MAX_TAPS, "fm_conv_wgrad: bad sizes");
+  for (const fm_wgrad_operand* o : {&d->a, &d->b}) {
+    FM_CHECK_ARG(o->C > 0 && o->H > 0 && o->W > 0 && o->cstride >= o->C && o->cstride % 8 == 0,
+                 "fm_conv_wgrad: operand channel stride must be a multiple of 8 and >= C");
+    FM_CHECK_ARG(o->stride >= 1 && o->stride <= 2, "fm_conv_wgrad: operand stride must be 1 or 2");
+    FM_CHECK_ARG((reinterpret_cast<uintptr_t>(o->ptr) & 15) == 0, "fm_conv_wgrad: operands must be 16-byte aligned");
+  }
+  FM_CHECK_ARG(d->dw_row_stride >= d->b.C, "fm_conv_wgrad: dw_row_stride < Cb");
   EncodeTiledFn encode = get_encode_fn();
-  if (!encode) { set_error("fm_wgrad_gemm: cuTensorMapEncodeTiled driver entry point unavailable"); return FM_ERR_NO_DEVICE; }
+  if (!encode) { set_error("fm_conv_wgrad: cuTensorMapEncodeTiled driver entry point unavailable"); return FM_ERR_NO_DEVICE; }
 
-  int bn = d->Cb > 128 ? 256 : (d->Cb > 64 ? 128 : (d->Cb > 32 ? 64 : (d->Cb > 16 ? 32 : 16)));
+  const int Cb = d->b.C;
+  const int bn = Cb > 128 ? 256 : (Cb > 64 ? 128 : (Cb > 32 ? 64 : (Cb > 16 ? 32 : 16)));
   WgradParams p{};
-  p.Ca = d->Ca; p.Cb = d->Cb;
-  p.m_tiles = (d->Ca + WG_BM - 1) / WG_BM;
-  p.n_tiles = (d->Cb + bn - 1) / bn;
+  p.Ca = d->a.C; p.Cb = Cb;
+  p.m_tiles = (p.Ca + WG_BM - 1) / WG_BM;
+  p.n_tiles = (Cb + bn - 1) / bn;
   p.ntaps = d->ntaps;
-  p.nchunks = static_cast<int>((d->L + WG_BK - 1) / WG_BK);
+  p.sa = d->a.stride; p.sb = d->b.stride;
+  // K chunk = 64 pixels of the contraction grid [B][GH][GW]: tw x th x tb
+  int tw = 1; while (tw < d->GW && tw < 64) tw <<= 1;
+  int th = 1; while (th < d->GH && tw * th < 64) th <<= 1;
+  const int tb = 64 / (tw * th);
+  p.tw = tw; p.th = th; p.tb = tb;
+  p.tiles_x = (d->GW + tw - 1) / tw;
+  p.tiles_y = (d->GH + th - 1) / th;
+  const int64_t nchunks = static_cast<int64_t>(p.tiles_x) * p.tiles_y * ((d->B + tb - 1) / tb);
+  FM_CHECK_ARG(nchunks < 0x7FFFFFFF, "fm_conv_wgrad: too many K chunks");
+  p.nchunks = static_cast<int>(nchunks);
   for (int i = 0; i < d->ntaps; ++i) {
-    FM_CHECK_ARG(d->tap_slab_a[i] >= 0 && d->tap_slab_a[i] < d->nslabs_a && d->tap_slab_b[i] >= 0 && d->tap_slab_b[i] < d->nslabs_b,
-                 "fm_wgrad_gemm: tap %d: slab out of range", i);
-    p.off_a[i] = d->tap_off_a[i]; p.off_b[i] = d->tap_off_b[i];
-    p.slab_a[i] = d->tap_slab_a[i]; p.slab_b[i] = d->tap_slab_b[i];
+    p.dya[i] = d->tap_dy_a[i]; p.dxa[i] = d->tap_dx_a[i]; p.dyb[i] = d->tap_dy_b[i]; p.dxb[i] = d->tap_dx_b[i];
   }
   // split-K over pixels: aim at >= 2 items per SM, keep >= 8 chunks per item
   const int64_t items0 = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.ntaps;
@@ -294,31 +305,15 @@ extern "C" int fm_wgrad_gemm(const fm_wgrad_desc* d, void* stream) {
   p.kper = (p.nchunks + ksplit - 1) / ksplit;
   p.ksplit = (p.nchunks + p.kper - 1) / p.kper;
   const int64_t items = items0 * p.ksplit;
-  FM_CHECK_ARG(items < 0x7FFFFFFF, "fm_wgrad_gemm: too many work items");
+  FM_CHECK_ARG(items < 0x7FFFFFFF, "fm_conv_wgrad: too many work items");
   p.num_items = static_cast<int>(items);
   p.dw = d->dw; p.dw_tap_stride = d->dw_tap_stride; p.dw_row_stride = d->dw_row_stride;
 
   CUtensorMap tmA, tmB;
-  {
-    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d->La), static_cast<cuuint64_t>(d->nslabs_a) * d->Ca};
-    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d->La) * 2};
-    const cuuint32_t box[2] = {WG_BK, WG_BM};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->a), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("fm_wgrad_gemm: cuTensorMapEncodeTiled(A) failed with CUresult %d", (int)r); return FM_ERR_CUDA; }
-  }
-  {
-    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d->Lb), static_cast<cuuint64_t>(d->nslabs_b) * d->Cb};
-    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d->Lb) * 2};
-    const cuuint32_t box[2] = {WG_BK, static_cast<cuuint32_t>(bn)};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->b), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("fm_wgrad_gemm: cuTensorMapEncodeTiled(B) failed with CUresult %d", (int)r); return FM_ERR_CUDA; }
-  }
+  int rc = encode_operand(encode, &tmA, d->a, d->B, tw, th, tb, d->a.stride, "A");
+  if (rc != FM_OK) return rc;
+  rc = encode_operand(encode, &tmB, d->b, d->B, tw, th, tb, d->b.stride, "B");
+  if (rc != FM_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (bn) {
     case 16: return launch_wgrad<16>(tmA, tmB, p, st);

@@ -35,18 +35,23 @@ class ConvDesc(C.Structure):
         ("block_n", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("out_cgroup_ow_shrink", C.c_int32),
         ("residual_up_h", C.c_int32), ("residual_up_w", C.c_int32),
         ("out_pitch_h", C.c_int32), ("out_pitch_w", C.c_int32),
+        ("nphases", C.c_int32), ("phase_ntaps", C.c_int32 * 4), ("phase_out_y0", C.c_int32 * 4), ("phase_out_x0", C.c_int32 * 4),
     ]
+
+
+class WgradOperand(C.Structure):
+    """fm_wgrad_operand (include/fm3d.h)."""
+    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int32), ("cstride", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("stride", C.c_int32)]
 
 
 class WgradDesc(C.Structure):
     """fm_wgrad_desc (include/fm3d.h)."""
     _fields_ = [
-        ("a", C.c_void_p), ("b", C.c_void_p),
-        ("Ca", C.c_int32), ("Cb", C.c_int32), ("nslabs_a", C.c_int32), ("nslabs_b", C.c_int32),
-        ("La", C.c_int64), ("Lb", C.c_int64), ("L", C.c_int64),
-        ("ntaps", C.c_int32),
-        ("tap_off_a", C.c_int32 * FM_MAX_TAPS), ("tap_off_b", C.c_int32 * FM_MAX_TAPS),
-        ("tap_slab_a", C.c_int8 * FM_MAX_TAPS), ("tap_slab_b", C.c_int8 * FM_MAX_TAPS),
+        ("a", WgradOperand), ("b", WgradOperand),
+        ("B", C.c_int32), ("GH", C.c_int32), ("GW", C.c_int32), ("ntaps", C.c_int32),
+        ("tap_dy_a", C.c_int8 * FM_MAX_TAPS), ("tap_dx_a", C.c_int8 * FM_MAX_TAPS),
+        ("tap_dy_b", C.c_int8 * FM_MAX_TAPS), ("tap_dx_b", C.c_int8 * FM_MAX_TAPS),
         ("dw", C.c_void_p), ("dw_tap_stride", C.c_int64), ("dw_row_stride", C.c_int32), ("ksplit", C.c_int32),
     ]
 
@@ -76,8 +81,7 @@ _SIGNATURES = {
     "fm_upfirdn2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int] * 12 + [C.c_int, C.c_void_p]),
     "fm_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "fm_igemm_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
-    "fm_wgrad_gemm": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
-    "fm_nchw_to_cpl_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
+    "fm_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
     "fm_style_affine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fm_build_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fm_tensor2im_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),

@@ -7,7 +7,7 @@ convolution is made of are ``autograd.Function``s over ``libfm3d.so``:
     ConvFwd(x, w)        y[b,o,oy,ox]  = sum w[o,i,ky,kx] * x[b,i,oy*s+ky-p,ox*s+kx-p]     fm_conv_igemm
     ConvBwdData(g, w)    gx[b,i,y,x]   = sum w[o,i,ky,kx] * g[b,o,oy,ox]  (y = oy*s+ky-p)   fm_conv_igemm, one launch per
                                                                                            output phase (y+p mod s)
-    ConvBwdWeight(x, g)  gw[o,i,ky,kx] = sum x[b,i,oy*s+ky-p,ox*s+kx-p] * g[b,o,oy,ox]     fm_wgrad_gemm (GEMM over pixels)
+    ConvBwdWeight(x, g)  gw[o,i,ky,kx] = sum x[b,i,oy*s+ky-p,ox*s+kx-p] * g[b,o,oy,ox]     fm_conv_wgrad (GEMM over pixels)
 
 Each is bilinear and the derivative of each is again one of the three ("gradfix" pattern), so
 second-order passes -- R1 through the discriminator (Util/training_util.py:46-52) and path-length regularisation
@@ -103,58 +103,33 @@ def conv_backward_data(g, w, stride, pad, in_hw):
     return out
 
 
-def to_cpl(x, s, y0, x0, Hq, Wq, scale_bc=None):
-    """fp32 NCHW -> bf16 [s*s*C, B*Hq*Wq] (fm_nchw_to_cpl_bf16)."""
-    x = x.contiguous().float()
-    B, Cc, H, W = x.shape
-    out = torch.empty(s * s * Cc, B * Hq * Wq, device=x.device, dtype=torch.bfloat16)
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().fm_nchw_to_cpl_bf16(out.data_ptr(), x.data_ptr(), None if scale_bc is None else scale_bc.data_ptr(),
-                                                  B, Cc, H, W, s, y0, x0, Hq, Wq, torch.cuda.current_stream().cuda_stream),
-                   "fm_nchw_to_cpl_bf16")
-    return out
-
-
-def wgrad_gemm(a, b, Ca, Cb, nslabs_a, nslabs_b, L, taps, ksplit=0):
-    """dw[t][a][b] = sum_l A[slab_a*Ca + a][l + off_a] * Bm[slab_b*Cb + b][l + off_b]; taps = [(slab_a, off_a, slab_b, off_b)]."""
+def conv_wgrad(a, b, Ca, Cb, B, GH, GW, taps, stride_a=1, stride_b=1, ksplit=0):
+    """fm_conv_wgrad: a, b bf16 NHWC [B,H,W,cs]; taps = [(dy_a, dx_a, dy_b, dx_b)] -> dw fp32 [ntaps, Ca, Cb]."""
     dw = torch.zeros(len(taps), Ca, (Cb + 3) // 4 * 4, device=a.device, dtype=torch.float32)
     d = WgradDesc()
-    d.a, d.b = a.data_ptr(), b.data_ptr()
-    d.Ca, d.Cb, d.nslabs_a, d.nslabs_b = Ca, Cb, nslabs_a, nslabs_b
-    d.La, d.Lb, d.L = a.shape[1], b.shape[1], L
-    d.ntaps = len(taps)
-    for i, (sa, oa, sb, ob) in enumerate(taps):
-        d.tap_slab_a[i], d.tap_off_a[i], d.tap_slab_b[i], d.tap_off_b[i] = sa, oa, sb, ob
+    for o, t, c, s in ((d.a, a, Ca, stride_a), (d.b, b, Cb, stride_b)):
+        o.ptr, o.C, o.cstride, o.H, o.W, o.stride = t.data_ptr(), c, t.shape[3], t.shape[1], t.shape[2], s
+    d.B, d.GH, d.GW, d.ntaps = B, GH, GW, len(taps)
+    for i, (dya, dxa, dyb, dxb) in enumerate(taps):
+        d.tap_dy_a[i], d.tap_dx_a[i], d.tap_dy_b[i], d.tap_dx_b[i] = dya, dxa, dyb, dxb
     d.dw, d.dw_tap_stride, d.dw_row_stride, d.ksplit = dw.data_ptr(), dw.shape[1] * dw.shape[2], dw.shape[2], ksplit
     with torch.cuda.device(a.device):
-        _lib.check(_lib.lib().fm_wgrad_gemm(C.byref(d), torch.cuda.current_stream().cuda_stream), "fm_wgrad_gemm")
+        _lib.check(_lib.lib().fm_conv_wgrad(C.byref(d), torch.cuda.current_stream().cuda_stream), "fm_conv_wgrad")
     return dw[..., :Cb]
 
 
 def conv_backward_weight(x, g, stride, pad, k):
-    """x [B,I,H,W], g [B,O,OH,OW] -> gw [O,I,k,k].  Geometry (see csrc/wgrad.cu): both operands live on one pixel grid
-    [B][Hq][Wq]; g sits at its own coordinates, x is split into the stride^2 parity planes the conv reads, shifted by a
-    margin m = ceil(pad/stride) so that every tap is a non-negative linear offset (dyq+m)*Wq + (dxq+m)."""
+    """x [B,I,H,W], g [B,O,OH,OW] -> gw [O,I,k,k]: one GEMM over the B*OH*OW output pixels per tap (csrc/wgrad.cu).  Both
+    operands are read as NHWC bf16 -- the layout the forward / dgrad kernels use; tap (ky,kx) shifts x by (ky-p, kx-p)."""
     B, I, H, W = x.shape
     _, O, OH, OW = g.shape
-    s = stride
-    m = (pad + s - 1) // s
-    dmax = ((k - 1 - pad) - ((k - 1 - pad) % s)) // s
-    Hq = OH + dmax + m                                    # last row a tap reads: (OH-1) + dmax + m
-    Wq = (OW + dmax + m + 7) // 8 * 8                     # no wrap into the next row: (OW-1) + dmax + m < Wq
-    xp = to_cpl(x, s, s * m, s * m, Hq, Wq)               # [s*s*I, L]
-    gp = to_cpl(g, 1, 0, 0, Hq, Wq)                       # [O, L]
-    L = B * Hq * Wq
-    taps = []
-    for ky in range(k):
-        py, dyq = (ky - pad) % s, ((ky - pad) - (ky - pad) % s) // s
-        for kx in range(k):
-            px, dxq = (kx - pad) % s, ((kx - pad) - (kx - pad) % s) // s
-            taps.append((py * s + px, (dyq + m) * Wq + (dxq + m)))
+    xq = ops.nchw_to_nhwc_bf16(x)
+    gq = ops.nchw_to_nhwc_bf16(g)
+    shifts = [(ky - pad, kx - pad) for ky in range(k) for kx in range(k)]
     if O >= I:          # the larger channel count takes the 128-row M side, the smaller one the N side (>= 16 wide)
-        dw = wgrad_gemm(gp, xp, O, I, 1, s * s, L, [(0, 0, sl, off) for (sl, off) in taps])         # [t][o][i]
+        dw = conv_wgrad(gq, xq, O, I, B, OH, OW, [(0, 0, dy, dx) for (dy, dx) in shifts], 1, stride)      # [t][o][i]
         return dw.permute(1, 2, 0).reshape(O, I, k, k).contiguous()
-    dw = wgrad_gemm(xp, gp, I, O, s * s, 1, L, [(sl, off, 0, 0) for (sl, off) in taps])             # [t][i][o]
+    dw = conv_wgrad(xq, gq, I, O, B, OH, OW, [(dy, dx, 0, 0) for (dy, dx) in shifts], stride, 1)          # [t][i][o]
     return dw.permute(2, 1, 0).reshape(O, I, k, k).contiguous()
 
 

@@ -193,7 +193,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
                tab_per_sample=False, noise=None, noise_per_sample=True, noise_w=None, residual=None,
                rgb=None, block_n=0, tile_w=0, tile_h=0, stride_x=0, stride_y=0, x_pixstride=0, x_rowstride=0,
                x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None, ksplit=0, upmode=False,
-               out_cgroup_ow_shrink=0, algo_flops=None, residual_up=None, out_pitch_h=0, out_pitch_w=0):
+               out_cgroup_ow_shrink=0, algo_flops=None, residual_up=None, out_pitch_h=0, out_pitch_w=0, phases=None):
     """Launch fm_conv_igemm.  x: bf16 NHWC [B,H,W,cs]; w: bf16 [slabs, w_rows, cin_stride];
     out: bf16 NHWC [B,out_H,out_W,cs_out] or fp32 NCHW; tab: fp32 [B|1, Cout, 8]."""
     d = ConvDesc()
@@ -231,6 +231,10 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     ws = _splitk_workspace(x.device)
     d.splitk_ws, d.splitk_ws_bytes, d.ksplit = ws.data_ptr(), ws.numel() * 4, ksplit
     d.upmode = 1 if upmode else 0
+    if phases is not None:               # [(ntaps, out_y0, out_x0)]: several output phases in one launch (taps concatenated)
+        d.nphases = len(phases)
+        for i, (nt, py0, px0) in enumerate(phases):
+            d.phase_ntaps[i], d.phase_out_y0[i], d.phase_out_x0[i] = nt, py0, px0
     prof = PROFILE
     with torch.cuda.device(x.device):
         if prof is not None:

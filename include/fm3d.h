@@ -172,6 +172,14 @@ typedef struct {
    * synthesis engine stores every activation that feeds a stride-2 transposed conv with one zero row and column of
    * padding, so that the batch is ONE tall image whose separator rows are the conv's zero padding. */
   int32_t out_pitch_h, out_pitch_w;
+  /* nphases > 1: ONE launch computes several output phases of a stride-2 transposed conv (stylegan2.py:276) that
+   * share the input tensor and the tile grid: the tap list is the concatenation of the phases' tap lists
+   * (phase_ntaps[i] taps each, 4/2/2/1 for the 3x3 kernel), phase i is written to
+   * (oy*out_ys + phase_out_y0[i], ox*out_xs + phase_out_x0[i]); out_y0 / out_x0 are ignored.  The phase is a tile
+   * coordinate of the persistent grid, so the weight-bound 1- and 2-tap tiles run next to the tensor-bound 4-tap tiles
+   * instead of in launches of their own.  Stride 1, ungrouped, halo-patch eligible shapes only (OH >= 12, OW >= 8). */
+  int32_t nphases;
+  int32_t phase_ntaps[4], phase_out_y0[4], phase_out_x0[4];
 } fm_conv_desc;
 
 int fm_conv_igemm(const fm_conv_desc* desc, void* stream);
@@ -246,42 +254,37 @@ int fm_prep_weight(void* wq, float* wsq, const float* w_oikk, int cout, int cin,
 /* ------------------------------------------------------------------------------------
  * Weight gradient of a convolution (training, BASELINE config 4).
  * Replaces the wgrad half of ATen autograd over F.conv2d / F.conv_transpose2d
- * (stylegan2.py:129,276,285,291; cuDNN in the reference).  With activations x and the
- * upstream gradient g stored channel-major / pixel-linear ("CPL", bf16 [channels][B*Hq*Wq],
- * made by fm_nchw_to_cpl_bf16), dL/dW is one GEMM over pixels on the tcgen05 tensor cores:
+ * (stylegan2.py:129,276,285,291; cuDNN in the reference).  dL/dW is one GEMM over pixels on the
+ * tcgen05 tensor cores, reading both operands as NHWC bf16 (the layout of fm_conv_igemm):
  *
- *   dw[t*dw_tap_stride + a*dw_row_stride + b] +=
- *       sum_{l in [0,L)}  A[(tap_slab_a[t]*Ca + a)][l + tap_off_a[t]] * Bm[(tap_slab_b[t]*Cb + b)][l + tap_off_b[t]]
+ *   dw[t*dw_tap_stride + ca*dw_row_stride + cb] +=
+ *       sum_{n < B, gy < GH, gx < GW}  a[n, gy*a.stride + tap_dy_a[t], gx*a.stride + tap_dx_a[t], ca]
+ *                                    * b[n, gy*b.stride + tap_dy_b[t], gx*b.stride + tap_dx_b[t], cb]
  *
- * (fp32 atomics: dw must be zero-initialised by the caller; positions outside a row read as 0).
- * A conv tap (ky,kx) is the linear offset ky*Wq + kx into a zero-haloed pixel grid, a stride-2
- * conv reads one of the 4 parity planes (slabs) of its input.  dL/dW of the modulated conv in
- * its shared-weight form (one wgrad GEMM over M = B*HW on d*g and s*x) is this
- * call with the two scalings folded into the layout pass.
+ * (fp32 atomics: dw must be zero-initialised by the caller; pixels outside an operand read as 0 --
+ * the conv's zero padding).  For y = conv(x, w, stride s, padding p): the grid is y's, a = dL/dy
+ * (stride 1, no shift), b = x (stride s, shift (ky - p, kx - p)) or the two swapped (the operand with
+ * fewer channels should be b).  dL/dW of the modulated conv in its shared-weight form (SURVEY
+ * Appendix D: one wgrad GEMM over M = B*HW on d*g and s*x) is this call on the scaled tensors.
  * ---------------------------------------------------------------------------------- */
 typedef struct {
-  const void* a;            /* bf16 [nslabs_a*Ca][La] */
-  const void* b;            /* bf16 [nslabs_b*Cb][Lb] */
-  int32_t Ca, Cb, nslabs_a, nslabs_b;
-  int64_t La, Lb;           /* row lengths in elements (multiples of 8) */
-  int64_t L;                /* contraction length */
+  const void* ptr;          /* bf16 NHWC [B][H][W][cstride] */
+  int32_t C, cstride;       /* logical channels, physical channel stride (multiple of 8) */
+  int32_t H, W;
+  int32_t stride;           /* 1 or 2: step of this operand per grid pixel */
+} fm_wgrad_operand;
+
+typedef struct {
+  fm_wgrad_operand a, b;
+  int32_t B, GH, GW;        /* contraction grid */
   int32_t ntaps;
-  int32_t tap_off_a[FM_MAX_TAPS], tap_off_b[FM_MAX_TAPS];
-  int8_t tap_slab_a[FM_MAX_TAPS], tap_slab_b[FM_MAX_TAPS];
+  int8_t tap_dy_a[FM_MAX_TAPS], tap_dx_a[FM_MAX_TAPS], tap_dy_b[FM_MAX_TAPS], tap_dx_b[FM_MAX_TAPS];
   float* dw;                /* fp32, accumulated into */
   int64_t dw_tap_stride;
   int32_t dw_row_stride;
   int32_t ksplit;           /* 0 = choose (split-K over pixels so that every SM has work) */
 } fm_wgrad_desc;
-int fm_wgrad_gemm(const fm_wgrad_desc* desc, void* stream);
-
-/* fp32 NCHW [B,C,H,W] -> bf16 CPL [s*s][C][B][Hq][Wq] (Wq a multiple of 8):
- *   dst[py*s+px][c][b][yq][xq] = scale_bc[b*C+c] * src[b][c][yq*s + py - y0][xq*s + px - x0]   (0 outside the image)
- * s = 1: zero-haloed copy (y0 = x0 = conv padding); s = 2: the four parity planes a stride-2 conv
- * (or the gradient of a stride-2 transposed conv) reads.  scale_bc may be NULL; it carries the
- * style modulation s[b,i] of x or the demodulation d[b,o] of g (stylegan2.py:257-262). */
-int fm_nchw_to_cpl_bf16(void* dst, const float* src, const float* scale_bc, int B, int C, int H, int W,
-                        int s, int y0, int x0, int Hq, int Wq, void* stream);
+int fm_conv_wgrad(const fm_wgrad_desc* desc, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Encoder-path helpers (NHWC bf16, bandwidth-bound).  They replace the ATen kernels behind

@@ -56,12 +56,12 @@ def test_conv_desc_layout_matches_header():
 
 
 def test_wgrad_desc_layout_matches_header():
-    """fm_wgrad_desc vs its ctypes mirror, and argument validation of the two training entry points without a GPU."""
+    """fm_wgrad_desc vs its ctypes mirror, and argument validation of the training entry point without a GPU."""
     import subprocess
     import tempfile
     from fm3d import _lib
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "fm3d.h"\nint main(){printf("%zu %zu %zu %zu %zu",' \
-          'sizeof(fm_wgrad_desc),offsetof(fm_wgrad_desc,L),offsetof(fm_wgrad_desc,tap_off_b),offsetof(fm_wgrad_desc,dw),' \
+          'sizeof(fm_wgrad_desc),offsetof(fm_wgrad_desc,GW),offsetof(fm_wgrad_desc,tap_dy_b),offsetof(fm_wgrad_desc,dw),' \
           'offsetof(fm_wgrad_desc,ksplit));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
@@ -69,8 +69,7 @@ def test_wgrad_desc_layout_matches_header():
         out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
     size, off_l, off_tb, off_dw, off_ks = map(int, out)
     assert ctypes.sizeof(_lib.WgradDesc) == size
-    assert _lib.WgradDesc.L.offset == off_l and _lib.WgradDesc.tap_off_b.offset == off_tb
+    assert _lib.WgradDesc.GW.offset == off_l and _lib.WgradDesc.tap_dy_b.offset == off_tb
     assert _lib.WgradDesc.dw.offset == off_dw and _lib.WgradDesc.ksplit.offset == off_ks
     lib = _lib.lib()
-    assert lib.fm_wgrad_gemm(None, None) == 1 and b"null" in lib.fm_last_error()
-    assert lib.fm_nchw_to_cpl_bf16(None, None, None, 1, 1, 1, 1, 1, 0, 0, 1, 8, None) == 1
+    assert lib.fm_conv_wgrad(None, None) == 1 and b"null" in lib.fm_last_error()

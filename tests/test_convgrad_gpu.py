@@ -1,5 +1,5 @@
 """Differentiable convolutions on the tcgen05 kernels (fm3d/convgrad.py: fm_conv_igemm for forward and dgrad,
-fm_wgrad_gemm for the weight gradient) against ATen autograd in strict fp32: forward, first-order gradients and the
+fm_conv_wgrad for the weight gradient) against ATen autograd in strict fp32: forward, first-order gradients and the
 second-order passes R1 / path-length regularisation need.  Operands are rounded to bf16, so the tolerance is 2e-2 of
 each tensor's max magnitude (measured ~4e-3)."""
 import pytest
@@ -106,40 +106,32 @@ def test_double_backward(cuda, kind, B, I, O, H, k, s, p):
     assert max(errs[:3]) < 2e-2 and max(errs[3:]) < 4e-2, errs
 
 
-def test_wgrad_gemm_direct(cuda):
-    """fm_wgrad_gemm on hand-made CPL operands: slabs, positive / negative offsets, ragged channel counts, split-K."""
+def test_conv_wgrad_direct(cuda):
+    """fm_conv_wgrad on hand-made NHWC operands: ragged channel counts (3, 40, 136), shifts on either operand, a strided
+    operand, grids that do not fill the 64-pixel K chunk, forced split-K."""
     from fm3d import convgrad
     g = torch.Generator(device=cuda).manual_seed(3)
-    Ca, Cb, L = 136, 40, 1000
-    a = torch.randn(2 * Ca, 1008, generator=g, device=cuda).to(torch.bfloat16)
-    b = torch.randn(3 * Cb, 1040, generator=g, device=cuda).to(torch.bfloat16)
-    taps = [(0, 0, 0, 0), (1, 0, 2, 5), (0, 3, 1, 0), (1, -2, 0, 7)]
-    for ksplit in (0, 1, 5):
-        dw = convgrad.wgrad_gemm(a, b, Ca, Cb, 2, 3, L, taps, ksplit=ksplit)
-        for t, (sa, oa, sb, ob) in enumerate(taps):
-            A = torch.zeros(Ca, L, device=cuda); Bm = torch.zeros(Cb, L, device=cuda)
-            la = torch.arange(L, device=cuda) + oa
-            lb = torch.arange(L, device=cuda) + ob
-            ma, mb = (la >= 0) & (la < a.shape[1]), (lb >= 0) & (lb < b.shape[1])
-            A[:, ma] = a[sa * Ca:(sa + 1) * Ca][:, la[ma]].float()
-            Bm[:, mb] = b[sb * Cb:(sb + 1) * Cb][:, lb[mb]].float()
-            ref = A @ Bm.t()
-            assert _rel(dw[t], ref) < 2e-3, (ksplit, t, _rel(dw[t], ref))
-
-
-def test_cpl_layout(cuda):
-    from fm3d import convgrad
-    x = torch.randn(2, 5, 7, 9, device=cuda)
-    sc = torch.rand(2, 5, device=cuda) + 0.5
-    out = convgrad.to_cpl(x, 2, 2, 2, 6, 8, sc)          # parity planes with one margin row / column
-    assert out.shape == (4 * 5, 2 * 6 * 8)
-    ref = torch.zeros(2, 2, 5, 2, 6, 8)
-    xs = (x * sc[:, :, None, None]).cpu()
-    for py in range(2):
-        for px in range(2):
-            for yq in range(6):
-                for xq in range(8):
-                    y, xx = yq * 2 + py - 2, xq * 2 + px - 2
-                    if 0 <= y < 7 and 0 <= xx < 9:
-                        ref[py, px, :, :, yq, xq] = xs[:, :, y, xx].t()
-    assert torch.equal(out.float().cpu().view(2, 2, 5, 2, 6, 8), ref.to(torch.bfloat16).float())
+    B, GH, GW = 3, 6, 10
+    for (Ca, Cb, sa, sb) in ((136, 40, 1, 1), (64, 3, 1, 2), (200, 264, 2, 1)):
+        cs = lambda c: (c + 7) // 8 * 8
+        Ha, Wa, Hb, Wb = GH * sa + 1, GW * sa + 1, GH * sb + 2, GW * sb + 2
+        a = torch.zeros(B, Ha, Wa, cs(Ca), device=cuda, dtype=torch.bfloat16)
+        b = torch.zeros(B, Hb, Wb, cs(Cb), device=cuda, dtype=torch.bfloat16)
+        a[..., :Ca] = torch.randn(B, Ha, Wa, Ca, generator=g, device=cuda).to(torch.bfloat16)
+        b[..., :Cb] = torch.randn(B, Hb, Wb, Cb, generator=g, device=cuda).to(torch.bfloat16)
+        taps = [(0, 0, 0, 0), (0, 1, 1, 2), (1, 0, -1, -1), (-1, -1, 2, 0)]
+        for ksplit in (0, 1, 3):
+            dw = convgrad.conv_wgrad(a, b, Ca, Cb, B, GH, GW, taps, sa, sb, ksplit=ksplit)
+            for t, (dya, dxa, dyb, dxb) in enumerate(taps):
+                def gather(src, C_, s, dy, dx, H_, W_):
+                    out = torch.zeros(B, GH, GW, C_, device=cuda)
+                    for gy in range(GH):
+                        for gx in range(GW):
+                            y, x = gy * s + dy, gx * s + dx
+                            if 0 <= y < H_ and 0 <= x < W_:
+                                out[:, gy, gx] = src[:, y, x, :C_].float()
+                    return out.reshape(-1, C_)
+                A = gather(a, Ca, sa, dya, dxa, Ha, Wa)
+                Bm = gather(b, Cb, sb, dyb, dxb, Hb, Wb)
+                ref = A.t() @ Bm
+                assert _rel(dw[t], ref) < 2e-3, (Ca, Cb, ksplit, t, _rel(dw[t], ref))

@@ -240,9 +240,11 @@ def main_ours(args):
     noise4 = [torch.randn(4, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), generator=torch.Generator().manual_seed(40 + i)).to(dev)
               for i in range(13)]
     parity = {}
-    for mode in ("engine_bf16", "composition_fp32"):
+    for mode in ("engine_bf16", "composition_native_bf16", "composition_fp32"):
+        if mode != "engine_bf16":
+            os.environ["FM3D_ENGINE"] = "0"           # module-by-module composition (the autograd-capable path) ...
         if mode == "composition_fp32":
-            os.environ["FM3D_ENGINE"] = "0"
+            os.environ["FM3D_NATIVE_GRAD"] = "0"      # ... on ATen convolutions in strict fp32: pins the algebra itself
         try:
             with torch.no_grad():
                 t4, w4, wp4 = e_tsr(r[:4]), e_w(r[:4]), e_wp(p[:4])
@@ -253,14 +255,17 @@ def main_ours(args):
                          use_external_input_tensor=True, external_input_tensor=rt)
         finally:
             os.environ.pop("FM3D_ENGINE", None)
+            os.environ.pop("FM3D_NATIVE_GRAD", None)
         parity[mode] = {"e_tsr_rel": rel(t4, ref["enc"]["e_tsr"]), "e_w_rel": rel(w4, ref["enc"]["e_w"]),
                         "e_wp_rel": rel(wp4, ref["enc"]["e_wp"]), "generator_image_rel": rel(img4, ref["enc"]["img"]),
                         "generator_image_max_abs": mabs(img4, ref["enc"]["img"])}
     os.environ["FM3D_ENGINE"] = "0"
+    os.environ["FM3D_NATIVE_GRAD"] = "0"
     try:
         mine = layer_dump(g, *small_inputs(dev))
     finally:
         os.environ.pop("FM3D_ENGINE", None)
+        os.environ.pop("FM3D_NATIVE_GRAD", None)
     layers = {k: {"max_abs": mabs(mine[k], v), "rel": rel(mine[k], v)} for k, v in ref["layers"].items()}
     with torch.no_grad():
         lat, ext, noise = small_inputs(dev)
