@@ -1055,6 +1055,21 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   const int G = d->groups > 1 ? d->groups : 1;
   FM_CHECK_ARG(d->B % G == 0, "fm_conv_igemm: batch %d not divisible by groups %d", d->B, G);
   const int Bg = d->B / G;
+  const int nph = d->nphases > 1 ? d->nphases : 1;
+  int ph_tmin = d->ntaps;
+  if (nph > 1) {
+    FM_CHECK_ARG(nph <= 4 && sx == 1 && sy == 1 && G == 1 && !d->upmode && !d->rgb && !d->residual && !d->border_tab && !d->noise,
+                 "fm_conv_igemm: nphases > 1 needs a stride-1 ungrouped conv without rgb / residual / border_tab / noise");
+    int tot = 0;
+    for (int i = 0; i < nph; ++i) {
+      FM_CHECK_ARG(d->phase_ntaps[i] >= 1 && d->phase_out_y0[i] >= 0 && d->phase_out_x0[i] >= 0, "fm_conv_igemm: bad phase %d", i);
+      FM_CHECK_ARG((d->OH - 1) * d->out_ys + d->phase_out_y0[i] < d->out_H && (d->OW - 1) * d->out_xs + d->phase_out_x0[i] < d->out_W,
+                   "fm_conv_igemm: phase %d does not fit the output tensor", i);
+      tot += d->phase_ntaps[i];
+      if (d->phase_ntaps[i] < ph_tmin) ph_tmin = d->phase_ntaps[i];
+    }
+    FM_CHECK_ARG(tot == d->ntaps, "fm_conv_igemm: phase_ntaps sum to %d, ntaps is %d", tot, d->ntaps);
+  }
 
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) { set_error("fm_conv_igemm: cuTensorMapEncodeTiled driver entry point unavailable"); return FM_ERR_NO_DEVICE; }
@@ -1081,7 +1096,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   int ksplit = 1;
   {
     static const int env_split = []() { const char* e = getenv("FM3D_SPLITK"); return e ? atoi(e) : 1; }();
-    const bool eligible = env_split && d->tab && d->residual_up_h <= 0 && d->ksplit != 1 && d->splitk_ws && !d->rgb && !d->border_tab && !d->out_nchw_f32 &&
+    const bool eligible = env_split && nph == 1 && d->tab && d->residual_up_h <= 0 && d->ksplit != 1 && d->splitk_ws && !d->rgb && !d->border_tab && !d->out_nchw_f32 &&
                           !d->out_cgroup && d->block_n <= 0 && !d->upmode;
     if (eligible) {
       const int bn_wide = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
@@ -1171,7 +1186,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     bool std33 = d->ntaps == 9 && sx == 1 && sy == 1 && d->x_pixstride == 0 && d->x_rowstride == 0 && d->x_imgstride == 0;
     for (int i = 0; std33 && i < 9; ++i)
       std33 = d->tap_dy[i] == i / 3 - 1 && d->tap_dx[i] == i % 3 - 1 && d->tap_widx[i] == i;
-    p.patch = (env_patch && std33 && tw == 128 && th == 1 && tb == 1 && bn <= 128 && p.ksplit == 1 && !d->upmode) ? 1 : 0;
+    p.patch = (env_patch && nph == 1 && std33 && tw == 128 && th == 1 && tb == 1 && bn <= 128 && p.ksplit == 1 && !d->upmode) ? 1 : 0;
     if (p.patch) {
       int R = env_rows > 0 ? env_rows : (bn == 64 ? 4 : 2);
       while (R > 1 && (2 * R * bn > 512 || R > d->OH)) R >>= 1;
@@ -1258,11 +1273,13 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       // The patch of virtual chunk c + D is requested when the weights of chunk c start; its slot was last read
       // by chunk c + D - NA (NA = D + E, E >= 2), whose MMAs only need loads issued earlier: no deadlock, and with
       // S <= (E - 1) * T + 1 weight stages (T = taps per virtual chunk) the request does not even block.
-      const int T = (d->ntaps + np - 1) / np;
+      // several phases in one launch: the weight cursor may run S / T chunks ahead of the MMAs, with T the SMALLEST
+      // phase (a 1-tap phase: one weight tile per chunk), so more patch slots are kept behind the prefetch distance
+      const int T = nph > 1 ? ph_tmin : (d->ntaps + np - 1) / np;
       const int bbytes = bn * 128;
       const int st_max = bn == 256 ? 4 : (bn == 128 ? 6 : 8);
-      int D = T >= 5 ? 2 : (T >= 3 ? 3 : 4);
-      const int E = T >= 3 ? 2 : 3;
+      int D = nph > 1 ? 2 : (T >= 5 ? 2 : (T >= 3 ? 3 : 4));
+      const int E = nph > 1 ? 4 : (T >= 3 ? 2 : 3);
       int st = 0;
       for (; D >= 1; --D) {
         st = (200 * 1024 - (D + E) * p.hp_bytes) / bbytes;
@@ -1314,7 +1331,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     // of a tile at 2x its tensor-pipe time with ~470 clk per TMA box: the ring depth over the load latency was the limit.
     if (p.hp) {
       static const int env_deep = []() { const char* e = getenv("FM3D_HP_DEEP"); return e ? atoi(e) : 1; }();
-      const int np = p.hp_np, T = (d->ntaps + np - 1) / np, E = p.hp_na - p.hp_dist;
+      const int np = p.hp_np, T = nph > 1 ? ph_tmin : (d->ntaps + np - 1) / np, E = p.hp_na - p.hp_dist;
       const int bstride = p.pair ? bn * 64 : bn * 128;
       int st = (200 * 1024 - p.hp_na * p.hp_bytes) / bstride;
       if (st > IG_MAX_STAGES) st = IG_MAX_STAGES;
@@ -1330,7 +1347,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       static const int env_hpw_min = []() { const char* e = getenv("FM3D_HPW_MIN"); return e ? atoi(e) : 2; }();
       // two patch slots are enough to keep the weights resident (128 -> 128 pair layers: 144 KB of weights + 2 x 23 KB):
       // the next chunk's patch loads while the current chunk's 36 MMAs run
-      if (env_hpw && p.tiles_n == 1 && na >= env_hpw_min) {
+      if (env_hpw && nph == 1 && p.tiles_n == 1 && na >= env_hpw_min) {
         p.hpw = 1;
         p.hp_na = na;
       }
@@ -1351,6 +1368,25 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       }
     }
     p.num_super = p.tiles_n * p.ksplit * ((p.m_tiles + cs - 1) / cs);
+    p.nph = nph;
+    p.nsup1 = p.num_super;
+    if (nph > 1) {
+      if (!p.hp) {
+        set_error("fm_conv_igemm: nphases > 1 needs the halo-patch mode (OH >= 12, OW >= 8, dense NHWC input, FM3D_HPATCH != 0)");
+        return FM_ERR_UNSUPPORTED;
+      }
+      int first = 0;
+      for (int i = 0; i < nph; ++i) {
+        p.ph_first[i] = static_cast<int8_t>(first);
+        p.ph_oy0[i] = static_cast<int16_t>(d->phase_out_y0[i]);
+        p.ph_ox0[i] = static_cast<int16_t>(d->phase_out_x0[i]);
+        first += d->phase_ntaps[i];
+      }
+      p.ph_first[nph] = static_cast<int8_t>(first);
+      const int64_t tot = static_cast<int64_t>(p.num_super) * nph;
+      FM_CHECK_ARG(tot < 0x7FFFFFFF, "fm_conv_igemm: too many tiles");
+      p.num_super = static_cast<int>(tot);
+    }
   }
   // ---- tensor maps
   CUtensorMap tmA, tmB;

@@ -267,6 +267,18 @@ extern "C" int fm_conv_wgrad(const fm_wgrad_desc* d, void* stream) {
     FM_CHECK_ARG((reinterpret_cast<uintptr_t>(o->ptr) & 15) == 0, "fm_conv_wgrad: operands must be 16-byte aligned");
   }
   FM_CHECK_ARG(d->dw_row_stride >= d->b.C, "fm_conv_wgrad: dw_row_stride < Cb");
+  {
+    // K chunks are 64-pixel tiles that may reach past the grid: one operand must BE the grid (same size, stride 1, no
+    // shift), so that its out-of-bounds zero fill masks those pixels (for a conv: dL/dy)
+    auto is_grid = [&](const fm_wgrad_operand& o, const int8_t* dy, const int8_t* dx) {
+      if (o.H != d->GH || o.W != d->GW || o.stride != 1) return false;
+      for (int i = 0; i < d->ntaps; ++i)
+        if (dy[i] != 0 || dx[i] != 0) return false;
+      return true;
+    };
+    FM_CHECK_ARG(is_grid(d->a, d->tap_dy_a, d->tap_dx_a) || is_grid(d->b, d->tap_dy_b, d->tap_dx_b),
+                 "fm_conv_wgrad: one operand must be the contraction grid itself (H = GH, W = GW, stride 1, zero tap offsets)");
+  }
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) { set_error("fm_conv_wgrad: cuTensorMapEncodeTiled driver entry point unavailable"); return FM_ERR_NO_DEVICE; }
 

@@ -38,6 +38,9 @@ import os
 # Cout <= 128 up-convs: the two column parities of an output-row parity share one launch as a 2*Cout-wide GEMM
 # (N = 256 tiles instead of N = 128: the tensor pipe is no longer starved by the per-SM L2 fill rate)
 _PAIR_UP = os.environ.get("FM3D_UPPAIR", "1") != "0"
+# all output-parity phases of an up-conv in ONE launch (the phase is a tile coordinate of the persistent grid): the
+# weight-bound 1- and 2-tap tiles interleave with the tensor-bound 4-tap tiles instead of running in launches of their own
+_MERGE_UP = os.environ.get("FM3D_UPMERGE", "1") != "0"
 
 # views (dy, dx) of the input a stride-2 transposed 3x3 conv reads, and for each output-row parity py the
 # (view, tap of column parity 0, tap of column parity 1 or None) triples -- see _up_phase_taps
@@ -64,7 +67,7 @@ def _up_phase_taps(py, px):
 class _ConvLayer:
     """One modulated 3x3 conv of the plan."""
     __slots__ = ("mod", "act_bias", "noise_w", "cin", "cout", "up", "res_in", "res_out", "latent_idx",
-                 "wq", "wsq", "s", "tab", "rgb_mod", "next_idx", "kernel", "name", "wpair")
+                 "wq", "wsq", "s", "tab", "rgb_mod", "next_idx", "kernel", "name", "wpair", "wpair_all")
 
 
 class SynthesisPlan:
@@ -169,14 +172,16 @@ class SynthesisPlan:
             w = L.mod.weight.detach()[0]
             if rebuild:
                 L.wq, L.wsq = ops.prep_weight(w, L.mod.scale, want_wsq=True)
-                L.wpair = None
+                L.wpair = L.wpair_all = None
             else:
                 ops.prep_weight(w, L.mod.scale, want_wsq=True, out=(L.wq, L.wsq))
             if L.up and _PAIR_UP and L.cout % 32 == 0 and L.cout <= 128 and L.res_in >= 12:
                 # [view][P_x0 rows | P_x1 rows][cin]: zero block where the odd column parity has no tap for the view
                 if rebuild:
-                    L.wpair = {py: torch.zeros(len(views), 2 * L.cout, L.wq.shape[2], device=dev, dtype=torch.bfloat16)
-                               for py, views in _PAIR_VIEWS.items()}
+                    # one tensor behind both row parities (views 0-3 | 4-5), so that one launch can address either
+                    n0 = len(_PAIR_VIEWS[0])
+                    L.wpair_all = torch.zeros(n0 + len(_PAIR_VIEWS[1]), 2 * L.cout, L.wq.shape[2], device=dev, dtype=torch.bfloat16)
+                    L.wpair = {0: L.wpair_all[:n0], 1: L.wpair_all[n0:]}
                 for py, views in _PAIR_VIEWS.items():
                     wp = L.wpair[py]
                     for v, (_, t0, t1) in enumerate(views):
@@ -260,7 +265,26 @@ class SynthesisPlan:
         th_ = 128 // tw_
         kw = dict(B=1, H=Ht, W=Wt, Cin=L.cin, OH=Ht, OW=Wt, out_H=B * (2 * h + 2), out_W=2 * h + 2, out_ys=2, out_xs=2,
                   tab_per_sample=False, tile_w=tw_, tile_h=th_)
-        if L.wpair is not None:
+        # halo-patch eligibility of the tall image (igemm.cu): only then can the phase be a tile coordinate
+        merged = _MERGE_UP and Wt >= 8 and Ht >= 12
+        if merged and L.wpair is not None:
+            cs_t = t.shape[-1]
+            taps, phases, v0 = [], [], 0
+            for py, views in _PAIR_VIEWS.items():
+                taps += [(dy, dx, v0 + v) for v, ((dy, dx), _, _) in enumerate(views)]
+                phases.append((len(views), py, 0))
+                v0 += len(views)
+            ops.conv_igemm(x, L.wpair_all, taps, t, None, Cout=2 * L.cout, out_cgroup=L.cout, out_gstride=cs_t,
+                           out_cstride=cs_t, algo_flops=up_flops * 9, phases=phases, **kw)
+        elif merged:
+            taps, phases = [], []
+            for py in (0, 1):
+                for px in (0, 1):
+                    tp = _up_phase_taps(py, px)
+                    taps += tp
+                    phases.append((len(tp), py, px))
+            ops.conv_igemm(x, L.wq, taps, t, None, Cout=L.cout, algo_flops=up_flops * 9, phases=phases, **kw)
+        elif L.wpair is not None:
             # one launch per output-row parity: N = [even columns | odd columns] (2*Cout wide)
             cs_t = t.shape[-1]
             for py, views in _PAIR_VIEWS.items():

@@ -262,7 +262,8 @@ int fm_prep_weight(void* wq, float* wsq, const float* w_oikk, int cout, int cin,
  *                                    * b[n, gy*b.stride + tap_dy_b[t], gx*b.stride + tap_dx_b[t], cb]
  *
  * (fp32 atomics: dw must be zero-initialised by the caller; pixels outside an operand read as 0 --
- * the conv's zero padding).  For y = conv(x, w, stride s, padding p): the grid is y's, a = dL/dy
+ * the conv's zero padding).  One operand must BE the grid (H = GH, W = GW, stride 1, zero tap offsets): its
+ * out-of-bounds zero fill masks the pixels of the last 64-pixel K chunk that lie beyond the grid.  For y = conv(x, w, stride s, padding p): the grid is y's, a = dL/dy
  * (stride 1, no shift), b = x (stride s, shift (ky - p, kx - p)) or the two swapped (the operand with
  * fewer channels should be b).  dL/dW of the modulated conv in its shared-weight form (SURVEY
  * Appendix D: one wgrad GEMM over M = B*HW on d*g and s*x) is this call on the scaled tensors.

@@ -107,31 +107,33 @@ def test_double_backward(cuda, kind, B, I, O, H, k, s, p):
 
 
 def test_conv_wgrad_direct(cuda):
-    """fm_conv_wgrad on hand-made NHWC operands: ragged channel counts (3, 40, 136), shifts on either operand, a strided
-    operand, grids that do not fill the 64-pixel K chunk, forced split-K."""
+    """fm_conv_wgrad on hand-made NHWC operands: ragged channel counts (3, 40, 136), a shifted / strided operand on either
+    side, grids that do not fill the 64-pixel K chunk, forced split-K.  Contract: one operand IS the grid (H = GH, W = GW,
+    stride 1, no shift) -- its out-of-bounds zero fill masks the tile pixels beyond the grid."""
     from fm3d import convgrad
     g = torch.Generator(device=cuda).manual_seed(3)
     B, GH, GW = 3, 6, 10
-    for (Ca, Cb, sa, sb) in ((136, 40, 1, 1), (64, 3, 1, 2), (200, 264, 2, 1)):
-        cs = lambda c: (c + 7) // 8 * 8
-        Ha, Wa, Hb, Wb = GH * sa + 1, GW * sa + 1, GH * sb + 2, GW * sb + 2
-        a = torch.zeros(B, Ha, Wa, cs(Ca), device=cuda, dtype=torch.bfloat16)
-        b = torch.zeros(B, Hb, Wb, cs(Cb), device=cuda, dtype=torch.bfloat16)
-        a[..., :Ca] = torch.randn(B, Ha, Wa, Ca, generator=g, device=cuda).to(torch.bfloat16)
-        b[..., :Cb] = torch.randn(B, Hb, Wb, Cb, generator=g, device=cuda).to(torch.bfloat16)
-        taps = [(0, 0, 0, 0), (0, 1, 1, 2), (1, 0, -1, -1), (-1, -1, 2, 0)]
+    cs = lambda c: (c + 7) // 8 * 8
+    for (Cg, Cs, s, swap) in ((136, 40, 1, False), (64, 3, 2, False), (200, 264, 2, True), (24, 130, 1, True)):
+        Hs, Ws = GH * s + 2, GW * s + 1
+        grid = torch.zeros(B, GH, GW, cs(Cg), device=cuda, dtype=torch.bfloat16)
+        other = torch.zeros(B, Hs, Ws, cs(Cs), device=cuda, dtype=torch.bfloat16)
+        grid[..., :Cg] = torch.randn(B, GH, GW, Cg, generator=g, device=cuda).to(torch.bfloat16)
+        other[..., :Cs] = torch.randn(B, Hs, Ws, Cs, generator=g, device=cuda).to(torch.bfloat16)
+        shifts = [(0, 0), (1, 2), (-1, -1), (2, 0)]
+        Gm = grid[..., :Cg].float().reshape(-1, Cg)
         for ksplit in (0, 1, 3):
-            dw = convgrad.conv_wgrad(a, b, Ca, Cb, B, GH, GW, taps, sa, sb, ksplit=ksplit)
-            for t, (dya, dxa, dyb, dxb) in enumerate(taps):
-                def gather(src, C_, s, dy, dx, H_, W_):
-                    out = torch.zeros(B, GH, GW, C_, device=cuda)
-                    for gy in range(GH):
-                        for gx in range(GW):
-                            y, x = gy * s + dy, gx * s + dx
-                            if 0 <= y < H_ and 0 <= x < W_:
-                                out[:, gy, gx] = src[:, y, x, :C_].float()
-                    return out.reshape(-1, C_)
-                A = gather(a, Ca, sa, dya, dxa, Ha, Wa)
-                Bm = gather(b, Cb, sb, dyb, dxb, Hb, Wb)
-                ref = A.t() @ Bm
-                assert _rel(dw[t], ref) < 2e-3, (Ca, Cb, ksplit, t, _rel(dw[t], ref))
+            if swap:      # a = shifted / strided operand, b = grid
+                dw = convgrad.conv_wgrad(other, grid, Cs, Cg, B, GH, GW, [(dy, dx, 0, 0) for (dy, dx) in shifts], s, 1, ksplit=ksplit)
+            else:
+                dw = convgrad.conv_wgrad(grid, other, Cg, Cs, B, GH, GW, [(0, 0, dy, dx) for (dy, dx) in shifts], 1, s, ksplit=ksplit)
+            for t, (dy, dx) in enumerate(shifts):
+                S = torch.zeros(B, GH, GW, Cs, device=cuda)
+                for gy in range(GH):
+                    for gx in range(GW):
+                        y, x = gy * s + dy, gx * s + dx
+                        if 0 <= y < Hs and 0 <= x < Ws:
+                            S[:, gy, gx] = other[:, y, x, :Cs].float()
+                S = S.reshape(-1, Cs)
+                ref = S.t() @ Gm if swap else Gm.t() @ S
+                assert _rel(dw[t], ref) < 2e-3, (Cg, Cs, s, swap, ksplit, t, _rel(dw[t], ref))

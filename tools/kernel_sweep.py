@@ -104,16 +104,17 @@ def sweep_modconv_up(B, h, Cin, Cout, cm):
     w = (torch.randn(9, Cout, Cin, device=dev) / (Cin * 9) ** 0.5).to(torch.bfloat16)
     tp = torch.empty(B, 2 * h + 2, 2 * h + 2, Cout, device=dev, dtype=torch.bfloat16)
     y = torch.empty(B, 2 * h, 2 * h, Cout, device=dev, dtype=torch.bfloat16)
-    L = types.SimpleNamespace(cin=Cin, cout=Cout, wq=w, wpair=None)
+    L = types.SimpleNamespace(cin=Cin, cout=Cout, wq=w, wpair=None, wpair_all=None)
     if Cout <= 128 and Cout % 32 == 0 and h >= 12:
-        L.wpair = {}
+        n0 = len(engine._PAIR_VIEWS[0])
+        L.wpair_all = torch.zeros(n0 + len(engine._PAIR_VIEWS[1]), 2 * Cout, Cin, device=dev, dtype=torch.bfloat16)
+        L.wpair = {0: L.wpair_all[:n0], 1: L.wpair_all[n0:]}
         for py, views in engine._PAIR_VIEWS.items():
-            wp = torch.zeros(len(views), 2 * Cout, Cin, device=dev, dtype=torch.bfloat16)
+            wp = L.wpair[py]
             for v, (_, t0, t1) in enumerate(views):
                 wp[v, :Cout] = w[t0]
                 if t1 is not None:
                     wp[v, Cout:] = w[t1]
-            L.wpair[py] = wp
     k = torch.tensor([1., 3., 3., 1.]); k = (k[None] * k[:, None]); k = (k / k.sum() * 4).to(dev)
     tab = torch.zeros(B, Cout, 8, device=dev); tab[..., 0] = 1; tab[..., 2] = 0.2; tab[..., 3] = 1.4
     noise = torch.randn(B, 1, 2 * h, 2 * h, device=dev)
