@@ -227,3 +227,34 @@ def conv_transpose2d(x, w, stride=1, padding=0):
     k, s, p = w.shape[2], int(stride), int(padding)
     out_hw = ((x.shape[2] - 1) * s + k - 2 * p, (x.shape[3] - 1) * s + k - 2 * p)
     return ConvBwdData.apply(x.float(), w.float(), s, p, out_hw)
+
+
+# ---------------------------------------------------------------------------------------------- nn.Conv2d on the native kernels
+class NativeConv2d(torch.nn.Conv2d):
+    """``nn.Conv2d`` whose forward runs on the tcgen05 kernels (forward, dgrad, wgrad; closed under double backward).
+    Instances are made by re-classing existing modules (``use_native_convs``): parameters, buffers, state-dict keys and
+    ``isinstance(m, nn.Conv2d)`` are unchanged, and copies / pickles of the module keep working."""
+
+    def forward(self, x):
+        import os
+        if x.is_cuda and x.dtype == torch.float32 and x.ndim == 4 and os.environ.get("FM3D_NATIVE_GRAD", "1") != "0":
+            return conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0])
+        return super().forward(x)
+
+
+def use_native_convs(module):
+    """Route every eligible ``nn.Conv2d`` inside ``module`` (square kernel up to 7x7, symmetric stride 1 / 2 and zero
+    padding, no dilation, groups = 1) through ``convgrad.conv2d``.  Used for the encoders in training
+    (resnet_encoder.py:36,42,193; helpers.py:80-131; psp_encoders.py:27-31) and for frozen loss networks on the gradient
+    path of the image (LPIPS-VGG16 lpips/networks_basic.py:36-101, ArcFace Util/arcface_pytorch: SURVEY 8f rank 2).
+    Returns the number of convolutions switched."""
+    n = 0
+    for m in module.modules():
+        if type(m) is torch.nn.Conv2d:
+            ok = (m.groups == 1 and m.dilation == (1, 1) and m.kernel_size[0] == m.kernel_size[1] and
+                  m.stride[0] == m.stride[1] and m.stride[0] in (1, 2) and isinstance(m.padding, tuple) and
+                  m.padding[0] == m.padding[1] and m.padding_mode == "zeros" and m.kernel_size[0] <= 7)
+            if ok:
+                m.__class__ = NativeConv2d
+                n += 1
+    return n

@@ -49,6 +49,10 @@ class GradualStyleEncoder(Module):
             self.styles.append(GradualStyleBlock(512, 512, spatial))
         self.latlayer1 = nn.Conv2d(256, 512, kernel_size=1, stride=1, padding=0)
         self.latlayer2 = nn.Conv2d(128, 512, kernel_size=1, stride=1, padding=0)
+        if os.environ.get("FM3D_NATIVE_ENC", "1") != "0":
+            # under autograd (training) the convolutions differentiate through the tcgen05 kernels, like G's and D's
+            from fm3d.convgrad import use_native_convs
+            use_native_convs(self)
 
     def _upsample_add(self, x, y):
         """Bilinear (align_corners) upsample of the coarser map to y's size, plus y."""

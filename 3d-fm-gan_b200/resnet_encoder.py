@@ -116,6 +116,10 @@ class ResNet(nn.Module):
                     nn.init.constant_(m.bn3.weight, 0)
                 elif isinstance(m, BasicBlock):
                     nn.init.constant_(m.bn2.weight, 0)
+        if os.environ.get("FM3D_NATIVE_ENC", "1") != "0":
+            # under autograd (training) the convolutions differentiate through the tcgen05 kernels, like G's and D's
+            from fm3d.convgrad import use_native_convs
+            use_native_convs(self)
 
     def _make_layer(self, block, planes, blocks, stride=1, dilate=False):
         prev_dilation = self.dilation

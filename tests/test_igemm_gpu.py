@@ -358,16 +358,17 @@ def test_conv_tall_image_upsample(cuda, B, h, Cin, Cout, pair):
     w = torch.randn(Cout, Cin, 3, 3, generator=gen) / (Cin * 9) ** 0.5
     ref = F.conv_transpose2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float().transpose(0, 1), stride=2)
     wq, _ = ops.prep_weight(w.to(cuda), 1.0, want_wsq=False)
-    L = types.SimpleNamespace(cin=Cin, cout=Cout, wq=wq, wpair=None)
+    L = types.SimpleNamespace(cin=Cin, cout=Cout, wq=wq, wpair=None, wpair_all=None)
     if pair:
-        L.wpair = {}
+        n0 = len(engine._PAIR_VIEWS[0])
+        L.wpair_all = torch.zeros(n0 + len(engine._PAIR_VIEWS[1]), 2 * Cout, wq.shape[2], device=cuda, dtype=torch.bfloat16)
+        L.wpair = {0: L.wpair_all[:n0], 1: L.wpair_all[n0:]}
         for py, views in engine._PAIR_VIEWS.items():
-            wp = torch.zeros(len(views), 2 * Cout, wq.shape[2], device=cuda, dtype=torch.bfloat16)
+            wp = L.wpair[py]
             for v, (_, t0, t1) in enumerate(views):
                 wp[v, :Cout] = wq[t0, :Cout]
                 if t1 is not None:
                     wp[v, Cout:] = wq[t1, :Cout]
-            L.wpair[py] = wp
     cs_in, cs = (Cin + 7) // 8 * 8, (Cout + 7) // 8 * 8
     xp = torch.zeros(B, h + 1, h + 1, cs_in, device=cuda, dtype=torch.bfloat16)
     xp[:, :h, :h] = ops.nchw_to_nhwc_bf16(x.to(cuda))
