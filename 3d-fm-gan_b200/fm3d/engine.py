@@ -41,6 +41,7 @@ _PAIR_UP = os.environ.get("FM3D_UPPAIR", "1") != "0"
 # all output-parity phases of an up-conv in ONE launch (the phase is a tile coordinate of the persistent grid): the
 # weight-bound 1- and 2-tap tiles interleave with the tensor-bound 4-tap tiles instead of running in launches of their own
 _MERGE_UP = os.environ.get("FM3D_UPMERGE", "1") != "0"
+_MERGE_UP_PAIR = os.environ.get("FM3D_UPMERGE", "1") == "2"
 
 # views (dy, dx) of the input a stride-2 transposed 3x3 conv reads, and for each output-row parity py the
 # (view, tap of column parity 0, tap of column parity 1 or None) triples -- see _up_phase_taps
@@ -266,7 +267,9 @@ class SynthesisPlan:
         kw = dict(B=1, H=Ht, W=Wt, Cin=L.cin, OH=Ht, OW=Wt, out_H=B * (2 * h + 2), out_W=2 * h + 2, out_ys=2, out_xs=2,
                   tab_per_sample=False, tile_w=tw_, tile_h=th_)
         # halo-patch eligibility of the tall image (igemm.cu): only then can the phase be a tile coordinate
-        merged = _MERGE_UP and Wt >= 8 and Ht >= 12
+        # (measured, B=32: 8->16 98 -> 85 us, 16->32 120 -> 78, 32->64 229 -> 199, 64->128 346 -> 344; the paired-parity
+        # 128->256 layer is better off with its two launches: 405 vs 414 us, FM3D_UPMERGE=2 merges it too)
+        merged = _MERGE_UP and Wt >= 8 and Ht >= 12 and (L.wpair is None or _MERGE_UP_PAIR)
         if merged and L.wpair is not None:
             cs_t = t.shape[-1]
             taps, phases, v0 = [], [], 0

@@ -103,6 +103,20 @@ def install_shims():
             sm.compare_ssim = _unavailable("skimage.measure.compare_ssim")
     if _absent("IPython"):
         _stub("IPython", embed=_unavailable("IPython.embed"))
+    # lpips/pretrained_networks.py builds its backbone with torchvision.models.vgg16(pretrained=True), a download: offline the
+    # architecture is kept and the weights stay random-init (the LPIPS linear heads are in the tree: lpips/weights/v0.1)
+    try:
+        import torchvision
+        if not getattr(torchvision.models.vgg16, "__fm3d_offline__", False):
+            _orig_vgg16 = torchvision.models.vgg16
+
+            def vgg16(pretrained=False, **kw):
+                kw.pop("weights", None)
+                return _orig_vgg16(weights=None, **kw)
+            vgg16.__fm3d_offline__ = True
+            torchvision.models.vgg16 = vgg16
+    except Exception:
+        pass
     # torch 1.9 re-exported typing names from torch.utils.data.sampler; dataset.py:17 imports them from there
     import typing
     import torch.utils.data.sampler as _sampler

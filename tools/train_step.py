@@ -15,8 +15,10 @@ The iteration below is the body of ``train()`` (:786-815) without its data loade
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_step.py
 
 Needs the reference source: /root/reference in the build container, baseline/_ref (tools/stage_reference.sh) on a GPU
-box.  Losses that need pretrained blobs which are not in the tree (LPIPS-VGG weights, ArcFace, face_alignment)
-are fed stub networks that return zeros; the GAN, R1, path-length, L1 and face-regional terms are the reference's code.
+box.  Loss networks whose pretrained blobs are not in the tree (LPIPS-VGG backbone, ArcFace)
+run as random-init networks of the reference's own architecture (LPIPS-VGG16 with the shipped linear heads, ArcFace
+ResNet-18) on the native conv path; the heat-map term stays off (face_alignment is not installed; hmap_iter_thres = inf
+in the reference's config as well).
 Synthetic data, random-init weights.  Every convolution of G and D -- forward, dgrad, wgrad, and the second-order passes
 of R1 / path length -- runs on the tcgen05 kernels (fm3d/convgrad.py); ``FM3D_NATIVE_GRAD=0`` runs them on ATen.
 Prints one JSON line."""
@@ -56,6 +58,8 @@ def main():
     ap.add_argument("--g-reg-every", type=int, default=4)
     ap.add_argument("--path-batch-shrink", type=int, default=2)
     ap.add_argument("--bucket-mb", type=int, default=32)
+    ap.add_argument("--loss-nets", default="real", choices=["real", "zero"],
+                    help="LPIPS-VGG16 / ArcFace-ResNet18 as real (random-init) networks on the native conv path, or zero stubs")
     args_cli = ap.parse_args()
 
     ts = ref_env.load_train_script()                 # the reference's functions, bound to the mirrored classes
@@ -99,14 +103,30 @@ def main():
     g_red.enable_timing(); d_red.enable_timing()
     g_step, d_step = SteppedOptimizer(g_enc_optim, g_red), SteppedOptimizer(d_optim, d_red)
 
-    class ZeroLPIPS(torch.nn.Module):                 # lpips.PerceptualLoss needs VGG weights from the network
-        def forward(self, a, b):
-            return (a[:, :1, :1, :1] * 0).flatten()
+    # Frozen loss networks: the reference's own LPIPS (lpips/networks_basic.py:36-101: VGG16 backbone +
+    # the linear heads shipped in lpips/weights/v0.1) and ArcFace ResNet-18 (Util/arcface_pytorch), both random-init where
+    # their pretrained blobs are not in the tree (the VGG16 backbone is a download, resnet18_arcfacenet.pth is in
+    # .MISSING_LARGE_BLOBS).  They sit on the gradient path of the generated image: their convolutions run forward and
+    # dgrad on the tcgen05 kernels (fm3d.convgrad.use_native_convs).  --loss-nets zero: stub networks that return 0.
+    fa_model = None
+    if args_cli.loss_nets == "real":
+        import lpips
+        from fm3d.convgrad import use_native_convs
+        from Util.arcface_pytorch.resnet_face_recognition import resnet_face18
+        lpips_model = lpips.PerceptualLoss(model='net-lin', net='vgg', use_gpu=True, gpu_ids=[local_rank])   # :391-392
+        face_rec_model = resnet_face18(use_se=False).to(dev)
+        ts.requires_grad(face_rec_model, False)
+        face_rec_model.eval()
+        n_native = use_native_convs(lpips_model.model.net) + use_native_convs(face_rec_model)
+    else:
+        class ZeroLPIPS(torch.nn.Module):
+            def forward(self, a, b):
+                return (a[:, :1, :1, :1] * 0).flatten()
 
-    class ZeroFaceNet(torch.nn.Module):               # ArcFace weights are not in the tree (.MISSING_LARGE_BLOBS)
-        def forward(self, x):
-            return x.mean(dim=(1, 2, 3), keepdim=False)[:, None] * 0
-    lpips_model, face_rec_model, fa_model = ZeroLPIPS(), ZeroFaceNet(), None
+        class ZeroFaceNet(torch.nn.Module):
+            def forward(self, x):
+                return x.mean(dim=(1, 2, 3), keepdim=False)[:, None] * 0
+        lpips_model, face_rec_model, n_native = ZeroLPIPS(), ZeroFaceNet(), 0
 
     B = args_cli.batch
     gen = torch.Generator(device="cpu").manual_seed(100 + rank)
@@ -170,6 +190,7 @@ def main():
             "ms_per_iter": sec * 1e3 / args_cli.iters, "size": args.size, "losses_finite": finite,
             "losses": {k: float(v) for k, v in red.items()},
             "native_grad": os.environ.get("FM3D_NATIVE_GRAD", "1") != "0",
+            "loss_nets": args_cli.loss_nets, "loss_net_convs_on_native_path": n_native,
             "allreduce": {"world": world, "bucket_mb": args_cli.bucket_mb,
                           "bytes_per_step": {"g_enc": sum(g_red.bucket_bytes()), "d": sum(d_red.bucket_bytes())},
                           "buckets": {"g_enc": len(g_red.buckets), "d": len(d_red.buckets)},
