@@ -153,31 +153,39 @@ __global__ void __launch_bounds__(256) build_tables_kernel(const fm_table_layer*
 // ------------------------------------------------------------------------------------
 // layout converts
 // ------------------------------------------------------------------------------------
+// fp32 NCHW -> bf16 NHWC through a shared-memory tile of 64 pixels x 64 channels: the loads are coalesced along the
+// pixels of a channel plane, the stores along the channels of a pixel (a warp writes whole 128-byte lines; the first
+// version stored 16 bytes per thread 2*cs bytes apart -- half-used sectors, and this pass is the most-launched kernel of
+// a training iteration: every differentiable conv converts its operands).  grid = (pixel tiles, channel tiles, B).
+constexpr int NT_PIX = 64, NT_CH = 64, NT_ROW = NT_CH * 2 + 8;   // row pitch 136 B: 8-byte reads stay aligned, 2-way conflicts at most
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x,
-                                                           const float* __restrict__ scale, int C, int HW, int cs,
-                                                           int64_t total) {
-  const int groups = cs / 8;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int pix = static_cast<int>(idx % HW);
-    const int64_t t = idx / HW;
-    const int g = static_cast<int>(t % groups);
-    const int64_t b = t / groups;
-    float v[8];
+                                                           const float* __restrict__ scale, int C, int HW, int cs) {
+  __shared__ __align__(16) uint8_t tile[NT_PIX * NT_ROW];
+  const int p0 = blockIdx.x * NT_PIX, c0 = blockIdx.y * NT_CH;
+  const int64_t b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      float f = 0.f;
-      if (c < C) {
-        f = x[(b * C + c) * HW + pix];
-        if (scale) f *= __ldg(scale + b * C + c);
-      }
-      v[j] = f;
+  for (int k = 0; k < NT_CH / 8; ++k) {
+    const int cl = warp + 8 * k, c = c0 + cl;
+    float v0 = 0.f, v1 = 0.f;
+    if (c < C) {
+      const float* src = x + (b * C + c) * HW;
+      const float sc = scale ? __ldg(scale + b * C + c) : 1.f;
+      if (p0 + lane < HW) v0 = __ldg(src + p0 + lane) * sc;
+      if (p0 + lane + 32 < HW) v1 = __ldg(src + p0 + lane + 32) * sc;
     }
-    uint4 w;
-    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
-    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(out + (b * HW + pix) * cs + g * 8) = w;
+    *reinterpret_cast<__nv_bfloat16*>(tile + lane * NT_ROW + cl * 2) = __float2bfloat16_rn(v0);
+    *reinterpret_cast<__nv_bfloat16*>(tile + (lane + 32) * NT_ROW + cl * 2) = __float2bfloat16_rn(v1);
+  }
+  __syncthreads();
+  // 64 pixels x 16 quads of 4 channels (8 bytes): consecutive threads write consecutive quads of a pixel
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int id = threadIdx.x + 256 * k;
+    const int pl = id >> 4, q = id & 15;
+    const int ch = c0 + q * 4;
+    if (p0 + pl < HW && ch < cs)
+      *reinterpret_cast<uint2*>(out + (b * HW + p0 + pl) * cs + ch) = *reinterpret_cast<const uint2*>(tile + pl * NT_ROW + q * 8);
   }
 }
 
@@ -567,9 +575,12 @@ extern "C" int fm_nchw_to_nhwc_bf16(void* out, const float* x, const float* scal
                                     int out_cstride, void* stream) {
   FM_CHECK_ARG(out && x && B > 0 && C > 0 && H > 0 && W > 0, "fm_nchw_to_nhwc_bf16: bad args");
   FM_CHECK_ARG(out_cstride % 8 == 0 && out_cstride >= C, "fm_nchw_to_nhwc_bf16: cstride must be a multiple of 8 >= C");
-  const int64_t total = static_cast<int64_t>(B) * (out_cstride / 8) * H * W;
-  nchw_to_nhwc_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(out), x, scale_bc, C, H * W, out_cstride, total);
+  const int HW = H * W;
+  FM_CHECK_ARG(B <= 65535 && (out_cstride + NT_CH - 1) / NT_CH <= 65535, "fm_nchw_to_nhwc_bf16: batch / channel count exceeds the grid");
+  const dim3 grid(static_cast<unsigned>((HW + NT_PIX - 1) / NT_PIX), static_cast<unsigned>((out_cstride + NT_CH - 1) / NT_CH),
+                  static_cast<unsigned>(B));
+  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(out), x, scale_bc, C, HW,
+                                                                        out_cstride);
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;

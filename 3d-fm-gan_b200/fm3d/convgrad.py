@@ -49,6 +49,56 @@ def _out_size(h, k, s, p):
     return (h + 2 * p - k) // s + 1
 
 
+# ---------------------------------------------------------------------------------------------- operand memo
+# Every map converts its NCHW fp32 operands to the kernels' layout (NHWC bf16 activations, K-major bf16 weights).  The same
+# tensor is needed more than once: the upstream gradient by dgrad AND wgrad of one layer, the layer input by forward AND
+# wgrad, a weight by several passes.  In a training iteration the conversion pass was the most-launched kernel (21 % of the
+# GPU time), so converted operands are memoised: keyed on the tensor's storage address, version counter and geometry, with a
+# strong reference to the source tensor so that the address cannot be recycled while the entry lives.  Small and bounded
+# (activations: the last few; weights: the last few dozen), cleared by ``clear_memo()``.
+class _Memo:
+    def __init__(self, size):
+        self.size, self.items = size, {}
+
+    @staticmethod
+    def key(t, tag):
+        return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.device.index, tag)
+
+    def get(self, t, tag):
+        e = self.items.get(self.key(t, tag))
+        return None if e is None else e[1]
+
+    def put(self, t, tag, val):
+        if len(self.items) >= self.size:
+            self.items.pop(next(iter(self.items)))          # oldest entry
+        self.items[self.key(t, tag)] = (t, val)
+        return val
+
+
+_ACT_MEMO = _Memo(4)
+_W_MEMO = _Memo(96)
+
+
+def clear_memo():
+    _ACT_MEMO.items.clear()
+    _W_MEMO.items.clear()
+
+
+def _nhwc(t):
+    """fp32 NCHW -> bf16 NHWC (memoised)."""
+    v = _ACT_MEMO.get(t, "nhwc")
+    return v if v is not None else _ACT_MEMO.put(t, "nhwc", ops.nchw_to_nhwc_bf16(t))
+
+
+def _wq(w, transposed):
+    """fp32 [O,I,k,k] -> bf16 [k*k][O][I] (or [k*k][I][O] for the data gradient), memoised."""
+    tag = "wT" if transposed else "w"
+    v = _W_MEMO.get(w, tag)
+    if v is None:
+        v = _W_MEMO.put(w, tag, ops.prep_weight(w.transpose(0, 1) if transposed else w, 1.0, want_wsq=False)[0])
+    return v
+
+
 # ---------------------------------------------------------------------------------------------- kernels
 def conv_forward(x, w, stride, pad):
     """x [B,I,H,W] fp32, w [O,I,k,k] fp32 -> [B,O,OH,OW] fp32."""
@@ -58,8 +108,8 @@ def conv_forward(x, w, stride, pad):
     out = torch.empty(B, O, OH, OW, device=x.device, dtype=torch.float32)
     if out.numel() == 0:
         return out
-    xq = ops.nchw_to_nhwc_bf16(x)
-    wq, _ = ops.prep_weight(w, 1.0, want_wsq=False)
+    xq = _nhwc(x)
+    wq = _wq(w, False)
     ops.conv_igemm(xq, wq, ops.conv_taps(k, k, pad), out, _ident_tab(O, x.device), B=B, H=H, W=W, Cin=I, Cout=O,
                    OH=OH, OW=OW, stride=stride, out_nchw_f32=True)
     return out
@@ -77,8 +127,8 @@ def conv_backward_data(g, w, stride, pad, in_hw):
     out = (torch.zeros if multi else torch.empty)(B, I, H, W, device=g.device, dtype=torch.float32)
     if out.numel() == 0 or g.numel() == 0:
         return out.zero_()
-    gq = ops.nchw_to_nhwc_bf16(g)
-    wq, _ = ops.prep_weight(w.transpose(0, 1), 1.0, want_wsq=False)        # [k*k][I rows][O]: K dimension = g's channels
+    gq = _nhwc(g)
+    wq = _wq(w, True)                                                     # [k*k][I rows][O]: K dimension = g's channels
     tab = _ident_tab(I, g.device)
 
     def phase_1d(r, n_in, n_out):
@@ -123,8 +173,8 @@ def conv_backward_weight(x, g, stride, pad, k):
     operands are read as NHWC bf16 -- the layout the forward / dgrad kernels use; tap (ky,kx) shifts x by (ky-p, kx-p)."""
     B, I, H, W = x.shape
     _, O, OH, OW = g.shape
-    xq = ops.nchw_to_nhwc_bf16(x)
-    gq = ops.nchw_to_nhwc_bf16(g)
+    xq = _nhwc(x)
+    gq = _nhwc(g)
     shifts = [(ky - pad, kx - pad) for ky in range(k) for kx in range(k)]
     if O >= I:          # the larger channel count takes the 128-row M side, the smaller one the N side (>= 16 wide)
         dw = conv_wgrad(gq, xq, O, I, B, OH, OW, [(0, 0, dy, dx) for (dy, dx) in shifts], 1, stride)      # [t][o][i]
@@ -139,7 +189,12 @@ class ConvFwd(Function):
     def forward(ctx, x, w, stride, pad):
         ctx.save_for_backward(x, w)
         ctx.cfg = (stride, pad)
-        return conv_forward(x.detach(), w.detach(), stride, pad)
+        xd = x.detach()
+        y = conv_forward(xd, w.detach(), stride, pad)
+        # the bf16 NHWC copy of the input is what the weight gradient reads: keep it with the graph instead of converting
+        # the saved fp32 tensor again in backward (+50 % of this layer's saved activation bytes, one conversion pass less)
+        ctx.xq = _ACT_MEMO.get(xd, "nhwc") if w.requires_grad else None
+        return y
 
     @staticmethod
     def backward(ctx, gy):
@@ -149,6 +204,8 @@ class ConvFwd(Function):
         if ctx.needs_input_grad[0]:
             gx = ConvBwdData.apply(gy, w, stride, pad, (x.shape[2], x.shape[3]))
         if ctx.needs_input_grad[1]:
+            if ctx.xq is not None and _ACT_MEMO.get(x.detach(), "nhwc") is None:
+                _ACT_MEMO.put(x.detach(), "nhwc", ctx.xq)
             gw = ConvBwdWeight.apply(x, gy, stride, pad, w.shape[2])
         return gx, gw, None, None
 

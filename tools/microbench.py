@@ -75,16 +75,17 @@ def bench_upconv(res):
         xp = torch.zeros(B, h + 1, h + 1, Cin, device=dev, dtype=torch.bfloat16)
         xp[:, :h, :h] = x
         tp = torch.empty(B, 2 * h + 2, 2 * h + 2, Cout, device=dev, dtype=torch.bfloat16)
-        L = types.SimpleNamespace(cin=Cin, cout=Cout, wq=w, wpair=None)
+        L = types.SimpleNamespace(cin=Cin, cout=Cout, wq=w, wpair=None, wpair_all=None)
         if Cout <= 128:
-            L.wpair = {}
+            n0 = len(engine._PAIR_VIEWS[0])
+            L.wpair_all = torch.zeros(n0 + len(engine._PAIR_VIEWS[1]), 2 * Cout, Cin, device=dev, dtype=torch.bfloat16)
+            L.wpair = {0: L.wpair_all[:n0], 1: L.wpair_all[n0:]}
             for py, views in engine._PAIR_VIEWS.items():
-                wp = torch.zeros(len(views), 2 * Cout, Cin, device=dev, dtype=torch.bfloat16)
+                wp = L.wpair[py]
                 for v, (_, t0, t1) in enumerate(views):
                     wp[v, :Cout] = w[t0]
                     if t1 is not None:
                         wp[v, Cout:] = w[t1]
-                L.wpair[py] = wp
 
         def tall():
             engine.SynthesisPlan._up_conv(None, L, xp, tp, B, h)
@@ -95,9 +96,50 @@ def bench_upconv(res):
         del x, t_out, xp, tp
 
 
+def bench_train(res):
+    """The three maps of a differentiable conv (fm3d/convgrad.py) at the generator's / discriminator's layer shapes, B = 32:
+    forward and data gradient on fm_conv_igemm, weight gradient on fm_conv_wgrad (NHWC bf16 operands already in place:
+    the layout passes from the NCHW fp32 autograd tensors are timed separately as 'nchw->nhwc')."""
+    from fm3d import convgrad
+    B = 32
+    for (H, Cin, Cout, k, s) in [(64, 512, 512, 3, 1), (128, 256, 256, 3, 1), (256, 128, 128, 3, 1), (32, 512, 512, 3, 1),
+                                 (257, 128, 256, 3, 2), (129, 256, 512, 3, 2), (256, 3, 128, 1, 1), (256, 128, 3, 1, 1)]:
+        p = k // 2 if s == 1 else 0
+        OH = (H + 2 * p - k) // s + 1
+        cs = lambda c: (c + 7) // 8 * 8
+        x = torch.zeros(B, H, H, cs(Cin), device=dev, dtype=torch.bfloat16)
+        x[..., :Cin] = torch.randn(B, H, H, Cin, device=dev).to(torch.bfloat16)
+        g = torch.zeros(B, OH, OH, cs(Cout), device=dev, dtype=torch.bfloat16)
+        g[..., :Cout] = torch.randn(B, OH, OH, Cout, device=dev).to(torch.bfloat16)
+        shifts = [(ky - p, kx - p) for ky in range(k) for kx in range(k)]
+        fl = 2.0 * B * OH * OH * Cin * Cout * k * k
+        if Cout >= Cin:
+            fn = lambda: convgrad.conv_wgrad(g, x, Cout, Cin, B, OH, OH, [(0, 0, dy, dx) for (dy, dx) in shifts], 1, s)
+        else:
+            fn = lambda: convgrad.conv_wgrad(x, g, Cin, Cout, B, OH, OH, [(dy, dx, 0, 0) for (dy, dx) in shifts], s, 1)
+        t = timeit(fn, iters=5, warm=2)
+        res.append(dict(kernel="conv_wgrad", H=H, Cin=Cin, Cout=Cout, k=k, stride=s, ms=t * 1e3, TFLOPs=fl / t / 1e12))
+        if H <= 128 or Cin <= 128:
+            xf = torch.randn(B, Cin, H, H, device=dev)
+            gf = torch.randn(B, Cout, OH, OH, device=dev)
+            w = torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5
+            t = timeit(lambda: convgrad.conv_forward(xf, w, s, p), iters=5, warm=2)
+            res.append(dict(kernel="conv_forward (nchw fp32 in/out)", H=H, Cin=Cin, Cout=Cout, k=k, stride=s, ms=t * 1e3, TFLOPs=fl / t / 1e12))
+            t = timeit(lambda: convgrad.conv_backward_data(gf, w, s, p, (H, H)), iters=5, warm=2)
+            res.append(dict(kernel="conv_backward_data (nchw fp32 in/out)", H=H, Cin=Cin, Cout=Cout, k=k, stride=s, ms=t * 1e3, TFLOPs=fl / t / 1e12))
+            t = timeit(lambda: convgrad.conv_backward_weight(xf, gf, s, p, k), iters=5, warm=2)
+            res.append(dict(kernel="conv_backward_weight (nchw fp32 in)", H=H, Cin=Cin, Cout=Cout, k=k, stride=s, ms=t * 1e3, TFLOPs=fl / t / 1e12))
+            t = timeit(lambda: ops.nchw_to_nhwc_bf16(xf), iters=5, warm=2)
+            res.append(dict(kernel="nchw->nhwc bf16", H=H, C=Cin, ms=t * 1e3, GBs=xf.numel() * 6 / t / 1e9))
+            del xf, gf
+        del x, g
+
+
 def main():
     res = []
     which = sys.argv[1:] or ["ops", "igemm", "synth", "upconv"]
+    if "train" in which:
+        bench_train(res)
     if "synth" in which:
         bench_synth(res)
     if "upconv" in which:

@@ -30,6 +30,9 @@ import warnings
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
+# an iteration allocates and frees ~50 GB of activations in blocks of very different sizes: without expandable segments the
+# caching allocator fragments and falls back to synchronous cudaFree / cudaMalloc (iteration time varied 385 .. 740 ms)
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 import ref_env  # noqa: E402
 
 
@@ -58,6 +61,7 @@ def main():
     ap.add_argument("--g-reg-every", type=int, default=4)
     ap.add_argument("--path-batch-shrink", type=int, default=2)
     ap.add_argument("--bucket-mb", type=int, default=32)
+    ap.add_argument("--profile", default="", help="write a per-kernel CUDA time table of one full regulariser cycle to this file")
     ap.add_argument("--loss-nets", default="real", choices=["real", "zero"],
                     help="LPIPS-VGG16 / ArcFace-ResNet18 as real (random-init) networks on the native conv path, or zero stubs")
     args_cli = ap.parse_args()
@@ -157,6 +161,20 @@ def main():
 
     for i in range(args_cli.warmup):
         iteration(i)
+    if args_cli.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        n_prof = args_cli.g_reg_every
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(n_prof):
+                iteration(i)
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+        tot = sum(e.device_time_total for e in rows)
+        with open(args_cli.profile, "w") as f:
+            f.write(f"# {n_prof} iterations (D + R1 + G + path length at i = 0), batch {B}/GPU: CUDA kernel time {tot / n_prof / 1e3:.1f} ms/iter\n")
+            for e in rows[:60]:
+                f.write(f"{e.device_time_total / n_prof / 1e3:9.3f} ms/iter {100 * e.device_time_total / tot:5.1f}% {e.count // n_prof:5d}x  {e.key[:150]}\n")
     g_red.enable_timing(); d_red.enable_timing()
     D_.synchronize()
     torch.cuda.synchronize()
