@@ -20,6 +20,7 @@ import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402,F401
 
 _SIDE_STREAMS = {}
+_RESNET_PAIR = os.environ.get("FM3D_RESNET_PAIR", "0") != "0"
 
 
 def _side_streams(device):
@@ -71,10 +72,21 @@ def Forward_Inference_3_Encoder(p_input, r_input, E_Tsr, E_W, E_W_Plus, g_ema, t
         s1, s2 = _side_streams(p_input.device)
         s1.wait_stream(main)
         s2.wait_stream(main)
-        with torch.cuda.stream(s1):
-            encoded_tensor = E_Tsr(tsr_in)
-        with torch.cuda.stream(s2):
-            encoded_W = E_W(r_input)
+        pair = None
+        if _RESNET_PAIR and tsr_in is r_input:
+            # both ResNet-18s encode the render: one grouped launch sequence (fm3d/encoder_engine.py:ResNetPlan)
+            from fm3d.encoder_engine import run_resnet_pair
+            ma, mb = getattr(E_Tsr, "module", E_Tsr), getattr(E_W, "module", E_W)
+            if all(hasattr(m, "_engine_ok") and hasattr(m, "layer1") and m._engine_ok(r_input) for m in (ma, mb)):
+                with torch.cuda.stream(s1):
+                    pair = run_resnet_pair(ma, mb, r_input)
+        if pair is not None:
+            encoded_tensor, encoded_W = pair
+        else:
+            with torch.cuda.stream(s1):
+                encoded_tensor = E_Tsr(tsr_in)
+            with torch.cuda.stream(s2):
+                encoded_W = E_W(r_input)
         encoded_W_plus = E_W_Plus(p_input)
         main.wait_stream(s1)
         main.wait_stream(s2)

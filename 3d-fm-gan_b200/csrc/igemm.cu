@@ -1236,7 +1236,10 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       du0 = du[i] < du0 ? du[i] : du0; du1 = du[i] > du1 ? du[i] : du1;
       dv0 = dv[i] < dv0 ? dv[i] : dv0; dv1 = dv[i] > dv1 ? dv[i] : dv1;
     }
-    if (want && stride_ok && plain_x && G == 1 && p.ksplit == 1 && !d->upmode && d->ntaps >= 2 && d->OH >= 12 &&
+    // grouped convs: a halo-patch tile lies inside one image, so its group is known per tile (weights are not resident
+    // across tiles of different groups: hpw below stays ungrouped)
+    static const int env_hp_groups = []() { const char* e = getenv("FM3D_HPATCH_GROUPS"); return e ? atoi(e) : 1; }();
+    if (want && stride_ok && plain_x && (G == 1 || env_hp_groups) && p.ksplit == 1 && !d->upmode && d->ntaps >= 2 && d->OH >= 12 &&
         d->OW >= 8 && dv1 - dv0 <= 8 && du1 - du0 <= 8 && sx * sy <= 4 && (!d->tab_bstride || bn <= IG_TAB_ROWS)) {
       p.hp = 1;
       p.patch = 0; p.prows = 1;
@@ -1347,7 +1350,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       static const int env_hpw_min = []() { const char* e = getenv("FM3D_HPW_MIN"); return e ? atoi(e) : 2; }();
       // two patch slots are enough to keep the weights resident (128 -> 128 pair layers: 144 KB of weights + 2 x 23 KB):
       // the next chunk's patch loads while the current chunk's 36 MMAs run
-      if (env_hpw && nph == 1 && p.tiles_n == 1 && na >= env_hpw_min) {
+      if (env_hpw && nph == 1 && G == 1 && p.tiles_n == 1 && na >= env_hpw_min) {
         p.hpw = 1;
         p.hp_na = na;
       }

@@ -89,66 +89,96 @@ _FUSE_UPSAMPLE = os.environ.get("FM3D_FUSE_UPSAMPLE", "1") != "0"
 
 
 class ResNetPlan:
-    model = property(lambda self: self._model())      # weak: the plan cache is keyed weakly on the module
+    """One ResNet-18, or SEVERAL of identical architecture on the same input batch as the groups of grouped launches
+    (E_Tsr and E_W both encode the render under ``tsr_encode='Render Image'``, Util/network_util.py:310-314: at B = 32 a
+    ResNet-18 layer is a 20-40 us latency-bound launch, so running the two networks as one sequence with twice the GEMM M
+    dimension per launch halves the launches).  Activations are [G*B, h, w, c] group-major, weights [G*taps, Cout, Cin]."""
+    models = property(lambda self: [m() for m in self._models])      # weak: the plan cache is keyed weakly on the module
 
-    def __init__(self, model, B, H, W, device):
-        self._model, self.B, self.H, self.W, self.device = weakref.ref(model), B, H, W, device
+    def __init__(self, models, B, H, W, device):
+        self._models, self.B, self.H, self.W, self.device = [weakref.ref(m) for m in models], B, H, W, device
+        self.G = len(models)
         self.versions = None
         bf = dict(device=device, dtype=torch.bfloat16)
+        GB = self.G * B
         # stem geometry: 7x7 stride 2 pad 3; a window of 8 padded pixels x 8 channels per (ky, out x)
         self.oh, self.ow = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         self.Hp, self.Wp = H + 6, max(W + 6, 2 * (self.ow - 1) + 8)
-        self.packed = torch.zeros(B, self.Hp, self.Wp, 8, **bf)
-        self.stem_out = torch.empty(B, self.oh, self.ow, 64, **bf)
+        self.packed = torch.zeros(GB, self.Hp, self.Wp, 8, **bf)
+        self.stem_out = torch.empty(GB, self.oh, self.ow, 64, **bf)
         ph, pw = (self.oh - 1) // 2 + 1, (self.ow - 1) // 2 + 1
-        self.pool_out = torch.empty(B, ph, pw, 64, **bf)
+        self.pool_out = torch.empty(GB, ph, pw, 64, **bf)
         self.bufs = {}
         self.runner = GraphRunner(self._run)
         self.refresh()
 
-    def _buf(self, key, B, h, w, c):
+    def _buf(self, key, n, h, w, c):
         t = self.bufs.get(key)
-        if t is None or t.shape != (B, h, w, _cs(c)):
-            t = torch.empty(B, h, w, _cs(c), device=self.device, dtype=torch.bfloat16)
+        if t is None or t.shape != (n, h, w, _cs(c)):
+            t = torch.empty(n, h, w, _cs(c), device=self.device, dtype=torch.bfloat16)
             self.bufs[key] = t
         return t
 
     def refresh(self):
-        v = _versions(self.model)
+        models = self.models
+        v = [_versions(m) for m in models]
         if v == self.versions:
             return
         self.versions = v
         self.runner.invalidate()
-        m, dev = self.model, self.device
-        a, b = _fold_bn(m.bn1)
-        self.stem_w = _stem_weight(m.conv1.weight)
-        self.stem_tab = _table(64, dev, a, b, slope=0.0)
+        dev, G = self.device, self.G
+
+        def conv(mods, bns, stride, pad, slope):
+            """Grouped conv: the same layer of every model (weights [G*taps, O, I], table [G, O, 8])."""
+            tabs, ws = [], []
+            for cm, bn in zip(mods, bns):
+                a, b = _fold_bn(bn)
+                tabs.append(_table(cm.out_channels, dev, a, b, slope)[0])
+                ws.append(ops.prep_weight(cm.weight.detach(), 1.0, want_wsq=False)[0])
+            c = _Conv.__new__(_Conv)
+            c.k, c.cout, c.cin = mods[0].weight.shape[-1], mods[0].weight.shape[0], mods[0].weight.shape[1]
+            c.stride, c.pad = stride, pad
+            c.wq = torch.cat(ws, 0).contiguous()
+            c.taps = ops.conv_taps(c.k, c.k, pad)
+            c.tab = torch.stack(tabs, 0).contiguous()
+            c.border = None
+            c.groups = G
+            return c
+        self.stem_w = torch.cat([_stem_weight(m.conv1.weight) for m in models], 0).contiguous()
+        self.stem_tab = torch.stack([_table(64, dev, *_fold_bn(m.bn1), slope=0.0)[0] for m in models], 0).contiguous()
         self.blocks = []
-        for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
-            for blk in layer:
-                a1, b1 = _fold_bn(blk.bn1)
-                a2, b2 = _fold_bn(blk.bn2)
-                c1 = _Conv(blk.conv1.weight, blk.stride, 1, _table(blk.conv1.out_channels, dev, a1, b1, 0.0))
-                c2 = _Conv(blk.conv2.weight, 1, 1, _table(blk.conv2.out_channels, dev, a2, b2, 0.0))
+        for li in range(4):
+            layers = [getattr(m, f"layer{li + 1}") for m in models]
+            for bi in range(len(layers[0])):
+                blks = [l[bi] for l in layers]
+                c1 = conv([b.conv1 for b in blks], [b.bn1 for b in blks], blks[0].stride, 1, 0.0)
+                c2 = conv([b.conv2 for b in blks], [b.bn2 for b in blks], 1, 1, 0.0)
                 ds = None
-                if blk.downsample is not None:
-                    ad, bd = _fold_bn(blk.downsample[1])
-                    dconv = blk.downsample[0]
-                    ds = _Conv(dconv.weight, dconv.stride[0], 0, _table(dconv.out_channels, dev, ad, bd, 1.0))
+                if blks[0].downsample is not None:
+                    ds = conv([b.downsample[0] for b in blks], [b.downsample[1] for b in blks], blks[0].downsample[0].stride[0], 0, 1.0)
                 self.blocks.append((c1, c2, ds))
 
     def run(self, x):
         self.refresh()
         return self.runner(x.contiguous().float())
 
+    def _conv(self, c, x, out, n, H, W, residual=None):
+        OH, OW = c.out_size(H), c.out_size(W)
+        kw = dict(groups=self.G, w_rows=c.cout) if self.G > 1 else {}
+        return ops.conv_igemm(x, c.wq, c.taps, out, c.tab, B=n, H=H, W=W, Cin=c.cin, Cout=c.cout, OH=OH, OW=OW,
+                              stride=c.stride, residual=residual, **kw)
+
     def _run(self, x):
-        B = self.B
-        ops.image_to_nhwc8_padded(x, 3, 3, self.Hp, self.Wp, out=self.packed)
+        B, G = self.B, self.G
+        GB = G * B
+        for g in range(G):                       # the same image batch for every group
+            ops.image_to_nhwc8_padded(x, 3, 3, self.Hp, self.Wp, out=self.packed[g * B:(g + 1) * B])
+        kw = dict(groups=G, w_rows=64) if G > 1 else {}
         # algorithmic FLOPs of the 7x7 conv on 3 channels (the K dimension is padded to 7 x 64 for the tensor core)
         ops.conv_igemm(self.packed, self.stem_w, [(ky, 0, ky) for ky in range(7)], self.stem_out, self.stem_tab,
-                       B=B, H=self.Hp, W=self.ow, Cin=64, Cout=64, OH=self.oh, OW=self.ow, stride_x=1, stride_y=2,
+                       B=GB, H=self.Hp, W=self.ow, Cin=64, Cout=64, OH=self.oh, OW=self.ow, stride_x=1, stride_y=2,
                        x_pixstride=16, x_rowstride=self.Wp * 8, x_imgstride=self.Hp * self.Wp * 8,
-                       algo_flops=2.0 * B * self.oh * self.ow * 3 * 64 * 49)
+                       algo_flops=2.0 * GB * self.oh * self.ow * 3 * 64 * 49, **kw)
         ops.maxpool3x3s2_nhwc(self.stem_out, self.pool_out)
         cur = self.pool_out
         h, w = cur.shape[1], cur.shape[2]
@@ -156,27 +186,47 @@ class ResNetPlan:
             oh, ow = c1.out_size(h), c1.out_size(w)
             identity = cur
             if ds is not None:
-                identity = ds.run(cur, self._buf(("ds", i), B, oh, ow, ds.cout), B, h, w)
-            y = c1.run(cur, self._buf(("a", i), B, oh, ow, c1.cout), B, h, w)
-            cur = c2.run(y, self._buf(("b", i), B, oh, ow, c2.cout), B, oh, ow, residual=identity)
+                identity = self._conv(ds, cur, self._buf(("ds", i), GB, oh, ow, ds.cout), GB, h, w)
+            y = self._conv(c1, cur, self._buf(("a", i), GB, oh, ow, c1.cout), GB, h, w)
+            cur = self._conv(c2, y, self._buf(("b", i), GB, oh, ow, c2.cout), GB, oh, ow, residual=identity)
             h, w = oh, ow
-        m = self.model
-        if m.tensor_encoding:
-            return ops.avgpool_nhwc_to_nchw(cur, 512, 2, 2)                       # nn.AvgPool2d(2, 2)
-        return ops.avgpool_nhwc_to_nchw(cur, 512, h, w).flatten(1)               # AdaptiveAvgPool2d((1,1)) + flatten
+        outs = []
+        for g, m in enumerate(self.models):
+            part = cur[g * B:(g + 1) * B]
+            if m.tensor_encoding:
+                outs.append(ops.avgpool_nhwc_to_nchw(part, 512, 2, 2))                     # nn.AvgPool2d(2, 2)
+            else:
+                outs.append(ops.avgpool_nhwc_to_nchw(part, 512, h, w).flatten(1))         # AdaptiveAvgPool2d((1,1)) + flatten
+        return outs
+
+
+def _resnet_ok(model, x):
+    if x.ndim != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
+        return False
+    return [len(l) for l in (model.layer1, model.layer2, model.layer3, model.layer4)] == [2, 2, 2, 2] and \
+        type(model.layer1[0]).__name__ == "BasicBlock"
 
 
 def run_resnet(model, x):
-    if x.ndim != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
-        return None
-    if [len(l) for l in (model.layer1, model.layer2, model.layer3, model.layer4)] != [2, 2, 2, 2] or \
-            type(model.layer1[0]).__name__ != "BasicBlock":
+    if not _resnet_ok(model, x):
         return None
     plans = plans_of(model)
     key = (tuple(x.shape), x.device.index, ops.current_slot())
     plan = plans.get(key)
     if plan is None:
-        plan = plans[key] = ResNetPlan(model, x.shape[0], x.shape[2], x.shape[3], x.device)
+        plan = plans[key] = ResNetPlan([model], x.shape[0], x.shape[2], x.shape[3], x.device)
+    return plan.run(x)[0]
+
+
+def run_resnet_pair(model_a, model_b, x):
+    """Both ResNet-18 encoders on the same input as one grouped launch sequence -> (out_a, out_b), or None."""
+    if model_a is model_b or not (_resnet_ok(model_a, x) and _resnet_ok(model_b, x)):
+        return None
+    plans = plans_of(model_a)
+    key = ("pair", id(model_b), tuple(x.shape), x.device.index, ops.current_slot())
+    plan = plans.get(key)
+    if plan is None or plan.models[1] is not model_b:
+        plan = plans[key] = ResNetPlan([model_a, model_b], x.shape[0], x.shape[2], x.shape[3], x.device)
     return plan.run(x)
 
 

@@ -18,10 +18,10 @@ import ref_env  # noqa: E402
 needs_reference = pytest.mark.skipif(ref_env.reference_root() is None, reason="no reference source here")
 
 
-def _run(env_extra=None):
+def _run(env_extra=None, iters=4, warmup=1):
     env = dict(os.environ, **(env_extra or {}))
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "train_step.py"), "--size", "256", "--batch", "4",
-                          "--iters", "4", "--warmup", "1", "--d-reg-every", "2", "--g-reg-every", "2"],
+                          "--iters", str(iters), "--warmup", str(warmup), "--d-reg-every", "2", "--g-reg-every", "2"],
                          capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stderr[-3000:]
     return json.loads(out.stdout.strip().splitlines()[-1])
@@ -34,12 +34,14 @@ def test_reference_train_functions_run_on_native_kernels(cuda):
     assert line["losses_finite"], line
     assert set(line["losses"]) >= {"d", "r1", "g", "l1", "g_reg", "face_reg", "lpips", "face_id"}
     assert line["value"] > 0
-    # same seeds on the ATen cross-check path: the first iterations' losses agree to bf16 accuracy
-    ref = _run({"FM3D_NATIVE_GRAD": "0"})
-    assert not ref["native_grad"]
-    for k in ("d", "g", "l1"):
-        a, b = line["losses"][k], ref["losses"][k]
-        assert abs(a - b) <= 0.1 * max(abs(b), 0.1), (k, a, b)
+    # the FIRST iteration from identical weights and data, native kernels vs the ATen cross-check path: the losses agree
+    # to bf16 accuracy (later iterations of an adversarial game drift apart chaotically, so they are not compared)
+    one = _run(iters=1, warmup=0)
+    ref = _run({"FM3D_NATIVE_GRAD": "0"}, iters=1, warmup=0)
+    assert one["native_grad"] and not ref["native_grad"]
+    for k in ("d", "g", "l1", "lpips", "face_reg", "r1"):
+        a, b = one["losses"][k], ref["losses"][k]
+        assert abs(a - b) <= 0.05 * max(abs(b), 0.05), (k, a, b)
 
 
 def test_two_devices_in_one_process_threads(cuda):
