@@ -160,7 +160,11 @@ class ResNetPlan:
 
     def run(self, x):
         self.refresh()
-        return self.runner(x.contiguous().float())
+        prev, ops.PROFILE_TAG = ops.PROFILE_TAG, "resnet"
+        try:
+            return self.runner(x.contiguous().float())
+        finally:
+            ops.PROFILE_TAG = prev
 
     def _conv(self, c, x, out, n, H, W, residual=None):
         OH, OW = c.out_size(H), c.out_size(W)
@@ -353,7 +357,11 @@ class PspPlan:
 
     def run(self, x):
         self.refresh()
-        return self.runner(x.contiguous().float())
+        prev, ops.PROFILE_TAG = ops.PROFILE_TAG, "psp"
+        try:
+            return self.runner(x.contiguous().float())
+        finally:
+            ops.PROFILE_TAG = prev
 
     def _run(self, x):
         B, S = self.B, self.S

@@ -253,7 +253,11 @@ class SynthesisPlan:
         N(0,1) drawn in the reference's order) -> list of fp32 NCHW RGB images per resolution."""
         self._refresh_weights()
         noise = [None if n is None else n.contiguous().float() for n in noise]
-        return self._runner(latent.contiguous().float(), start.contiguous().float(), *noise)
+        prev, ops.PROFILE_TAG = ops.PROFILE_TAG, "generator"
+        try:
+            return self._runner(latent.contiguous().float(), start.contiguous().float(), *noise)
+        finally:
+            ops.PROFILE_TAG = prev
 
     def _up_conv(self, L, x, t, B, h):
         """Stride-2 transposed 3x3 conv (no epilogue) of the tall image x [B*(h+1), h+1] (zero separator row / column

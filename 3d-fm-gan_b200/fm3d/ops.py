@@ -37,8 +37,10 @@ def current_slot():
     return _SLOT.value
 
 
-# bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops) per conv launch
+# bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops, tag) per conv launch;
+# PROFILE_TAG names the network the launches belong to (set by the engines: "generator", "resnet", "psp")
 PROFILE = None
+PROFILE_TAG = ""
 
 _DTYPES = {torch.float32: FM_F32, torch.float16: FM_F16, torch.bfloat16: FM_BF16}
 
@@ -246,7 +248,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
             # up mode: algorithmic FLOPs of the stride-2 transposed conv = 9 taps at the INPUT resolution
             # launches that pad their weights with zero blocks pass their algorithmic FLOPs explicitly
             prof.append((e0, e1, algo_flops if algo_flops is not None else
-                         2.0 * B * (H * W if upmode else OH * OW) * Cin * Cout * len(taps)))
+                         2.0 * B * (H * W if upmode else OH * OW) * Cin * Cout * len(taps), PROFILE_TAG))
     _lib.check(st, "fm_conv_igemm")
     return out
 

@@ -375,8 +375,12 @@ def main():
         else:
             os.environ["FM3D_STREAMS"] = prev_streams
         ops.PROFILE = None
-    flops = sum(f for (_, _, f) in prof)
-    ksec = sum(a.elapsed_time(b) for (a, b, _) in prof) * 1e-3
+    flops = sum(r[2] for r in prof)
+    ksec = sum(r[0].elapsed_time(r[1]) for r in prof) * 1e-3
+    by_net = {}
+    for (a, b, f, tag) in prof:
+        e = by_net.setdefault(tag or "other", [0.0, 0.0, 0])
+        e[0] += f; e[1] += a.elapsed_time(b) * 1e-3; e[2] += 1
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -400,9 +404,49 @@ def main():
                 "peak_burst": peak_burst, "frac_burst": achieved / peak_burst,
                 "flops_counted": "algorithmic: 3-channel stems counted with Cin=3 (not their padded K), transposed convs "
                                  "with 9 taps at the input resolution, zero weight blocks not credited",
+                # the same figure per network: "generator" = the modulated convolutions (13 3x3 layers incl. the stride-2
+                # transposed ones; the 1x1 ToRGBs are fused into their epilogues) -- BASELINE's "modconv TC util"
+                "by_network": {k: {"achieved": v[0] / v[1] / 1e12, "frac": v[0] / v[1] / 1e12 / peak_tf,
+                                   "frac_burst": v[0] / v[1] / 1e12 / peak_burst, "launches_per_step": v[2] // 2,
+                                   "kernel_ms_per_step": v[1] * 1e3 / 2, "algorithmic_gflop_per_step": v[0] / 2 / 1e9}
+                               for k, v in sorted(by_net.items()) if v[1] > 0},
                 "launches_per_step": len(prof) // 2, "kernel_ms_per_step": ksec * 1e3 / 2,
                 "algorithmic_gflop_per_step": flops / 2 / 1e9,
                 "traffic": traffic, "traffic_unit": traffic_src}
+
+    # ---------------- the bandwidth-bound ops of the boundary (BASELINE metric: "upfirdn GB/s"), measured live on rank 0:
+    # the largest generator blur through the op API (fp32 NCHW [32,128,257,257] -> 256^2) and fused bias-act on its output
+    hbm = None
+    if rank == 0:
+        import op as op_api
+        hbm_peak = peaks.get("hbm_gbs", 6500.0)
+        kk = torch.tensor([1., 3., 3., 1.], device=device)
+        kk = torch.outer(kk, kk); kk = kk / kk.sum() * 4
+        xb = torch.randn(32, 128, 257, 257, device=device)
+        bb = torch.zeros(128, device=device)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+        def timed(fn, n=5):
+            ts = []
+            with torch.no_grad():
+                fn()
+                for _ in range(n):
+                    flush.zero_()                       # > L2: the next iteration finds nothing of its input cached
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); y = fn(); b.record()
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b) * 1e-3)
+            return sorted(ts)[len(ts) // 2], y
+        t_up, yb = timed(lambda: op_api.upfirdn2d(xb, kk, pad=(1, 1)))
+        t_ba, _ = timed(lambda: op_api.fused_leaky_relu(yb, bb))
+        up_bytes = (xb.numel() + yb.numel()) * 4
+        ba_bytes = 2 * yb.numel() * 4
+        hbm = {"peak": hbm_peak, "unit": "GB/s",
+               "upfirdn2d_blur_fp32_257": {"achieved": up_bytes / t_up / 1e9, "frac": up_bytes / t_up / 1e9 / hbm_peak,
+                                           "ms": t_up * 1e3, "algorithmic_bytes": up_bytes},
+               "fused_bias_act_fp32_256": {"achieved": ba_bytes / t_ba / 1e9, "frac": ba_bytes / t_ba / 1e9 / hbm_peak,
+                                           "ms": t_ba * 1e3, "algorithmic_bytes": ba_bytes}}
+        del xb, yb, flush
 
     if rank != 0:
         if world > 1:
@@ -433,6 +477,7 @@ def main():
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": roofline,
+        "hbm_kernels": hbm,
         "cpu_baseline": cpu,
         "tflops_algorithmic": value * GFLOP_PER_IMAGE / 1e3,
     }
