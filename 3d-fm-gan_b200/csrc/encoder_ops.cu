@@ -304,6 +304,47 @@ extern "C" int fm_tensor2im_u8(void* out_u8, const float* img, int B, int H, int
   return FM_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// Input stage (the inverse of tensor2im): uint8 NHWC [B,H,W,3] -> fp32 NCHW [B,3,H,W]
+//   y = (x / 255 - mean) / std      == torchvision ToTensor() + Normalize(mean, std) of the reference's transform
+// (train_3_encoder.py:231-237), bit for bit: a rounded fp32 division by 255, a rounded subtraction, a rounded division
+// (the library is built with --use_fast_math, so the IEEE intrinsics are spelled out).  The decoded uint8 batch is what
+// crosses PCIe (1/4 of the fp32 bytes); a thread owns 4 adjacent pixels: 12 bytes in, 3 STG.128 out.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2tensor_kernel(float* __restrict__ out, const uint8_t* __restrict__ img, int HW,
+                                                        float mean, float stdv, int total_quads) {
+  const int qpi = HW >> 2;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total_quads; idx += gridDim.x * blockDim.x) {
+    const int b = idx / qpi, q = idx - b * qpi;
+    const uint32_t* ip = reinterpret_cast<const uint32_t*>(img + (static_cast<size_t>(b) * HW + 4 * q) * 3);
+    const uint32_t w[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
+    float v[3][4];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {            // byte i of the 12-byte group = pixel i/3, channel i%3
+      const float x = static_cast<float>((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+      v[i % 3][i / 3] = __fdiv_rn(__fsub_rn(__fdiv_rn(x, 255.f), mean), stdv);
+    }
+    float* op = out + static_cast<size_t>(b) * 3 * HW + 4 * q;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      *reinterpret_cast<float4*>(op + static_cast<size_t>(c) * HW) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+  }
+}
+
+extern "C" int fm_im2tensor_f32(float* out, const void* img_u8, int B, int H, int W, float mean, float stdv, void* stream) {
+  FM_CHECK_ARG(out && img_u8 && B > 0 && H > 0 && W > 0 && stdv != 0.f, "fm_im2tensor_f32: bad args");
+  FM_CHECK_ARG((static_cast<int64_t>(H) * W) % 4 == 0, "fm_im2tensor_f32: H*W must be a multiple of 4");
+  FM_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(img_u8) & 3) == 0,
+               "fm_im2tensor_f32: output must be 16-byte aligned, image 4-byte aligned");
+  const int64_t total = static_cast<int64_t>(B) * H * W / 4;
+  FM_CHECK_ARG(total < 0x7FFFFFFF, "fm_im2tensor_f32: too many pixels");
+  im2tensor_kernel<<<grid_for2(total), 256, 0, ST>>>(out, static_cast<const uint8_t*>(img_u8), H * W, mean, stdv,
+                                                     static_cast<int>(total));
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
 extern "C" int fm_channel_sum_nhwc(float* sum_bc, const void* x, int B, int HW, int C, int cs, void* stream) {
   FM_CHECK_ARG(sum_bc && x && B > 0 && HW > 0 && C > 0 && cs >= C && cs % 8 == 0 && cs <= 512 && 256 % (cs / 8) == 0,
                "fm_channel_sum_nhwc: bad args (cs must be 8*2^k <= 512)");

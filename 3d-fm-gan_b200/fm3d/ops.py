@@ -412,3 +412,18 @@ def tensor2im_batch(img, cent=1.0, factor=255.0 / 2.0, out=None):
     with torch.cuda.device(img.device):
         _call("fm_tensor2im_u8", _ptr(out), _ptr(img), B, H, W, float(cent), float(factor), _stream())
     return out
+
+
+def im2tensor_batch(img_u8, mean=0.5, std=0.5, out=None):
+    """uint8 NHWC [B,H,W,3] -> fp32 NCHW [B,3,H,W] = (x / 255 - mean) / std on the device: torchvision's ``ToTensor()`` +
+    ``Normalize((mean,)*3, (std,)*3)`` of the reference's transform (train_3_encoder.py:231-237), bit-exact."""
+    _check_cuda(img_u8, "image")
+    if img_u8.dtype != torch.uint8 or img_u8.ndim != 4 or img_u8.shape[3] != 3:
+        raise RuntimeError(f"im2tensor_batch expects uint8 [B,H,W,3], got {img_u8.dtype} {tuple(img_u8.shape)}")
+    img_u8 = img_u8.contiguous()
+    B, H, W, _ = img_u8.shape
+    if out is None:
+        out = torch.empty(B, 3, H, W, device=img_u8.device, dtype=torch.float32)
+    with torch.cuda.device(img_u8.device):
+        _call("fm_im2tensor_f32", _ptr(out), _ptr(img_u8), B, H, W, float(mean), float(std), _stream())
+    return out

@@ -299,6 +299,10 @@ int fm_image_to_nhwc8_padded(void* out, const float* x, int B, int C, int H, int
 /* tensor2im of the whole batch (replaces Evaluation/visual_eval.py:24-38, which converts one image at a time on
  * the host): img fp32 NCHW [B,3,H,W] -> out uint8 NHWC [B,H,W,3] = trunc((clip(img,-1,1) + cent) * factor). */
 int fm_tensor2im_u8(void* out_u8, const float* img, int B, int H, int W, float cent, float factor, void* stream);
+/* Input stage, the inverse of fm_tensor2im_u8 (replaces torchvision ToTensor() + Normalize(mean, std) of the reference's
+ * transform, train_3_encoder.py:231-237, run per image on the loader workers, and the fp32 H2D copy that follows it,
+ * dataset.py:401): img uint8 NHWC [B,H,W,3] -> out fp32 NCHW [B,3,H,W] = (img / 255 - mean) / std, bit-exact. */
+int fm_im2tensor_f32(float* out, const void* img_u8, int B, int H, int W, float mean, float stdv, void* stream);
 /* MaxPool2d(3, stride 2, padding 1): [B,H,W,cs] -> [B,(H-1)/2+1,(W-1)/2+1,cs]. */
 int fm_maxpool3x3s2_nhwc(void* out, const void* x, int B, int H, int W, int cs, void* stream);
 /* Non-overlapping ph x pw average pooling, output fp32 NCHW [B,C,H/ph,W/pw]. */

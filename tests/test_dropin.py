@@ -58,16 +58,20 @@ def test_train_script_and_visual_eval_import_unchanged():
         import Util.training_util, Evaluation.quant_eval
 
         import stylegan2, resnet_encoder, op, Util.network_util as nu, Evaluation.visual_eval as ve, Miscellaneous.distributed as dist
+        import dataset
         inside = lambda m, root: m.__file__.startswith(root + "/")
         # what this path owns comes from the mirror ...
-        for m in (stylegan2, resnet_encoder, op, psp_encoders, nu, ve, dist):
+        for m in (stylegan2, resnet_encoder, op, psp_encoders, nu, ve, dist, dataset):
             assert inside(m, mirror), m.__file__
         # ... and everything else from the reference checkout
-        import dataset
-        for m in (dataset, lpips, Util.training_util, Evaluation.quant_eval, sys.modules["Evaluation.fid"]):
+        for m in (lpips, Util.training_util, Evaluation.quant_eval, sys.modules["Evaluation.fid"]):
             assert inside(m, ref), m.__file__
         assert nu.__shadowed_file__ == ref + "/Util/network_util.py"
         assert ve.__shadowed_file__ == ref + "/Evaluation/visual_eval.py"
+        assert dataset.__shadowed_file__ == ref + "/dataset.py"
+        # dataset classes are the reference's, Data_Loading is the device-side one
+        assert Synthetic_Dataset.__module__ == "dataset" and DualSupervisionSampler.__init__.__code__.co_filename.startswith(ref)
+        assert Data_Loading.__code__.co_filename.startswith(mirror)
         # the funnel and tensor2im are the mirror's; the reference's loops call them
         assert Forward_Inference_3_Encoder.__code__.co_filename.startswith(mirror)
         assert ve.tensor2im.__code__.co_filename.startswith(mirror)

@@ -61,3 +61,43 @@ def test_lpips_and_arcface_on_native_convs(cuda):
                        env=dict(os.environ, PYTHONPATH=""))
     assert r.returncode == 0 and "lossnets-ok" in r.stdout, r.stdout[-2000:] + "\n" + r.stderr[-3000:]
     print(r.stdout[-400:])
+
+
+@pytest.mark.skipif(ref_env.reference_root() is None, reason="no reference source here")
+def test_fid_inception_features_on_native_convs(cuda):
+    """the FID feature extractor (Evaluation/fid.py:27-47 over Evaluation/inception.py, random-init
+    offline) with its 60 square convolutions on the native path (the 34 1x7 / 7x1 / 1x3 / 3x1 ones stay on ATen), against
+    the same module on ATen in strict fp32; and calc_fid (fid.py:50-73) of the two feature sets."""
+    script = """
+        import sys, os
+        sys.path.insert(0, "tools")
+        import ref_env
+        ref_env.activate()
+        import numpy as np
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        from Evaluation.fid import load_patched_inception_v3, calc_fid
+        from fm3d.convgrad import use_native_convs
+        dev = torch.device("cuda:0")
+        torch.manual_seed(0)
+        inc = load_patched_inception_v3().to(dev).eval()
+        assert use_native_convs(inc) == 60
+        g = torch.Generator(device=dev).manual_seed(2)
+        img = torch.rand(64, 3, 256, 256, generator=g, device=dev) * 2 - 1
+
+        def feats(native):
+            os.environ["FM3D_NATIVE_GRAD"] = "1" if native else "0"
+            with torch.no_grad():
+                return inc(img)[0].view(img.shape[0], -1).cpu()
+        a, b = feats(True), feats(False)
+        rel = float((a - b).abs().max() / b.abs().max())
+        cos = float(torch.nn.functional.cosine_similarity(a, b, dim=1).min())
+        print("inception features rel", rel, "min cosine", cos)
+        assert rel < 3e-2 and cos > 0.9995
+        print("inception-ok")
+    """
+    r = subprocess.run([sys.executable, "-c", textwrap.dedent(script)], cwd=ROOT, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, PYTHONPATH=""))
+    assert r.returncode == 0 and "inception-ok" in r.stdout, r.stdout[-2000:] + "\n" + r.stderr[-3000:]
+    print(r.stdout[-300:])

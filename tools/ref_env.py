@@ -117,6 +117,30 @@ def install_shims():
             torchvision.models.vgg16 = vgg16
     except Exception:
         pass
+    # Evaluation/inception.py downloads the FID Inception weights (torch.utils.model_zoo.load_url) into a freshly built
+    # torchvision inception_v3: offline the download is replaced by the state dict of that very instance (random-init)
+    try:
+        import torch.utils.model_zoo as _zoo
+        import torchvision
+        if not getattr(_zoo.load_url, "__fm3d_offline__", False):
+            _orig_inc, _orig_load, _last = torchvision.models.inception_v3, _zoo.load_url, {}
+
+            def inception_v3(*a, **k):
+                k.pop("pretrained", None)
+                k.setdefault("weights", None)
+                k.setdefault("init_weights", False)
+                _last["m"] = _orig_inc(*a, **k)
+                return _last["m"]
+
+            def load_url(url, *a, **k):
+                if "pt_inception" in str(url) and "m" in _last:
+                    return _last["m"].state_dict()
+                return _orig_load(url, *a, **k)
+            load_url.__fm3d_offline__ = True
+            torchvision.models.inception_v3 = inception_v3
+            _zoo.load_url = load_url
+    except Exception:
+        pass
     # torch 1.9 re-exported typing names from torch.utils.data.sampler; dataset.py:17 imports them from there
     import typing
     import torch.utils.data.sampler as _sampler
