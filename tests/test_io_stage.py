@@ -64,8 +64,10 @@ def test_im2tensor_bit_exact(cuda):
     ref = torch.stack([tf(img) for img in imgs])
     got = ops.im2tensor_batch(torch.from_numpy(imgs).to(cuda))
     assert got.shape == (5, 3, 64, 48) and torch.equal(got.cpu(), ref)
-    # and it inverts tensor2im exactly on the uint8 grid
-    assert torch.equal(ops.tensor2im_batch(got).cpu(), torch.from_numpy(imgs))
+    # round trip through the output stage: the reference's tensor2im TRUNCATES (astype(uint8), visual_eval.py:38), so a byte
+    # comes back as itself or one less, never more
+    back = ops.tensor2im_batch(got).cpu().to(torch.int16) - torch.from_numpy(imgs).to(torch.int16)
+    assert int(back.max()) == 0 and int(back.min()) >= -1
 
 
 @pytest.mark.gpu
