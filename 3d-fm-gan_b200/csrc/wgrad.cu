@@ -14,8 +14,14 @@
 // the instruction descriptor just marks A and B as MN-major.
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (TMEM lane quarter =
-// warp % 4).  Persistent CTAs over work items (m-tile, n-tile, tap, k-slice); the fp32 accumulator of an item is added to
-// dW with vector atomics (split-K over pixels: a 128 x 256 tile of one tap would otherwise be one SM's whole job).
+// warp % 4).  Persistent CTAs over work items (m-tile, n-tile, tap group, k-slice); the fp32 accumulators of an item are
+// added to dW with vector atomics (split-K over pixels: a 128 x 256 tile of one tap would otherwise be one SM's whole job).
+//
+// Tap groups: the taps of a conv shift only ONE operand (x); the other (dL/dy) is the same for all of them.  An item takes
+// a group of T taps (T accumulators of BN columns in TMEM, T*BN <= 512): per 64-pixel chunk the shared operand is loaded
+// once and only the T shifted tiles stream -- a one-tap item streams 16 KB + N*128 B per 2N tensor-pipe clocks (96 B/clk
+// per SM at N = 256, 128 at N = 128, against the ~42 B/clk L2->SM budget of the chip), a group of T taps
+// (16 KB + T*N*128 B) per 2*N*T clocks (80 at N = 256 / T = 2, 83 at N = 128 / T = 3).
 //
 // Algorithmic FLOPs per launch: 2 * B*GH*GW * Ca * Cb * ntaps.
 #include <stdlib.h>
@@ -33,6 +39,9 @@ constexpr int WG_MAX_STAGES = 8;
 struct WgradParams {
   int Ca, Cb;
   int m_tiles, n_tiles, ntaps, ksplit, kper, nchunks, num_items;
+  int tg, ngroups;                 // taps per item, number of tap groups
+  int share_a;                     // 1: the A operand is common to the taps of a group (B tiles stream), 0: the B operand is
+  int stages, stage_bytes, a_slot_bytes, b_slot_bytes, nbuf;
   int tw, th, tb, tiles_x, tiles_y;
   int sa, sb;
   float* dw;
@@ -46,10 +55,9 @@ struct WgradCfg {
   static constexpr int NB_BOXES = BN >= 64 ? BN / 64 : 1;
   static constexpr int A_BYTES = 2 * WG_BOX_BYTES;                 // 128 channels
   static constexpr int B_BYTES = NB_BOXES * WG_BOX_BYTES;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (192 * 1024 / STAGE_BYTES) > WG_MAX_STAGES ? WG_MAX_STAGES : (192 * 1024 / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int RING_BYTES = 192 * 1024;
+  static constexpr int SMEM_BYTES = RING_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int TMEM_COLS = 512;    // up to T accumulators of BN columns (x2 when they fit twice)
 };
 
 // Instruction descriptor: D = f32, A = B = bf16, both MN-major (bits 15, 16), dense, M x N.
@@ -84,7 +92,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   using Cfg = WgradCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES);
   uint64_t* full_bar = bars;                         // [STAGES] TMA -> MMA
   uint64_t* empty_bar = bars + WG_MAX_STAGES;        // [STAGES] MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * WG_MAX_STAGES;    // [2] MMA -> epilogue
@@ -95,7 +103,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < WG_MAX_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     fence_barrier_init();
   }
@@ -108,9 +116,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   pdl_launch_dependents();
 
   // item -> (m-tile, n-tile, tap, k-slice); k-slice fastest so that the CTAs working on one dW tile run concurrently
+  // (`tap` is the first tap of the item's group; the group holds min(tg, ntaps - tap) taps)
   auto decode = [&](int it, int& mt, int& nt, int& tap, int& c0, int& c1) {
     const int ks = it % p.ksplit; it /= p.ksplit;
-    tap = it % p.ntaps; it /= p.ntaps;
+    tap = (it % p.ngroups) * p.tg; it /= p.ngroups;
     nt = it % p.n_tiles;
     mt = it / p.n_tiles;
     c0 = ks * p.kper;
@@ -124,26 +133,36 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       int mt, nt, tap, c0, c1;
       decode(it, mt, nt, tap, c0, c1);
-      const int dya = p.dya[tap], dxa = p.dxa[tap], dyb = p.dyb[tap], dxb = p.dxb[tap];
+      const int nt_g = min(p.tg, p.ntaps - tap);           // taps in this group
+      const int na = p.share_a ? 1 : nt_g, nb = p.share_a ? nt_g : 1;
+      const uint32_t tx = static_cast<uint32_t>(na) * Cfg::A_BYTES + static_cast<uint32_t>(nb) * Cfg::B_BYTES;
       // chunk c -> tile (bx, by, bb) of the contraction grid
       int bx = c0 % p.tiles_x, t = c0 / p.tiles_x;
       int by = t % p.tiles_y, bb = t / p.tiles_y;
       for (int c = c0; c < c1; ++c) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
+          uint8_t* sa = smem + stage * p.stage_bytes;
+          uint8_t* sb = sa + p.a_slot_bytes;
           const int gx = bx * p.tw, gy = by * p.th, gb = bb * p.tb;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          for (int i = 0; i < na; ++i) {
+            const int dya = p.dya[tap + i], dxa = p.dxa[tap + i];
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-            tma_load_4d(sa + j * WG_BOX_BYTES, &tmA, &full_bar[stage], mt * WG_BM + j * 64, gx * p.sa + dxa, gy * p.sa + dya, gb);
+            for (int j = 0; j < 2; ++j)
+              tma_load_4d(sa + i * Cfg::A_BYTES + j * WG_BOX_BYTES, &tmA, &full_bar[stage], mt * WG_BM + j * 64, gx * p.sa + dxa,
+                          gy * p.sa + dya, gb);
+          }
+          for (int i = 0; i < nb; ++i) {
+            const int dyb = p.dyb[tap + i], dxb = p.dxb[tap + i];
 #pragma unroll
-          for (int j = 0; j < Cfg::NB_BOXES; ++j)
-            tma_load_4d(sb + j * WG_BOX_BYTES, &tmB, &full_bar[stage], nt * BN + j * 64, gx * p.sb + dxb, gy * p.sb + dyb, gb);
+            for (int j = 0; j < Cfg::NB_BOXES; ++j)
+              tma_load_4d(sb + i * Cfg::B_BYTES + j * WG_BOX_BYTES, &tmB, &full_bar[stage], nt * BN + j * 64, gx * p.sb + dxb,
+                          gy * p.sb + dyb, gb);
+          }
         }
         __syncwarp();
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
         if (++bx == p.tiles_x) { bx = 0; if (++by == p.tiles_y) { by = 0; ++bb; } }
       }
     }
@@ -159,20 +178,23 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       decode(it, mt, nt, tap, c0, c1);
       mbar_wait(&tempty_bar[buf], aphase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + buf * BN;
+      const int nt_g = min(p.tg, p.ntaps - tap);
+      const uint32_t tmem_d = tmem_base + buf * (p.tg * BN);
       for (int c = c0; c < c1; ++c) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = ring + stage * Cfg::STAGE_BYTES;
+        const uint32_t sa = ring + stage * p.stage_bytes, sb = sa + p.a_slot_bytes;
         if (elect_one()) {
-          umma_bf16_x4_mn(tmem_d, umma_desc_lo_mn(sa), dhi, umma_desc_lo_mn(sa + Cfg::A_BYTES), dhi, idesc, c > c0 ? 1u : 0u);
+          for (int i = 0; i < nt_g; ++i)
+            umma_bf16_x4_mn(tmem_d + i * BN, umma_desc_lo_mn(sa + (p.share_a ? 0 : i) * Cfg::A_BYTES), dhi,
+                            umma_desc_lo_mn(sb + (p.share_a ? i : 0) * Cfg::B_BYTES), dhi, idesc, c > c0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (c == c1 - 1) umma_commit(&tfull_bar[buf]);
         }
         __syncwarp();
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (++buf == 2) { buf = 0; aphase ^= 1; }
+      if (++buf == p.nbuf) { buf = 0; aphase ^= 1; }
     }
   } else {
     // ============================== epilogue (4 warps) ==============================
@@ -185,27 +207,30 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int mt, nt, tap, c0, c1;
       decode(it, mt, nt, tap, c0, c1);
       const int a = mt * WG_BM + row;
-      float* base = p.dw + static_cast<long long>(tap) * p.dw_tap_stride + static_cast<long long>(a) * p.dw_row_stride + nt * BN;
+      const int nt_g = min(p.tg, p.ntaps - tap);
       mbar_wait(&tfull_bar[buf], aphase);
       tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+      for (int i = 0; i < nt_g; ++i) {
+        float* base = p.dw + static_cast<long long>(tap + i) * p.dw_tap_stride + static_cast<long long>(a) * p.dw_row_stride + nt * BN;
+        const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (p.tg * BN) + i * BN;
 #pragma unroll 1
-      for (int cb = 0; cb < BN; cb += 16) {
-        uint32_t acc[16];
-        tmem_ld_32x16(tmem_acc + cb, acc);
-        tmem_ld_wait();
-        if (a < p.Ca) {
-          const int b0 = nt * BN + cb;
+        for (int cb = 0; cb < BN; cb += 16) {
+          uint32_t acc[16];
+          tmem_ld_32x16(tmem_acc + cb, acc);
+          tmem_ld_wait();
+          if (a < p.Ca) {
+            const int b0 = nt * BN + cb;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            if (vec_ok && b0 + j + 3 < p.Cb) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + cb + j), "f"(__uint_as_float(acc[j])),
-                           "f"(__uint_as_float(acc[j + 1])), "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3]))
-                           : "memory");
-            } else {
+            for (int j = 0; j < 16; j += 4) {
+              if (vec_ok && b0 + j + 3 < p.Cb) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + cb + j), "f"(__uint_as_float(acc[j])),
+                             "f"(__uint_as_float(acc[j + 1])), "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3]))
+                             : "memory");
+              } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (b0 + j + e < p.Cb) atomicAdd(base + cb + j + e, __uint_as_float(acc[j + e]));
+                for (int e = 0; e < 4; ++e)
+                  if (b0 + j + e < p.Cb) atomicAdd(base + cb + j + e, __uint_as_float(acc[j + e]));
+              }
             }
           }
         }
@@ -213,7 +238,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-      if (++buf == 2) { buf = 0; aphase ^= 1; }
+      if (++buf == p.nbuf) { buf = 0; aphase ^= 1; }
     }
   }
   tc_fence_before();
@@ -303,8 +328,38 @@ extern "C" int fm_conv_wgrad(const fm_wgrad_desc* d, void* stream) {
   for (int i = 0; i < d->ntaps; ++i) {
     p.dya[i] = d->tap_dy_a[i]; p.dxa[i] = d->tap_dx_a[i]; p.dyb[i] = d->tap_dy_b[i]; p.dxb[i] = d->tap_dx_b[i];
   }
+  // tap groups: the operand whose shift is the same for every tap (the grid operand, dL/dy) is loaded once per chunk
+  {
+    static const int env_tg = []() { const char* e = getenv("FM3D_WGRAD_TG"); return e ? atoi(e) : 0; }();
+    bool same_a = true, same_b = true;
+    for (int i = 1; i < d->ntaps; ++i) {
+      same_a = same_a && p.dya[i] == p.dya[0] && p.dxa[i] == p.dxa[0];
+      same_b = same_b && p.dyb[i] == p.dyb[0] && p.dxb[i] == p.dxb[0];
+    }
+    const int a_bytes = 2 * WG_BOX_BYTES, b_bytes = (bn >= 64 ? bn / 64 : 1) * WG_BOX_BYTES;
+    int tg = 1;
+    p.share_a = same_a ? 1 : 0;
+    if (d->ntaps > 1 && (same_a || same_b)) {
+      const int streamed = same_a ? b_bytes : a_bytes, shared = same_a ? a_bytes : b_bytes;
+      tg = 512 / bn;                                              // T accumulators of BN columns
+      while (tg > 1 && shared + tg * streamed > 96 * 1024) --tg;  // at least two stages in the 192 KB ring
+      if (tg > d->ntaps) tg = d->ntaps;
+      // balanced groups: 9 taps as 3 x 3 rather than 4 + 4 + 1
+      const int ng = (d->ntaps + tg - 1) / tg;
+      tg = (d->ntaps + ng - 1) / ng;
+      if (env_tg > 0 && env_tg < tg) tg = env_tg;
+    }
+    p.tg = tg;
+    p.ngroups = (d->ntaps + tg - 1) / tg;
+    p.a_slot_bytes = (p.share_a ? 1 : tg) * a_bytes;
+    p.b_slot_bytes = (p.share_a ? tg : 1) * b_bytes;
+    p.stage_bytes = p.a_slot_bytes + p.b_slot_bytes;
+    p.stages = (192 * 1024) / p.stage_bytes;
+    if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
+    p.nbuf = (2 * tg * bn <= 512) ? 2 : 1;
+  }
   // split-K over pixels: aim at >= 2 items per SM, keep >= 8 chunks per item
-  const int64_t items0 = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.ntaps;
+  const int64_t items0 = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.ngroups;
   int ksplit = d->ksplit;
   if (ksplit <= 0) {
     const int sms = sm_count();
