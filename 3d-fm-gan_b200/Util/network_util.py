@@ -72,30 +72,46 @@ def Forward_Inference_3_Encoder(p_input, r_input, E_Tsr, E_W, E_W_Plus, g_ema, t
         s1, s2 = _side_streams(p_input.device)
         s1.wait_stream(main)
         s2.wait_stream(main)
+        # SM partition: the ResNets' ~40 launches of 10-40 us each are latency-bound on the whole chip; confined to a
+        # few SMs they take about as long, and the W+ encoder's large layers keep the rest instead of time-slicing
+        from fm3d import ops as _ops
+        cap_r, cap_p, cap_g = _ops.sm_partition(p_input.device)
         pair = None
         if _RESNET_PAIR and tsr_in is r_input:
             # both ResNet-18s encode the render: one grouped launch sequence (fm3d/encoder_engine.py:ResNetPlan)
             from fm3d.encoder_engine import run_resnet_pair
             ma, mb = getattr(E_Tsr, "module", E_Tsr), getattr(E_W, "module", E_W)
             if all(hasattr(m, "_engine_ok") and hasattr(m, "layer1") and m._engine_ok(r_input) for m in (ma, mb)):
-                with torch.cuda.stream(s1):
+                with torch.cuda.stream(s1), _ops.cta_cap(2 * cap_r):
                     pair = run_resnet_pair(ma, mb, r_input)
         if pair is not None:
             encoded_tensor, encoded_W = pair
         else:
-            with torch.cuda.stream(s1):
+            with torch.cuda.stream(s1), _ops.cta_cap(cap_r):
                 encoded_tensor = E_Tsr(tsr_in)
-            with torch.cuda.stream(s2):
+            with torch.cuda.stream(s2), _ops.cta_cap(cap_r):
                 encoded_W = E_W(r_input)
-        encoded_W_plus = E_W_Plus(p_input)
+        with _ops.cta_cap(cap_p):
+            encoded_W_plus = E_W_Plus(p_input)
         main.wait_stream(s1)
         main.wait_stream(s2)
         for t in (encoded_tensor, encoded_W, p_input, r_input):
             t.record_stream(main)
     else:
-        encoded_tensor = E_Tsr(tsr_in)
-        encoded_W = E_W(r_input)
-        encoded_W_plus = E_W_Plus(p_input)
+        cap_r = cap_p = cap_g = 0
+        if p_input.is_cuda and os.environ.get("FM3D_PARTITION_SERIAL", "0") != "0":
+            # measurement aid (bench.py's per-launch roofline pass): the launches of the concurrent path, one stream
+            from fm3d import ops as _ops
+            cap_r, cap_p, cap_g = _ops.sm_partition(p_input.device)
+            with _ops.cta_cap(cap_r):
+                encoded_tensor = E_Tsr(tsr_in)
+                encoded_W = E_W(r_input)
+            with _ops.cta_cap(cap_p):
+                encoded_W_plus = E_W_Plus(p_input)
+        else:
+            encoded_tensor = E_Tsr(tsr_in)
+            encoded_W = E_W(r_input)
+            encoded_W_plus = E_W_Plus(p_input)
 
     n = encoded_W_plus.shape[1]
     if sliced_layer is None:
@@ -104,9 +120,15 @@ def Forward_Inference_3_Encoder(p_input, r_input, E_Tsr, E_W, E_W_Plus, g_ema, t
     w = encoded_W.unsqueeze(1)
     encoded_latent = w * encoded_W_plus * gate + w * (1.0 - gate)
 
-    g_output = g_ema(noise_z=None, latent_styles=[encoded_latent], input_is_latent=True,
-                     use_external_input_tensor=True, external_input_tensor=encoded_tensor,
-                     PPL_regularize=PPL_regularize)
+    if cap_g:
+        with _ops.cta_cap(cap_g):
+            g_output = g_ema(noise_z=None, latent_styles=[encoded_latent], input_is_latent=True,
+                             use_external_input_tensor=True, external_input_tensor=encoded_tensor,
+                             PPL_regularize=PPL_regularize)
+    else:
+        g_output = g_ema(noise_z=None, latent_styles=[encoded_latent], input_is_latent=True,
+                         use_external_input_tensor=True, external_input_tensor=encoded_tensor,
+                         PPL_regularize=PPL_regularize)
     if use_tanh:
         if PPL_regularize:
             g_output = (torch.tanh(g_output[0]), g_output[1])

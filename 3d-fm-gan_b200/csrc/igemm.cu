@@ -28,6 +28,7 @@ constexpr int IG_BK = 64;      // channels per k-step (128 B rows, SWIZZLE_128B)
 constexpr int IG_TRACE_N = 64;     // trace slots per CTA (debug)
 constexpr int IG_HP_MAXA = 8;      // halo-patch slots (barrier pairs reserved)
 constexpr int IG_MAX_STAGES = 12;  // operand-ring barrier pairs reserved (generic ring: Cfg::STAGES; halo-patch weight ring: hp_stages)
+constexpr int IG_TILEQ = 32;      // entries of the dynamic tile queue
 constexpr int IG_TAB_ROWS = 512;  // staged table rows per tile (tile_b_eff * BLOCK_N <= 512)
 
 struct IgemmParams {
@@ -70,6 +71,8 @@ struct IgemmParams {
   const float* border_tab;
   long long* trace;                // debug (FM3D_TRACE=1): per-CTA event timestamps [grid][IG_TRACE_N]
   int out_cgroup, cg_shrink;
+  int max_ctas;                    // host only: cap of the persistent grid (0 = every SM)
+  int* tile_ctr;                   // dynamic tile schedule: [0] next super tile, [1] clusters done (NULL = static round robin)
   long long out_gstride;
   void* out;
   int out_H, out_W, out_cstride, out_y0, out_x0, out_ys, out_xs, out_nchw_f32;
@@ -119,6 +122,27 @@ __constant__ int8_t c_up_acc[4][4] = {{0, 1, 2, 3}, {0, 2, 0, 0}, {0, 1, 0, 0}, 
 __constant__ int8_t c_up_dy[4] = {0, 0, -1, -1};
 __constant__ int8_t c_up_dx[4] = {0, -1, 0, -1};
 
+// Reader side of the dynamic tile queue (see igemm_conv_kernel): wait until slot k % IG_TILEQ carries the generation of
+// the cluster's k-th tile and return the tile index.  Not inlined: called once per tile per warp, and its temporaries
+// stay out of the register allocation of the epilogue (which sits at the 168-register ceiling).
+__device__ __noinline__ int tileq_wait(const uint32_t* q, int k) {
+  const uint32_t gen = ((static_cast<uint32_t>(k) / IG_TILEQ) & 1u) + 1u;
+  const volatile uint32_t* slotp = reinterpret_cast<const volatile uint32_t*>(q + (k & (IG_TILEQ - 1)));
+  uint32_t w = *slotp;
+  if ((w >> 24) != gen) {
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (((w = *slotp) >> 24) != gen) {
+      __nanosleep(20);
+      if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
+        printf("fm3d: tile queue wait timeout (block %d thread %d, k %d)\n", blockIdx.x, threadIdx.x, k);
+        __trap();
+      }
+    }
+  }
+  return static_cast<int>(w & 0xffffffu);
+}
+
 // PAIR: cta_group::2 instantiation (a kernel that contains 2-CTA tcgen05 instructions can only be launched with an
 // even cluster size, so the single-CTA paths live in their own instantiation).
 template <int BN, int EPI, bool PAIR>
@@ -143,8 +167,17 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tempty_bar = bars + 2 * IG_MAX_STAGES + 2;  // [2]   epilogue -> MMA
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * IG_MAX_STAGES + 4);
   uint64_t* afull_bar = bars + 2 * IG_MAX_STAGES + 5;   // [IG_HP_MAXA] halo-patch slots: TMA -> MMA
-  static_assert((2 * IG_MAX_STAGES + 5 + 2 * IG_HP_MAXA) * 8 <= 512, "barrier region");
   uint64_t* aempty_bar = afull_bar + IG_HP_MAXA;      // [IG_HP_MAXA] MMA -> TMA
+  // dynamic tile schedule: the cluster leader's producer draws super-tile indices from a global counter and publishes
+  // them, in order, into every CTA's queue.  An entry is ONE word, (generation << 24) | tile with generation =
+  // (k / IG_TILEQ) % 2 + 1 for the cluster's k-th tile (a slot holds 0, the previous round's entry or this round's):
+  // readers poll the slot with plain volatile loads until the generation matches (no fences: nothing else is communicated through it; acquire/release at cluster scope compile
+  // to MEMBAR.GPU and an L1 invalidate per poll).  The producer runs at most IG_MAX_STAGES + 1 tiles ahead of the MMA
+  // warp (one stage per tile at least) and the MMA warp at most 2 tiles ahead of the epilogue, so a slot is never
+  // overwritten while a reader still needs it.
+  uint32_t* s_tileq = reinterpret_cast<uint32_t*>(aempty_bar + IG_HP_MAXA);
+  static_assert((2 * IG_MAX_STAGES + 5 + 2 * IG_HP_MAXA) * 8 + IG_TILEQ * 4 <= 512, "barrier region");
+  static_assert(IG_TILEQ >= IG_MAX_STAGES + 1 + 2 + 4 && (IG_TILEQ & (IG_TILEQ - 1)) == 0, "tile queue depth");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -165,6 +198,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], IG_EPI_WARPS * (kPair ? 2 : 1));   // one arrive per epilogue warp (of both CTAs of a pair)
     }
+    for (int i = 0; i < IG_TILEQ; ++i) reinterpret_cast<volatile uint32_t*>(s_tileq)[i] = 0;
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -189,6 +223,45 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int cluster_id = blockIdx.x / p.cluster, num_clusters = gridDim.x / p.cluster;
   const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1);
 
+  // ---- tile schedule.  tile_at(k) = the k-th super tile of this cluster (>= num_super: no more work).
+  // Static: round robin over the clusters of the grid.  Dynamic (tile_ctr != NULL): drawn from a global counter, so a
+  // CTA that got its SM late (another stream's kernel was still on it) simply takes fewer tiles instead of delaying the
+  // whole grid -- what lets small layers of other networks run on a few SMs next to this kernel.
+  const bool dyn = p.tile_ctr != nullptr;
+  const bool q_leader = dyn && warp == 0 && crank == 0;
+  // leader producer only.  The first tile of every cluster is its static one (no round trip to the counter before the
+  // first load); tile k >= 1 is num_clusters + (a draw from the counter).  A draw is issued (tile_draw) one tile before
+  // it is published, so its latency hides behind a tile's worth of loads.
+  int q_fetched = 1;            // entries known so far (entry 0 is implicit)
+  bool q_ended = false, q_pending = false;
+  int q_id = 0;                 // lane 0: the draw in flight
+  auto tile_draw = [&]() {
+    if (q_leader && !q_pending && !q_ended) {
+      if (lane == 0) q_id = atomicAdd(p.tile_ctr, 1);
+      q_pending = true;
+    }
+  };
+  auto tile_at = [&](int k) -> int {
+    if (!dyn || k == 0) return cluster_id + k * num_clusters;
+    if (q_leader) {
+      while (q_fetched <= k && !q_ended) {
+        tile_draw();
+        int id = __shfl_sync(0xffffffffu, q_id, 0) + num_clusters;
+        q_pending = false;
+        if (id >= p.num_super) { id = p.num_super; q_ended = true; }
+        if (lane == 0) {
+          const uint32_t slot = smem_u32(&s_tileq[q_fetched & (IG_TILEQ - 1)]);
+          const uint32_t word = (static_cast<uint32_t>(((q_fetched / IG_TILEQ) & 1) + 1) << 24) | static_cast<uint32_t>(id);
+          for (int r = 0; r < p.cluster; ++r) st_cluster_u32(mapa_rank(slot, r), word);
+        }
+        ++q_fetched;
+        __syncwarp();
+      }
+      if (k >= q_fetched) return p.num_super;      // past the end marker
+    }
+    return tileq_wait(s_tileq, k);
+  };
+
   const int kiters = p.ntaps * p.kchunks;
   // debug trace: slot i of this CTA <- clock (one writer per slot)
   long long* trc = p.trace ? p.trace + static_cast<size_t>(blockIdx.x) * IG_TRACE_N : nullptr;
@@ -201,7 +274,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t phase = 0;
     const uint32_t tx_bytes = static_cast<uint32_t>(p.rows) * (IG_BK * 2) + Cfg::B_BYTES;
     // halo-patch mode: patch cursor (tile, chunk) runs hp_dist chunks ahead of the weight cursor, across tiles
-    int pst = cluster_id, pkc = 0, pslot = 0;
+    int pk = 0, pst = (p.hp || p.hpw) ? tile_at(0) : 0, pkc = 0, pslot = 0;      // patch cursor: pst = tile_at(pk)
+    tile_draw();
     uint32_t pphase = 0;
     const uint32_t patch_tx = static_cast<uint32_t>(p.hp_pw) * p.hp_ph * (IG_BK * 2);
     const int nvc = p.kchunks * p.hp_np;          // virtual chunks: (channel chunk, parity plane)
@@ -226,7 +300,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       __syncwarp();
-      if (++pkc == nvc) { pkc = 0; pst += num_clusters; }
+      if (++pkc == nvc) { pkc = 0; pst = tile_at(++pk); tile_draw(); }
       if (++pslot == p.hp_na) { pslot = 0; pphase ^= 1; }
     };
     if (p.hpw) {
@@ -245,12 +319,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
       }
       __syncwarp();
-      for (int st = cluster_id; st < p.num_super; st += num_clusters)
-        for (int vc = 0; vc < nvc; ++vc) hp_prefetch();           // blocks on the patch ring only
+      while (pst < p.num_super) hp_prefetch();                    // blocks on the patch ring only
     } else {
     if (p.hp)
       for (int i = 0; i < p.hp_dist; ++i) hp_prefetch();
-    if (p.wres && lane == 0 && cluster_id < p.num_super) {
+    const bool any_tile = p.wres && tile_at(0) < p.num_super;
+    if (p.wres && lane == 0 && any_tile) {
       // resident weights: every (tap, chunk) tile once per CTA (a TMA load costs ~5-6 clk per 128-byte row, and the
       // 3- and 7-tap stem convs spent a third of their rows re-loading the same 64 weight rows per tap for every tile)
       mbar_arrive_expect_tx(&afull_bar[0], static_cast<uint32_t>(kiters) * Cfg::B_BYTES);
@@ -262,7 +336,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncwarp();
     if (lane == 0) IG_TRACE(1);
     int ptile = 0;
-    for (int st = cluster_id; st < p.num_super; st += num_clusters) {
+    for (int tk = 0;; ++tk) {
+      const int st = tile_at(tk);
+      if (st >= p.num_super) break;
+      tile_draw();                    // tile tk + 1: drawn now, published when the producer gets there (the consumers are a
+                                      // ring of stages behind), so the counter's round trip hides behind this tile's loads
       const int ph = p.nph > 1 ? st / p.nsup1 : 0;
       const int stl = st - ph * p.nsup1;
       const int nt = stl % p.tiles_n;
@@ -416,7 +494,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int hp_nvc = p.kchunks * p.hp_np;
     const bool hp_np1 = p.hp_np == 1;
     // CTA pair: only the leader issues (its MMAs read both CTAs' operands and write both CTAs' TMEM)
-    for (int st = (kPair && crank != 0) ? p.num_super : cluster_id; st < p.num_super; st += num_clusters, ++titer, next_acc()) {
+    for (;; ++titer, next_acc()) {
+      const int st = (kPair && crank != 0) ? p.num_super : tile_at(titer);
+      if (st >= p.num_super) break;
       mbar_wait(&tempty_bar[buf], aphase ^ 1);     // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * BN;
@@ -613,7 +693,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int buf = 0;
     uint32_t aphase = 0;
     auto next_acc = [&]() { if (++buf == p.nbuf) { buf = 0; aphase ^= 1; } };
-    for (int st = cluster_id; st < p.num_super; st += num_clusters, ++titer, next_acc()) {
+    for (;; ++titer, next_acc()) {
+      const int st = tile_at(titer);
+      if (st >= p.num_super) break;
       // tile coordinates: the common single-n-tile / unsplit / ungrouped cases skip their integer divisions (each costs
       // ~25 dependent instructions, and a 64-channel tile's whole epilogue is only ~300 per warp)
       const int eph = p.nph > 1 ? st / p.nsup1 : 0;
@@ -877,6 +959,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   if (threadIdx.x == 64) IG_TRACE(IG_TRACE_N - 1);           // epilogue finished its last tile
+  if (dyn && crank == 0 && threadIdx.x == 0) {
+    // this cluster drew its last index (the end marker) earlier in this thread's program order; the last cluster to
+    // get here re-arms both counters for the next launch that shares them (stream-ordered after this grid)
+    __threadfence();
+    if (atomicAdd(p.tile_ctr + 1, 1) == num_clusters - 1) {
+      atomicExch(p.tile_ctr, 0);
+      atomicExch(p.tile_ctr + 1, 0);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (p.cluster > 1) cluster_sync_all();           // no CTA exits while a peer may still multicast into it
@@ -957,7 +1048,8 @@ static int launch_igemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const I
   using Cfg = IgemmCfg<BN>;
   static SmemOptIn opt_in;        // per instantiation, per device
   FM_CUDA_OK(smem_opt_in(opt_in, igemm_conv_kernel<BN, EPI, PAIR>, Cfg::SMEM_BYTES));
-  const int sms = sm_count();
+  int sms = sm_count();
+  if (p.max_ctas > 0 && p.max_ctas < sms) sms = p.max_ctas < p.cluster ? p.cluster : p.max_ctas;
   const int max_clusters = sms / p.cluster;
   const int nclusters = p.num_super < max_clusters ? p.num_super : max_clusters;
   cudaLaunchConfig_t cfg{};
@@ -973,7 +1065,7 @@ static int launch_igemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const I
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = (pdl_enabled() && p.max_ctas <= 0) ? 2 : 1;
   FM_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_conv_kernel<BN, EPI, PAIR>, tmA, tmB, p));
   count_launch();
   FM_LAUNCH_OK();
@@ -998,7 +1090,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     if (rc != FM_OK) return rc;
     const int64_t total = static_cast<int64_t>(p.B) * p.OH * p.OW * (p.ws_cs / 8);
     int64_t blocks = (total + 255) / 256;
-    const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
+    const int64_t cap = p.max_ctas > 0 ? static_cast<int64_t>(p.max_ctas) * 8 : static_cast<int64_t>(sm_count()) * 32;
     if (blocks > cap) blocks = cap;
     FM_CUDA_OK(launch_pdl(igemm_splitk_finalize_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, p, total));
     count_launch();
@@ -1101,7 +1193,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     if (eligible) {
       const int bn_wide = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
       const int64_t tiles_wide = static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.tiles_b * ((d->Cout + bn_wide - 1) / bn_wide);
-      const int sms = sm_count();
+      const int sms = (d->max_ctas > 0 && d->max_ctas < sm_count()) ? d->max_ctas : sm_count();
       int want = d->ksplit > 1 ? d->ksplit : static_cast<int>(sms / (tiles_wide > 0 ? tiles_wide : 1));
       if (want > kiters_total / 6) want = kiters_total / 6;       // keep >= 6 k-iterations per CTA
       if (want > 16) want = 16;
@@ -1122,7 +1214,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   } else if (bn <= 0) {
     bn = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
     // small problems: more, narrower tiles fill more SMs
-    const int sms = sm_count();
+    const int sms = (d->max_ctas > 0 && d->max_ctas < sm_count()) ? d->max_ctas : sm_count();
     while (bn > 64 && static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.tiles_b * ((d->Cout + bn - 1) / bn) < sms) bn >>= 1;
   }
   if (d->upmode && bn > 128) bn = 128;      // 4 accumulators x BN columns must fit the 512 TMEM columns
@@ -1160,6 +1252,8 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   p.rgb = d->rgb;
   p.border_tab = d->border_tab;
   p.out_cgroup = d->out_cgroup; p.out_gstride = d->out_gstride; p.cg_shrink = d->out_cgroup_ow_shrink;
+  p.max_ctas = d->max_ctas;
+  p.tile_ctr = d->tile_counter;       // dropped below when the tile index does not fit the queue's 24 bits
   int max_widx = 0;
   for (int i = 0; i < d->ntaps; ++i) {
     p.tap_dy[i] = d->tap_dy[i]; p.tap_dx[i] = d->tap_dx[i]; p.tap_widx[i] = d->tap_widx[i];
@@ -1391,6 +1485,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       p.num_super = static_cast<int>(tot);
     }
   }
+  if (p.num_super >= (1 << 24) - 1) p.tile_ctr = nullptr;      // queue entries carry 24 bits of tile index
   // ---- tensor maps
   CUtensorMap tmA, tmB;
   {

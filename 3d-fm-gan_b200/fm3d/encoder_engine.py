@@ -86,6 +86,7 @@ class _Conv:
 # ResNet-18
 # ======================================================================================
 _FUSE_UPSAMPLE = os.environ.get("FM3D_FUSE_UPSAMPLE", "1") != "0"
+_SKIP_RESNET = os.environ.get("FM3D_SKIP_RESNET", "0") != "0"       # experiment: replay the outputs of the third call
 
 
 class ResNetPlan:
@@ -160,9 +161,16 @@ class ResNetPlan:
 
     def run(self, x):
         self.refresh()
+        if _SKIP_RESNET:
+            self._calls = getattr(self, "_calls", 0) + 1
+            if self._calls > 4:
+                return [o.clone() for o in self._kept]
         prev, ops.PROFILE_TAG = ops.PROFILE_TAG, "resnet"
         try:
-            return self.runner(x.contiguous().float())
+            out = self.runner(x.contiguous().float())
+            if _SKIP_RESNET:
+                self._kept = out
+            return out
         finally:
             ops.PROFILE_TAG = prev
 
@@ -215,7 +223,7 @@ def run_resnet(model, x):
     if not _resnet_ok(model, x):
         return None
     plans = plans_of(model)
-    key = (tuple(x.shape), x.device.index, ops.current_slot())
+    key = (tuple(x.shape), x.device.index, ops.current_slot(), ops.current_cap())      # captured graphs bake the grid sizes in
     plan = plans.get(key)
     if plan is None:
         plan = plans[key] = ResNetPlan([model], x.shape[0], x.shape[2], x.shape[3], x.device)
@@ -227,7 +235,7 @@ def run_resnet_pair(model_a, model_b, x):
     if model_a is model_b or not (_resnet_ok(model_a, x) and _resnet_ok(model_b, x)):
         return None
     plans = plans_of(model_a)
-    key = ("pair", id(model_b), tuple(x.shape), x.device.index, ops.current_slot())
+    key = ("pair", id(model_b), tuple(x.shape), x.device.index, ops.current_slot(), ops.current_cap())
     plan = plans.get(key)
     if plan is None or plan.models[1] is not model_b:
         plan = plans[key] = ResNetPlan([model_a, model_b], x.shape[0], x.shape[2], x.shape[3], x.device)
@@ -445,7 +453,7 @@ def run_psp(model, x):
     if m.style_count < m.middle_ind + 1 or m.coarse_ind != 3 or m.middle_ind != 7:
         return None
     plans = plans_of(m)
-    key = (x.shape[0], x.device.index, ops.current_slot())
+    key = (x.shape[0], x.device.index, ops.current_slot(), ops.current_cap())
     plan = plans.get(key)
     if plan is None:
         plan = plans[key] = PspPlan(m, x.shape[0], x.device)

@@ -414,7 +414,7 @@ def check_inputs(gen, latent, start, noise):
 def run_synthesis(gen, latent, start, noise):
     """Entry used by ``stylegan2.Generator.forward``: cached plan per (batch, device, engine slot)."""
     plans = plans_of(gen)
-    key = (latent.shape[0], latent.device.index, ops.current_slot())
+    key = (latent.shape[0], latent.device.index, ops.current_slot(), ops.current_cap())
     plan = plans.get(key)
     if plan is None:
         plan = plans[key] = SynthesisPlan(gen, latent.shape[0], latent.device)

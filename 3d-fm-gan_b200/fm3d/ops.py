@@ -37,7 +37,48 @@ def current_slot():
     return _SLOT.value
 
 
-# bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops, tag) per conv launch;
+# ---- SM partitions: ``with cta_cap(n):`` confines the persistent grids of the implicit-GEMM launches issued inside to
+# n CTAs (one CTA owns an SM).  The two ResNet-18 encoders are ~40 launches of 10-40 us that are latency-bound on 148
+# SMs; on a few SMs they take about as long and the rest of the chip keeps running the large layers of the other
+# networks (fm_conv_desc.max_ctas).
+class _Cap(threading.local):
+    value = 0
+
+
+_CAP = _Cap()
+
+
+def current_cap():
+    return _CAP.value
+
+
+def sm_partition(device):
+    """(CTAs per ResNet-18, CTAs of the W+ encoder's launches, CTAs of the generator's launches; 0 = every SM) for the
+    3-encoder forward when its three encoders run concurrently.  Measured on B200 at batch 32 (tools/exp_partition.sh,
+    profiles/r02_sm_partition.txt): 16 / 116 / all is +5.5 % images/s over every launch taking all 148 SMs.
+    FM3D_PARTITION=0 turns it off, FM3D_PARTITION=r,p,g sets the three numbers."""
+    env = __import__("os").environ.get("FM3D_PARTITION", "")
+    if env == "0":
+        return 0, 0, 0
+    if env:
+        r, p, g = (int(v) for v in env.split(","))
+        return r, p, g
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    r = max(2, (sms * 16 // 148) // 2 * 2)
+    return r, sms - 2 * r, 0
+
+
+@contextlib.contextmanager
+def cta_cap(n):
+    prev = _CAP.value
+    _CAP.value = int(n or 0)
+    try:
+        yield
+    finally:
+        _CAP.value = prev
+
+
+# bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops, tag, max_ctas) per conv launch;
 # PROFILE_TAG names the network the launches belong to (set by the engines: "generator", "resnet", "psp")
 PROFILE = None
 PROFILE_TAG = ""
@@ -185,6 +226,30 @@ def _splitk_workspace(device):
     return ws
 
 
+_DYN_TILES = __import__("os").environ.get("FM3D_DYNTILES", "0") != "0"
+_DYN_TILES_ALL = __import__("os").environ.get("FM3D_DYNTILES", "0") == "2"     # tools: also eager launches, one pair per stream
+_EAGER_CTR = {}
+
+
+def _tile_counter(device):
+    """Counter pair of the dynamic tile schedule (fm_conv_desc.tile_counter), one per engine plan: a plan's launches
+    are stream-ordered, and plans that run concurrently (other streams, other batches in flight) are other owners.
+    Outside a plan (eager calls from autograd, tools) launches keep the static schedule."""
+    owner = _SCOPE.owner
+    if not _DYN_TILES:
+        return None
+    if owner is None:
+        if not _DYN_TILES_ALL:
+            return None
+        store, device = _EAGER_CTR, (device, torch.cuda.current_stream(device).cuda_stream)
+    else:
+        store = owner.__dict__.setdefault("_tile_ctr", {})
+    ctr = store.get(device)
+    if ctr is None:
+        ctr = store[device] = torch.zeros(2, device=device[0] if isinstance(device, tuple) else device, dtype=torch.int32)
+    return ctr
+
+
 def conv_taps(kh, kw, pad):
     """Tap list (dy, dx, weight slab) of a plain correlation (F.conv2d semantics)."""
     return [(ky - pad, kx - pad, ky * kw + kx) for ky in range(kh) for kx in range(kw)]
@@ -195,7 +260,8 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
                tab_per_sample=False, noise=None, noise_per_sample=True, noise_w=None, residual=None,
                rgb=None, block_n=0, tile_w=0, tile_h=0, stride_x=0, stride_y=0, x_pixstride=0, x_rowstride=0,
                x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None, ksplit=0, upmode=False,
-               out_cgroup_ow_shrink=0, algo_flops=None, residual_up=None, out_pitch_h=0, out_pitch_w=0, phases=None):
+               out_cgroup_ow_shrink=0, algo_flops=None, residual_up=None, out_pitch_h=0, out_pitch_w=0, phases=None,
+               max_ctas=None, tile_counter=None):
     """Launch fm_conv_igemm.  x: bf16 NHWC [B,H,W,cs]; w: bf16 [slabs, w_rows, cin_stride];
     out: bf16 NHWC [B,out_H,out_W,cs_out] or fp32 NCHW; tab: fp32 [B|1, Cout, 8]."""
     d = ConvDesc()
@@ -233,6 +299,8 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     ws = _splitk_workspace(x.device)
     d.splitk_ws, d.splitk_ws_bytes, d.ksplit = ws.data_ptr(), ws.numel() * 4, ksplit
     d.upmode = 1 if upmode else 0
+    d.max_ctas = _CAP.value if max_ctas is None else max_ctas
+    d.tile_counter = _ptr(tile_counter if tile_counter is not None else _tile_counter(x.device))
     if phases is not None:               # [(ntaps, out_y0, out_x0)]: several output phases in one launch (taps concatenated)
         d.nphases = len(phases)
         for i, (nt, py0, px0) in enumerate(phases):
@@ -248,7 +316,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
             # up mode: algorithmic FLOPs of the stride-2 transposed conv = 9 taps at the INPUT resolution
             # launches that pad their weights with zero blocks pass their algorithmic FLOPs explicitly
             prof.append((e0, e1, algo_flops if algo_flops is not None else
-                         2.0 * B * (H * W if upmode else OH * OW) * Cin * Cout * len(taps), PROFILE_TAG))
+                         2.0 * B * (H * W if upmode else OH * OW) * Cin * Cout * len(taps), PROFILE_TAG, int(d.max_ctas)))
     _lib.check(st, "fm_conv_igemm")
     return out
 

@@ -203,7 +203,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=int(os.environ.get("FM3D_BENCH_INFLIGHT", "2")),
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("FM3D_BENCH_INFLIGHT", "3")),
                     help="batches in flight per GPU: consecutive steps alternate between this many streams (each with "
                          "its own engine plan), so one batch's large kernels fill the SMs another batch's small ones leave idle")
     args = ap.parse_args()
@@ -365,22 +365,32 @@ def main():
         # stream's kernel holds (every igemm CTA owns a whole SM), not the kernel itself.
         prof = []
         ops.PROFILE = prof
-        prev_streams = os.environ.get("FM3D_STREAMS")
+        prev_env = {k: os.environ.get(k) for k in ("FM3D_STREAMS", "FM3D_PARTITION_SERIAL")}
         os.environ["FM3D_STREAMS"] = "0"
+        os.environ["FM3D_PARTITION_SERIAL"] = "1"        # the same launches (SM partitions included) as the timed region
         for i in range(2):
             step(*dev_in[i % n_sets])
         torch.cuda.synchronize()
-        if prev_streams is None:
-            del os.environ["FM3D_STREAMS"]
-        else:
-            os.environ["FM3D_STREAMS"] = prev_streams
+        for k, v in prev_env.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
         ops.PROFILE = None
+    # A launch confined to n of the device's SMs (fm_conv_desc.max_ctas: the ResNet-18s on 16 SMs each, the W+ encoder
+    # on the other 116) is measured against the peak of those n SMs: its duration counts with weight n / SMs -- in the
+    # timed region the other SMs run the other networks' kernels at the same time.  The unweighted sum (every launch
+    # charged the whole chip for its duration, as if the rest idled) is reported next to it.
+    n_sms = torch.cuda.get_device_properties(device).multi_processor_count
+    share = lambda cap: (min(cap, n_sms) / n_sms) if cap and cap > 0 else 1.0
     flops = sum(r[2] for r in prof)
-    ksec = sum(r[0].elapsed_time(r[1]) for r in prof) * 1e-3
+    ksec_raw = sum(r[0].elapsed_time(r[1]) for r in prof) * 1e-3
+    ksec = sum(r[0].elapsed_time(r[1]) * share(r[4]) for r in prof) * 1e-3
     by_net = {}
-    for (a, b, f, tag) in prof:
-        e = by_net.setdefault(tag or "other", [0.0, 0.0, 0])
-        e[0] += f; e[1] += a.elapsed_time(b) * 1e-3; e[2] += 1
+    for (a, b, f, tag, cap) in prof:
+        e = by_net.setdefault(tag or "other", [0.0, 0.0, 0, 0.0, 0.0])
+        dt = a.elapsed_time(b) * 1e-3
+        e[0] += f; e[1] += dt * share(cap); e[2] += 1; e[3] += dt; e[4] = share(cap)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -408,9 +418,16 @@ def main():
                 # transposed ones; the 1x1 ToRGBs are fused into their epilogues) -- BASELINE's "modconv TC util"
                 "by_network": {k: {"achieved": v[0] / v[1] / 1e12, "frac": v[0] / v[1] / 1e12 / peak_tf,
                                    "frac_burst": v[0] / v[1] / 1e12 / peak_burst, "launches_per_step": v[2] // 2,
-                                   "kernel_ms_per_step": v[1] * 1e3 / 2, "algorithmic_gflop_per_step": v[0] / 2 / 1e9}
+                                   "sm_share": v[4], "kernel_ms_per_step": v[3] * 1e3 / 2,
+                                   "tflops_on_its_sms": v[0] / v[3] / 1e12,
+                                   "algorithmic_gflop_per_step": v[0] / 2 / 1e9}
                                for k, v in sorted(by_net.items()) if v[1] > 0},
-                "launches_per_step": len(prof) // 2, "kernel_ms_per_step": ksec * 1e3 / 2,
+                "sm_share_weighted": "a launch confined to n SMs is measured against the peak of n SMs (duration x n/SMs); "
+                                     "achieved_unweighted charges every launch the whole chip",
+                "achieved_unweighted": flops / ksec_raw / 1e12 if ksec_raw > 0 else 0.0,
+                "frac_unweighted": (flops / ksec_raw / 1e12 / peak_tf) if ksec_raw > 0 else 0.0,
+                "launches_per_step": len(prof) // 2, "kernel_ms_per_step": ksec_raw * 1e3 / 2,
+                "sm_weighted_ms_per_step": ksec * 1e3 / 2,
                 "algorithmic_gflop_per_step": flops / 2 / 1e9,
                 "traffic": traffic, "traffic_unit": traffic_src}
 
@@ -467,6 +484,8 @@ def main():
         "config": {"workload": WORKLOAD.format(B=B),
                    "global_batch": B * world, "parallelism": f"batch-sharded replicas x{world} (no collective)",
                    "batches_in_flight": f"{NS} per GPU (consecutive steps alternate between {NS} streams, each with its own plan)",
+                   "sm_partition": "CTAs per launch (one CTA owns an SM): ResNet-18 {} each / W+ encoder {} / generator {}".format(
+                       *[v or "all" for v in ops.sm_partition(device)]),
                    "l2": f"{n_sets} distinct input batches rotate ({n_sets * 2 * img_bytes / 1e6:.0f} MB > L2); "
                          "a step streams > 2 GB of activations"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * img_bytes, "d2h_bytes_per_step": img_bytes,

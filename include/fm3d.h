@@ -180,6 +180,17 @@ typedef struct {
    * instead of in launches of their own.  Stride 1, ungrouped, halo-patch eligible shapes only (OH >= 12, OW >= 8). */
   int32_t nphases;
   int32_t phase_ntaps[4], phase_out_y0[4], phase_out_x0[4];
+  /* max_ctas > 0: the persistent grid takes at most this many CTAs (= SMs: one CTA owns an SM) instead of every SM of
+   * the device.  A latency-bound network of small layers (the two ResNet-18 encoders) confined to a few SMs runs next
+   * to the large layers of the other networks instead of time-slicing the whole chip with them; such launches do not
+   * use programmatic dependent launch (the next kernel's CTAs would wait on SMs outside the partition). */
+  int32_t max_ctas;
+  /* tile_counter != NULL: dynamic tile schedule.  Two int32 in device memory, zero before the first launch; the CTAs
+   * draw their tiles from [0] instead of taking them round robin, and the last cluster to finish re-zeroes both, so
+   * launches that are stream-ordered (or programmatically dependent) may share one pair.  Launches that can run
+   * concurrently must not.  A CTA that got its SM late -- another stream's kernel still held it -- then takes fewer
+   * tiles instead of delaying the grid. */
+  int32_t* tile_counter;
 } fm_conv_desc;
 
 int fm_conv_igemm(const fm_conv_desc* desc, void* stream);

@@ -404,3 +404,75 @@ def test_conv_output_pitch(cuda):
     assert torch.equal(outs[1][:, :H, :H], outs[0])
     assert float(outs[1][:, H].abs().max()) == 0.0 and float(outs[1][:, :, H].abs().max()) == 0.0
     torch.testing.assert_close(rgbs[1], rgbs[0], rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------ dynamic tile schedule / SM partitions
+@pytest.mark.parametrize("B,H,Cin,Cout,k,stride,cap", [
+    (4, 64, 64, 64, 3, 1, 0),       # halo patch, resident weights (hpw)
+    (4, 64, 64, 64, 3, 1, 5),       # the same confined to 5 SMs
+    (2, 64, 128, 256, 3, 1, 0),     # CTA pairs + halo patch
+    (2, 64, 128, 256, 3, 1, 7),     # CTA pairs, odd cap (rounded down to whole clusters)
+    (2, 128, 64, 128, 3, 1, 12),    # row-patch mode
+    (2, 64, 128, 512, 1, 1, 0),     # 1x1, several n-tiles
+    (3, 32, 128, 256, 3, 2, 9),     # stride 2, generic ring
+    (8, 16, 256, 256, 3, 1, 0),     # small M (split-K eligible when a workspace is given)
+    (2, 64, 8, 64, 3, 1, 3),        # single K chunk: many more stages than a tile uses (queue depth)
+])
+def test_dynamic_tile_schedule_matches_static(cuda, B, H, Cin, Cout, k, stride, cap):
+    """fm_conv_desc.tile_counter / max_ctas change which CTA computes a tile, never the tile: outputs are identical to
+    the static round robin, and the counter pair is back at zero after every launch."""
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(H + Cin + cap)
+    x = torch.randn(B, H, H, (Cin + 7) // 8 * 8, generator=gen).to(torch.bfloat16).to(cuda)
+    w = (torch.randn(k * k, Cout, (Cin + 7) // 8 * 8, generator=gen) / (Cin * k * k) ** 0.5).to(torch.bfloat16).to(cuda)
+    tab = torch.zeros(1, Cout, 8, device=cuda)
+    tab[..., 0] = torch.rand(Cout, generator=gen).to(cuda) + 0.5
+    tab[..., 1] = 0.1
+    tab[..., 2] = 0.2
+    tab[..., 3] = 1.0
+    OH = (H + 2 * (k // 2) - k) // stride + 1
+    outs = []
+    ctr = torch.zeros(2, device=cuda, dtype=torch.int32)
+    for c in (None, ctr, ctr):                           # static, dynamic, dynamic again on the re-armed counters
+        out = torch.zeros(B, OH, OH, Cout, device=cuda, dtype=torch.bfloat16)
+        ops.conv_igemm(x, w, ops.conv_taps(k, k, k // 2), out, tab, B=B, H=H, W=H, Cin=Cin, Cout=Cout, OH=OH, OW=OH,
+                       stride=stride, tile_counter=c, max_ctas=cap if c is not None else 0, ksplit=1)
+        torch.cuda.synchronize()
+        assert ctr.tolist() == [0, 0]
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = F.conv2d(x[..., :Cin].float().permute(0, 3, 1, 2).cpu(), w[..., :Cin].float().view(k, k, Cout, Cin).permute(2, 3, 0, 1).cpu(),
+                   stride=stride, padding=k // 2)
+    ref = ref * tab[0, :, 0].cpu().view(1, -1, 1, 1) + 0.1
+    ref = torch.where(ref > 0, ref, 0.2 * ref)
+    torch.testing.assert_close(outs[1].float().permute(0, 3, 1, 2).cpu(), ref, rtol=2e-2, atol=2e-2)
+
+
+def test_dynamic_tile_schedule_up_phases(cuda):
+    """Several output phases in one launch (phase = tile coordinate) under the dynamic schedule and an SM cap."""
+    from fm3d import ops
+    B, h, Cin, Cout = 2, 32, 128, 128
+    gen = torch.Generator().manual_seed(3)
+    x = torch.zeros(B, h + 1, h + 1, Cin, dtype=torch.bfloat16)
+    x[:, :h, :h] = torch.randn(B, h, h, Cin, generator=gen).to(torch.bfloat16)
+    x = x.to(cuda)
+    w = (torch.randn(9, Cout, Cin, generator=gen) / (Cin * 9) ** 0.5).to(torch.bfloat16).to(cuda)
+    from fm3d.engine import _up_phase_taps
+    taps, ph = [], []
+    for py in (0, 1):
+        for px in (0, 1):
+            tl = _up_phase_taps(py, px)
+            taps += tl
+            ph.append((len(tl), py, px))
+    outs = []
+    ctr = torch.zeros(2, device=cuda, dtype=torch.int32)
+    for c, cap in ((None, 0), (ctr, 0), (ctr, 10)):
+        out = torch.zeros(1, B * (2 * h + 2), 2 * h + 2, Cout, device=cuda, dtype=torch.bfloat16)
+        ops.conv_igemm(x.view(1, B * (h + 1), h + 1, Cin), w, taps, out, None, B=1, H=B * (h + 1), W=h + 1, Cin=Cin, Cout=Cout,
+                       OH=B * (h + 1), OW=h + 1, out_H=B * (2 * h + 2), out_W=2 * h + 2, out_ys=2, out_xs=2, phases=ph,
+                       tile_counter=c, max_ctas=cap)
+        torch.cuda.synchronize()
+        assert ctr.tolist() == [0, 0]
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert float(outs[0].float().abs().max()) > 0.1

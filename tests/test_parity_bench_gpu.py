@@ -74,6 +74,46 @@ def test_three_encoder_forward_benchmarked_batch(cuda, B):
     np.testing.assert_allclose([float(img.mean()), float(img.std())], g["img.stats"], rtol=0, atol=2e-2)
 
 
+def test_sm_partition_does_not_change_the_result(cuda, monkeypatch):
+    """The 3-encoder forward with the ResNets / W+ encoder confined to SM partitions (fm_conv_desc.max_ctas, the
+    default of the concurrent funnel) against every launch on the whole chip: the partition decides where a tile
+    runs (and, through the SM count, a split-K factor), never what it computes."""
+    from Util.network_util import Forward_Inference_3_Encoder
+    from fm3d import ops
+    B = 8
+    (e_tsr, e_w, e_wp, gen), p, r, noise = build_three_encoder_models(cuda, B=B)
+    p, r = p.to(cuda), r.to(cuda)
+    noise = [n.to(cuda) for n in noise]
+
+    class _G(torch.nn.Module):                     # fixed noise: the generator draws fresh noise otherwise
+        def __init__(s, m):
+            super().__init__(); s.module = m
+        def forward(s, *a, **k):
+            k["noise"] = noise
+            return s.module(*a, **k)
+    gen = _G(gen)
+    outs = {}
+    for part in ("0", "", "6,20,40"):
+        monkeypatch.setenv("FM3D_PARTITION", part)
+        assert ops.sm_partition(cuda) == {"0": (0, 0, 0), "6,20,40": (6, 20, 40)}.get(part, ops.sm_partition(cuda))
+        with torch.no_grad():
+            for _ in range(3):         # eager, eager, graph capture + replay
+                img = Forward_Inference_3_Encoder(p, r, e_tsr, e_w, e_wp, gen, tsr_encode='Render Image')
+        outs[part] = img.float().cpu()
+    monkeypatch.delenv("FM3D_PARTITION")
+    r16, rp, rg = ops.sm_partition(cuda)
+    assert r16 > 0 and rp > 0 and 2 * r16 + rp == torch.cuda.get_device_properties(cuda).multi_processor_count and rg == 0
+    # not bit-identical: the SM count enters the split-K factor and block_n of the small layers, i.e. the order of fp32
+    # sums, and a flipped bf16 rounding (2^-8) early in 30 layers grows to ~1 % of the image's range at single pixels
+    # (measured: max 1.7 %, rms 0.1 %) -- the same bar as the bf16 engine against the reference
+    scale = float(outs["0"].abs().max())
+    for part in ("", "6,20,40"):
+        d = outs[part] - outs["0"]
+        err, rms = float(d.abs().max()) / scale, float(d.pow(2).mean().sqrt()) / scale
+        print(f"partition {part or 'auto'}: max {err:.4f} rms {rms:.5f}")
+        assert err < 3e-2 and rms < 5e-3, (part, err, rms)
+
+
 def test_generator_b32_engine_vs_fp32_composition(cuda, monkeypatch):
     """All 13 modulated layers + 7 ToRGBs at B=32 on the engine vs the differentiable fp32 composition (cuDNN fp32,
     TF32 off), every resolution's RGB: localises a wrong layer to its resolution."""
