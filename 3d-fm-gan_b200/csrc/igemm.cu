@@ -72,6 +72,7 @@ struct IgemmParams {
   long long* trace;                // debug (FM3D_TRACE=1): per-CTA event timestamps [grid][IG_TRACE_N]
   int out_cgroup, cg_shrink;
   int max_ctas;                    // host only: cap of the persistent grid (0 = every SM)
+  float* colsum;                   // plain epilogue only: colsum[b][o] += sum over the tile's pixels of the stored value (SE squeeze)
   int* tile_ctr;                   // dynamic tile schedule: [0] next super tile, [1] clusters done (NULL = static round robin)
   long long out_gstride;
   void* out;
@@ -904,6 +905,31 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           v[j] = x * t0.w;
         }
         }
+        if constexpr (EPI == 0) {
+          if (p.colsum != nullptr) {
+            // per-channel sums of the tile's outputs (the squeeze of an SE block, psp model_irse bottleneck_IR_SE: the
+            // AdaptiveAvgPool2d(1) over this conv's output): 16 columns x 32 rows per warp, reduced by a transposing
+            // butterfly (16 shuffles: each step halves the columns a lane carries) and added with one fp32 reduction
+            // per column and warp.  tile_b == 1: the warp's rows belong to one image.
+            float s8[8], s4[4], s2[2];
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float lo = valid ? v[j] : 0.f, hi = valid ? v[8 + j] : 0.f;
+              s8[j] = (h16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h16 ? lo : hi, 16);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s4[j] = (h8 ? s8[4 + j] : s8[j]) + __shfl_xor_sync(0xffffffffu, h8 ? s8[j] : s8[4 + j], 8);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) s2[j] = (h4 ? s4[2 + j] : s4[j]) + __shfl_xor_sync(0xffffffffu, h4 ? s4[j] : s4[2 + j], 4);
+            float s1 = (h2 ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? s2[0] : s2[1], 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            const int colj = (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);      // the column this lane pair ended up with
+            const int bt = bb * p.tb;
+            if (!(lane & 1) && o0 + colj < p.Cout && bt < p.B)
+              atomicAdd(p.colsum + static_cast<size_t>(bt) * p.Cout + o0 + colj, s1);
+          }
+        }
         if (valid && p.out && ox < p.OW - og * p.cg_shrink) {   // out == NULL: only the fused ToRGB sums are wanted
           if (p.out_nchw_f32) {
             const size_t plane = static_cast<size_t>(p.out_H) * p.out_W;
@@ -1144,6 +1170,9 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   FM_CHECK_ARG(!d->out_cgroup || (!d->out_nchw_f32 && d->out_cgroup % 32 == 0 && d->Cout % d->out_cgroup == 0 &&
                                   d->out_cstride % 8 == 0 && d->out_cstride >= d->out_cgroup && d->out_gstride % 8 == 0),
                "fm_conv_igemm: bad grouped-output parameters");
+  FM_CHECK_ARG(!d->colsum || (d->tab && !d->rgb && !d->residual && !d->border_tab && !d->out_nchw_f32 && !d->out_cgroup && !d->upmode &&
+                              d->nphases <= 1 && d->ksplit <= 1 && d->groups <= 1),
+               "fm_conv_igemm: colsum needs the plain epilogue (no rgb / residual / border_tab / grouped or fp32 output / split-K)");
   const int G = d->groups > 1 ? d->groups : 1;
   FM_CHECK_ARG(d->B % G == 0, "fm_conv_igemm: batch %d not divisible by groups %d", d->B, G);
   const int Bg = d->B / G;
@@ -1188,7 +1217,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   int ksplit = 1;
   {
     static const int env_split = []() { const char* e = getenv("FM3D_SPLITK"); return e ? atoi(e) : 1; }();
-    const bool eligible = env_split && nph == 1 && d->tab && d->residual_up_h <= 0 && d->ksplit != 1 && d->splitk_ws && !d->rgb && !d->border_tab && !d->out_nchw_f32 &&
+    const bool eligible = env_split && nph == 1 && d->tab && !d->colsum && d->residual_up_h <= 0 && d->ksplit != 1 && d->splitk_ws && !d->rgb && !d->border_tab && !d->out_nchw_f32 &&
                           !d->out_cgroup && d->block_n <= 0 && !d->upmode;
     if (eligible) {
       const int bn_wide = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
@@ -1253,6 +1282,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   p.border_tab = d->border_tab;
   p.out_cgroup = d->out_cgroup; p.out_gstride = d->out_gstride; p.cg_shrink = d->out_cgroup_ow_shrink;
   p.max_ctas = d->max_ctas;
+  p.colsum = d->colsum;
   p.tile_ctr = d->tile_counter;       // dropped below when the tile index does not fit the queue's 24 bits
   int max_widx = 0;
   for (int i = 0; i < d->ntaps; ++i) {
@@ -1485,6 +1515,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       p.num_super = static_cast<int>(tot);
     }
   }
+  FM_CHECK_ARG(!p.colsum || p.tb == 1, "fm_conv_igemm: colsum needs tiles inside one image (OH*OW >= 128 per image)");
   if (p.num_super >= (1 << 24) - 1) p.tile_ctr = nullptr;      // queue entries carry 24 bits of tile index
   // ---- tensor maps
   CUtensorMap tmA, tmB;

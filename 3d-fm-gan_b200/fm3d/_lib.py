@@ -36,7 +36,7 @@ class ConvDesc(C.Structure):
         ("residual_up_h", C.c_int32), ("residual_up_w", C.c_int32),
         ("out_pitch_h", C.c_int32), ("out_pitch_w", C.c_int32),
         ("nphases", C.c_int32), ("phase_ntaps", C.c_int32 * 4), ("phase_out_y0", C.c_int32 * 4), ("phase_out_x0", C.c_int32 * 4),
-        ("max_ctas", C.c_int32), ("tile_counter", C.c_void_p),
+        ("max_ctas", C.c_int32), ("tile_counter", C.c_void_p), ("colsum", C.c_void_p),
     ]
 
 

@@ -86,6 +86,7 @@ class _Conv:
 # ResNet-18
 # ======================================================================================
 _FUSE_UPSAMPLE = os.environ.get("FM3D_FUSE_UPSAMPLE", "1") != "0"
+_FUSE_SE_SUM = os.environ.get("FM3D_FUSE_SE_SUM", "1") != "0"
 _SKIP_RESNET = os.environ.get("FM3D_SKIP_RESNET", "0") != "0"       # experiment: replay the outputs of the third call
 
 
@@ -385,13 +386,15 @@ class PspPlan:
         for i, u in enumerate(self.units):
             oh = u.c2.out_size(h)
             r1 = u.c1.run(cur, self._buf(("r1", i), B, h, h, u.c1.cout), B, h, h)
-            r2 = u.c2.run(r1, self._buf(("r2", i), B, oh, oh, u.depth), B, h, h)
+            # the SE squeeze (per-channel mean of r2) rides on this conv's epilogue when a tile lies inside one image
+            fused_sum = _FUSE_SE_SUM and oh * oh >= 128 and (oh * oh) % 128 == 0
+            r2 = u.c2.run(r1, self._buf(("r2", i), B, oh, oh, u.depth), B, h, h, **(dict(colsum=self.sum_buf, ksplit=1) if fused_sum else {}))
             if u.sc is not None:
                 sc, ss = u.sc.run(cur, self._buf(("sc", i), B, oh, oh, u.depth), B, h, h), 1
             else:
                 sc, ss = cur, u.stride
             cur = ops.se_block_nhwc(r2, u.depth, u.se_w1, u.se_w2, sc, ss, self.sum_buf, self.gate_buf,
-                                    self._buf(("out", i), B, oh, oh, u.depth))
+                                    self._buf(("out", i), B, oh, oh, u.depth), summed=fused_sum)
             h = oh
             feats[i] = (cur, h)
         (c1, h1), (c2, h2), (c3, h3) = feats[3], feats[5], feats[7]

@@ -261,7 +261,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
                rgb=None, block_n=0, tile_w=0, tile_h=0, stride_x=0, stride_y=0, x_pixstride=0, x_rowstride=0,
                x_imgstride=0, groups=1, border_tab=None, out_cgroup=0, out_gstride=0, out_cstride=None, ksplit=0, upmode=False,
                out_cgroup_ow_shrink=0, algo_flops=None, residual_up=None, out_pitch_h=0, out_pitch_w=0, phases=None,
-               max_ctas=None, tile_counter=None):
+               max_ctas=None, tile_counter=None, colsum=None):
     """Launch fm_conv_igemm.  x: bf16 NHWC [B,H,W,cs]; w: bf16 [slabs, w_rows, cin_stride];
     out: bf16 NHWC [B,out_H,out_W,cs_out] or fp32 NCHW; tab: fp32 [B|1, Cout, 8]."""
     d = ConvDesc()
@@ -301,6 +301,7 @@ def conv_igemm(x, w, taps, out, tab, *, B, H, W, Cin, Cout, OH, OW, stride=1, w_
     d.upmode = 1 if upmode else 0
     d.max_ctas = _CAP.value if max_ctas is None else max_ctas
     d.tile_counter = _ptr(tile_counter if tile_counter is not None else _tile_counter(x.device))
+    d.colsum = _ptr(colsum)
     if phases is not None:               # [(ntaps, out_y0, out_x0)]: several output phases in one launch (taps concatenated)
         d.nphases = len(phases)
         for i, (nt, py0, px0) in enumerate(phases):
@@ -448,12 +449,14 @@ def avgpool_nhwc_to_nchw(x, channels, ph, pw):
     return out
 
 
-def se_block_nhwc(r, channels, w1, w2, shortcut, sc_stride, sum_buf, gate_buf, out):
-    """out = r * sigmoid(w2 relu(w1 mean_hw(r))) + shortcut[:, ::s, ::s]  (3 launches)."""
+def se_block_nhwc(r, channels, w1, w2, shortcut, sc_stride, sum_buf, gate_buf, out, summed=False):
+    """out = r * sigmoid(w2 relu(w1 mean_hw(r))) + shortcut[:, ::s, ::s]  (3 launches; 2 when the conv that produced r
+    already accumulated the channel sums into sum_buf: ``conv_igemm(..., colsum=sum_buf)``)."""
     B, H, W, cs = r.shape
     st = _stream()
     with torch.cuda.device(r.device):
-        _call("fm_channel_sum_nhwc", _ptr(sum_buf), _ptr(r), B, H * W, channels, cs, st)
+        if not summed:
+            _call("fm_channel_sum_nhwc", _ptr(sum_buf), _ptr(r), B, H * W, channels, cs, st)
         _call("fm_se_gate", _ptr(gate_buf), _ptr(sum_buf), 1.0 / (H * W), _ptr(w1), _ptr(w2), B, channels, w1.shape[0], st)
         _call("fm_se_combine_nhwc", _ptr(out), _ptr(r), _ptr(gate_buf), _ptr(shortcut), B, H, W, channels, cs,
               shortcut.shape[1], shortcut.shape[2], shortcut.shape[3], sc_stride, st)

@@ -191,6 +191,11 @@ typedef struct {
    * concurrently must not.  A CTA that got its SM late -- another stream's kernel still held it -- then takes fewer
    * tiles instead of delaying the grid. */
   int32_t* tile_counter;
+  /* colsum != NULL (plain epilogue only: tab, no rgb / residual / border_tab / split-K / groups, bf16 NHWC output, tiles
+   * inside one image): colsum[b][o] += sum over the pixels of out[b,:,:,o] (the values before bf16 rounding), fp32
+   * [B][Cout], accumulated with atomics -- the squeeze (global average pool) of the SE block that follows the second
+   * conv of a bottleneck_IR_SE unit (psp_encoder_model/encoders/helpers.py), without a pass over the output. */
+  float* colsum;
 } fm_conv_desc;
 
 int fm_conv_igemm(const fm_conv_desc* desc, void* stream);

@@ -476,3 +476,41 @@ def test_dynamic_tile_schedule_up_phases(cuda):
         outs.append(out)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert float(outs[0].float().abs().max()) > 0.1
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,stride,bn", [
+    (3, 32, 64, 64, 1, 0),       # halo patch, resident weights
+    (2, 64, 64, 128, 2, 0),      # stride 2
+    (2, 128, 64, 64, 1, 0),      # row-patch mode (R accumulators per tile)
+    (2, 16, 128, 320, 1, 0),     # ragged Cout, several n-tiles, CTA pairs
+    (5, 16, 256, 512, 2, 128),   # 8x8 outputs: half-empty tiles would straddle images -> tile_b must stay 1
+])
+def test_conv_fused_channel_sums(cuda, B, H, Cin, Cout, stride, bn):
+    """fm_conv_desc.colsum: per-(sample, channel) sums of the conv's output accumulated in the epilogue (the SE squeeze)
+    against a sum over the stored tensor."""
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(H + Cout)
+    x = torch.randn(B, H, H, Cin, generator=gen).to(torch.bfloat16).to(cuda)
+    w = (torch.randn(9, Cout, Cin, generator=gen) / (Cin * 9) ** 0.5).to(torch.bfloat16).to(cuda)
+    tab = torch.zeros(1, Cout, 8, device=cuda)
+    tab[..., 0] = torch.rand(Cout, generator=gen).to(cuda) + 0.5
+    tab[..., 1] = torch.randn(Cout, generator=gen).to(cuda) * 0.3
+    tab[..., 2] = 0.25
+    tab[..., 3] = 1.0
+    OH = (H + 2 - 3) // stride + 1
+    out = torch.zeros(B, OH, OH, (Cout + 7) // 8 * 8, device=cuda, dtype=torch.bfloat16)
+    sums = torch.zeros(B, Cout, device=cuda)
+    if OH * OH < 128:
+        with pytest.raises(RuntimeError, match="colsum"):
+            ops.conv_igemm(x, w, ops.conv_taps(3, 3, 1), out, tab, B=B, H=H, W=H, Cin=Cin, Cout=Cout, OH=OH, OW=OH,
+                           stride=stride, colsum=sums, ksplit=1, block_n=bn)
+        return
+    for _ in range(2):                 # accumulates: two launches = twice the sums
+        ops.conv_igemm(x, w, ops.conv_taps(3, 3, 1), out, tab, B=B, H=H, W=H, Cin=Cin, Cout=Cout, OH=OH, OW=OH,
+                       stride=stride, colsum=sums, ksplit=1, block_n=bn)
+    torch.cuda.synchronize()
+    ref = 2.0 * out[..., :Cout].float().sum((1, 2))
+    # out is bf16-rounded, the fused sums are taken before rounding: relative to the sum of magnitudes
+    mag = 2.0 * out[..., :Cout].float().abs().sum((1, 2)) + 1e-3
+    assert float(((sums - ref).abs() / mag).max()) < 2e-3
+    assert float(sums.abs().max()) > 1.0
