@@ -257,6 +257,13 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// Relaxed variant: orders nothing but the barrier itself.  For hand-overs whose payload is not in memory -- a drained TMEM
+// accumulator, ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.  The release form compiles to MEMBAR.ALL.GPU +
+// ERRBAR, i.e. the arriving lane waits until every global store of the tile it just wrote is visible device-wide
+// (ncu: 12 % of the samples of a small-K pair kernel sat on it).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

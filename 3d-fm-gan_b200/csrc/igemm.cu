@@ -72,6 +72,9 @@ struct IgemmParams {
   long long* trace;                // debug (FM3D_TRACE=1): per-CTA event timestamps [grid][IG_TRACE_N]
   int out_cgroup, cg_shrink;
   int max_ctas;                    // host only: cap of the persistent grid (0 = every SM)
+  // EPI_RESUP: per tile, the box of the low-resolution residual that the tile's bilinear taps touch is staged in smem by
+  // TMA (two channel slabs of res_slab_ch channels, pixel pitch res_pitch bytes = 16 mod 128: conflict-free 16-byte reads)
+  int res_bw, res_bh, res_pitch, res_box_bytes, res_slab_bytes, res_slot_bytes, res_off, res_nslab;   // slab stride = box bytes rounded to 128
   float* colsum;                   // plain epilogue only: colsum[b][o] += sum over the tile's pixels of the stored value (SE squeeze)
   int* tile_ctr;                   // dynamic tile schedule: [0] next super tile, [1] clusters done (NULL = static round robin)
   long long out_gstride;
@@ -108,7 +111,7 @@ template <int BN> struct IgemmCfg {
   static constexpr int RING_BYTES = 200 * 1024;
   static constexpr int TAB_BYTES = IG_TAB_ROWS * 32;
   static constexpr int RGB_BYTES = IG_BM * 16;
-  static constexpr int SMEM_BYTES = RING_BYTES + TAB_BYTES + RGB_BYTES + 512 /*barriers*/;
+  static constexpr int SMEM_BYTES = RING_BYTES + TAB_BYTES + RGB_BYTES + 1024 /*barriers, tile queue*/;
   static constexpr int TMEM_COLS = 512;   // 2 buffers x R rows x BN columns; one CTA per SM owns all of TMEM
 };
 
@@ -148,7 +151,8 @@ __device__ __noinline__ int tileq_wait(const uint32_t* q, int k) {
 // even cluster size, so the single-CTA paths live in their own instantiation).
 template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(IG_THREADS2, 1)
-igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p_in) {
+igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmR, const IgemmParams p_in) {
   using Cfg = IgemmCfg<BN>;
   // kPair as a compile-time constant inside the kernel
   const IgemmParams& p = p_in;
@@ -177,7 +181,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // warp (one stage per tile at least) and the MMA warp at most 2 tiles ahead of the epilogue, so a slot is never
   // overwritten while a reader still needs it.
   uint32_t* s_tileq = reinterpret_cast<uint32_t*>(aempty_bar + IG_HP_MAXA);
-  static_assert((2 * IG_MAX_STAGES + 5 + 2 * IG_HP_MAXA) * 8 + IG_TILEQ * 4 <= 512, "barrier region");
+  uint64_t* rfull_bar = reinterpret_cast<uint64_t*>(s_tileq + IG_TILEQ);      // [2] EPI_RESUP: residual box landed (TMA -> epilogue)
+  uint64_t* rempty_bar = rfull_bar + 2;                                        // [2] epilogue -> TMA
+  static_assert((2 * IG_MAX_STAGES + 5 + 2 * IG_HP_MAXA) * 8 + IG_TILEQ * 4 + 4 * 8 <= 1024, "barrier region");
   static_assert(IG_TILEQ >= IG_MAX_STAGES + 1 + 2 + 4 && (IG_TILEQ & (IG_TILEQ - 1)) == 0, "tile queue depth");
 
   const int warp = threadIdx.x >> 5;
@@ -187,6 +193,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if ((smem_u32(smem) & 1023u) != 0) { printf("fm3d: dynamic smem base not 1024-aligned\n"); __trap(); }
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (EPI & EPI_RESUP) tma_prefetch_desc(&tmR);
     for (int i = 0; i < IG_MAX_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], kPair ? 1 : p.cluster);   // multicast commit of every CTA (cluster) / of the leader (pair)
@@ -200,6 +207,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tempty_bar[i], IG_EPI_WARPS * (kPair ? 2 : 1));   // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int i = 0; i < IG_TILEQ; ++i) reinterpret_cast<volatile uint32_t*>(s_tileq)[i] = 0;
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&rfull_bar[i], 1);
+      mbar_init(&rempty_bar[i], IG_EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -337,6 +348,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncwarp();
     if (lane == 0) IG_TRACE(1);
     int ptile = 0;
+    int rslot = 0;
+    uint32_t rphase = 0;
     for (int tk = 0;; ++tk) {
       const int st = tile_at(tk);
       if (st >= p.num_super) break;
@@ -446,6 +459,22 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (++stage == p.wres_stages) { stage = 0; phase ^= 1; }
         }
         continue;
+      }
+      if (EPI & EPI_RESUP) {
+        // the low-resolution pixels this tile's bilinear taps touch: one box per channel slab, requested before the
+        // tile's operands (its slot was released by the epilogue of the tile before last, which also owned the TMEM
+        // buffer this tile's MMAs wait for)
+        mbar_wait(&rempty_bar[rslot], rphase ^ 1);
+        if (lane == 0) {
+          const int sx0 = min(static_cast<int>(p.res_rx * (bx * p.tw + p.out_x0)), p.res_iw - 1);
+          const int sy0 = min(static_cast<int>(p.res_ry * (by * p.th + p.out_y0)), p.res_ih - 1);
+          uint8_t* dst = s_stage + p.res_off + rslot * p.res_slot_bytes;
+          mbar_arrive_expect_tx(&rfull_bar[rslot], static_cast<uint32_t>(p.res_nslab * p.res_box_bytes));
+          for (int sl = 0; sl < p.res_nslab; ++sl)
+            tma_load_4d(dst + sl * p.res_slab_bytes, &tmR, &rfull_bar[rslot], n0 + sl * (BN < 128 ? BN : 128), sx0, sy0, b0);
+        }
+        __syncwarp();
+        if (++rslot == 2) { rslot = 0; rphase ^= 1; }
       }
       for (int it = it0; it < it1; ++it) {
         const int tap = it / p.kchunks;
@@ -693,6 +722,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool e_tn1 = p.tiles_n == 1, e_ty1 = p.tiles_y == 1, e_g1 = p.Bg == p.B;
     int buf = 0;
     uint32_t aphase = 0;
+    int eslot = 0;                 // EPI_RESUP: residual box slot / phase of the current tile
+    uint32_t ephase = 0;
     auto next_acc = [&]() { if (++buf == p.nbuf) { buf = 0; aphase ^= 1; } };
     for (;; ++titer, next_acc()) {
       const int st = tile_at(titer);
@@ -757,17 +788,24 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
       // EPI_RESUP: the four source pixels and weights of this thread's output pixel (F.interpolate, bilinear,
       // align_corners=True: psp_encoders.py:81-98 -- the FPN top-down path, fused here instead of materialised)
-      size_t ru00 = 0, ru01 = 0, ru10 = 0, ru11 = 0;
+      uint32_t ru00 = 0, ru01 = 0, ru10 = 0, ru11 = 0;       // byte offsets of the four taps inside the staged box
       float rw00 = 0.f, rw01 = 0.f, rw10 = 0.f, rw11 = 0.f;
+      const uint8_t* rbox = nullptr;
       if (EPI & EPI_RESUP) {
         const float fy = p.res_ry * Y, fx = p.res_rx * X;
         const int y0 = min(static_cast<int>(fy), p.res_ih - 1), x0 = min(static_cast<int>(fx), p.res_iw - 1);
         const int y1 = min(y0 + 1, p.res_ih - 1), x1 = min(x0 + 1, p.res_iw - 1);
         const float ly = fy - y0, lx = fx - x0;
-        const size_t ib = static_cast<size_t>(min(b, p.B - 1)) * p.res_ih;
-        ru00 = ((ib + y0) * p.res_iw + x0) * p.out_cstride; ru01 = ((ib + y0) * p.res_iw + x1) * p.out_cstride;
-        ru10 = ((ib + y1) * p.res_iw + x0) * p.out_cstride; ru11 = ((ib + y1) * p.res_iw + x1) * p.out_cstride;
+        // box origin = the taps of the tile's first pixel (the producer computes the same); rows / columns past the
+        // tile (threads whose pixel is not valid) are clamped into the box and their results are never stored
+        const int sx0 = min(static_cast<int>(p.res_rx * (bx * p.tw + p.out_x0)), p.res_iw - 1);
+        const int sy0 = min(static_cast<int>(p.res_ry * (by * p.th + p.out_y0)), p.res_ih - 1);
+        const int u0 = min(max(x0 - sx0, 0), p.res_bw - 1), u1 = min(max(x1 - sx0, 0), p.res_bw - 1);
+        const int v0 = min(max(y0 - sy0, 0), p.res_bh - 1), v1 = min(max(y1 - sy0, 0), p.res_bh - 1);
+        ru00 = static_cast<uint32_t>((v0 * p.res_bw + u0) * p.res_pitch); ru01 = static_cast<uint32_t>((v0 * p.res_bw + u1) * p.res_pitch);
+        ru10 = static_cast<uint32_t>((v1 * p.res_bw + u0) * p.res_pitch); ru11 = static_cast<uint32_t>((v1 * p.res_bw + u1) * p.res_pitch);
         rw00 = (1.f - ly) * (1.f - lx); rw01 = (1.f - ly) * lx; rw10 = ly * (1.f - lx); rw11 = ly * lx;
+        rbox = s_stage + p.res_off + eslot * p.res_slot_bytes;
       }
       const float* btab = nullptr;      // folded-input-BN border correction (per-thread: thread = pixel)
       bool warp_has_border = false;
@@ -791,6 +829,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (EPI & EPI_RES) res_fetch(half);
       if (r == 0) {
         // everything above (noise, residual, bilinear taps) is in flight while the MMAs of this tile finish
+        if (EPI & EPI_RESUP) mbar_wait(&rfull_bar[eslot], ephase);
         mbar_wait(&tfull_bar[buf], aphase);
         tc_fence_after();
         if (threadIdx.x == 64) IG_TRACE(5 + 4 * titer);         // epilogue: accumulator complete
@@ -830,12 +869,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (EPI & EPI_RESUP) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
-            uint4 qa = make_uint4(0, 0, 0, 0), qb = qa, qc = qa, qd = qa;
-            if (valid && ol0 + 8 * g < p.out_cstride) {
-              const __nv_bfloat16* rb = p.residual + ol0 + 8 * g;
-              qa = __ldg(reinterpret_cast<const uint4*>(rb + ru00)); qb = __ldg(reinterpret_cast<const uint4*>(rb + ru01));
-              qc = __ldg(reinterpret_cast<const uint4*>(rb + ru10)); qd = __ldg(reinterpret_cast<const uint4*>(rb + ru11));
-            }
+            // channels [c*16 + 8g, +8) of the n-tile: slab (c*16) / 128, 16 bytes at pitch res_pitch (16 mod 128: the 8
+            // lanes of a shared-memory wavefront read different bank groups, lanes with the same source pixel broadcast)
+            constexpr int SLAB_CH = BN < 128 ? BN : 128;
+            const uint8_t* rb = rbox + ((c * 16) / SLAB_CH) * p.res_slab_bytes + ((c * 16) % SLAB_CH) * 2 + 16 * g;
+            const uint4 qa = *reinterpret_cast<const uint4*>(rb + ru00), qb = *reinterpret_cast<const uint4*>(rb + ru01);
+            const uint4 qc = *reinterpret_cast<const uint4*>(rb + ru10), qd = *reinterpret_cast<const uint4*>(rb + ru11);
             const uint32_t wa[4] = {qa.x, qa.y, qa.z, qa.w}, wb2[4] = {qb.x, qb.y, qb.z, qb.w};
             const uint32_t wc[4] = {qc.x, qc.y, qc.z, qc.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w};
 #pragma unroll
@@ -976,8 +1015,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
+      if (EPI & EPI_RESUP) {
+        if (lane == 0) mbar_arrive(&rempty_bar[eslot]);      // this warp no longer reads the residual box
+        if (++eslot == 2) { eslot = 0; ephase ^= 1; }
+      }
       if (lane == 0) {
-        if (kPair) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[buf]), 0));   // the leader's MMA warp waits for both CTAs
+        if (kPair) mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&tempty_bar[buf]), 0));   // the leader's MMA warp waits for both CTAs
         else mbar_arrive(&tempty_bar[buf]);
       }
       if (threadIdx.x == 64 && p.hpw) IG_TRACE(2 + 4 * titer);    // epilogue (warp 2) drained this tile
@@ -1070,7 +1113,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 template <int BN, int EPI, bool PAIR>
-static int launch_igemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
+static int launch_igemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const IgemmParams& p, cudaStream_t st) {
   using Cfg = IgemmCfg<BN>;
   static SmemOptIn opt_in;        // per instantiation, per device
   FM_CUDA_OK(smem_opt_in(opt_in, igemm_conv_kernel<BN, EPI, PAIR>, Cfg::SMEM_BYTES));
@@ -1092,27 +1135,27 @@ static int launch_igemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const I
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (pdl_enabled() && p.max_ctas <= 0) ? 2 : 1;
-  FM_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_conv_kernel<BN, EPI, PAIR>, tmA, tmB, p));
+  FM_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_conv_kernel<BN, EPI, PAIR>, tmA, tmB, tmR, p));
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;
 }
 
 template <int BN, int EPI>
-static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
+static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const IgemmParams& p, cudaStream_t st) {
   // pair instantiations exist for the feature sets the N >= 128 layers use
   if constexpr (EPI == 0 || EPI == EPI_RGB || EPI == EPI_RES || EPI == EPI_BTAB || EPI == EPI_IDENT || EPI == EPI_RESUP) {
-    if (p.pair) return launch_igemm3<BN, EPI, true>(tmA, tmB, p, st);
+    if (p.pair) return launch_igemm3<BN, EPI, true>(tmA, tmB, tmR, p, st);
   }
   if (p.pair) { set_error("fm_conv_igemm: internal: no CTA-pair instantiation for block_n %d epilogue %d", BN, EPI); return FM_ERR_INVALID; }
-  return launch_igemm3<BN, EPI, false>(tmA, tmB, p, st);
+  return launch_igemm3<BN, EPI, false>(tmA, tmB, tmR, p, st);
 }
 
 template <int BN>
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const IgemmParams& p, cudaStream_t st) {
   // one instantiation per epilogue feature set in use (generator: RGB; ResNet: RES; IR block: BTAB)
   if (p.ksplit > 1) {
-    const int rc = launch_igemm2<BN, EPI_SPLIT>(tmA, tmB, p, st);
+    const int rc = launch_igemm2<BN, EPI_SPLIT>(tmA, tmB, tmR, p, st);
     if (rc != FM_OK) return rc;
     const int64_t total = static_cast<int64_t>(p.B) * p.OH * p.OW * (p.ws_cs / 8);
     int64_t blocks = (total + 255) / 256;
@@ -1122,18 +1165,18 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     count_launch();
     return FM_OK;
   }
-  if (!p.tab) return launch_igemm2<BN, EPI_IDENT>(tmA, tmB, p, st);
+  if (!p.tab) return launch_igemm2<BN, EPI_IDENT>(tmA, tmB, tmR, p, st);
   if (p.residual && p.res_ih > 0) {
     if (p.rgb || p.border_tab) { set_error("fm_conv_igemm: an upsampled residual excludes rgb / border_tab"); return FM_ERR_INVALID; }
-    return launch_igemm2<BN, EPI_RESUP>(tmA, tmB, p, st);
+    return launch_igemm2<BN, EPI_RESUP>(tmA, tmB, tmR, p, st);
   }
   const int epi = (p.rgb ? EPI_RGB : 0) | (p.residual ? EPI_RES : 0) | (p.border_tab ? EPI_BTAB : 0);
   switch (epi) {
-    case 0: return launch_igemm2<BN, 0>(tmA, tmB, p, st);
-    case EPI_RGB: return launch_igemm2<BN, EPI_RGB>(tmA, tmB, p, st);
-    case EPI_RES: return launch_igemm2<BN, EPI_RES>(tmA, tmB, p, st);
-    case EPI_BTAB: return launch_igemm2<BN, EPI_BTAB>(tmA, tmB, p, st);
-    default: return launch_igemm2<BN, EPI_RGB | EPI_RES | EPI_BTAB>(tmA, tmB, p, st);
+    case 0: return launch_igemm2<BN, 0>(tmA, tmB, tmR, p, st);
+    case EPI_RGB: return launch_igemm2<BN, EPI_RGB>(tmA, tmB, tmR, p, st);
+    case EPI_RES: return launch_igemm2<BN, EPI_RES>(tmA, tmB, tmR, p, st);
+    case EPI_BTAB: return launch_igemm2<BN, EPI_BTAB>(tmA, tmB, tmR, p, st);
+    default: return launch_igemm2<BN, EPI_RGB | EPI_RES | EPI_BTAB>(tmA, tmB, tmR, p, st);
   }
 }
 
@@ -1197,6 +1240,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
 
   IgemmParams p{};
   p.OH = d->OH; p.OW = d->OW; p.B = d->B; p.Bg = Bg;
+  const bool resup = d->residual && d->residual_up_h > 0;      // bilinear residual: generic ring only (its box is staged beside it)
   // ---- tile shape: tw*th*tb <= 128 pixels (a tile never straddles two groups)
   int tw = d->tile_w, th = d->tile_h;
   if (tw <= 0 || th <= 0) {
@@ -1310,7 +1354,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     bool std33 = d->ntaps == 9 && sx == 1 && sy == 1 && d->x_pixstride == 0 && d->x_rowstride == 0 && d->x_imgstride == 0;
     for (int i = 0; std33 && i < 9; ++i)
       std33 = d->tap_dy[i] == i / 3 - 1 && d->tap_dx[i] == i % 3 - 1 && d->tap_widx[i] == i;
-    p.patch = (env_patch && nph == 1 && std33 && tw == 128 && th == 1 && tb == 1 && bn <= 128 && p.ksplit == 1 && !d->upmode) ? 1 : 0;
+    p.patch = (env_patch && nph == 1 && !resup && std33 && tw == 128 && th == 1 && tb == 1 && bn <= 128 && p.ksplit == 1 && !d->upmode) ? 1 : 0;
     if (p.patch) {
       int R = env_rows > 0 ? env_rows : (bn == 64 ? 4 : 2);
       while (R > 1 && (2 * R * bn > 512 || R > d->OH)) R >>= 1;
@@ -1363,7 +1407,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     // grouped convs: a halo-patch tile lies inside one image, so its group is known per tile (weights are not resident
     // across tiles of different groups: hpw below stays ungrouped)
     static const int env_hp_groups = []() { const char* e = getenv("FM3D_HPATCH_GROUPS"); return e ? atoi(e) : 1; }();
-    if (want && stride_ok && plain_x && (G == 1 || env_hp_groups) && p.ksplit == 1 && !d->upmode && d->ntaps >= 2 && d->OH >= 12 &&
+    if (want && !resup && stride_ok && plain_x && (G == 1 || env_hp_groups) && p.ksplit == 1 && !d->upmode && d->ntaps >= 2 && d->OH >= 12 &&
         d->OW >= 8 && dv1 - dv0 <= 8 && du1 - du0 <= 8 && sx * sy <= 4 && (!d->tab_bstride || bn <= IG_TAB_ROWS)) {
       p.hp = 1;
       p.patch = 0; p.prows = 1;
@@ -1452,6 +1496,24 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       if (st > IG_MAX_STAGES) st = IG_MAX_STAGES;
       p.gen_sbytes = p.pair ? sb : IG_BM * IG_BK * 2 + bn * 128;
       p.gen_stages = p.pair ? st : st_cfg;
+      if (resup) {
+        // two slots of (channel slabs x box pixels) above a shortened operand ring
+        FM_CHECK_ARG(G == 1 && p.ksplit == 1 && p.tb == 1, "fm_conv_igemm: an upsampled residual needs an ungrouped, unsplit conv with tiles inside one image");
+        const int slab_ch = bn < 128 ? bn : 128;
+        p.res_nslab = bn / slab_ch;
+        p.res_pitch = (slab_ch + 8) * 2;
+        p.res_bw = static_cast<int>(p.res_rx * (p.tw - 1)) + 3;
+        p.res_bh = static_cast<int>(p.res_ry * (p.th - 1)) + 3;
+        FM_CHECK_ARG(p.res_bw <= 256 && p.res_bh <= 256, "fm_conv_igemm: residual box too large");
+        p.res_box_bytes = p.res_pitch * p.res_bw * p.res_bh;
+        p.res_slab_bytes = (p.res_box_bytes + 127) & ~127;          // a TMA destination is 128-byte aligned
+        p.res_slot_bytes = p.res_nslab * p.res_slab_bytes;
+        int stg = (200 * 1024 - 2 * p.res_slot_bytes) / p.gen_sbytes;
+        if (stg > p.gen_stages) stg = p.gen_stages;
+        FM_CHECK_ARG(stg >= 2, "fm_conv_igemm: residual box (%d bytes) leaves no room for the operand ring", p.res_slot_bytes);
+        p.gen_stages = stg;
+        p.res_off = (p.gen_stages * p.gen_sbytes + 127) & ~127;
+      }
     }
     // halo-patch weight ring, now that the pair decision is known: a CTA of a pair stages only its half of each weight
     // tile, so the same smem holds twice as many stages.  Per-CTA traces of the 64x64 128->128 layer showed the MMA phase
@@ -1487,7 +1549,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       int nst = static_cast<int>((200 * 1024 - wbytes) / (IG_BM * IG_BK * 2));
       const int st_max = bn == 256 ? 4 : (bn == 128 ? 6 : 8);
       if (nst > st_max) nst = st_max;
-      if (env_wres && !p.hp && !p.patch && !p.upmode && !p.pair && p.ksplit == 1 && G == 1 && p.tiles_n == 1 && nst >= 3 &&
+      if (env_wres && !resup && !p.hp && !p.patch && !p.upmode && !p.pair && p.ksplit == 1 && G == 1 && p.tiles_n == 1 && nst >= 3 &&
           kiters_total >= 2) {
         p.wres = 1;
         p.wres_stages = nst;
@@ -1544,6 +1606,21 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("fm_conv_igemm: cuTensorMapEncodeTiled(B) failed with CUresult %d", (int)r); return FM_ERR_CUDA; }
   }
+  CUtensorMap tmR = tmB;      // unused unless the residual is upsampled
+  if (resup) {
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->out_cstride), static_cast<cuuint64_t>(d->residual_up_w),
+                                static_cast<cuuint64_t>(d->residual_up_h), static_cast<cuuint64_t>(d->B)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(d->out_cstride) * 2, static_cast<cuuint64_t>(d->out_cstride) * d->residual_up_w * 2,
+                                   static_cast<cuuint64_t>(d->out_cstride) * d->residual_up_w * d->residual_up_h * 2};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(p.res_pitch / 2), static_cast<cuuint32_t>(p.res_bw),
+                               static_cast<cuuint32_t>(p.res_bh), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    FM_CHECK_ARG((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0, "fm_conv_igemm: residual must be 16-byte aligned");
+    CUresult r = encode(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->residual), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("fm_conv_igemm: cuTensorMapEncodeTiled(residual) failed with CUresult %d", (int)r); return FM_ERR_CUDA; }
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     // debug: FM3D_TRACE=1 records per-CTA event clocks of every launch into one device buffer (fm_igemm_trace)
@@ -1555,9 +1632,9 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     }
   }
   switch (bn) {
-    case 64: return launch_igemm<64>(tmA, tmB, p, st);
-    case 128: return launch_igemm<128>(tmA, tmB, p, st);
-    default: return launch_igemm<256>(tmA, tmB, p, st);
+    case 64: return launch_igemm<64>(tmA, tmB, tmR, p, st);
+    case 128: return launch_igemm<128>(tmA, tmB, tmR, p, st);
+    default: return launch_igemm<256>(tmA, tmB, tmR, p, st);
   }
 }
 

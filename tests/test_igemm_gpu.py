@@ -326,7 +326,7 @@ def test_conv_paired_parity_upsample(cuda, B, h, Cin, Cout):
     torch.testing.assert_close(out[..., :Cout].float().permute(0, 3, 1, 2).cpu(), ref, rtol=1e-2, atol=1e-2)
 
 
-@pytest.mark.parametrize("B,h,Cin,Cout", [(2, 16, 128, 512), (1, 8, 64, 64)])
+@pytest.mark.parametrize("B,h,Cin,Cout", [(2, 16, 128, 512), (1, 8, 64, 64), (3, 12, 64, 128), (2, 32, 128, 320), (5, 20, 72, 96)])
 def test_conv_upsampled_residual(cuda, B, h, Cin, Cout):
     """1x1 lateral conv + bilinear (align_corners=True) upsampling of a half-resolution map sampled in the
     epilogue: the FPN top-down add of the pSp encoder (psp_encoders.py:81-98) without the intermediate tensor."""
