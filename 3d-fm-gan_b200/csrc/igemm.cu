@@ -291,15 +291,23 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t pphase = 0;
     const uint32_t patch_tx = static_cast<uint32_t>(p.hp_pw) * p.hp_ph * (IG_BK * 2);
     const int nvc = p.kchunks * p.hp_np;          // virtual chunks: (channel chunk, parity plane)
-    auto hp_prefetch = [&]() {
+    // tile coordinates of the patch cursor: decomposed once per tile, and (chunk, plane) are counters -- the integer
+    // divisions used to run once per patch (ncu source view of a merged-phase up-conv: a third of the producer's samples
+    // in MUFU.RCP / IABS chains, ~300 clk per chunk against 512 clk of MMA time for a 1-tap chunk)
+    int pbx = 0, pby = 0, pbb = 0, pkr = 0, ppl = 0;
+    auto hp_tile_coords = [&]() {
       if (pst >= p.num_super) return;
       const int pstl = p.nph > 1 ? pst % p.nsup1 : pst;   // the patch depends on the tile position only, not on the phase
       int m = (pstl / p.tiles_n) * p.cluster + crank;   // ksplit == 1 in this mode
-      const int bx = m % p.tiles_x; m /= p.tiles_x;
-      const int by = m % p.tiles_y;
-      const int bb = m / p.tiles_y;
+      pbx = m % p.tiles_x; m /= p.tiles_x;
+      pby = m % p.tiles_y;
+      pbb = m / p.tiles_y;
+    };
+    hp_tile_coords();
+    auto hp_prefetch = [&]() {
+      if (pst >= p.num_super) return;
+      const int bx = pbx, by = pby, bb = pbb;
       mbar_wait(&aempty_bar[pslot], pphase ^ 1);
-      const int pkr = pkc / p.hp_np, ppl = pkc - pkr * p.hp_np;
       const int cx = bx * 8 * p.hp_sx + p.hp_pl_x[ppl], cy = by * 16 * p.hp_sy + p.hp_pl_y[ppl];
       if (lane == 0) {
         if (kPair) {
@@ -312,7 +320,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       __syncwarp();
-      if (++pkc == nvc) { pkc = 0; pst = tile_at(++pk); tile_draw(); }
+      if (++ppl == p.hp_np) { ppl = 0; ++pkr; }
+      if (++pkc == nvc) { pkc = 0; pkr = 0; pst = tile_at(++pk); tile_draw(); hp_tile_coords(); }
       if (++pslot == p.hp_na) { pslot = 0; pphase ^= 1; }
     };
     if (p.hpw) {
@@ -420,9 +429,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // chunk-major weight stages; the input patch of chunk c + hp_dist is requested when chunk c starts
         // (its slot was last read hp_na - hp_dist >= 2 chunks ago, so the wait below never blocks the weights)
         uint8_t* sb0 = s_stage + p.hp_na * p.hp_bytes;
-        for (int vc = 0; vc < nvc; ++vc) {
+        for (int vc = 0, kc = 0, pl = 0; vc < nvc; ++vc) {
           hp_prefetch();
-          const int kc = vc / p.hp_np, pl = vc - kc * p.hp_np;
           const int tp0 = p.nph > 1 ? p.ph_first[ph] : p.hp_pl_first[pl], tp1 = p.nph > 1 ? p.ph_first[ph + 1] : p.hp_pl_first[pl + 1];
           for (int tap = tp0; tap < tp1; ++tap) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -439,6 +447,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __syncwarp();
             if (++stage == p.hp_stages) { stage = 0; phase ^= 1; }
           }
+          if (++pl == p.hp_np) { pl = 0; ++kc; }
         }
         if (lane == 0) IG_TRACE(2 + 4 * ptile);      // producer: all loads of this tile issued
         ++ptile;
@@ -594,11 +603,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (titer == 0) { mbar_wait(&full_bar[0], 0); tc_fence_after(); }      // resident weights have landed
         if (lane == 0) IG_TRACE(3 + 4 * titer);
         const int nvc = hp_nvc;
-        for (int vc = 0; vc < nvc; ++vc) {
+        for (int vc = 0, kc = 0, pl = 0; vc < nvc; ++vc) {
           mbar_wait(&afull_bar[aslot], aslot_phase);
           tc_fence_after();
           if (lane == 0 && vc == 0) IG_TRACE(4 + 4 * titer);
-          const int kc = hp_np1 ? vc : vc / p.hp_np, pl = hp_np1 ? 0 : vc - kc * p.hp_np;
           const uint32_t alo0 = umma_desc_lo(ring + aslot * p.hp_bytes);
           const uint32_t blo0 = umma_desc_lo(sw + static_cast<uint32_t>(kc * p.ntaps) * wb);
           if (elect_one()) {
@@ -619,6 +627,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           __syncwarp();
           if (++aslot == p.hp_na) { aslot = 0; aslot_phase ^= 1; }
+          if (++pl == p.hp_np) { pl = 0; ++kc; }
         }
         continue;
       }
@@ -626,12 +635,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t sb0 = hp_sw, ahi = hp_ahi;
         if (lane == 0) IG_TRACE(3 + 4 * titer);               // MMA: accumulator free
         const int nvc = hp_nvc;
-        for (int vc = 0; vc < nvc; ++vc) {
+        const int mph = p.nph > 1 ? st / p.nsup1 : 0;         // once per tile (a division per chunk sat in the issue path)
+        for (int vc = 0, pl = 0; vc < nvc; ++vc) {
           mbar_wait(&afull_bar[aslot], aslot_phase);          // this (chunk, plane)'s input patch has landed
           if (lane == 0 && vc == 0) IG_TRACE(4 + 4 * titer);  // MMA: first patch landed
-          const int pl = hp_np1 ? 0 : vc % p.hp_np;
           const uint32_t alo0 = umma_desc_lo(ring + aslot * p.hp_bytes);
-          const int mph = p.nph > 1 ? st / p.nsup1 : 0;
           const int t0 = p.nph > 1 ? p.ph_first[mph] : p.hp_pl_first[pl], t1 = p.nph > 1 ? p.ph_first[mph + 1] : p.hp_pl_first[pl + 1];
           for (int tap = t0; tap < t1; ++tap) {
             mbar_wait(&full_bar[stage], phase);
@@ -660,6 +668,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (++stage == p.hp_stages) { stage = 0; phase ^= 1; }
           }
           if (++aslot == p.hp_na) { aslot = 0; aslot_phase ^= 1; }
+          if (++pl == p.hp_np) pl = 0;
         }
         continue;
       }

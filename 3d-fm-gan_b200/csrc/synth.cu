@@ -334,6 +334,24 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
   const uint8_t* my = bl_smem + (4 * cg) * BC::PIX + g * 8;
   __nv_bfloat16* orow0 = out + (static_cast<size_t>(b) * OH * OW + X) * cs + ch;
 
+  // The strip's noise ((Y1 - Y0) rows x TW columns of fp32) is staged in shared memory once, with every load in flight
+  // at the same time, while the first TMA stages land.  Requested row by row (even one row ahead) it was an L2 round
+  // trip per row on the critical path: ncu put a third of the kernel's stall samples on the first use of that register.
+  float* s_nz = reinterpret_cast<float*>(bl_smem + BC::SMEM);
+  const bool nz_smem = noise != nullptr && nz_vec;
+  if (nz_smem) {
+    constexpr int Q = BC::TW / 4;
+    const int n4 = (Y1 - Y0) * Q;
+    const float* nbase = noise + static_cast<size_t>(noise_bstride ? b : 0) * OH * OW;
+    for (int i = tid; i < n4; i += 256) {
+      const int r = i / Q, q = i - r * Q;
+      float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (x0 + 4 * q < OW) v4 = __ldg(reinterpret_cast<const float4*>(nbase + static_cast<size_t>(Y0 + r) * OW + x0 + 4 * q));
+      *reinterpret_cast<float4*>(s_nz + r * BC::TW + 4 * q) = v4;
+    }
+    // visible to the other warps after the first per-stage __syncthreads below, two input rows before the first output row
+  }
+
   auto load_noise = [&](int Y) -> float4 {
     float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (nzp && active) {
@@ -349,7 +367,6 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
     }
     return n4;
   };
-  float4 npre = load_noise(Y0);
   auto do_row = [&](auto uc, int j, const uint8_t* rowp) {
     constexpr int u = decltype(uc)::value;
     f32x2 v[7][2];
@@ -388,10 +405,9 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_kernel(const __grid_cons
     }
     const int Y = Y0 + j - 3;
     if (j >= 3 && Y < Y1) {
-      // the noise of this row was requested one row ago (a load issued here would sit on the row's critical path; two rows
-      // ahead measured the same)
+      // (widths that are not a multiple of 4 -- no generator resolution -- load the row's noise here, unvectorised)
+      const float4 npre = nz_smem ? *reinterpret_cast<const float4*>(s_nz + (Y - Y0) * BC::TW + 4 * cg) : load_noise(Y);
       const float nz[4] = {npre.x * nw, npre.y * nw, npre.z * nw, npre.w * nw};
-      if (Y + 1 < Y1) npre = load_noise(Y + 1);
       __nv_bfloat16* orow = orow0 + static_cast<size_t>(Y) * OW * cs;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -649,13 +665,15 @@ extern "C" int fm_blur_act_nhwc(void* out, const void* t, const float* kernel4x4
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static SmemOptIn opt_in[4];     // per kernel instantiation, per device
-  FM_CUDA_OK(smem_opt_in(opt_in[0], blur_act_nhwc_kernel<true, 64>, BlurCfg<64>::SMEM));
-  FM_CUDA_OK(smem_opt_in(opt_in[1], blur_act_nhwc_kernel<false, 64>, BlurCfg<64>::SMEM));
-  FM_CUDA_OK(smem_opt_in(opt_in[2], blur_act_nhwc_kernel<true, 128>, BlurCfg<128>::SMEM));
-  FM_CUDA_OK(smem_opt_in(opt_in[3], blur_act_nhwc_kernel<false, 128>, BlurCfg<128>::SMEM));
+  // + the strip's noise: at most 128 rows x TW columns of fp32
+  FM_CUDA_OK(smem_opt_in(opt_in[0], blur_act_nhwc_kernel<true, 64>, BlurCfg<64>::SMEM + 128 * BlurCfg<64>::TW * 4));
+  FM_CUDA_OK(smem_opt_in(opt_in[1], blur_act_nhwc_kernel<false, 64>, BlurCfg<64>::SMEM + 128 * BlurCfg<64>::TW * 4));
+  FM_CUDA_OK(smem_opt_in(opt_in[2], blur_act_nhwc_kernel<true, 128>, BlurCfg<128>::SMEM + 128 * BlurCfg<128>::TW * 4));
+  FM_CUDA_OK(smem_opt_in(opt_in[3], blur_act_nhwc_kernel<false, 128>, BlurCfg<128>::SMEM + 128 * BlurCfg<128>::TW * 4));
+  FM_CHECK_ARG(strip_rows <= 128, "fm_blur_act_nhwc: FM3D_BLUR_ROWS must be <= 128");
   auto fn = CBv == 128 ? (separable ? blur_act_nhwc_kernel<true, 128> : blur_act_nhwc_kernel<false, 128>)
                        : (separable ? blur_act_nhwc_kernel<true, 64> : blur_act_nhwc_kernel<false, 64>);
-  FM_CUDA_OK(launch_pdl(fn, dim3(static_cast<unsigned>(blocks)), dim3(256), CBv == 128 ? BlurCfg<128>::SMEM : BlurCfg<64>::SMEM, st,
+  FM_CUDA_OK(launch_pdl(fn, dim3(static_cast<unsigned>(blocks)), dim3(256), (CBv == 128 ? BlurCfg<128>::SMEM : BlurCfg<64>::SMEM) + (noise ? strip_rows * TWv * 4 : 0), st,
                         tmT, static_cast<__nv_bfloat16*>(out), kernel4x4, tab, noise, noise_bstride, noise_w,
                         OH, OW, C, cstride, tiles_x, tiles_y, cblocks, strip_rows));
   count_launch();
