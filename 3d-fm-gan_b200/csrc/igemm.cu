@@ -59,9 +59,11 @@ struct IgemmParams {
   int hp_np, hp_sx, hp_sy;
   int8_t hp_pl_first[5];           // taps [first[pl], first[pl+1]) belong to plane pl (taps are sorted by plane)
   int16_t hp_pl_x[4], hp_pl_y[4];  // input-space offset of a plane's patch origin relative to (sx*x0, sy*y0)
-  // several output phases of a stride-2 transposed conv in one launch: super tile st -> (phase = st / nsup1, tile = st % nsup1);
+  // several output phases of a stride-2 transposed conv in one launch: super tile st -> tile t = st / nph, phase = (st % nph + t) % nph
+  // (a cluster takes whole tiles, i.e. all phases of a tile back to back, starting with a different phase per tile);
   // taps [ph_first[ph], ph_first[ph+1]) and the output offset (ph_oy0, ph_ox0) belong to the phase
   int nph, nsup1;
+  int ph_whole;                    // a cluster takes whole tiles (all phases back to back, rotated start) -- enough tiles per cluster
   int8_t ph_first[5];
   int16_t ph_oy0[4], ph_ox0[4];
   int hpw;                         // halo-patch mode with ALL weight tiles of the (single) n-tile resident in smem
@@ -254,7 +256,18 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   };
   auto tile_at = [&](int k) -> int {
-    if (!dyn || k == 0) return cluster_id + k * num_clusters;
+    if (dyn && k == 0) return cluster_id;      // the counter hands out num_clusters, num_clusters + 1, ...
+    if (!dyn) {
+      if (p.ph_whole) {
+        // several phases per tile: a cluster takes WHOLE tiles (all phases back to back), so every cluster gets the same
+        // mix of 4- / 2- / 1-tap work, and (see ig_phase) starts each tile with a different phase: the clusters are in
+        // different phases at any time and the chip-wide L2 demand is the average of the phases, not the 1-tap peak
+        const int kk = k / p.nph, j = k - kk * p.nph;
+        const int t = cluster_id + kk * num_clusters;
+        return t < p.nsup1 ? t * p.nph + j : p.num_super;
+      }
+      return cluster_id + k * num_clusters;
+    }
     if (q_leader) {
       while (q_fetched <= k && !q_ended) {
         tile_draw();
@@ -274,6 +287,18 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     return tileq_wait(s_tileq, k);
   };
 
+  // super tile -> (tile, phase) when a launch carries several phases
+  auto ig_phase = [&](int st, int& t) -> int {
+    if (p.nph <= 1) { t = st; return 0; }
+    if (!p.ph_whole) {                       // phase-major: all tiles of phase 0, then phase 1, ...
+      const int ph = st / p.nsup1;
+      t = st - ph * p.nsup1;
+      return ph;
+    }
+    t = st / p.nph;
+    const int j = st - t * p.nph + t;
+    return j % p.nph;
+  };
   const int kiters = p.ntaps * p.kchunks;
   // debug trace: slot i of this CTA <- clock (one writer per slot)
   long long* trc = p.trace ? p.trace + static_cast<size_t>(blockIdx.x) * IG_TRACE_N : nullptr;
@@ -297,7 +322,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int pbx = 0, pby = 0, pbb = 0, pkr = 0, ppl = 0;
     auto hp_tile_coords = [&]() {
       if (pst >= p.num_super) return;
-      const int pstl = p.nph > 1 ? pst % p.nsup1 : pst;   // the patch depends on the tile position only, not on the phase
+      int pstl;
+      ig_phase(pst, pstl);                                // the patch depends on the tile position only, not on the phase
       int m = (pstl / p.tiles_n) * p.cluster + crank;   // ksplit == 1 in this mode
       pbx = m % p.tiles_x; m /= p.tiles_x;
       pby = m % p.tiles_y;
@@ -364,8 +390,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (st >= p.num_super) break;
       tile_draw();                    // tile tk + 1: drawn now, published when the producer gets there (the consumers are a
                                       // ring of stages behind), so the counter's round trip hides behind this tile's loads
-      const int ph = p.nph > 1 ? st / p.nsup1 : 0;
-      const int stl = st - ph * p.nsup1;
+      int stl;
+      const int ph = ig_phase(st, stl);
       const int nt = stl % p.tiles_n;
       int m = stl / p.tiles_n;
       const int ks = m % p.ksplit; m /= p.ksplit;
@@ -635,7 +661,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t sb0 = hp_sw, ahi = hp_ahi;
         if (lane == 0) IG_TRACE(3 + 4 * titer);               // MMA: accumulator free
         const int nvc = hp_nvc;
-        const int mph = p.nph > 1 ? st / p.nsup1 : 0;         // once per tile (a division per chunk sat in the issue path)
+        int mstl;
+        const int mph = ig_phase(st, mstl);                   // once per tile (a division per chunk sat in the issue path)
         for (int vc = 0, pl = 0; vc < nvc; ++vc) {
           mbar_wait(&afull_bar[aslot], aslot_phase);          // this (chunk, plane)'s input patch has landed
           if (lane == 0 && vc == 0) IG_TRACE(4 + 4 * titer);  // MMA: first patch landed
@@ -739,8 +766,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (st >= p.num_super) break;
       // tile coordinates: the common single-n-tile / unsplit / ungrouped cases skip their integer divisions (each costs
       // ~25 dependent instructions, and a 64-channel tile's whole epilogue is only ~300 per warp)
-      const int eph = p.nph > 1 ? st / p.nsup1 : 0;
-      const int stl = st - eph * p.nsup1;
+      int stl;
+      const int eph = ig_phase(st, stl);
       const int nt = e_tn1 ? 0 : stl % p.tiles_n;
       int m = e_tn1 ? stl : stl / p.tiles_n;
       if (p.ksplit > 1) m /= p.ksplit;
@@ -1587,6 +1614,15 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     }
   }
   FM_CHECK_ARG(!p.colsum || p.tb == 1, "fm_conv_igemm: colsum needs tiles inside one image (OH*OW >= 128 per image)");
+  {
+    // whole tiles per cluster only when a cluster gets enough of them for the rounding not to matter (64 -> 128 at B = 32:
+    // 7.9 per cluster, 312 -> 292 us; 32 -> 64 with 2.2 per cluster lost 8 %)
+    static const int env_whole = []() { const char* e = getenv("FM3D_PHASE_WHOLE"); return e ? atoi(e) : 6; }();
+    int sms = sm_count();
+    if (d->max_ctas > 0 && d->max_ctas < sms) sms = d->max_ctas;
+    const int ncl = sms / p.cluster > 0 ? sms / p.cluster : 1;
+    p.ph_whole = (p.nph > 1 && env_whole > 0 && p.nsup1 >= static_cast<int64_t>(env_whole) * ncl && !p.tile_ctr) ? 1 : 0;
+  }
   if (p.num_super >= (1 << 24) - 1) p.tile_ctr = nullptr;      // queue entries carry 24 bits of tile index
   // ---- tensor maps
   CUtensorMap tmA, tmB;
