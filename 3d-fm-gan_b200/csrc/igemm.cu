@@ -760,6 +760,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t aphase = 0;
     int eslot = 0;                 // EPI_RESUP: residual box slot / phase of the current tile
     uint32_t ephase = 0;
+    // colsum: partial column sums [tile parity][lane quarter][BN] in the upper half of the table region (the tables
+    // are shared by the batch there: BN rows of 32 bytes)
+    float* s_csum = reinterpret_cast<float*>(smem + Cfg::RING_BYTES + Cfg::TAB_BYTES / 2);
+    static_assert(2 * 4 * BN * 4 <= Cfg::TAB_BYTES / 2, "colsum scratch");
     auto next_acc = [&]() { if (++buf == p.nbuf) { buf = 0; aphase ^= 1; } };
     for (;; ++titer, next_acc()) {
       const int st = tile_at(titer);
@@ -988,9 +992,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // per column and warp.  tile_b == 1: the warp's rows belong to one image.
             float s8[8], s4[4], s2[2];
             const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+            if (!__all_sync(0xffffffffu, valid)) {       // partial tiles only: rows past the image do not count
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = valid ? v[j] : 0.f;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float lo = valid ? v[j] : 0.f, hi = valid ? v[8 + j] : 0.f;
+              const float lo = v[j], hi = v[8 + j];
               s8[j] = (h16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, h16 ? lo : hi, 16);
             }
 #pragma unroll
@@ -1000,9 +1008,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float s1 = (h2 ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? s2[0] : s2[1], 2);
             s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
             const int colj = (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);      // the column this lane pair ended up with
-            const int bt = bb * p.tb;
-            if (!(lane & 1) && o0 + colj < p.Cout && bt < p.B)
-              atomicAdd(p.colsum + static_cast<size_t>(bt) * p.Cout + o0 + colj, s1);
+            // the four lane quarters (and the rows of a row-patch tile) meet in shared memory -- each warp owns its slots
+            // (quarter q, the columns of its chunks), so plain stores / adds: a shared-memory float atomicAdd is a CAS spin
+            // loop -- and one thread per column then issues one global reduction per tile
+            if (!(lane & 1)) {
+              float* slot = s_csum + ((titer & 1) * 4 + q) * BN + c * 16 + colj;
+              *slot = (r == 0 ? 0.f : *slot) + s1;
+            }
           }
         }
         if (valid && p.out && ox < p.OW - og * p.cg_shrink) {   // out == NULL: only the fused ToRGB sums are wanted
@@ -1048,6 +1060,17 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("bar.sync 2, 256;" ::: "memory");   // s_rgb may be overwritten by the next tile
       }
       }   // rows of the tile
+      if constexpr (EPI == 0) {
+        if (p.colsum != nullptr) {
+          asm volatile("bar.sync 3, 256;" ::: "memory");         // every warp's partial sums of this tile are in place
+          // (double buffered by tile parity: the next tile's stores go to the other half, and the barrier of the tile
+          // after that orders them behind these reads)
+          if (etid < BN && n0 + etid < p.Cout && bb * p.tb < p.B) {
+            const float* sc = s_csum + (titer & 1) * 4 * BN + etid;
+            atomicAdd(p.colsum + static_cast<size_t>(bb * p.tb) * p.Cout + n0 + etid, (sc[0] + sc[BN]) + (sc[2 * BN] + sc[3 * BN]));
+          }
+        }
+      }
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -1249,7 +1272,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
   FM_CHECK_ARG(!d->out_cgroup || (!d->out_nchw_f32 && d->out_cgroup % 32 == 0 && d->Cout % d->out_cgroup == 0 &&
                                   d->out_cstride % 8 == 0 && d->out_cstride >= d->out_cgroup && d->out_gstride % 8 == 0),
                "fm_conv_igemm: bad grouped-output parameters");
-  FM_CHECK_ARG(!d->colsum || (d->tab && !d->rgb && !d->residual && !d->border_tab && !d->out_nchw_f32 && !d->out_cgroup && !d->upmode &&
+  FM_CHECK_ARG(!d->colsum || (d->tab && !d->tab_bstride && !d->rgb && !d->residual && !d->border_tab && !d->out_nchw_f32 && !d->out_cgroup && !d->upmode &&
                               d->nphases <= 1 && d->ksplit <= 1 && d->groups <= 1),
                "fm_conv_igemm: colsum needs the plain epilogue (no rgb / residual / border_tab / grouped or fp32 output / split-K)");
   const int G = d->groups > 1 ? d->groups : 1;
