@@ -322,6 +322,13 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((
 __host__ __device__ constexpr uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) /* version 1 (bit 46) */ | (2u << 29) /* SWIZZLE_128B (bits 61-63) */;
 }
+// High word of a K-major descriptor WITHOUT swizzle: core matrices of 8 rows x 16 bytes (rows 16 bytes apart), LBO (low
+// word, bits 16-29) between core matrices along K, SBO between 8-row groups.  With LBO = 16 and SBO = 128 over an image
+// stored as 16-byte pixels (8 channels), row m / K core k addresses pixel m + k: the horizontal taps of a convolution on
+// <= 8 channels are an im2col done by the descriptor (the stems).
+__host__ __device__ constexpr uint32_t umma_desc_hi_nosw(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) /* version 1 (bit 46) */;
+}
 // The four K=16 steps of one 64-channel (128-byte) K block: D[tmem] (+)= A * B with both start addresses
 // advancing 32 bytes (+2 in the >>4 address field) per step.  One asm block: ptxas keeps the descriptors
 // in uniform registers and emits 4 UTCHMMA with a handful of uniform adds between them.

@@ -68,6 +68,12 @@ struct IgemmParams {
   int16_t ph_oy0[4], ph_ox0[4];
   int hpw;                         // halo-patch mode with ALL weight tiles of the (single) n-tile resident in smem
   int wres, wres_stages;           // generic mode with all (tap, chunk) weight tiles of the single n-tile resident: only A tiles stream
+  // strip (a wres sub-mode; 3-channel stems stored as 16-byte pixels, stride 1 in x): ONE compact box of the packed image
+  // per tile -- strip_rows input rows x 136 pixels x 16 bytes -- serves every tap through a no-swizzle descriptor whose K
+  // core stride is one pixel (the overlapping 8-pixel windows are never materialised: 6 KB per tile instead of 48 KB)
+  int strip, strip_rows, strip_sbytes, strip_y0;
+  int lean;                        // epilogue: the launch qualifies for the lean path (see the epilogue)
+  int8_t strip_trow[FM_MAX_TAPS];  // input row of each tap inside the box
   int16_t hp_aoff[FM_MAX_TAPS];    // per-tap start offset of the A descriptor inside the patch (16-byte units)
   int Bg, nslabs;                  // images per group, weight slabs per group
   const float* border_tab;
@@ -479,6 +485,18 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ++ptile;
         continue;
       }
+      if (p.strip) {
+        // weights resident; a stage holds the tile's strip of the packed image
+        uint8_t* sa0 = s_stage + static_cast<size_t>(kiters) * Cfg::B_BYTES;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.strip_rows) * (136 * 16));
+          tma_load_4d(sa0 + stage * p.strip_sbytes, &tmA, &full_bar[stage], 0, x0, y0 + p.strip_y0, b0);
+        }
+        __syncwarp();
+        if (++stage == p.wres_stages) { stage = 0; phase ^= 1; }
+        continue;
+      }
       if (p.wres) {
         // weights were loaded once (below the tile loop); a stage holds one A tile
         uint8_t* sa0 = s_stage + static_cast<size_t>(kiters) * Cfg::B_BYTES;
@@ -699,6 +717,25 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
+      if (p.strip) {
+        if (titer == 0) { mbar_wait(&afull_bar[0], 0); tc_fence_after(); }      // resident weights have landed
+        const uint32_t sa = ring + static_cast<uint32_t>(kiters) * Cfg::B_BYTES + stage * p.strip_sbytes;
+        constexpr uint32_t ahi = umma_desc_hi_nosw(128);                         // 8 pixels of 16 bytes per row group
+        if (lane == 0) IG_TRACE(3 + 4 * titer);                                  // MMA: accumulator free
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) IG_TRACE(4 + 4 * titer);                                  // MMA: strip landed
+        if (elect_one()) {
+          for (int tap = 0; tap < p.ntaps; ++tap)
+            umma_bf16_x4(tmem_d, umma_desc_lo(sa + p.strip_trow[tap] * (136 * 16)), ahi,
+                         umma_desc_lo(ring + static_cast<uint32_t>(tap) * Cfg::B_BYTES), dhi, idesc, tap > 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tfull_bar[buf]);
+        }
+        __syncwarp();
+        if (++stage == p.wres_stages) { stage = 0; phase ^= 1; }
+        continue;
+      }
       if (p.wres) {
         if (titer == 0) { mbar_wait(&afull_bar[0], 0); tc_fence_after(); }      // resident weights have landed
         const uint32_t sa0 = ring + static_cast<uint32_t>(kiters) * Cfg::B_BYTES;
@@ -811,6 +848,88 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
 
+
+      // ---- lean path (host flag p.lean): plain or residual epilogue, bf16 NHWC output, every 16-column chunk inside
+      // Cout, one accumulator per tile, no noise.  The general loop below spends ~310 instructions per tile and ~225 per
+      // chunk and warp (ncu source view of a 64-channel ResNet layer), half of them address arithmetic, bounds tests and
+      // constant-bank reloads for features these launches do not use -- and per-CTA traces of the 3-channel stem showed
+      // the epilogue warps, not TMA or the tensor pipe, setting the tile period (3600 clk for 768 clk of MMAs).
+      bool lean_done = false;
+      if constexpr (EPI == 0 || EPI == EPI_RES) {
+        if (p.lean) {
+          lean_done = true;
+          const int oy = by * p.th + ly;
+          const bool valid = row < p.rows && ox < p.OW && oy < p.OH && b < p.B;
+          const int Y = oy * p.out_ys + p.out_y0, X = ox * p.out_xs + p.out_x0;
+          const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+          __nv_bfloat16* const op = static_cast<__nv_bfloat16*>(p.out) +
+                                    ((static_cast<size_t>(b) * p.out_PH + Y) * p.out_PW + X) * p.out_cstride + n0;
+          const __nv_bfloat16* const rp = (EPI & EPI_RES) ? p.residual + ((static_cast<size_t>(b) * p.out_H + Y) * p.out_W + X) * p.out_cstride + n0
+                                                          : nullptr;
+          const int nch = min(BN, p.Cout - n0) >> 4;           // chunks of this n-tile (Cout % 16 == 0)
+          uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
+          if ((EPI & EPI_RES) && valid && half < nch) {
+            rn0 = __ldg(reinterpret_cast<const uint4*>(rp + half * 16));
+            rn1 = __ldg(reinterpret_cast<const uint4*>(rp + half * 16) + 1);
+          }
+          mbar_wait(&tfull_bar[buf], aphase);
+          tc_fence_after();
+          if (threadIdx.x == 64) IG_TRACE(5 + 4 * titer);
+#pragma unroll 1
+          for (int c = half; c < nch; c += 2) {
+            uint32_t acc[16];
+            tmem_ld_32x16(tmem_acc + c * 16, acc);
+            uint32_t rw[8];
+            if (EPI & EPI_RES) {
+              rw[0] = rn0.x; rw[1] = rn0.y; rw[2] = rn0.z; rw[3] = rn0.w; rw[4] = rn1.x; rw[5] = rn1.y; rw[6] = rn1.z; rw[7] = rn1.w;
+              if (valid && c + 2 < nch) {                        // the next chunk's residual, one iteration ahead
+                rn0 = __ldg(reinterpret_cast<const uint4*>(rp + (c + 2) * 16));
+                rn1 = __ldg(reinterpret_cast<const uint4*>(rp + (c + 2) * 16) + 1);
+              }
+            }
+            const float4* tr = trow + 2 * (c * 16);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4 t0 = tr[2 * j];
+              float x = fmaf(__uint_as_float(acc[j]), t0.x, t0.y);
+              if (EPI & EPI_RES) x += __uint_as_float((j & 1) ? (rw[j >> 1] & 0xffff0000u) : (rw[j >> 1] << 16));
+              x = x > 0.f ? x : x * t0.z;
+              v[j] = x * t0.w;
+            }
+            if constexpr (EPI == 0) {
+              if (p.colsum != nullptr) {
+                float s8[8], s4[4], s2[2];
+                const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+                if (!__all_sync(0xffffffffu, valid)) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = valid ? v[j] : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s8[j] = (h16 ? v[8 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, h16 ? v[j] : v[8 + j], 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s4[j] = (h8 ? s8[4 + j] : s8[j]) + __shfl_xor_sync(0xffffffffu, h8 ? s8[j] : s8[4 + j], 8);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) s2[j] = (h4 ? s4[2 + j] : s4[j]) + __shfl_xor_sync(0xffffffffu, h4 ? s4[j] : s4[2 + j], 4);
+                float s1 = (h2 ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? s2[0] : s2[1], 2);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+                const int colj = (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);
+                if (!(lane & 1)) s_csum[((titer & 1) * 4 + q) * BN + c * 16 + colj] = s1;
+              }
+            }
+            if (valid) {
+              uint4 w0, w1;
+              w0.x = pack_bf16x2(v[0], v[1]); w0.y = pack_bf16x2(v[2], v[3]); w0.z = pack_bf16x2(v[4], v[5]); w0.w = pack_bf16x2(v[6], v[7]);
+              w1.x = pack_bf16x2(v[8], v[9]); w1.y = pack_bf16x2(v[10], v[11]); w1.z = pack_bf16x2(v[12], v[13]); w1.w = pack_bf16x2(v[14], v[15]);
+              uint4* o4 = reinterpret_cast<uint4*>(op + c * 16);
+              o4[0] = w0;
+              o4[1] = w1;
+            }
+          }
+        }
+      }
+      if (!lean_done) {
       const int nrows = p.upmode ? 4 : (p.patch ? p.prows : 1);
 #pragma unroll 1
       for (int r = 0; r < nrows; ++r) {
@@ -1060,6 +1179,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("bar.sync 2, 256;" ::: "memory");   // s_rgb may be overwritten by the next tile
       }
       }   // rows of the tile
+      }   // general path
       if constexpr (EPI == 0) {
         if (p.colsum != nullptr) {
           asm volatile("bar.sync 3, 256;" ::: "memory");         // every warp's partial sums of this tile are in place
@@ -1082,7 +1202,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (kPair) mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&tempty_bar[buf]), 0));   // the leader's MMA warp waits for both CTAs
         else mbar_arrive(&tempty_bar[buf]);
       }
-      if (threadIdx.x == 64 && p.hpw) IG_TRACE(2 + 4 * titer);    // epilogue (warp 2) drained this tile
+      if (threadIdx.x == 64 && (p.hpw || p.strip)) IG_TRACE(2 + 4 * titer);    // epilogue (warp 2) drained this tile
     }
   }
 
@@ -1613,6 +1733,30 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
         p.wres = 1;
         p.wres_stages = nst;
         p.cluster = cs = 1;
+        // strip sub-mode: 16-byte pixels (x_pixstride = 8 elements: the 3-channel stems), stride 1 in x, taps that differ
+        // only in dy, one K chunk (the 8-pixel window).  pSp stem (256^2, 3 taps): 384 TMA rows of 128 bytes per tile
+        // became one 6.5 KB box; the layer was TMA-row bound (205 us for 40 us of output writes).
+        static const int env_strip = []() { const char* e = getenv("FM3D_STRIP"); return e ? atoi(e) : 1; }();
+        bool ok = env_strip && pixs == 8 && rows_ % 8 == 0 && imgs % rows_ == 0 && d->Cin <= 64 && sx == 1 && p.kchunks == 1 && p.tw == 128 &&
+                  p.th == 1 && p.tb == 1 && d->ntaps <= 16;
+        int dy0 = 127, dy1 = -127;
+        for (int i = 0; ok && i < d->ntaps; ++i) {
+          ok = d->tap_dx[i] == 0;
+          dy0 = d->tap_dy[i] < dy0 ? d->tap_dy[i] : dy0;
+          dy1 = d->tap_dy[i] > dy1 ? d->tap_dy[i] : dy1;
+        }
+        if (ok && dy1 - dy0 + 1 <= 16) {
+          p.strip_rows = dy1 - dy0 + 1;
+          p.strip_y0 = dy0;
+          p.strip_sbytes = (p.strip_rows * 136 * 16 + 127) & ~127;
+          int sst = static_cast<int>((200 * 1024 - wbytes) / p.strip_sbytes);
+          if (sst > IG_MAX_STAGES) sst = IG_MAX_STAGES;
+          if (sst >= 3) {
+            p.strip = 1;
+            p.wres_stages = sst;
+            for (int i = 0; i < d->ntaps; ++i) p.strip_trow[i] = static_cast<int8_t>(d->tap_dy[i] - dy0);
+          }
+        }
       }
     }
     p.num_super = p.tiles_n * p.ksplit * ((p.m_tiles + cs - 1) / cs);
@@ -1646,6 +1790,12 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     const int ncl = sms / p.cluster > 0 ? sms / p.cluster : 1;
     p.ph_whole = (p.nph > 1 && env_whole > 0 && p.nsup1 >= static_cast<int64_t>(env_whole) * ncl && !p.tile_ctr) ? 1 : 0;
   }
+  {
+    static const int env_lean = []() { const char* e = getenv("FM3D_LEAN_EPI"); return e ? atoi(e) : 1; }();
+    p.lean = (env_lean && d->tab && d->out && !d->out_nchw_f32 && !d->out_cgroup && !d->rgb && !d->border_tab && !d->noise && !resup &&
+              !p.upmode && !p.patch && p.nph == 1 && p.ksplit == 1 && d->Cout % 16 == 0 && d->out_cstride >= d->Cout &&
+              (!d->tab_bstride)) ? 1 : 0;
+  }
   if (p.num_super >= (1 << 24) - 1) p.tile_ctr = nullptr;      // queue entries carry 24 bits of tile index
   // ---- tensor maps
   CUtensorMap tmA, tmB;
@@ -1659,7 +1809,17 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
                                static_cast<cuuint32_t>(p.hp ? p.hp_ph * sy : (p.patch ? p.prows : th * sy)),
                                static_cast<cuuint32_t>(p.hp ? 1 : tb)};
     const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(sx), static_cast<cuuint32_t>(sy), 1};
-    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
+    CUresult r;
+    if (p.strip) {
+      // the packed image as it is: [B][rows][16-byte pixels][8 channels], dense boxes of strip_rows x 136 pixels
+      const cuuint64_t sdims[4] = {8, static_cast<cuuint64_t>(rows_ / 8), static_cast<cuuint64_t>(imgs / rows_), static_cast<cuuint64_t>(d->B)};
+      const cuuint32_t sbox[4] = {8, 136, static_cast<cuuint32_t>(p.strip_rows), 1};
+      const cuuint32_t one[4] = {1, 1, 1, 1};
+      r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), sdims, strides, sbox, one,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else
+    r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("fm_conv_igemm: cuTensorMapEncodeTiled(A) failed with CUresult %d", (int)r); return FM_ERR_CUDA; }
