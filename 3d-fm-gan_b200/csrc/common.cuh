@@ -349,6 +349,20 @@ __device__ __forceinline__ void umma_bf16_x4(uint32_t tmem_d, uint32_t a_lo, uin
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Two K=16 steps (K = 32): operands whose K chunk is half empty (the 3x3 stem: 3 pixels x 8 channels per kernel row).
+__device__ __forceinline__ void umma_bf16_x2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.u32 q, 0, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "add.u32 al, %1, 2;\n\tadd.u32 bl, %3, 2;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // CTA-pair form (cta_group::2, issued by the leader CTA only): M = 256 (128 rows from each CTA's A tile at the
 // same smem offset), B = N/2 rows from each CTA; each CTA's TMEM receives its own 128 x N block of D.
 __device__ __forceinline__ void umma_bf16_x4_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,

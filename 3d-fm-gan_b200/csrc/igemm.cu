@@ -71,7 +71,7 @@ struct IgemmParams {
   // strip (a wres sub-mode; 3-channel stems stored as 16-byte pixels, stride 1 in x): ONE compact box of the packed image
   // per tile -- strip_rows input rows x 136 pixels x 16 bytes -- serves every tap through a no-swizzle descriptor whose K
   // core stride is one pixel (the overlapping 8-pixel windows are never materialised: 6 KB per tile instead of 48 KB)
-  int strip, strip_rows, strip_sbytes, strip_y0;
+  int strip, strip_rows, strip_sbytes, strip_y0, strip_k32;
   int lean;                        // epilogue: the launch qualifies for the lean path (see the epilogue)
   int8_t strip_trow[FM_MAX_TAPS];  // input row of each tap inside the box
   int16_t hp_aoff[FM_MAX_TAPS];    // per-tap start offset of the A descriptor inside the patch (16-byte units)
@@ -726,9 +726,14 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         if (lane == 0) IG_TRACE(4 + 4 * titer);                                  // MMA: strip landed
         if (elect_one()) {
-          for (int tap = 0; tap < p.ntaps; ++tap)
-            umma_bf16_x4(tmem_d, umma_desc_lo(sa + p.strip_trow[tap] * (136 * 16)), ahi,
-                         umma_desc_lo(ring + static_cast<uint32_t>(tap) * Cfg::B_BYTES), dhi, idesc, tap > 0 ? 1u : 0u);
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            const uint32_t alo = umma_desc_lo(sa + p.strip_trow[tap] * (136 * 16));
+            const uint32_t blo = umma_desc_lo(ring + static_cast<uint32_t>(tap) * Cfg::B_BYTES);
+            // Cin <= 32: the window's second half multiplies zero weights -- two K = 16 steps instead of four (traces: the
+            // stem's tile period was the 12 no-swizzle MMAs of its three taps)
+            if (p.strip_k32) umma_bf16_x2(tmem_d, alo, ahi, blo, dhi, idesc, tap > 0 ? 1u : 0u);
+            else umma_bf16_x4(tmem_d, alo, ahi, blo, dhi, idesc, tap > 0 ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);
           umma_commit(&tfull_bar[buf]);
         }
@@ -1753,6 +1758,7 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
           if (sst > IG_MAX_STAGES) sst = IG_MAX_STAGES;
           if (sst >= 3) {
             p.strip = 1;
+            p.strip_k32 = d->Cin <= 32 ? 1 : 0;
             p.wres_stages = sst;
             for (int i = 0; i < d->ntaps; ++i) p.strip_trow[i] = static_cast<int8_t>(d->tap_dy[i] - dy0);
           }

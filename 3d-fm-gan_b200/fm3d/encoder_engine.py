@@ -377,8 +377,9 @@ class PspPlan:
         m = self.model
         ops.image_to_nhwc8_padded(x, 1, 1, self.Hp, self.Wp, out=self.packed)
         cur = self._buf("in", B, S, S, 64)
+        # Cin = 3 pixels x 8 channels of the 8-pixel window carry weights (the rest multiplies zeros): K = 32 per kernel row
         ops.conv_igemm(self.packed, self.in_w, [(ky, 0, ky) for ky in range(3)], cur, self.in_tab,
-                       B=B, H=self.Hp, W=S, Cin=64, Cout=64, OH=S, OW=S, stride_x=1, stride_y=1,
+                       B=B, H=self.Hp, W=S, Cin=24, Cout=64, OH=S, OW=S, stride_x=1, stride_y=1,
                        x_pixstride=8, x_rowstride=self.Wp * 8, x_imgstride=self.Hp * self.Wp * 8,
                        algo_flops=2.0 * B * S * S * 3 * 64 * 9)          # 3x3 conv on 3 channels, not the padded K
         h = S

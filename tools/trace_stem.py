@@ -22,7 +22,7 @@ out = torch.empty(B, S, S, 64, device=dev, dtype=torch.bfloat16)
 
 
 def run():
-    ops.conv_igemm(packed, w, [(ky, 0, ky) for ky in range(3)], out, tab, B=B, H=Hp, W=S, Cin=64, Cout=64, OH=S, OW=S,
+    ops.conv_igemm(packed, w, [(ky, 0, ky) for ky in range(3)], out, tab, B=B, H=Hp, W=S, Cin=24, Cout=64, OH=S, OW=S,
                    stride_x=1, stride_y=1, x_pixstride=8, x_rowstride=Wp * 8, x_imgstride=Hp * Wp * 8)
 
 
