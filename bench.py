@@ -371,6 +371,14 @@ def main():
         for i in range(2):
             step(*dev_in[i % n_sets])
         torch.cuda.synchronize()
+        # the same step with every launch on all SMs, each timed alone: kernel quality at full width, the figure that is
+        # comparable with runs without SM partitions (round 1)
+        prof_full = []
+        ops.PROFILE = prof_full
+        os.environ["FM3D_PARTITION_SERIAL"] = "0"
+        for i in range(2):
+            step(*dev_in[i % n_sets])
+        torch.cuda.synchronize()
         for k, v in prev_env.items():
             if v is None:
                 del os.environ[k]
@@ -424,6 +432,10 @@ def main():
                                for k, v in sorted(by_net.items()) if v[1] > 0},
                 "sm_share_weighted": "a launch confined to n SMs is measured against the peak of n SMs (duration x n/SMs); "
                                      "achieved_unweighted charges every launch the whole chip",
+                "full_chip": (lambda f, t: {"achieved": f / t / 1e12, "frac": f / t / 1e12 / peak_tf, "frac_burst": f / t / 1e12 / peak_burst,
+                                            "kernel_ms_per_step": t * 1e3 / 2,
+                                            "note": "the same launches without SM partitions: every launch on all SMs, timed alone"})(
+                    sum(r[2] for r in prof_full), sum(r[0].elapsed_time(r[1]) for r in prof_full) * 1e-3) if prof_full else None,
                 "achieved_unweighted": flops / ksec_raw / 1e12 if ksec_raw > 0 else 0.0,
                 "frac_unweighted": (flops / ksec_raw / 1e12 / peak_tf) if ksec_raw > 0 else 0.0,
                 "launches_per_step": len(prof) // 2, "kernel_ms_per_step": ksec_raw * 1e3 / 2,
