@@ -466,7 +466,9 @@ def test_dynamic_tile_schedule_up_phases(cuda):
             ph.append((len(tl), py, px))
     outs = []
     ctr = torch.zeros(2, device=cuda, dtype=torch.int32)
-    for c, cap in ((None, 0), (ctr, 0), (ctr, 10)):
+    # (static, all SMs: phase-major), (dynamic), (dynamic, 10 SMs), (static, 4 SMs: >= 6 tiles per cluster, so a cluster
+    # takes whole tiles with a rotated phase order)
+    for c, cap in ((None, 0), (ctr, 0), (ctr, 10), (None, 4)):
         out = torch.zeros(1, B * (2 * h + 2), 2 * h + 2, Cout, device=cuda, dtype=torch.bfloat16)
         ops.conv_igemm(x.view(1, B * (h + 1), h + 1, Cin), w, taps, out, None, B=1, H=B * (h + 1), W=h + 1, Cin=Cin, Cout=Cout,
                        OH=B * (h + 1), OW=h + 1, out_H=B * (2 * h + 2), out_W=2 * h + 2, out_ys=2, out_xs=2, phases=ph,
@@ -474,7 +476,7 @@ def test_dynamic_tile_schedule_up_phases(cuda):
         torch.cuda.synchronize()
         assert ctr.tolist() == [0, 0]
         outs.append(out)
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]) and torch.equal(outs[0], outs[3])
     assert float(outs[0].float().abs().max()) > 0.1
 
 
