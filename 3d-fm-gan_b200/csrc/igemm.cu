@@ -1630,11 +1630,18 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
       // S <= (E - 1) * T + 1 weight stages (T = taps per virtual chunk) the request does not even block.
       // several phases in one launch: the weight cursor may run S / T chunks ahead of the MMAs, with T the SMALLEST
       // phase (a 1-tap phase: one weight tile per chunk), so more patch slots are kept behind the prefetch distance
-      const int T = nph > 1 ? ph_tmin : (d->ntaps + np - 1) / np;
+      static const int env_up_d = []() { const char* e = getenv("FM3D_UP_D"); return e ? atoi(e) : 2; }();
+      static const int env_up_e = []() { const char* e = getenv("FM3D_UP_E"); return e ? atoi(e) : 4; }();
+      // FM3D_UP_TCAP: the T of the "weights never run further ahead than the patches" cap below for multi-phase launches.
+      // The cap only keeps the patch request from blocking (there is no deadlock for any ring depth); with T = the 1-tap
+      // phase the weight ring of the merged up-conv was 4 stages, i.e. ONE chunk of a 4-tap phase in flight.  T = 4: 5
+      // stages, 32 -> 64 184 -> 171 us (64 -> 128 unchanged: not ring-depth bound).
+      static const int env_up_t = []() { const char* e = getenv("FM3D_UP_TCAP"); return e ? atoi(e) : 4; }();
+      const int T = nph > 1 ? (env_up_t > 0 ? env_up_t : ph_tmin) : (d->ntaps + np - 1) / np;
       const int bbytes = bn * 128;
       const int st_max = bn == 256 ? 4 : (bn == 128 ? 6 : 8);
-      int D = nph > 1 ? 2 : (T >= 5 ? 2 : (T >= 3 ? 3 : 4));
-      const int E = nph > 1 ? 4 : (T >= 3 ? 2 : 3);
+      int D = nph > 1 ? env_up_d : (T >= 5 ? 2 : (T >= 3 ? 3 : 4));
+      const int E = nph > 1 ? env_up_e : (T >= 3 ? 2 : 3);
       int st = 0;
       for (; D >= 1; --D) {
         st = (200 * 1024 - (D + E) * p.hp_bytes) / bbytes;
@@ -1704,7 +1711,8 @@ extern "C" int fm_conv_igemm(const fm_conv_desc* d, void* stream) {
     // of a tile at 2x its tensor-pipe time with ~470 clk per TMA box: the ring depth over the load latency was the limit.
     if (p.hp) {
       static const int env_deep = []() { const char* e = getenv("FM3D_HP_DEEP"); return e ? atoi(e) : 1; }();
-      const int np = p.hp_np, T = nph > 1 ? ph_tmin : (d->ntaps + np - 1) / np, E = p.hp_na - p.hp_dist;
+      static const int env_up_t2 = []() { const char* e = getenv("FM3D_UP_TCAP"); return e ? atoi(e) : 4; }();
+      const int np = p.hp_np, T = nph > 1 ? (env_up_t2 > 0 ? env_up_t2 : ph_tmin) : (d->ntaps + np - 1) / np, E = p.hp_na - p.hp_dist;
       const int bstride = p.pair ? bn * 64 : bn * 128;
       int st = (200 * 1024 - p.hp_na * p.hp_bytes) / bstride;
       if (st > IG_MAX_STAGES) st = IG_MAX_STAGES;
