@@ -85,6 +85,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
 }
+// 32 contiguous bytes in one store (sm_100: STG.E.ENL2.256): a whole sector per lane instead of two half-sector stores.
+// The address must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   __nv_bfloat162 p = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(p);

@@ -800,6 +800,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool e_tn1 = p.tiles_n == 1, e_ty1 = p.tiles_y == 1, e_g1 = p.Bg == p.B;
     int buf = 0;
     uint32_t aphase = 0;
+    // 32-byte stores when every 16-column chunk of a pixel starts on a 32-byte boundary
+    const bool st256 = !p.out_nchw_f32 && (p.out_cstride & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0 &&
+                       (p.out_gstride & 15) == 0;
     int eslot = 0;                 // EPI_RESUP: residual box slot / phase of the current tile
     uint32_t ephase = 0;
     // colsum: partial column sums [tile parity][lane quarter][BN] in the upper half of the table region (the tables
@@ -928,8 +931,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               w0.x = pack_bf16x2(v[0], v[1]); w0.y = pack_bf16x2(v[2], v[3]); w0.z = pack_bf16x2(v[4], v[5]); w0.w = pack_bf16x2(v[6], v[7]);
               w1.x = pack_bf16x2(v[8], v[9]); w1.y = pack_bf16x2(v[10], v[11]); w1.z = pack_bf16x2(v[12], v[13]); w1.w = pack_bf16x2(v[14], v[15]);
               uint4* o4 = reinterpret_cast<uint4*>(op + c * 16);
-              o4[0] = w0;
-              o4[1] = w1;
+              if (st256) {
+                st_global_256(o4, w0, w1);
+              } else {
+                o4[0] = w0;
+                o4[1] = w1;
+              }
             }
           }
         }
@@ -1152,16 +1159,20 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           } else {
             uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + og * p.out_gstride +
                                                  opix * p.out_cstride + ol0);
+            uint4 w[2];
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-              if (ol0 + 8 * g < p.out_cstride) {
-                uint4 w;
-                w.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
-                w.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-                w.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-                w.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-                op[g] = w;
-              }
+              w[g].x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+              w[g].y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+              w[g].z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+              w[g].w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+            }
+            if (st256 && ol0 + 16 <= p.out_cstride) {
+              st_global_256(op, w[0], w[1]);                 // one whole 32-byte sector per lane
+            } else {
+#pragma unroll
+              for (int g = 0; g < 2; ++g)
+                if (ol0 + 8 * g < p.out_cstride) op[g] = w[g];
             }
           }
         }
