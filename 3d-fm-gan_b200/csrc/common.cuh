@@ -92,6 +92,12 @@ __device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uin
                "r"(b.y), "r"(b.z), "r"(b.w)
                : "memory");
 }
+// 32 contiguous bytes in one read-only load (LDG.E.ENL2.256.CONSTANT); 32-byte aligned address
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   __nv_bfloat162 p = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(p);

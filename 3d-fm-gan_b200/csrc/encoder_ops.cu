@@ -88,6 +88,42 @@ __global__ void __launch_bounds__(256) maxpool_kernel(__nv_bfloat16* __restrict_
   }
 }
 
+// The same on 16 channels (32 bytes) per thread, packed bf16 maxima (max of bf16 values is exact in bf16: no fp32 round
+// trip) and 32-bit index arithmetic (the 64-bit divisions of the form above cost more than its nine loads).
+__global__ void __launch_bounds__(256) maxpool16_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ x,
+                                                        int H, int W, int OH, int OW, int cs, uint32_t total) {
+  const uint32_t groups = static_cast<uint32_t>(cs) / 16;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const uint32_t r1 = idx / groups, g = idx - r1 * groups;
+    const uint32_t r2 = r1 / OW, ox = r1 - r2 * OW;
+    const uint32_t b = r2 / OH, oy = r2 - b * OH;
+    __nv_bfloat162 m[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) m[c] = __float2bfloat162_rn(-INFINITY);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = static_cast<int>(oy) * 2 - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = static_cast<int>(ox) * 2 - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        uint4 a, c4;
+        ld_global_nc_256(x + ((static_cast<size_t>(b) * H + iy) * W + ix) * cs + g * 16, a, c4);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m[c] = __hmax2(m[c], *reinterpret_cast<const __nv_bfloat162*>(&w[c]));
+      }
+    }
+    uint4 o0, o1;
+    o0.x = *reinterpret_cast<uint32_t*>(&m[0]); o0.y = *reinterpret_cast<uint32_t*>(&m[1]);
+    o0.z = *reinterpret_cast<uint32_t*>(&m[2]); o0.w = *reinterpret_cast<uint32_t*>(&m[3]);
+    o1.x = *reinterpret_cast<uint32_t*>(&m[4]); o1.y = *reinterpret_cast<uint32_t*>(&m[5]);
+    o1.z = *reinterpret_cast<uint32_t*>(&m[6]); o1.w = *reinterpret_cast<uint32_t*>(&m[7]);
+    st_global_256(out + ((static_cast<size_t>(b) * OH + oy) * OW + ox) * cs + g * 16, o0, o1);
+  }
+}
+
 // non-overlapping ph x pw average pooling, NHWC bf16 -> NCHW fp32
 __global__ void __launch_bounds__(256) avgpool_kernel(float* __restrict__ out, const __nv_bfloat16* __restrict__ x, int H, int W,
                                                       int C, int cs, int ph, int pw, int64_t total) {
@@ -225,6 +261,42 @@ __global__ void __launch_bounds__(256) se_combine_kernel(__nv_bfloat16* __restri
   }
 }
 
+// The same with 16 channels (32 bytes) per thread: one 256-bit load of r and of the shortcut, one 256-bit store -- half
+// the memory instructions of the 8-channel form for the same bytes (cs, sc_cs multiples of 16; 32-byte aligned tensors).
+__global__ void __launch_bounds__(256) se_combine16_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ r,
+                                                           const float* __restrict__ gate, const __nv_bfloat16* __restrict__ sc,
+                                                           int H, int W, int C, int cs, int sc_H, int sc_W, int sc_cs, int ss,
+                                                           int64_t total) {
+  const int groups = cs / 16;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int g = static_cast<int>(idx % groups);
+    int64_t t = idx / groups;
+    const int x = static_cast<int>(t % W); t /= W;
+    const int y = static_cast<int>(t % H);
+    const int64_t b = t / H;
+    uint4 ra, rb, sa, sb;
+    ld_global_nc_256(r + ((b * H + y) * W + x) * cs + g * 16, ra, rb);
+    ld_global_nc_256(sc + ((b * sc_H + y * ss) * sc_W + x * ss) * sc_cs + g * 16, sa, sb);
+    const float4* gp = reinterpret_cast<const float4*>(gate + b * C + g * 16);
+    float gv[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = (g * 16 + 4 * q + 3 < C) ? __ldg(gp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gv[4 * q] = v.x; gv[4 * q + 1] = v.y; gv[4 * q + 2] = v.z; gv[4 * q + 3] = v.w;
+    }
+    float r0[8], r1[8], s0[8], s1[8], o0[8], o1[8];
+    unpack8(ra, r0); unpack8(rb, r1);
+    unpack8(sa, s0); unpack8(sb, s1);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      o0[c] = (g * 16 + c < C) ? fmaf(r0[c], gv[c], s0[c]) : 0.f;
+      o1[c] = (g * 16 + 8 + c < C) ? fmaf(r1[c], gv[8 + c], s1[c]) : 0.f;
+    }
+    st_global_256(out + ((b * H + y) * W + x) * cs + g * 16, pack8(o0), pack8(o1));
+  }
+}
+
 // bilinear resize with align_corners=True (F.interpolate, psp_encoders.py:98), NHWC bf16
 __global__ void __launch_bounds__(256) bilinear_kernel(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ x,
                                                        int IH, int IW, int OH, int OW, int cs, float ry, float rx,
@@ -273,6 +345,15 @@ extern "C" int fm_image_to_nhwc8_padded(void* out, const float* x, int B, int C,
 extern "C" int fm_maxpool3x3s2_nhwc(void* out, const void* x, int B, int H, int W, int cs, void* stream) {
   FM_CHECK_ARG(out && x && B > 0 && H > 0 && W > 0 && cs > 0 && cs % 8 == 0, "fm_maxpool3x3s2_nhwc: bad args");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  if (cs % 16 == 0 && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x)) & 31) == 0 &&
+      static_cast<int64_t>(B) * OH * OW * (cs / 16) < 0x7fffffffLL) {
+    const int64_t total16 = static_cast<int64_t>(B) * OH * OW * (cs / 16);
+    maxpool16_kernel<<<grid_for2(total16), 256, 0, ST>>>(static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(x), H, W,
+                                                         OH, OW, cs, static_cast<uint32_t>(total16));
+    count_launch();
+    FM_LAUNCH_OK();
+    return FM_OK;
+  }
   const int64_t total = static_cast<int64_t>(B) * OH * OW * (cs / 8);
   maxpool_kernel<<<grid_for2(total), 256, 0, ST>>>(static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(x), H, W,
                                                    OH, OW, cs, total);
@@ -407,6 +488,17 @@ extern "C" int fm_se_combine_nhwc(void* out, const void* r, const float* gate_bc
   FM_CHECK_ARG(out && r && gate_bc && sc && B > 0 && H > 0 && W > 0 && C > 0 && cs >= C && cs % 8 == 0 && sc_cs >= cs - 7 &&
                    sc_cs % 8 == 0 && sc_stride >= 1, "fm_se_combine_nhwc: bad args");
   FM_CHECK_ARG((H - 1) * sc_stride < sc_H && (W - 1) * sc_stride < sc_W, "fm_se_combine_nhwc: shortcut too small");
+  if (cs % 16 == 0 && sc_cs % 16 == 0 && C % 4 == 0 && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(r) |
+                                                          reinterpret_cast<uintptr_t>(sc)) & 31) == 0 &&
+      (reinterpret_cast<uintptr_t>(gate_bc) & 15) == 0) {
+    const int64_t total16 = static_cast<int64_t>(B) * H * W * (cs / 16);
+    se_combine16_kernel<<<grid_for2(total16), 256, 0, ST>>>(static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(r),
+                                                            gate_bc, static_cast<const __nv_bfloat16*>(sc), H, W, C, cs, sc_H, sc_W,
+                                                            sc_cs, sc_stride, total16);
+    count_launch();
+    FM_LAUNCH_OK();
+    return FM_OK;
+  }
   const int64_t total = static_cast<int64_t>(B) * H * W * (cs / 8);
   se_combine_kernel<<<grid_for2(total), 256, 0, ST>>>(static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(r),
                                                       gate_bc, static_cast<const __nv_bfloat16*>(sc), H, W, C, cs, sc_H, sc_W,
