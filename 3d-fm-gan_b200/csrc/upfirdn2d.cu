@@ -173,7 +173,8 @@ struct UfsItem {
 __device__ __forceinline__ UfsItem ufs_item(int64_t i, const UpfirdnParams& p, int64_t planes, int R, int P, int strips) {
   UfsItem it;
   if (strips > 1) {
-    it.plane0 = i / strips;
+    // (a 64-bit division is ~100 instructions on every thread of every item)
+    it.plane0 = (i >> 31) == 0 ? static_cast<int64_t>(static_cast<uint32_t>(i) / static_cast<uint32_t>(strips)) : i / strips;
     it.nplanes = 1;
     const int s = static_cast<int>(i - it.plane0 * strips);
     it.oy0 = s * R;
@@ -307,13 +308,141 @@ __device__ __forceinline__ void ufs_rows(const T* __restrict__ sp, T* __restrict
   }
 }
 
+// Packed row walk for the 2-byte types (rank-1 taps, zero-row layouts): a thread owns TWO adjacent output columns.
+// The kernel is bound by instruction issue, not by HBM: the walk above spends ~23 instructions per output on bf16
+// (4 LDS.U16 + 4 conversions + 8 FMAs + a store per 2 bytes written), twice what the HBM rate leaves room for.  Here a
+// row costs 3 aligned LDS.32 (the 5 inputs of the pair lie in 3 words whatever the parity of their address: rows are
+// in_w * 2 bytes apart, so odd widths flip the parity every row -- the words are re-aligned with two funnel shifts by a
+// per-thread 0 / 16, which rows j and j + 2 share), 5 unpacks, 8 FMAs for the two horizontal sums, 4 packed FFMA2 for
+// the vertical window of the pair, one conversion and one 4-byte store: ~13 instructions per output.
+// Edge columns AND the staged words with per-thread masks instead of testing loads.
+__device__ __forceinline__ uint32_t ufs_lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+template <typename T> __device__ __forceinline__ void ufs_unpack2(uint32_t w, float& lo, float& hi);
+template <> __device__ __forceinline__ void ufs_unpack2<__nv_bfloat16>(uint32_t w, float& lo, float& hi) {
+  lo = __uint_as_float(w << 16);
+  hi = __uint_as_float(w & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void ufs_unpack2<__half>(uint32_t w, float& lo, float& hi) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+  lo = f.x; hi = f.y;
+}
+template <> __device__ __forceinline__ void ufs_unpack2<float>(uint32_t, float&, float&) {}
+template <typename T> __device__ __forceinline__ uint32_t ufs_pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t ufs_pack2<__nv_bfloat16>(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t ufs_pack2<__half>(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t ufs_pack2<float>(float, float) { return 0u; }
+
+template <typename T, bool EDGE>
+__device__ __forceinline__ void ufs_rows_pk(const T* __restrict__ sp, T* __restrict__ op, const float (&kh1)[4],
+                                            const float (&kv1)[4], const UpfirdnParams& p, int ix0, int ox, int ty0, int ty1) {
+  static_assert(sizeof(T) == 2, "packed walk: 2-byte types");
+  uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu, m2 = 0xffffffffu;
+  if (EDGE) {
+    auto ok = [&](int q) { return ix0 + q >= 0 && ix0 + q < p.in_w; };
+    m0 = (ok(0) ? 0xffffu : 0u) | (ok(1) ? 0xffff0000u : 0u);
+    m1 = (ok(2) ? 0xffffu : 0u) | (ok(3) ? 0xffff0000u : 0u);
+    m2 = ok(4) ? 0xffffu : 0u;
+  }
+  f32x2 kv2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) kv2[i] = f2_pack(kv1[i], kv1[i]);
+  f32x2 acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = 0ull;
+  const int jn = (ty1 - ty0) + 3;
+  const uint32_t rb = static_cast<uint32_t>(p.in_w) * 2u;
+  const uint32_t a0 = smem_u32(sp + static_cast<int64_t>(ty0 - p.pad_y0) * p.in_w + ix0);
+  // rows j and j + 2 are 4 * in_w bytes apart: same parity
+  uint32_t pA = a0 & ~3u, pB = (a0 + rb) & ~3u;
+  const uint32_t sA = (a0 & 2u) << 3, sB = ((a0 + rb) & 2u) << 3;
+  T* orow = op + static_cast<int64_t>(ty0 - 3) * p.out_w;
+  const bool two = !EDGE || ox + 1 < p.out_w;
+  // one 4-byte store per row when every row of the pair is 4-byte aligned
+  const bool vec = two && (p.out_w & 1) == 0 && (reinterpret_cast<uintptr_t>(orow) & 3) == 0;
+  struct Row { uint32_t w0, w1, w2; };
+  auto row_load = [&](uint32_t a) { Row r; r.w0 = ufs_lds32(a); r.w1 = ufs_lds32(a + 4); r.w2 = ufs_lds32(a + 8); return r; };
+  auto row_math = [&](auto uc, const Row& r, uint32_t sh) {
+    constexpr int u = decltype(uc)::value;
+    uint32_t n0 = __funnelshift_r(r.w0, r.w1, sh), n1 = __funnelshift_r(r.w1, r.w2, sh), n2 = r.w2 >> sh;
+    if (EDGE) { n0 &= m0; n1 &= m1; n2 &= m2; }
+    float e0, e1, e2, e3, e4, e5;
+    ufs_unpack2<T>(n0, e0, e1);
+    ufs_unpack2<T>(n1, e2, e3);
+    ufs_unpack2<T>(n2, e4, e5);
+    (void)e5;
+    const float h0 = fmaf(e3, kh1[3], fmaf(e2, kh1[2], fmaf(e1, kh1[1], e0 * kh1[0])));
+    const float h1 = fmaf(e4, kh1[3], fmaf(e3, kh1[2], fmaf(e2, kh1[1], e1 * kh1[0])));
+    const f32x2 h = f2_pack(h0, h1);
+    acc[u & 3] = f2_mul(kv2[0], h);                          // tap row 0 opens output row j: no zeroing pass
+#pragma unroll
+    for (int a = 1; a < 4; ++a) acc[(u - a) & 3] = f2_fma(kv2[a], h, acc[(u - a) & 3]);
+  };
+  auto row_store = [&](auto uc, T* o) {                      // tap row 3 closed output row j - 3 (slot (u + 1) & 3)
+    constexpr int u = decltype(uc)::value;
+    float lo, hi;
+    f2_unpack(acc[(u + 1) & 3], lo, hi);
+    if (vec) {
+      *reinterpret_cast<uint32_t*>(o) = ufs_pack2<T>(lo, hi);
+    } else {
+      o[0] = from_f32<T>(lo);
+      if (two) o[1] = from_f32<T>(hi);
+    }
+  };
+  const uint32_t rb2 = 2u * rb, rb4 = 4u * rb;
+  int jb = 0;
+  for (; jb + 4 <= jn; jb += 4) {
+    const Row r0 = row_load(pA), r1 = row_load(pB), r2 = row_load(pA + rb2), r3 = row_load(pB + rb2);
+    const bool st012 = jb >= 4;                               // the first step only closes a row at u = 3
+    row_math(std::integral_constant<int, 0>{}, r0, sA);
+    if (st012) row_store(std::integral_constant<int, 0>{}, orow);
+    row_math(std::integral_constant<int, 1>{}, r1, sB);
+    if (st012) row_store(std::integral_constant<int, 1>{}, orow + p.out_w);
+    row_math(std::integral_constant<int, 2>{}, r2, sA);
+    if (st012) row_store(std::integral_constant<int, 2>{}, orow + 2 * p.out_w);
+    row_math(std::integral_constant<int, 3>{}, r3, sB);
+    row_store(std::integral_constant<int, 3>{}, orow + 3 * static_cast<int64_t>(p.out_w));
+    pA += rb4; pB += rb4;
+    orow += 4 * static_cast<int64_t>(p.out_w);
+  }
+  if (jb < jn) {                                              // tail: up to 3 rows (u = 0, 1, 2)
+    row_math(std::integral_constant<int, 0>{}, row_load(pA), sA);
+    if (jb >= 3) row_store(std::integral_constant<int, 0>{}, orow);
+  }
+  if (jb + 1 < jn) {
+    row_math(std::integral_constant<int, 1>{}, row_load(pB), sB);
+    if (jb + 1 >= 3) row_store(std::integral_constant<int, 1>{}, orow + p.out_w);
+  }
+  if (jb + 2 < jn) {
+    row_math(std::integral_constant<int, 2>{}, row_load(pA + rb2), sA);
+    if (jb + 2 >= 3) row_store(std::integral_constant<int, 2>{}, orow + 2 * p.out_w);
+  }
+}
+
 template <typename T, int COLS>
 __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __restrict__ out, const T* __restrict__ x,
                                                                        const float* __restrict__ kernel, UpfirdnParams p,
                                                                        int64_t planes, int R, int P, int strips,
-                                                                       int64_t n_items, int head, int nslots, int buf_bytes) {
-  // head > 0: strip mode with zero rows -- the staged range starts `head` bytes into the slot, preceded
-  // (top of the image) and followed (bottom) by three zeroed rows
+                                                                       int64_t n_items, int head, int nslots, int buf_bytes,
+                                                                       int ppitch, int rot) {
+  // head > 0: zero-row layouts -- rows above / below the image read zeros instead of being tested for.
+  //  * strip mode (strips > 1): the staged range starts `head` bytes into the slot, preceded (top of the image) and
+  //    followed (bottom) by three zeroed rows;
+  //  * whole planes (ppitch > 0): every plane of the item is copied on its own into a region of `ppitch` bytes
+  //    (first region `head` bytes into the slot), the gaps between regions hold >= 3 rows of zeros.  The ring is zeroed
+  //    once; after a copy lands only the few bytes around each plane that the 16-byte granules of the copy (or the
+  //    previous item, whose planes sat up to 15 bytes further along) dirtied are cleared again.
+  // rot: column groups are handed out rotated by `rot` so that the groups touching the right edge share a warp with the
+  // ones touching the left edge (a warp with any edge column runs the column-tested variant)
   extern __shared__ __align__(128) uint8_t ufs_smem[];
   __shared__ __align__(8) uint64_t s_bar[UFS_MAX_SLOTS];
   __shared__ float s_k[16];
@@ -326,6 +455,11 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
   if (tid == 0) {
     for (int i = 0; i < nslots; ++i) mbar_init(&s_bar[i], 1);
     fence_barrier_init();
+  }
+  if (ppitch > 0) {     // whole planes between zero rows: the ring starts out as zeros
+    uint4* z = reinterpret_cast<uint4*>(ufs_smem);
+    const int n16 = nslots * buf_bytes / 16;
+    for (int i = tid; i < n16; i += UFS_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
   float w[4][4];
@@ -349,10 +483,31 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
 
   const int64_t plane_elems = static_cast<int64_t>(p.in_h) * p.in_w;
   const uintptr_t xbase = reinterpret_cast<uintptr_t>(x);
+  const uint32_t plane_bytes = static_cast<uint32_t>(plane_elems * sizeof(T));     // (whole-plane modes: < one ring slot)
+  const uint32_t plane_cap = (plane_bytes + 15u + 15u) & ~15u;                      // most bytes one plane's copy can write
 
   // byte range of an item, widened to 16-byte boundaries (the extra bytes stay inside the 16-byte
   // granules that hold the first / last wanted byte, so they are always mapped)
   auto issue = [&](const UfsItem& it, int slot) {
+    if (ppitch > 0) {
+      fence_proxy_async();                     // earlier generic accesses of this slot precede the async writes
+      uint32_t total = 0;
+      for (int q = 0; q < it.nplanes; ++q) {
+        const uintptr_t lo = xbase + static_cast<uintptr_t>(it.plane0 + q) * plane_bytes;
+        total += static_cast<uint32_t>(((lo + plane_bytes + 15) & ~static_cast<uintptr_t>(15)) - (lo & ~static_cast<uintptr_t>(15)));
+      }
+      mbar_arrive_expect_tx(&s_bar[slot], total);
+      for (int q = 0; q < it.nplanes; ++q) {
+        const uintptr_t lo = xbase + static_cast<uintptr_t>(it.plane0 + q) * plane_bytes;
+        const uintptr_t lo_a = lo & ~static_cast<uintptr_t>(15);
+        const uint32_t bytes = static_cast<uint32_t>(((lo + plane_bytes + 15) & ~static_cast<uintptr_t>(15)) - lo_a);
+        uint8_t* dst = ufs_smem + slot * buf_bytes + head + q * ppitch;
+        for (uint32_t off = 0; off < bytes; off += UFS_CHUNK)
+          bulk_load_1d(dst + off, reinterpret_cast<const void*>(lo_a + off), min(static_cast<uint32_t>(UFS_CHUNK), bytes - off),
+                       &s_bar[slot]);
+      }
+      return;
+    }
     const uintptr_t lo = xbase + static_cast<uintptr_t>((it.plane0 * plane_elems + static_cast<int64_t>(it.r_lo) * p.in_w) * sizeof(T));
     const uintptr_t hi = xbase + static_cast<uintptr_t>(((it.plane0 + it.nplanes - 1) * plane_elems +
                                                          static_cast<int64_t>(it.r_hi + 1) * p.in_w) * sizeof(T));
@@ -379,12 +534,26 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
     // the slot refilled now was drained by the previous iteration (its closing __syncthreads)
     const int64_t ahead = item + static_cast<int64_t>(nslots - 1) * gridDim.x;
     if (tid == 0 && ahead < n_items) issue(ufs_item(ahead, p, planes, R, P, strips), ahead_slot);
-    if (tid < 32) mbar_wait(&s_bar[slot], parity);            // one warp polls, the rest sleep in the barrier
+    if (tid < 32) {                                           // one warp polls, the rest sleep in the barrier
+      mbar_wait(&s_bar[slot], parity);
+      if (ppitch > 0) {
+        // clear what the copies (16-byte granules) and the previous item left outside [plane start, plane end)
+        for (int q = 0; q < it.nplanes; ++q) {
+          const uint32_t off = static_cast<uint32_t>((xbase + static_cast<uintptr_t>(it.plane0 + q) * plane_bytes) & 15);
+          uint8_t* rb = ufs_smem + slot * buf_bytes + head + q * ppitch;
+          T* a = reinterpret_cast<T*>(rb);
+          T* b = reinterpret_cast<T*>(rb + off + plane_bytes);
+          const int na = static_cast<int>(off / sizeof(T)), nb = static_cast<int>((plane_cap - off - plane_bytes) / sizeof(T));
+          if (tid < na) a[tid] = from_f32<T>(0.f);
+          if (tid < nb) b[tid] = from_f32<T>(0.f);
+        }
+      }
+    }
     __syncthreads();
 
     const uintptr_t lo = xbase + static_cast<uintptr_t>((it.plane0 * plane_elems + static_cast<int64_t>(it.r_lo) * p.in_w) * sizeof(T));
     const T* sbuf = reinterpret_cast<const T*>(ufs_smem + slot * buf_bytes + head + (lo & 15));
-    if (head > 0) {
+    if (head > 0 && ppitch == 0) {
       const bool top = it.oy0 - p.pad_y0 < it.r_lo, bottom = it.oy1 - 1 - p.pad_y0 + 3 > it.r_hi;
       if (top || bottom) {                                    // uniform: only the first / last strip of a plane
         T* zb = const_cast<T*>(sbuf);
@@ -397,34 +566,53 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
         __syncthreads();
       }
     }
-    // thread tasks: (plane of the item, column group, row split)
+    // thread tasks: (plane of the item, column group, row split), handed out warp by warp so that the choice of the
+    // row-walk variant is warp-uniform: a warp whose lanes disagreed (column 0 is an edge column, 1..31 are not) used
+    // to run BOTH variants one after the other -- every warp of a 64-wide image, at 2-3x the instructions per output
     const int nrows = it.oy1 - it.oy0;
     const int ncg = it.nplanes * colgroups;
     int rs = UFS_THREADS / ncg;
     rs = rs < 1 ? 1 : (rs > 4 ? 4 : rs);
     const int rows_per = (nrows + rs - 1) / rs;
-    for (int task = tid; task < ncg * rs; task += UFS_THREADS) {
+    const int ntask = ncg * rs;
+    for (int tb = tid & ~31; tb < ntask; tb += UFS_THREADS) {
+      const int task = tb + (tid & 31);
       const int part = task / ncg;
       const int cgi = task - part * ncg;
       const int pl = cgi / colgroups;
-      const int ox = (cgi - pl * colgroups) * COLS;
+      int cgx = cgi - pl * colgroups - rot;
+      cgx += cgx < 0 ? colgroups : 0;
+      const int ox = cgx * COLS;
       const int ty0 = it.oy0 + part * rows_per;
       const int ty1 = min(it.oy1, ty0 + rows_per);
-      if (ty0 >= ty1) continue;
-      const T* sp = sbuf + static_cast<int64_t>(pl) * plane_elems - static_cast<int64_t>(it.r_lo) * p.in_w;   // row iy at sp + iy*in_w
+      const bool valid = task < ntask && ty0 < ty1;
+      const T* sp;                                                                                   // row iy at sp + iy*in_w
+      if (ppitch > 0) {
+        const uint32_t off = static_cast<uint32_t>((xbase + static_cast<uintptr_t>(it.plane0 + pl) * plane_bytes) & 15);
+        sp = reinterpret_cast<const T*>(ufs_smem + slot * buf_bytes + head + pl * ppitch + off);
+      } else {
+        sp = sbuf + static_cast<int64_t>(pl) * plane_elems - static_cast<int64_t>(it.r_lo) * p.in_w;
+      }
       const int ix0 = ox - p.pad_x0;
       T* op = out + ((it.plane0 + pl) * p.out_h) * static_cast<int64_t>(p.out_w) + ox;
       const bool interior = ix0 >= 0 && ix0 + COLS + 3 <= p.in_w && ox + COLS <= p.out_w;
-      // instantiations of the row walk: rank-1 taps take 8 instead of 16 FMAs per output, interior columns
-      // skip every column test, strip mode skips every row test (all warp-uniform almost everywhere)
+      const bool warp_interior = __all_sync(0xffffffffu, interior || !valid);
+      if (!valid) continue;
+      // instantiations of the row walk: rank-1 taps take 8 instead of 16 FMAs per output, interior warps
+      // skip every column test, the zero-row layouts skip every row test
 #define UFS_CALL(SEP_, EDGE_, RC_) \
   ufs_rows<T, COLS, SEP_, EDGE_, RC_>(sp, op, w, kh1, kv1, p, it.r_lo, it.r_hi, ix0, ox, ty0, ty1)
-      if (head > 0) {
-        if (sep) { if (interior) UFS_CALL(true, false, false); else UFS_CALL(true, true, false); }
-        else     { if (interior) UFS_CALL(false, false, false); else UFS_CALL(false, true, false); }
+      if (sizeof(T) == 2 && COLS == 2 && head > 0 && sep) {
+        if constexpr (sizeof(T) == 2 && COLS == 2) {
+          if (warp_interior) ufs_rows_pk<T, false>(sp, op, kh1, kv1, p, ix0, ox, ty0, ty1);
+          else ufs_rows_pk<T, true>(sp, op, kh1, kv1, p, ix0, ox, ty0, ty1);
+        }
+      } else if (head > 0) {
+        if (sep) { if (warp_interior) UFS_CALL(true, false, false); else UFS_CALL(true, true, false); }
+        else     { if (warp_interior) UFS_CALL(false, false, false); else UFS_CALL(false, true, false); }
       } else {
-        if (sep) { if (interior) UFS_CALL(true, false, true); else UFS_CALL(true, true, true); }
-        else     { if (interior) UFS_CALL(false, false, true); else UFS_CALL(false, true, true); }
+        if (sep) { if (warp_interior) UFS_CALL(true, false, true); else UFS_CALL(true, true, true); }
+        else     { if (warp_interior) UFS_CALL(false, false, true); else UFS_CALL(false, true, true); }
       }
 #undef UFS_CALL
     }
@@ -451,7 +639,21 @@ static int launch_stream_c(void* out, const void* x, const float* kernel, const 
   int R, P, strips, head = 0;
   const UfsRing ring = ufs_ring<T>(p);
   const int UFS_BUF_BYTES = ring.bytes, nslots = ring.slots;
-  if (plane_bytes + 32 <= UFS_BUF_BYTES) {
+  int ppitch = 0;
+  // the walk always spans 4 tap rows: with pad_y0 <= 3 and pad_y1 < kh it never leaves three rows of zeros above / below
+  const bool zrows = p.pad_y0 <= 3 && pad_y1 < p.kh;
+  static const int env_zplanes = []() { const char* e = getenv("FM3D_UFS_ZPLANES"); return e ? atoi(e) : 1; }();
+  const int64_t zgap = (3 * row_bytes + 15) / 16 * 16 + 16;                      // >= 3 rows after the furthest plane end
+  const int64_t zpitch = (plane_bytes + 15 + 15) / 16 * 16 + zgap;               // copy capacity + gap
+  if (zrows && env_zplanes && plane_bytes >= 2048 && zgap + zpitch <= UFS_BUF_BYTES) {
+    // whole planes between zero rows (see the kernel): [gap | plane 0 | gap | plane 1 | gap ...]
+    strips = 1; R = p.out_h;
+    head = static_cast<int>(zgap);
+    ppitch = static_cast<int>(zpitch);
+    P = static_cast<int>((UFS_BUF_BYTES - zgap) / zpitch);
+    const int64_t want_items = static_cast<int64_t>(sm_count()) * 6;
+    while (P > 1 && (planes + P - 1) / P < want_items) P >>= 1;
+  } else if (plane_bytes + 32 <= UFS_BUF_BYTES) {
     strips = 1; R = p.out_h;
     P = static_cast<int>((UFS_BUF_BYTES - 32) / plane_bytes);
     // keep enough items to fill the machine
@@ -460,8 +662,7 @@ static int launch_stream_c(void* out, const void* x, const float* kernel, const 
   } else {
     P = 1;
     // zero-row layout when the vertical padding fits three rows: [3 zero rows | staged rows | 3 zero rows]
-    // (the walk always spans 4 tap rows: the last output row reads pad_y1 - kh + 4 rows past the image)
-    const bool zrows = p.pad_y0 <= 3 && pad_y1 < p.kh;
+    // (the last output row reads pad_y1 - kh + 4 rows past the image)
     head = zrows ? static_cast<int>((3 * row_bytes + 15) / 16 * 16 + 16) : 0;
     R = static_cast<int>((UFS_BUF_BYTES - head - 32) / row_bytes) - 3 - (zrows ? 3 : 0);
     if (R > 40) R = 40;
@@ -477,8 +678,16 @@ static int launch_stream_c(void* out, const void* x, const float* kernel, const 
   cps = cps < 1 ? 1 : (cps > 4 ? 4 : cps);
   const int64_t cap = static_cast<int64_t>(sm_count()) * cps;
   const unsigned grid = static_cast<unsigned>(n_items < cap ? n_items : cap);
+  // column groups that touch the right edge (their taps read past the row, or the group is ragged): handed out first,
+  // next to the left-edge groups
+  const int colgroups = (p.out_w + COLS - 1) / COLS;
+  int last_int = (p.in_w + p.pad_x0 - COLS - 3) / COLS;             // last group with ix0 + COLS + 3 <= in_w
+  if (p.in_w + p.pad_x0 - COLS - 3 < 0) last_int = -1;
+  if (last_int > p.out_w / COLS - 1) last_int = p.out_w / COLS - 1;  // ... and ox + COLS <= out_w
+  int rot = colgroups - 1 - last_int;
+  rot = rot < 0 ? 0 : (rot >= colgroups ? 0 : rot);
   fn<<<grid, UFS_THREADS, smem, st>>>(static_cast<T*>(out), static_cast<const T*>(x), kernel, p, planes, R, P, strips,
-                                      n_items, head, nslots, UFS_BUF_BYTES);
+                                      n_items, head, nslots, UFS_BUF_BYTES, ppitch, rot);
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;
@@ -489,7 +698,9 @@ static int launch_stream_c(void* out, const void* x, const float* kernel, const 
 template <typename T>
 static int launch_stream(void* out, const void* x, const float* kernel, const UpfirdnParams& p, int pad_y1, int64_t planes,
                          cudaStream_t st) {
-  static const int cols = []() { const char* e = getenv("FM3D_UFS_COLS"); return e ? atoi(e) : 1; }();
+  // 2-byte types: column pairs, so that rank-1 taps in a zero-row layout take the packed walk (ufs_rows_pk)
+  static const int env_cols = []() { const char* e = getenv("FM3D_UFS_COLS"); return e ? atoi(e) : 0; }();
+  const int cols = env_cols ? env_cols : (sizeof(T) == 2 ? 2 : 1);
   if (cols == 2) return launch_stream_c<T, 2>(out, x, kernel, p, pad_y1, planes, st);
   return launch_stream_c<T, 1>(out, x, kernel, p, pad_y1, planes, st);
 }

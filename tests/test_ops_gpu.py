@@ -92,6 +92,40 @@ def test_upfirdn2d_stream_cases(cuda, shape, kshape, pads, dtype):
         torch.testing.assert_close(out.float().cpu(), ref, rtol=tol, atol=tol * 8)
 
 
+@pytest.mark.parametrize("shape,pads", [
+    ((37, 3, 65, 65), (1, 1, 1, 1)),          # G blur after the 32->64 up-conv: whole planes between zero rows, 2-3 per item
+    ((5, 7, 129, 129), (1, 1, 1, 1)),         # one plane per item in fp32, two in the 2-byte types
+    ((3, 4, 64, 64), (2, 2, 2, 2)),           # D blur before the stride-2 conv (out 65 wide: odd output pitch)
+    ((2, 9, 40, 51), (2, 1, 2, 1)),           # asymmetric pads, ragged last column pair
+    ((2, 3, 48, 33), (0, 3, 3, 0)),           # out_w = in_w, pads as far as the zero rows reach
+    ((1, 2, 200, 257), (1, 1, 1, 1)),         # strip mode, odd width
+    ((1, 2, 130, 300), (2, 2, 2, 2)),         # strip mode, even width, odd output pitch
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("sep", [True, False])
+def test_upfirdn2d_stream_zero_row_layouts(cuda, shape, pads, dtype, sep):
+    """The streaming kernel's zero-row layouts (strip mode and whole planes copied one by one between rows of zeros),
+    the warp-uniform choice of the edge / interior walk with rotated column groups, and the packed column-pair walk of
+    the 2-byte types (rank-1 taps) against the oracle, from element-aligned bases so that every parity of the staged
+    address occurs."""
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(sum(shape) * 7 + pads[0])
+    numel = 1
+    for d in shape:
+        numel *= d
+    base = torch.randn(numel + 5, generator=gen).to(dtype)
+    k = orc.make_kernel_ref([1, 3, 3, 1]) * 4 if sep else torch.randn(4, 4, generator=gen)
+    cfg = (1, 1, 1, 1) + pads
+    based = base.to(cuda)
+    for off in (0, 1, 2, 5):
+        x = base[off:off + numel].view(*shape)
+        ref = orc.upfirdn2d_ref(x.float(), k, *cfg)
+        out = ops.upfirdn2d_planes(based[off:off + numel].view(*shape), k.to(cuda), *cfg)
+        assert tuple(out.shape) == tuple(ref.shape) and out.dtype == dtype
+        tol = 1e-5 if dtype == torch.float32 else (2e-2 if dtype == torch.bfloat16 else 3e-3)
+        torch.testing.assert_close(out.float().cpu(), ref, rtol=tol, atol=tol * 8)
+
+
 def test_upfirdn2d_empty(cuda):
     from fm3d import ops
     k = orc.make_kernel_ref([1, 3, 3, 1]).to(cuda)
