@@ -156,8 +156,13 @@ static UfsRing ufs_ring(const UpfirdnParams& p) {
   // Measured on the largest generator blur (fp32 [4096,257,257], B200): 2 x 36 KB 534 us, 3 x 24 KB 698, 4 x 18 KB 924,
   // 3 x 36 KB (2 CTAs/SM) 670: a strip costs ~3.5k cycles of fixed work (halo rows, hand-over) on top of ~290 per
   // row, so fewer, taller strips beat a deeper ring.
-  UfsRing r{2, 36 * 1024};
-  (void)p;
+  // Round 2 (after the walks were cut to 1/2 - 1/3 of their instructions): whole planes still do best with 2 x 36 KB
+  // (3 CTAs per SM: bf16 129^2 3.89 TB/s vs 3.11 with 72 KB slots), but strips want to be tall -- 2 x 50 KB with up to 96
+  // rows per strip (2 CTAs per SM): fp32 257^2 5.60 -> 6.19 TB/s, 129^2 4.68 -> 5.62, bf16 257^2 3.44 -> 4.08.
+  const int64_t row_bytes = static_cast<int64_t>(p.in_w) * sizeof(T), plane_bytes = row_bytes * p.in_h;
+  const int64_t zgap = (3 * row_bytes + 15) / 16 * 16 + 16;
+  const bool whole = plane_bytes + 30 + 2 * zgap <= 36 * 1024 || plane_bytes + 32 <= 36 * 1024;
+  UfsRing r{2, (whole ? 36 : 50) * 1024};
   if (env_slots >= 2 && env_slots <= UFS_MAX_SLOTS) r.slots = env_slots;
   if (env_kb >= 8 && env_kb <= 100) r.bytes = env_kb * 1024;
   return r;
@@ -342,7 +347,7 @@ template <> __device__ __forceinline__ uint32_t ufs_pack2<__half>(float lo, floa
 }
 template <> __device__ __forceinline__ uint32_t ufs_pack2<float>(float, float) { return 0u; }
 
-template <typename T, bool EDGE>
+template <typename T, bool EDGE, bool VEC>
 __device__ __forceinline__ void ufs_rows_pk(const T* __restrict__ sp, T* __restrict__ op, const float (&kh1)[4],
                                             const float (&kv1)[4], const UpfirdnParams& p, int ix0, int ox, int ty0, int ty1) {
   static_assert(sizeof(T) == 2, "packed walk: 2-byte types");
@@ -366,9 +371,9 @@ __device__ __forceinline__ void ufs_rows_pk(const T* __restrict__ sp, T* __restr
   uint32_t pA = a0 & ~3u, pB = (a0 + rb) & ~3u;
   const uint32_t sA = (a0 & 2u) << 3, sB = ((a0 + rb) & 2u) << 3;
   T* orow = op + static_cast<int64_t>(ty0 - 3) * p.out_w;
-  const bool two = !EDGE || ox + 1 < p.out_w;
-  // one 4-byte store per row when every row of the pair is 4-byte aligned
-  const bool vec = two && (p.out_w & 1) == 0 && (reinterpret_cast<uintptr_t>(orow) & 3) == 0;
+  // VEC (even output pitch, 4-byte aligned plane: warp-uniform, chosen by the caller): one 4-byte store per row.  A
+  // run-time flag here left both store sequences in the loop as predicated instructions, which issue either way.
+  const bool two = VEC || !EDGE || ox + 1 < p.out_w;
   struct Row { uint32_t w0, w1, w2; };
   auto row_load = [&](uint32_t a) { Row r; r.w0 = ufs_lds32(a); r.w1 = ufs_lds32(a + 4); r.w2 = ufs_lds32(a + 8); return r; };
   auto row_math = [&](auto uc, const Row& r, uint32_t sh) {
@@ -391,7 +396,7 @@ __device__ __forceinline__ void ufs_rows_pk(const T* __restrict__ sp, T* __restr
     constexpr int u = decltype(uc)::value;
     float lo, hi;
     f2_unpack(acc[(u + 1) & 3], lo, hi);
-    if (vec) {
+    if (VEC) {
       *reinterpret_cast<uint32_t*>(o) = ufs_pack2<T>(lo, hi);
     } else {
       o[0] = from_f32<T>(lo);
@@ -433,7 +438,7 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
                                                                        const float* __restrict__ kernel, UpfirdnParams p,
                                                                        int64_t planes, int R, int P, int strips,
                                                                        int64_t n_items, int head, int nslots, int buf_bytes,
-                                                                       int ppitch, int rot) {
+                                                                       int ppitch, int rot, int rs_log2, uint32_t cg_magic) {
   // head > 0: zero-row layouts -- rows above / below the image read zeros instead of being tested for.
   //  * strip mode (strips > 1): the staged range starts `head` bytes into the slot, preceded (top of the image) and
   //    followed (bottom) by three zeroed rows;
@@ -529,8 +534,29 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
         issue(ufs_item(item + static_cast<int64_t>(a) * gridDim.x, p, planes, R, P, strips), a);
   int slot = 0, ahead_slot = nslots - 1;
   uint32_t parity = 0;
+  // strip mode: (plane, strip) of this CTA's items advance by a fixed step -- no division per item
+  const uint32_t step_q = strips > 1 ? gridDim.x / static_cast<uint32_t>(strips) : 0u;
+  const int step_r = strips > 1 ? static_cast<int>(gridDim.x - step_q * strips) : 0;
+  int64_t cur_plane = 0;
+  int cur_strip = 0;
+  if (strips > 1) {
+    const UfsItem f = ufs_item(item, p, planes, R, P, strips);
+    cur_plane = f.plane0;
+    cur_strip = f.oy0 / R;
+  }
   for (int k = 0; item < n_items; item += gridDim.x, ++k) {
-    const UfsItem it = ufs_item(item, p, planes, R, P, strips);
+    UfsItem it;
+    if (strips > 1) {
+      it.plane0 = cur_plane; it.nplanes = 1;
+      it.oy0 = cur_strip * R;
+      it.oy1 = min(p.out_h, it.oy0 + R);
+      it.r_lo = max(0, it.oy0 - p.pad_y0);
+      it.r_hi = min(p.in_h - 1, it.oy1 - 1 - p.pad_y0 + 3);
+      cur_plane += step_q; cur_strip += step_r;
+      if (cur_strip >= strips) { cur_strip -= strips; ++cur_plane; }
+    } else {
+      it = ufs_item(item, p, planes, R, P, strips);
+    }
     // the slot refilled now was drained by the previous iteration (its closing __syncthreads)
     const int64_t ahead = item + static_cast<int64_t>(nslots - 1) * gridDim.x;
     if (tid == 0 && ahead < n_items) issue(ufs_item(ahead, p, planes, R, P, strips), ahead_slot);
@@ -569,18 +595,23 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
     // thread tasks: (plane of the item, column group, row split), handed out warp by warp so that the choice of the
     // row-walk variant is warp-uniform: a warp whose lanes disagreed (column 0 is an edge column, 1..31 are not) used
     // to run BOTH variants one after the other -- every warp of a 64-wide image, at 2-3x the instructions per output
+    // (the row split is a power of two chosen by the host and column-group indices come from a multiply-high with
+    // ceil(2^32 / colgroups), exact for task < 2^16: the five integer divisions this block used to hold were a
+    // quarter of all instructions on the 2-byte types)
     const int nrows = it.oy1 - it.oy0;
     const int ncg = it.nplanes * colgroups;
-    int rs = UFS_THREADS / ncg;
-    rs = rs < 1 ? 1 : (rs > 4 ? 4 : rs);
-    const int rows_per = (nrows + rs - 1) / rs;
+    const int rs = 1 << rs_log2;
+    const int rows_per = (nrows + rs - 1) >> rs_log2;
     const int ntask = ncg * rs;
     for (int tb = tid & ~31; tb < ntask; tb += UFS_THREADS) {
       const int task = tb + (tid & 31);
-      const int part = task / ncg;
-      const int cgi = task - part * ncg;
-      const int pl = cgi / colgroups;
-      int cgx = cgi - pl * colgroups - rot;
+      const int t2 = cg_magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(task), cg_magic)) : task;   // task / colgroups
+      int part = 0, pl = t2;                                                                 // t2 = part * nplanes + pl
+      if (rs_log2 > 0) {
+        if (pl >= 2 * it.nplanes) { pl -= 2 * it.nplanes; part = 2; }
+        if (pl >= it.nplanes) { pl -= it.nplanes; part += 1; }
+      }
+      int cgx = task - t2 * colgroups - rot;
       cgx += cgx < 0 ? colgroups : 0;
       const int ox = cgx * COLS;
       const int ty0 = it.oy0 + part * rows_per;
@@ -604,8 +635,16 @@ __global__ void __launch_bounds__(UFS_THREADS) upfirdn2d_stream_kernel(T* __rest
   ufs_rows<T, COLS, SEP_, EDGE_, RC_>(sp, op, w, kh1, kv1, p, it.r_lo, it.r_hi, ix0, ox, ty0, ty1)
       if (sizeof(T) == 2 && COLS == 2 && head > 0 && sep) {
         if constexpr (sizeof(T) == 2 && COLS == 2) {
-          if (warp_interior) ufs_rows_pk<T, false>(sp, op, kh1, kv1, p, ix0, ox, ty0, ty1);
-          else ufs_rows_pk<T, true>(sp, op, kh1, kv1, p, ix0, ox, ty0, ty1);
+          // even output pitch and an even number of outputs per plane: every column pair of every row is 4-byte aligned
+          // when the tensor is (kernel-uniform)
+          const bool vec = (p.out_w & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+          if (vec) {
+            if (warp_interior) ufs_rows_pk<T, false, true>(sp, op, kh1, kv1, p, ix0, ox, ty0, ty1);
+            else ufs_rows_pk<T, true, true>(sp, op, kh1, kv1, p, ix0, ox, ty0, ty1);
+          } else {
+            if (warp_interior) ufs_rows_pk<T, false, false>(sp, op, kh1, kv1, p, ix0, ox, ty0, ty1);
+            else ufs_rows_pk<T, true, false>(sp, op, kh1, kv1, p, ix0, ox, ty0, ty1);
+          }
         }
       } else if (head > 0) {
         if (sep) { if (warp_interior) UFS_CALL(true, false, false); else UFS_CALL(true, true, false); }
@@ -653,19 +692,23 @@ static int launch_stream_c(void* out, const void* x, const float* kernel, const 
     P = static_cast<int>((UFS_BUF_BYTES - zgap) / zpitch);
     const int64_t want_items = static_cast<int64_t>(sm_count()) * 6;
     while (P > 1 && (planes + P - 1) / P < want_items) P >>= 1;
+    while (P > 1 && static_cast<int64_t>(P) * ((p.out_w + COLS - 1) / COLS) * 4 >= 65536) P >>= 1;   // task index < 2^16
   } else if (plane_bytes + 32 <= UFS_BUF_BYTES) {
     strips = 1; R = p.out_h;
     P = static_cast<int>((UFS_BUF_BYTES - 32) / plane_bytes);
     // keep enough items to fill the machine
     const int64_t want_items = static_cast<int64_t>(sm_count()) * 6;
     while (P > 1 && (planes + P - 1) / P < want_items) P >>= 1;
+    while (P > 1 && static_cast<int64_t>(P) * ((p.out_w + COLS - 1) / COLS) * 4 >= 65536) P >>= 1;   // task index < 2^16
   } else {
     P = 1;
     // zero-row layout when the vertical padding fits three rows: [3 zero rows | staged rows | 3 zero rows]
     // (the last output row reads pad_y1 - kh + 4 rows past the image)
     head = zrows ? static_cast<int>((3 * row_bytes + 15) / 16 * 16 + 16) : 0;
     R = static_cast<int>((UFS_BUF_BYTES - head - 32) / row_bytes) - 3 - (zrows ? 3 : 0);
-    if (R > 40) R = 40;
+    static const int env_rmax = []() { const char* e = getenv("FM3D_UFS_RMAX"); return e ? atoi(e) : 0; }();
+    const int rmax = env_rmax > 0 ? env_rmax : 96;
+    if (R > rmax) R = rmax;
     strips = (p.out_h + R - 1) / R;
     R = (p.out_h + strips - 1) / strips;          // balance the strips
   }
@@ -686,8 +729,17 @@ static int launch_stream_c(void* out, const void* x, const float* kernel, const 
   if (last_int > p.out_w / COLS - 1) last_int = p.out_w / COLS - 1;  // ... and ox + COLS <= out_w
   int rot = colgroups - 1 - last_int;
   rot = rot < 0 ? 0 : (rot >= colgroups ? 0 : rot);
+  // rows of an item split between 1, 2 or 4 thread groups when its column groups leave threads idle
+  static const int env_rs = []() { const char* e = getenv("FM3D_UFS_RS"); return e ? atoi(e) : 4; }();
+  int rs_log2 = 0;
+  // (each part re-walks 3 warm-up rows: measured, a split pays only while fewer than half of the threads have a task --
+  // fp32 65^2 5.33 -> 5.67 TB/s, 129^2 5.39 -> 5.68 without the needless split, bf16 129^2 2.87 -> 3.89 with the needed one)
+  while (rs_log2 < 2 && (2 << rs_log2) <= env_rs && static_cast<int64_t>(P) * colgroups * (1 << rs_log2) < UFS_THREADS / 2 &&
+         static_cast<int64_t>(P) * colgroups * (2 << rs_log2) <= UFS_THREADS) ++rs_log2;
+  FM_CHECK_ARG(static_cast<int64_t>(P) * colgroups * 4 < 65536, "fm_upfirdn2d: too many thread tasks per item");
+  const uint32_t cg_magic = colgroups > 1 ? static_cast<uint32_t>((0x100000000ull + colgroups - 1) / colgroups) : 0u;   // 0: identity
   fn<<<grid, UFS_THREADS, smem, st>>>(static_cast<T*>(out), static_cast<const T*>(x), kernel, p, planes, R, P, strips,
-                                      n_items, head, nslots, UFS_BUF_BYTES, ppitch, rot);
+                                      n_items, head, nslots, UFS_BUF_BYTES, ppitch, rot, rs_log2, cg_magic);
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;

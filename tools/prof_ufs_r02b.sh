@@ -7,7 +7,7 @@ for cfg in "65 16384 f32" "129 8192 f32" "257 4096 f32" "65 16384 bf16" "129 819
 done
 if [ "${NCU:-0}" = "1" ]; then
 i=0
-for cfg in "65 16384 f32" "257 4096 bf16"; do
+for cfg in "129 8192 f32" "257 4096 bf16"; do
   set -- $cfg
   ncu --set full --clock-control none --import-source on -k regex:upfirdn2d_stream --launch-skip 3 --launch-count 1 -o gpurun_out/ufs/cap$i python tools/prof_upfirdn_w.py $1 $2 $3 > gpurun_out/ufs/ncu$i.log 2>&1
   ncu -i gpurun_out/ufs/cap$i.ncu-rep --page raw --csv > gpurun_out/ufs/raw$i.csv 2>/dev/null
