@@ -143,6 +143,9 @@ __global__ void __launch_bounds__(256) upfirdn2d_tile_kernel(T* __restrict__ out
 // one coalesced store per row.  In strip mode the rows above / below the image are three zeroed rows in
 // front of / behind the staged range, so the steady-state loop has no bounds test at all (the kernel is
 // instruction-issue bound before it is HBM bound).  fp32 accumulation for every dtype.
+// Round 2: the variant of the walk (column-tested or not) is chosen per WARP, whole planes are staged one bulk copy each
+// between rows of zeros (so they take the untested walk too), the 2-byte types walk column pairs on aligned 32-bit
+// words (ufs_rows_pk), and the per-item setup holds no division -- DESIGN.md 4.3 has the instruction counts.
 // ------------------------------------------------------------------------------------
 constexpr int UFS_THREADS = 256;
 constexpr int UFS_MAX_SLOTS = 4;
@@ -734,7 +737,10 @@ static int launch_stream_c(void* out, const void* x, const float* kernel, const 
   int rs_log2 = 0;
   // (each part re-walks 3 warm-up rows: measured, a split pays only while fewer than half of the threads have a task --
   // fp32 65^2 5.33 -> 5.67 TB/s, 129^2 5.39 -> 5.68 without the needless split, bf16 129^2 2.87 -> 3.89 with the needed one)
-  while (rs_log2 < 2 && (2 << rs_log2) <= env_rs && static_cast<int64_t>(P) * colgroups * (1 << rs_log2) < UFS_THREADS / 2 &&
+  static const int env_busy = []() { const char* e = getenv("FM3D_UFS_BUSY"); return e ? atoi(e) : 0; }();
+  // ... except 4-byte strips (2 CTAs per SM, a cheap walk): 129^2 fp32 5.23 TB/s with 128 busy threads, 5.62 with 256
+  const int busy_min = env_busy > 0 ? env_busy : (strips > 1 && sizeof(T) == 4 ? 192 : UFS_THREADS / 2);
+  while (rs_log2 < 2 && (2 << rs_log2) <= env_rs && static_cast<int64_t>(P) * colgroups * (1 << rs_log2) < busy_min &&
          static_cast<int64_t>(P) * colgroups * (2 << rs_log2) <= UFS_THREADS) ++rs_log2;
   FM_CHECK_ARG(static_cast<int64_t>(P) * colgroups * 4 < 65536, "fm_upfirdn2d: too many thread tasks per item");
   const uint32_t cg_magic = colgroups > 1 ? static_cast<uint32_t>((0x100000000ull + colgroups - 1) / colgroups) : 0u;   // 0: identity

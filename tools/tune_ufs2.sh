@@ -1,13 +1,9 @@
-# sweep of the streaming kernel's geometry knobs (strip height cap, ring slot size, row split) per blur width / dtype
+# sweep of the streaming kernel's row-split threshold (threads that must have a task before rows stop being split)
 out=gpurun_out/ufs/sweep.txt; mkdir -p gpurun_out/ufs; rm -f $out
-run() { # W planes dt RMAX KB RS
-  echo -n "rmax $4 kb $5 rs $6: " >> $out
-  FM3D_UFS_RMAX=$4 FM3D_UFS_SLOT_KB=$5 FM3D_UFS_RS=$6 python tools/prof_upfirdn_w.py $1 $2 $3 2>&1 | tail -1 >> $out
+run() { # W planes dt BUSY
+  echo -n "busy $4: " >> $out
+  FM3D_UFS_BUSY=$4 python tools/prof_upfirdn_w.py $1 $2 $3 2>&1 | tail -1 >> $out
 }
-for k in "40 36 4" "64 36 4" "64 36 2" "64 36 1" "96 50 4" "96 50 2" "128 72 4"; do run 257 4096 bf16 $k; done
-for k in "40 36 4" "64 36 4" "64 36 1" "96 50 4" "128 72 4"; do run 129 8192 f32 $k; done
-for k in "40 36 4" "40 36 2" "40 36 1" "40 72 4" "40 72 2"; do run 129 8192 bf16 $k; done
-for k in "40 36 4" "40 36 2" "40 36 1" "40 72 2"; do run 65 16384 bf16 $k; done
-for k in "40 36 4" "40 36 2" "40 36 1"; do run 65 16384 f32 $k; done
-for k in "40 36 4" "96 50 4" "128 72 4"; do run 257 4096 f32 $k; done
+for b in 128 192; do run 129 8192 f32 $b; run 257 4096 bf16 $b; run 65 16384 bf16 $b; run 65 16384 f32 $b; run 33 32768 f32 $b; run 33 32768 bf16 $b; done
+run 129 8192 bf16 256
 cat $out
