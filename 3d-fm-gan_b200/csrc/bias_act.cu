@@ -46,27 +46,69 @@ template <typename T, typename IdxT, int MODE, bool HAS_BIAS, bool HAS_REF, int 
 __global__ void __launch_bounds__(256) bias_act_vec_kernel(T* __restrict__ out, const T* __restrict__ x,
                                                            const T* __restrict__ bias, const T* __restrict__ ref,
                                                            IdxT n_vec, IdxT vec_per_row, uint32_t channels,
-                                                           float alpha, float scale) {
+                                                           float alpha, float scale, FastDivU32 fd_row, FastDivU32 fd_ch) {
   constexpr int N = Vec16<T>::N;
-  const IdxT stride = static_cast<IdxT>(gridDim.x) * blockDim.x;
-  IdxT v0 = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (; v0 < n_vec; v0 += stride * UNROLL) {
+  const bool alpha01 = alpha >= 0.f && alpha <= 1.f;
+  const f32x2 aa = f2_pack(alpha, alpha), ss = f2_pack(scale, scale);
+  // A warp owns chunks of 32 * UNROLL consecutive vectors (UNROLL coalesced 512-byte requests per warp and tensor).  When
+  // a row (one channel of one sample) is a whole number of chunks, the channel -- and with it the bias -- is one
+  // computation per chunk instead of one per vector; per-vector index arithmetic was as many instructions as the math.
+  constexpr uint32_t CHUNK = 32u * UNROLL;
+  const uint32_t lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
+  const bool row_uniform = vec_per_row % CHUNK == 0;
+  auto channel_of = [&](IdxT v) -> uint32_t {
+    if (sizeof(IdxT) == 4) {
+      const uint32_t row = fastdiv(static_cast<uint32_t>(v), fd_row);
+      return row - fastdiv(row, fd_ch) * channels;
+    }
+    return static_cast<uint32_t>((v / vec_per_row) % channels);
+  };
+  const IdxT nchunk = (n_vec + CHUNK - 1) / CHUNK;
+  for (IdxT g = static_cast<IdxT>(blockIdx.x) * wpb + (threadIdx.x >> 5); g < nchunk; g += static_cast<IdxT>(gridDim.x) * wpb) {
+    const IdxT v0 = g * CHUNK + lane;
     Pack<T, N> xv[UNROLL], rv[UNROLL];
     float bv[UNROLL];
+    float b_chunk = 0.f;
+    if (HAS_BIAS && row_uniform) b_chunk = to_f32<T>(__ldg(bias + channel_of(g * CHUNK)));
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const IdxT v = v0 + stride * u;
+      const IdxT v = v0 + 32u * u;
       if (v < n_vec) {
         xv[u] = ld16<T>(x + static_cast<size_t>(v) * N);
         if (HAS_REF) rv[u] = ld16<T>(ref + static_cast<size_t>(v) * N);
-        if (HAS_BIAS) bv[u] = to_f32<T>(__ldg(bias + static_cast<uint32_t>((v / vec_per_row) % channels)));
+        if (HAS_BIAS) {
+          if (row_uniform) { bv[u] = b_chunk; continue; }
+          const uint32_t c = channel_of(v);
+          bv[u] = to_f32<T>(__ldg(bias + c));
+        }
       }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const IdxT v = v0 + stride * u;
+      const IdxT v = v0 + 32u * u;
       if (v < n_vec) {
         Pack<T, N> o;
+        if (MODE == 30 && alpha01) {
+          // forward leaky ReLU with 0 <= alpha <= 1: x > 0 ? x : alpha * x  ==  max(x, alpha * x) bit for bit (including
+          // -0 and NaN), so element pairs run on packed fp32 (FADD2 / FMUL2): ~4 instead of ~12 instructions per element
+          // for the 2-byte types, which were bound by instruction issue (bf16 forward 4.7 TB/s against 6.4 for the
+          // bias-free gradient pass with its select-only arithmetic)
+          const f32x2 bb = f2_pack(HAS_BIAS ? bv[u] : 0.f, HAS_BIAS ? bv[u] : 0.f);
+#pragma unroll
+          for (int j = 0; j < N; j += 2) {
+            f32x2 xx = f2_pack(to_f32<T>(xv[u].v[j]), to_f32<T>(xv[u].v[j + 1]));
+            if (HAS_BIAS) xx = f2_add(xx, bb);
+            const f32x2 ax = f2_mul(xx, aa);
+            float xl, xh, al, ah;
+            f2_unpack(xx, xl, xh);
+            f2_unpack(ax, al, ah);
+            const f32x2 y = f2_mul(f2_pack(fmaxf(xl, al), fmaxf(xh, ah)), ss);
+            float yl, yh;
+            f2_unpack(y, yl, yh);
+            o.v[j] = from_f32<T>(yl);
+            o.v[j + 1] = from_f32<T>(yh);
+          }
+        } else
 #pragma unroll
         for (int j = 0; j < N; ++j) {
           float xf = to_f32<T>(xv[u].v[j]);
@@ -112,11 +154,12 @@ static int launch_bias_act(void* out, const void* x, const void* bias, const voi
     if (n_vec < 0xFFFFFFFFull - 256ull * UNROLL * grid) {
       bias_act_vec_kernel<T, uint32_t, MODE, HAS_BIAS, HAS_REF, UNROLL><<<grid, 256, 0, st>>>(
           static_cast<T*>(out), static_cast<const T*>(x), static_cast<const T*>(bias), static_cast<const T*>(ref),
-          static_cast<uint32_t>(n_vec), static_cast<uint32_t>(inner / N), static_cast<uint32_t>(channels), alpha, scale);
+          static_cast<uint32_t>(n_vec), static_cast<uint32_t>(inner / N), static_cast<uint32_t>(channels), alpha, scale,
+          fastdiv_make(static_cast<uint32_t>(inner / N)), fastdiv_make(static_cast<uint32_t>(channels ? channels : 1)));
     } else {
       bias_act_vec_kernel<T, uint64_t, MODE, HAS_BIAS, HAS_REF, UNROLL><<<grid, 256, 0, st>>>(
           static_cast<T*>(out), static_cast<const T*>(x), static_cast<const T*>(bias), static_cast<const T*>(ref), n_vec,
-          static_cast<uint64_t>(inner / N), static_cast<uint32_t>(channels), alpha, scale);
+          static_cast<uint64_t>(inner / N), static_cast<uint32_t>(channels), alpha, scale, FastDivU32{}, FastDivU32{});
     }
   } else {
     const uint64_t want = (n + 255) / 256;
@@ -158,7 +201,7 @@ static int dispatch_mode(int mode, void* out, const void* x, const void* bias, c
 // atomicAdd per block into grad_bias[c]  (the reference runs a separate torch sum over the
 // whole tensor, op/fused_act.py:42-48: one extra full read).
 // ------------------------------------------------------------------------------------
-template <typename T, int MODE>
+template <typename T, int MODE, bool VEC>
 __global__ void __launch_bounds__(256) bias_act_grad_bias_kernel(T* __restrict__ gin, float* __restrict__ gbias,
                                                                  const T* __restrict__ gout, const T* __restrict__ ref,
                                                                  uint64_t inner, uint32_t channels, uint32_t slabs_per_row,
@@ -172,6 +215,37 @@ __global__ void __launch_bounds__(256) bias_act_grad_bias_kernel(T* __restrict__
   const T* r = ref + row * inner;
   T* o = gin + row * inner;
   float acc = 0.f;
+  if (VEC) {
+    // 16-byte accesses (the host checked alignment and that rows and slabs are whole vectors): the scalar loop moved 2
+    // or 4 bytes per lane and request -- 2.6 TB/s on bf16, 4.5 on fp32
+    constexpr int N = Vec16<T>::N;
+    const uint64_t v_hi = hi / N;
+    uint64_t iv = lo / N + threadIdx.x;
+    for (; iv + blockDim.x < v_hi; iv += 2 * blockDim.x) {          // two vectors of each tensor in flight
+      const Pack<T, N> g0 = ld16<T>(g + iv * N), r0 = ld16<T>(r + iv * N);
+      const Pack<T, N> g1 = ld16<T>(g + (iv + blockDim.x) * N), r1 = ld16<T>(r + (iv + blockDim.x) * N);
+      Pack<T, N> o0, o1;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        o0.v[j] = from_f32<T>(act_apply(to_f32<T>(g0.v[j]), to_f32<T>(r0.v[j]), MODE, alpha) * scale);
+        o1.v[j] = from_f32<T>(act_apply(to_f32<T>(g1.v[j]), to_f32<T>(r1.v[j]), MODE, alpha) * scale);
+        acc += to_f32<T>(o0.v[j]);
+        acc += to_f32<T>(o1.v[j]);
+      }
+      st16<T>(o + iv * N, o0);
+      st16<T>(o + (iv + blockDim.x) * N, o1);
+    }
+    if (iv < v_hi) {
+      const Pack<T, N> g0 = ld16<T>(g + iv * N), r0 = ld16<T>(r + iv * N);
+      Pack<T, N> o0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        o0.v[j] = from_f32<T>(act_apply(to_f32<T>(g0.v[j]), to_f32<T>(r0.v[j]), MODE, alpha) * scale);
+        acc += to_f32<T>(o0.v[j]);
+      }
+      st16<T>(o + iv * N, o0);
+    }
+  } else
   for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const float y = act_apply(to_f32<T>(g[i]), to_f32<T>(r[i]), MODE, alpha) * scale;
     const T yq = from_f32<T>(y);
@@ -200,17 +274,19 @@ static int launch_grad_bias(void* gin, float* gbias, const void* gout, const voi
   uint64_t slab = static_cast<uint64_t>(inner);
   const uint64_t target_blocks = static_cast<uint64_t>(sm_count()) * 32;
   while (slab > 2048 && rows * ((inner + slab - 1) / slab) < target_blocks) slab = (slab + 1) / 2;
+  constexpr int N = Vec16<T>::N;
+  const bool vec = inner % N == 0 && ((reinterpret_cast<uintptr_t>(gin) | reinterpret_cast<uintptr_t>(gout) |
+                                       reinterpret_cast<uintptr_t>(ref)) & 15) == 0;
+  if (vec) slab = (slab + N - 1) / N * N;          // slabs of whole vectors (rows are: inner % N == 0)
   const uint64_t slabs = (inner + slab - 1) / slab;
   const uint64_t blocks = rows * slabs;
   FM_CHECK_ARG(blocks < 0x7FFFFFFFull, "bias_act_grad_bias: too many blocks (%llu)", (unsigned long long)blocks);
-  if (act == 3)
-    bias_act_grad_bias_kernel<T, 31><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-        static_cast<T*>(gin), gbias, static_cast<const T*>(gout), static_cast<const T*>(ref), static_cast<uint64_t>(inner),
-        static_cast<uint32_t>(channels), static_cast<uint32_t>(slabs), slab, alpha, scale);
-  else
-    bias_act_grad_bias_kernel<T, 11><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-        static_cast<T*>(gin), gbias, static_cast<const T*>(gout), static_cast<const T*>(ref), static_cast<uint64_t>(inner),
-        static_cast<uint32_t>(channels), static_cast<uint32_t>(slabs), slab, alpha, scale);
+#define FM_GB(MODE_, VEC_) bias_act_grad_bias_kernel<T, MODE_, VEC_><<<static_cast<unsigned>(blocks), 256, 0, st>>>( \
+        static_cast<T*>(gin), gbias, static_cast<const T*>(gout), static_cast<const T*>(ref), static_cast<uint64_t>(inner), \
+        static_cast<uint32_t>(channels), static_cast<uint32_t>(slabs), slab, alpha, scale)
+  if (act == 3) { if (vec) FM_GB(31, true); else FM_GB(31, false); }
+  else          { if (vec) FM_GB(11, true); else FM_GB(11, false); }
+#undef FM_GB
   count_launch();
   FM_LAUNCH_OK();
   return FM_OK;

@@ -103,6 +103,25 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   return __bfloat1622float2(p);
 }
 
+// ---------------------------------------------------------------- exact unsigned division by a launch constant
+// Granlund-Montgomery (round-up magic with the add-back step): exact for every 32-bit dividend and divisor >= 1, five
+// instructions instead of the ~20 of a hardware-assisted integer division.
+struct FastDivU32 { uint32_t m, s1, s2, d; };
+inline FastDivU32 fastdiv_make(uint32_t d) {
+  int L = 0;
+  while ((1ull << L) < d) ++L;
+  FastDivU32 f;
+  f.m = static_cast<uint32_t>(((1ull << 32) * ((1ull << L) - d)) / d + 1);
+  f.s1 = L < 1 ? L : 1;
+  f.s2 = L > 1 ? L - 1 : 0;
+  f.d = d;
+  return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDivU32& f) {
+  const uint32_t t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+
 // ---------------------------------------------------------------- packed fp32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100)
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {

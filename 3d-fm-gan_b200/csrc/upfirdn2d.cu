@@ -809,6 +809,99 @@ static int launch_tile(void* out, const void* x, const float* kernel, UpfirdnPar
   return FM_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// up = 2, down = 1 (Upsample of the ToRGB skip path, stylegan2.py:65-80 -> op/upfirdn2d.py with up=2, pad (2,1)):
+// polyphase form.  Of the 4 x 4 taps only the 2 x 2 whose row / column parity matches the zero-stuffed grid meet a
+// sample, so an output is 4 FMAs on a 2 x 2 source patch.  A thread owns 2 output rows x 4 output columns = a 3 x 4
+// source patch read straight through L1 (the tensors are 3-channel images: the whole input is a few MB and every
+// source sample is used by 4 threads of neighbouring lanes), no shared-memory tile, no barrier; the parities of the two
+// pads are template parameters so every tap / patch index is static.  The tile kernel above spent its time on the
+// per-tap modulo tests and on staging with two barriers per 2048 outputs: 35 us for [96,128,128] -> [96,256,256].
+// ------------------------------------------------------------------------------------
+template <typename T, int PY, int PX>
+__global__ void __launch_bounds__(256) upfirdn2d_up2_kernel(T* __restrict__ out, const T* __restrict__ x,
+                                                            const float* __restrict__ kernel, UpfirdnParams p,
+                                                            uint32_t total, FastDivU32 fd_cq, FastDivU32 fd_rp) {
+  __shared__ float s_k[16];
+  if (threadIdx.x < 16) {
+    const int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+    // flipped, zero-padded to 4 x 4  (op/upfirdn2d_kernel.cu:137)
+    s_k[threadIdx.x] = (ky < p.kh && kx < p.kw) ? kernel[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)] : 0.f;
+  }
+  __syncthreads();
+  float kf[4][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kf[i >> 2][i & 3] = s_k[i];
+  const int yoff = (PY - p.pad_y0) >> 1, xoff = (PX - p.pad_x0) >> 1;      // PY - pad_y0, PX - pad_x0 are even
+  const bool vec = (p.out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & (4 * sizeof(T) - 1)) == 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t t = fastdiv(i, fd_cq);
+    const int cq = static_cast<int>(i - t * fd_cq.d);
+    const uint32_t plane = fastdiv(t, fd_rp);
+    const int rp = static_cast<int>(t - plane * fd_rp.d);
+    const int iy0 = rp + yoff, ix0 = 2 * cq + xoff;
+    const T* xp = x + static_cast<int64_t>(plane) * p.in_h * p.in_w;
+    float v[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int iy = iy0 + r, ix = ix0 + c;
+        v[r][c] = (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) ? to_f32<T>(__ldg(xp + static_cast<int64_t>(iy) * p.in_w + ix)) : 0.f;
+      }
+    T* op = out + (static_cast<int64_t>(plane) * p.out_h + 2 * rp) * p.out_w + 4 * cq;
+#pragma unroll
+    for (int tr = 0; tr < 2; ++tr) {
+      if (2 * rp + tr >= p.out_h) break;
+      const int ay = tr == 0 ? PY : 1 - PY;            // first matching tap row; the other one is ay + 2
+      const int rb = tr == 0 ? 0 : 1 - PY;             // patch row of tap ay
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ax = (PX - j) & 1;
+        const int cb = (j + ax - PX) >> 1;
+        o[j] = v[rb][cb] * kf[ay][ax];
+        o[j] = fmaf(v[rb][cb + 1], kf[ay][ax + 2], o[j]);
+        o[j] = fmaf(v[rb + 1][cb], kf[ay + 2][ax], o[j]);
+        o[j] = fmaf(v[rb + 1][cb + 1], kf[ay + 2][ax + 2], o[j]);
+      }
+      T* orow = op + static_cast<int64_t>(tr) * p.out_w;
+      if (vec) {
+        if (sizeof(T) == 4) {
+          *reinterpret_cast<float4*>(orow) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+          T q[4] = {from_f32<T>(o[0]), from_f32<T>(o[1]), from_f32<T>(o[2]), from_f32<T>(o[3])};
+          *reinterpret_cast<uint2*>(orow) = *reinterpret_cast<uint2*>(q);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (4 * cq + j < p.out_w) orow[j] = from_f32<T>(o[j]);
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_up2(void* out, const void* x, const float* kernel, const UpfirdnParams& p, int64_t planes, cudaStream_t st) {
+  const uint32_t cqs = static_cast<uint32_t>((p.out_w + 3) / 4), rps = static_cast<uint32_t>((p.out_h + 1) / 2);
+  const uint32_t total = static_cast<uint32_t>(planes) * cqs * rps;
+  const uint32_t want = (total + 255) / 256;
+  const uint32_t cap = static_cast<uint32_t>(sm_count()) * 64;
+  const unsigned grid = want < cap ? want : cap;
+  const FastDivU32 fc = fastdiv_make(cqs), fr = fastdiv_make(rps);
+  const int py = p.pad_y0 & 1, px = p.pad_x0 & 1;
+#define FM_UP2(PY_, PX_) upfirdn2d_up2_kernel<T, PY_, PX_><<<grid, 256, 0, st>>>(static_cast<T*>(out), static_cast<const T*>(x), kernel, p, total, fc, fr)
+  if (py == 0 && px == 0) FM_UP2(0, 0);
+  else if (py == 0) FM_UP2(0, 1);
+  else if (px == 0) FM_UP2(1, 0);
+  else FM_UP2(1, 1);
+#undef FM_UP2
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
 template <typename T>
 static int upfirdn2d_dispatch(void* out, const void* x, const float* kernel, int64_t planes, UpfirdnParams p, int pad_x1,
                               int pad_y1, cudaStream_t st) {
@@ -818,6 +911,10 @@ static int upfirdn2d_dispatch(void* out, const void* x, const float* kernel, int
   if (env_stream && stream_eligible<T>(p, pad_x1, pad_y1)) return launch_stream<T>(out, x, kernel, p, pad_y1, planes, st);
   const bool sq = p.up_x == p.up_y && p.down_x == p.down_y;
   const int kmax = p.kh > p.kw ? p.kh : p.kw;
+  static const int env_up2 = []() { const char* e = getenv("FM3D_UPFIRDN_UP2"); return e ? atoi(e) : 1; }();
+  if (env_up2 && sq && p.up_x == 2 && p.down_x == 1 && kmax <= 4 &&
+      planes * ((p.out_w + 3) / 4) * static_cast<int64_t>((p.out_h + 1) / 2) < 0x7FFFFFFF)
+    return launch_up2<T>(out, x, kernel, p, planes, st);
   // small images: shorter tiles keep more CTAs busy
   const bool small = p.out_h <= 16;
   if (sq && kmax <= 4) {

@@ -126,6 +126,29 @@ def test_upfirdn2d_stream_zero_row_layouts(cuda, shape, pads, dtype, sep):
         torch.testing.assert_close(out.float().cpu(), ref, rtol=tol, atol=tol * 8)
 
 
+@pytest.mark.parametrize("shape,kshape,pads", [
+    ((4, 3, 64, 64), (4, 4), (2, 1, 2, 1)),       # ToRGB skip upsample (stylegan2.py:65-80)
+    ((2, 3, 9, 13), (4, 4), (2, 1, 2, 1)),        # output width not a multiple of 4, odd heights
+    ((3, 2, 6, 5), (3, 4), (1, 2, 0, 3)),         # every parity of the two leading pads, non-square taps
+    ((1, 5, 4, 9), (4, 2), (3, 0, 1, 1)),
+    ((2, 2, 6, 6), (4, 4), (-1, 2, 2, -1)),       # negative pads crop
+    ((2, 1, 3, 3), (1, 1), (0, 0, 0, 0)),         # pure zero-stuffing
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_upfirdn2d_up2_polyphase(cuda, shape, kshape, pads, dtype):
+    """up = 2, down = 1 takes the polyphase kernel (2 x 2 live taps per output, pad parities as template parameters)."""
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(sum(shape) * 11 + kshape[0])
+    x = torch.randn(*shape, generator=gen).to(dtype)
+    k = torch.randn(*kshape, generator=gen)
+    cfg = (2, 2, 1, 1) + pads
+    ref = orc.upfirdn2d_ref(x.float(), k, *cfg)
+    out = ops.upfirdn2d_planes(x.to(cuda), k.to(cuda), *cfg)
+    assert tuple(out.shape) == tuple(ref.shape) and out.dtype == dtype
+    tol = 1e-5 if dtype == torch.float32 else (2e-2 if dtype == torch.bfloat16 else 3e-3)
+    torch.testing.assert_close(out.float().cpu(), ref, rtol=tol, atol=tol * 8)
+
+
 def test_upfirdn2d_empty(cuda):
     from fm3d import ops
     k = orc.make_kernel_ref([1, 3, 3, 1]).to(cuda)
