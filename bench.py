@@ -475,6 +475,16 @@ def main():
                                            "ms": t_up * 1e3, "algorithmic_bytes": up_bytes},
                "fused_bias_act_fp32_256": {"achieved": ba_bytes / t_ba / 1e9, "frac": ba_bytes / t_ba / 1e9 / hbm_peak,
                                            "ms": t_ba * 1e3, "algorithmic_bytes": ba_bytes}}
+        # the other two HBM-sized generator blurs (the 65^2 / 129^2 planes after the 32->64 and 64->128 up-convs) and the
+        # 2-byte walk on the largest one
+        for name, shp, dt in (("upfirdn2d_blur_fp32_129", (32, 256, 129, 129), torch.float32),
+                              ("upfirdn2d_blur_fp32_65", (32, 512, 65, 65), torch.float32),
+                              ("upfirdn2d_blur_bf16_257", (32, 128, 257, 257), torch.bfloat16)):
+            del xb, yb
+            xb = torch.randn(*shp, device=device).to(dt)
+            t_x, yb = timed(lambda: op_api.upfirdn2d(xb, kk, pad=(1, 1)))
+            nb = (xb.numel() + yb.numel()) * xb.element_size()
+            hbm[name] = {"achieved": nb / t_x / 1e9, "frac": nb / t_x / 1e9 / hbm_peak, "ms": t_x * 1e3, "algorithmic_bytes": nb}
         del xb, yb, flush
 
     if rank != 0:
