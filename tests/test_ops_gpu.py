@@ -198,7 +198,8 @@ def test_bias_act_golden(cuda):
             np.testing.assert_allclose(grads[1].cpu().numpy(), g[f"{name}.gb"], rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("shape", [(32, 512, 4, 4), (4, 128, 64, 64), (3, 5, 7, 11), (32, 512), (2, 3, 1, 1), (5,)])
+@pytest.mark.parametrize("shape", [(32, 512, 4, 4), (4, 128, 64, 64), (3, 5, 7, 11), (32, 512), (2, 3, 1, 1), (5,),
+                                   (2, 6, 24, 24), (3, 16, 40, 64)])     # rows that are / are not whole 128-vector chunks
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_bias_act_modes_vs_oracle(cuda, shape, dtype):
     from fm3d import ops
@@ -217,6 +218,27 @@ def test_bias_act_modes_vs_oracle(cuda, shape, dtype):
         out = ops.bias_act(x.to(cuda), b.to(cuda) if use_b else None, r.to(cuda) if use_r else None, act, grad, 0.2, 2 ** 0.5)
         assert out.dtype == dtype
         torch.testing.assert_close(out.float().cpu(), ref, rtol=tol, atol=tol, msg=f"act{act} grad{grad}")
+
+
+@pytest.mark.parametrize("shape", [(2, 6, 24, 24), (4, 16, 64, 64), (3, 5, 7, 11), (2, 8, 48, 130), (32, 512)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("act", [3, 1])
+def test_bias_act_grad_bias_fused(cuda, shape, dtype, act):
+    """Gradient + fused bias-gradient reduction (every FusedLeakyReLU.backward, op/fused_act.py:42-48): the 16-byte path
+    (rows of whole vectors, two vectors per thread in flight, tail vector) and the scalar fallback against the oracle; the
+    bias gradient is the sum of the ROUNDED input gradient, as in the reference."""
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(sum(shape) + act)
+    g = torch.randn(*shape, generator=gen).to(dtype)
+    r = torch.randn(*shape, generator=gen).to(dtype)
+    ref = orc.fused_bias_act_ref(g.float(), None, r.float(), act, 1, 0.2, 2 ** 0.5).to(dtype)
+    gin, gb = ops.bias_act_grad_bias(g.to(cuda), r.to(cuda), act, 0.2, 2 ** 0.5)
+    tol = 1e-6 if dtype == torch.float32 else 1.6e-2
+    torch.testing.assert_close(gin.float().cpu(), ref.float(), rtol=tol, atol=tol)
+    dims = [0] + list(range(2, len(shape)))
+    gb_ref = ref.float().sum(dim=dims)
+    torch.testing.assert_close(gb.float().cpu(), gb_ref, rtol=2e-2 if dtype == torch.bfloat16 else 1e-4,
+                               atol=(2e-2 if dtype == torch.bfloat16 else 1e-4) * max(1.0, float(gb_ref.abs().max())))
 
 
 def test_bias_act_unaligned_and_empty(cuda):
