@@ -164,18 +164,25 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(__nv_bfloat16* __rest
   const int p0 = blockIdx.x * NT_PIX, c0 = blockIdx.y * NT_CH;
   const int64_t b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // All 16 + 8 loads of the thread are issued before the first is used.  Written as one loop (load, scale, store to the
+  // tile per channel) ptxas kept the iterations in order -- eight waits on DRAM per CTA, 3 loads in flight per thread:
+  // ncu put 72 % of the stall samples on the eight multiplies and the pass moved 4.0 TB/s (Little's law: 24 KB in flight
+  // per SM).
+  float v0[NT_CH / 8], v1[NT_CH / 8], sc[NT_CH / 8];
 #pragma unroll
   for (int k = 0; k < NT_CH / 8; ++k) {
-    const int cl = warp + 8 * k, c = c0 + cl;
-    float v0 = 0.f, v1 = 0.f;
-    if (c < C) {
-      const float* src = x + (b * C + c) * HW;
-      const float sc = scale ? __ldg(scale + b * C + c) : 1.f;
-      if (p0 + lane < HW) v0 = __ldg(src + p0 + lane) * sc;
-      if (p0 + lane + 32 < HW) v1 = __ldg(src + p0 + lane + 32) * sc;
-    }
-    *reinterpret_cast<__nv_bfloat16*>(tile + lane * NT_ROW + cl * 2) = __float2bfloat16_rn(v0);
-    *reinterpret_cast<__nv_bfloat16*>(tile + (lane + 32) * NT_ROW + cl * 2) = __float2bfloat16_rn(v1);
+    const int c = c0 + warp + 8 * k;
+    const bool ok = c < C;
+    const float* src = x + (b * C + (ok ? c : 0)) * HW;
+    sc[k] = (ok && scale) ? __ldg(scale + b * C + c) : 1.f;
+    v0[k] = (ok && p0 + lane < HW) ? __ldg(src + p0 + lane) : 0.f;
+    v1[k] = (ok && p0 + lane + 32 < HW) ? __ldg(src + p0 + lane + 32) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < NT_CH / 8; ++k) {
+    const int cl = warp + 8 * k;
+    *reinterpret_cast<__nv_bfloat16*>(tile + lane * NT_ROW + cl * 2) = __float2bfloat16_rn(v0[k] * sc[k]);
+    *reinterpret_cast<__nv_bfloat16*>(tile + (lane + 32) * NT_ROW + cl * 2) = __float2bfloat16_rn(v1[k] * sc[k]);
   }
   __syncthreads();
   // 64 pixels x 16 quads of 4 channels (8 bytes): consecutive threads write consecutive quads of a pixel
