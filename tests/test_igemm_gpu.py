@@ -219,6 +219,21 @@ def test_conv_stem_window(cuda, k, stride, pad, S):
     torch.testing.assert_close(out.cpu(), ref, rtol=2e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("B,C,H,W,pad_t,pad_l,Hp,Wp", [(2, 3, 64, 64, 3, 3, 70, 72), (3, 3, 32, 32, 1, 1, 34, 34), (1, 5, 7, 9, 0, 2, 9, 13),
+                                                    (2, 8, 5, 6, 2, 0, 8, 7), (32, 3, 256, 256, 1, 1, 258, 258)])
+def test_image_pack_padded(cuda, B, C, H, W, pad_t, pad_l, Hp, Wp):
+    """fp32 NCHW image -> zero-padded bf16 [B, Hp, Wp, 8] (the stems' operand), four output pixels per thread: row tails
+    that are not a multiple of 4, every channel count up to 8, borders and spare channels zero."""
+    from fm3d import ops
+    gen = torch.Generator().manual_seed(B * 100 + W)
+    x = torch.randn(B, C, H, W, generator=gen)
+    ref = torch.zeros(B, Hp, Wp, 8)
+    ref[:, pad_t:pad_t + H, pad_l:pad_l + W, :C] = x.permute(0, 2, 3, 1)
+    out = torch.full((B, Hp, Wp, 8), float("nan"), device=cuda, dtype=torch.bfloat16)
+    ops.image_to_nhwc8_padded(x.to(cuda), pad_t, pad_l, Hp, Wp, out=out)
+    assert torch.equal(out.cpu(), ref.to(torch.bfloat16))
+
+
 def test_encoder_helper_kernels(cuda):
     from fm3d import ops
     gen = torch.Generator().manual_seed(9)
