@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(256) bias_act_vec_kernel(T* __restrict__ out, 
 #pragma unroll
         for (int j = 0; j < N; ++j) {
           float xf = to_f32<T>(xv[u].v[j]);
+          if (MODE == 40) { o.v[j] = from_f32<T>(xf * bv[u]); continue; }     // fm_channel_scale: x * s[row]
           if (HAS_BIAS) xf += bv[u];
           const float rf = HAS_REF ? to_f32<T>(rv[u].v[j]) : 0.f;
           o.v[j] = from_f32<T>(act_apply(xf, rf, MODE, alpha) * scale);
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(256) bias_act_scalar_kernel(T* __restrict__ ou
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     float xf = to_f32<T>(x[i]);
+    if (MODE == 40) { out[i] = from_f32<T>(xf * to_f32<T>(__ldg(bias + static_cast<uint32_t>((i / inner) % channels)))); continue; }
     if (HAS_BIAS) xf += to_f32<T>(__ldg(bias + static_cast<uint32_t>((i / inner) % channels)));
     const float rf = HAS_REF ? to_f32<T>(ref[i]) : 0.f;
     out[i] = from_f32<T>(act_apply(xf, rf, MODE, alpha) * scale);
@@ -292,7 +294,99 @@ static int launch_grad_bias(void* gin, float* gbias, const void* gout, const voi
   return FM_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// per-row dot product: out[r] += sum_i a[r, i] * b[r, i].  Same decomposition as the fused bias gradient: one block per slab
+// of a row, fp32 block reduction, one atomicAdd per block.
+// ------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) channel_dot_kernel(float* __restrict__ out, const T* __restrict__ a, const T* __restrict__ b,
+                                                          uint64_t inner, uint32_t slabs_per_row, uint64_t slab) {
+  const uint64_t row = blockIdx.x / slabs_per_row;
+  const uint32_t sl = blockIdx.x % slabs_per_row;
+  const uint64_t lo = static_cast<uint64_t>(sl) * slab;
+  const uint64_t hi = lo + slab < inner ? lo + slab : inner;
+  const T* pa = a + row * inner;
+  const T* pb = b + row * inner;
+  float acc = 0.f;
+  if (VEC) {
+    constexpr int N = Vec16<T>::N;
+    const uint64_t v_hi = hi / N;
+    uint64_t iv = lo / N + threadIdx.x;
+    for (; iv + blockDim.x < v_hi; iv += 2 * blockDim.x) {          // two vectors of each tensor in flight
+      const Pack<T, N> a0 = ld16<T>(pa + iv * N), b0 = ld16<T>(pb + iv * N);
+      const Pack<T, N> a1 = ld16<T>(pa + (iv + blockDim.x) * N), b1 = ld16<T>(pb + (iv + blockDim.x) * N);
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc = fmaf(to_f32<T>(a0.v[j]), to_f32<T>(b0.v[j]), fmaf(to_f32<T>(a1.v[j]), to_f32<T>(b1.v[j]), acc));
+    }
+    if (iv < v_hi) {
+      const Pack<T, N> a0 = ld16<T>(pa + iv * N), b0 = ld16<T>(pb + iv * N);
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc = fmaf(to_f32<T>(a0.v[j]), to_f32<T>(b0.v[j]), acc);
+    }
+  } else {
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc = fmaf(to_f32<T>(pa[i]), to_f32<T>(pb[i]), acc);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  __shared__ float wsum[8];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = wsum[threadIdx.x];
+#pragma unroll
+    for (int s = 4; s > 0; s >>= 1) v += __shfl_xor_sync(0xffu, v, s);
+    if (threadIdx.x == 0) atomicAdd(out + row, v);
+  }
+}
+
+template <typename T>
+static int launch_channel_dot(float* out, const void* a, const void* b, int64_t rows, int64_t inner, cudaStream_t st) {
+  if (rows == 0 || inner == 0) return FM_OK;
+  constexpr int N = Vec16<T>::N;
+  uint64_t slab = static_cast<uint64_t>(inner);
+  const uint64_t target_blocks = static_cast<uint64_t>(sm_count()) * 32;
+  while (slab > 2048 && static_cast<uint64_t>(rows) * ((inner + slab - 1) / slab) < target_blocks) slab = (slab + 1) / 2;
+  const bool vec = inner % N == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  if (vec) slab = (slab + N - 1) / N * N;
+  const uint64_t slabs = (inner + slab - 1) / slab;
+  const uint64_t blocks = static_cast<uint64_t>(rows) * slabs;
+  FM_CHECK_ARG(blocks < 0x7FFFFFFFull, "fm_channel_dot: too many blocks (%llu)", (unsigned long long)blocks);
+  if (vec)
+    channel_dot_kernel<T, true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(out, static_cast<const T*>(a), static_cast<const T*>(b),
+                                                                               static_cast<uint64_t>(inner), static_cast<uint32_t>(slabs), slab);
+  else
+    channel_dot_kernel<T, false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(out, static_cast<const T*>(a), static_cast<const T*>(b),
+                                                                                static_cast<uint64_t>(inner), static_cast<uint32_t>(slabs), slab);
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
 }  // namespace fm
+
+extern "C" int fm_channel_scale(void* out, const void* x, const void* s, int64_t rows, int64_t inner, int dtype, void* stream) {
+  FM_CHECK_ARG(rows >= 0 && inner >= 0, "fm_channel_scale: negative size");
+  FM_CHECK_ARG(out && x && s, "fm_channel_scale: null tensor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {     // bias_act_vec_kernel in mode 40: the per-channel "bias" is the per-row factor (n_outer = 1, channels = rows)
+    case FM_F32: return fm::launch_bias_act<float, 40, true, false>(out, x, s, nullptr, 1, rows, inner, 0.f, 1.f, st);
+    case FM_F16: return fm::launch_bias_act<__half, 40, true, false>(out, x, s, nullptr, 1, rows, inner, 0.f, 1.f, st);
+    case FM_BF16: return fm::launch_bias_act<__nv_bfloat16, 40, true, false>(out, x, s, nullptr, 1, rows, inner, 0.f, 1.f, st);
+    default: fm::set_error("fm_channel_scale: bad dtype %d", dtype); return FM_ERR_INVALID;
+  }
+}
+
+extern "C" int fm_channel_dot(float* out_f32, const void* a, const void* b, int64_t rows, int64_t inner, int dtype, void* stream) {
+  FM_CHECK_ARG(rows >= 0 && inner >= 0, "fm_channel_dot: negative size");
+  FM_CHECK_ARG(out_f32 && a && b, "fm_channel_dot: null tensor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case FM_F32: return fm::launch_channel_dot<float>(out_f32, a, b, rows, inner, st);
+    case FM_F16: return fm::launch_channel_dot<__half>(out_f32, a, b, rows, inner, st);
+    case FM_BF16: return fm::launch_channel_dot<__nv_bfloat16>(out_f32, a, b, rows, inner, st);
+    default: fm::set_error("fm_channel_dot: bad dtype %d", dtype); return FM_ERR_INVALID;
+  }
+}
 
 extern "C" int fm_bias_act(void* out, const void* x, const void* bias, const void* ref, int64_t n_outer, int64_t channels,
                            int64_t inner, int act, int grad, float alpha, float scale, int dtype, void* stream) {

@@ -160,6 +160,40 @@ def bias_act_grad_bias(grad_out, ref, act=3, alpha=0.2, scale=2 ** 0.5):
     return gin, gb.to(g.dtype)
 
 
+def channel_scale(x, s):
+    """x [B, C, ...] * s [B, C] broadcast over the trailing dims (fm_channel_scale)."""
+    _check_cuda(x, "input")
+    _check_cuda(s, "scale")
+    x = x.contiguous()
+    rows = x.shape[0] * x.shape[1]
+    s = s.contiguous().to(x.dtype)
+    if s.numel() != rows:
+        raise RuntimeError(f"channel_scale: scale has {s.numel()} elements for {rows} (sample, channel) rows")
+    out = torch.empty_like(x)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            st = _lib.lib().fm_channel_scale(_ptr(out), _ptr(x), _ptr(s), rows, x.numel() // rows, _dtype_code(x), _stream())
+        _lib.check(st, "fm_channel_scale")
+    return out
+
+
+def channel_dot(a, b):
+    """sum over the trailing dims of a * b, [B, C, ...] x [B, C, ...] -> [B, C] (fm_channel_dot)."""
+    _check_cuda(a, "a")
+    _check_cuda(b, "b")
+    if a.shape != b.shape:
+        raise RuntimeError(f"channel_dot: shapes differ: {tuple(a.shape)} vs {tuple(b.shape)}")
+    a = a.contiguous()
+    b = b.contiguous().to(a.dtype)
+    rows = a.shape[0] * a.shape[1]
+    out = torch.zeros(a.shape[0], a.shape[1], device=a.device, dtype=torch.float32)
+    if a.numel():
+        with torch.cuda.device(a.device):
+            st = _lib.lib().fm_channel_dot(_ptr(out), _ptr(a), _ptr(b), rows, a.numel() // rows, _dtype_code(a), _stream())
+        _lib.check(st, "fm_channel_dot")
+    return out.to(a.dtype)
+
+
 # ------------------------------------------------------------------ upfirdn2d
 def upfirdn2d_planes(x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
     """x [..., H, W] -> [..., out_h, out_w] (the reference's [major,H,W,1] layout,

@@ -38,6 +38,11 @@ def _native_grad(x):
     return x.is_cuda and os.environ.get("FM3D_NATIVE_GRAD", "1") != "0"
 
 
+def _convgrad():
+    from fm3d import convgrad
+    return convgrad
+
+
 def _conv2d(x, w, bias=None, stride=1, padding=0):
     if _native_grad(x):
         from fm3d import convgrad
@@ -195,7 +200,8 @@ class ModulatedConv2d(nn.Module):
         batch = input.shape[0]
         s = self.modulation(style)                                        # [B, I]
         w = self.weight[0] * self.scale                                   # [O, I, k, k]
-        x = input * s.view(batch, self.in_channel, 1, 1)
+        native = _native_grad(input) and input.dtype == torch.float32 and s.dtype == torch.float32
+        x = _convgrad().channel_scale(input, s) if native else input * s.view(batch, self.in_channel, 1, 1)
 
         if self.upsample:
             out = _conv_transpose2d(x, w.transpose(0, 1), stride=2)
@@ -208,7 +214,7 @@ class ModulatedConv2d(nn.Module):
         if self.demodulate:
             wsq = w.square().sum(dim=(2, 3))                              # [O, I]
             d = torch.rsqrt(F.linear(s.square(), wsq) + 1e-8)             # literal 1e-8, not self.eps
-            out = out * d.view(batch, self.out_channel, 1, 1)
+            out = _convgrad().channel_scale(out, d) if native else out * d.view(batch, self.out_channel, 1, 1)
 
         if return_style_scalars:
             return out, s.view(batch, 1, self.in_channel, 1, 1)

@@ -64,6 +64,14 @@ int fm_bias_act_grad_bias(void* grad_in, float* grad_bias_f32, const void* grad_
                           const void* ref, int64_t n_outer, int64_t channels, int64_t inner,
                           int act, float alpha, float scale, int dtype, void* stream);
 
+/* Per-row scale and per-row dot product: the two maps of the modulation / demodulation scaling of ModulatedConv2d's
+ * shared-weight composition (stylegan2.py:250-298: weight * style, demod), closed under differentiation --
+ *   fm_channel_scale: out[r, i] = x[r, i] * s[r]                 (x * s[:, :, None, None] with r = b * C + c)
+ *   fm_channel_dot:   out_f32[r] += sum_i a[r, i] * b[r, i]      (its gradient w.r.t. s; out_f32 zero-initialised by the caller)
+ * The gradient of each is built from the other.  s has the dtype of x. */
+int fm_channel_scale(void* out, const void* x, const void* s, int64_t rows, int64_t inner, int dtype, void* stream);
+int fm_channel_dot(float* out_f32, const void* a, const void* b, int64_t rows, int64_t inner, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * upfirdn2d: zero-stuff x up, pad/crop, correlate with the flipped kernel, decimate.
  * Replaces: upfirdn2d(input[major,H,W,minor], kernel[kh,kw], up_x, up_y, down_x, down_y,

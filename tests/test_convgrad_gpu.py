@@ -137,3 +137,42 @@ def test_conv_wgrad_direct(cuda):
                 S = S.reshape(-1, Cs)
                 ref = S.t() @ Gm if swap else Gm.t() @ S
                 assert _rel(dw[t], ref) < 2e-3, (Cg, Cs, s, swap, ksplit, t, _rel(dw[t], ref))
+
+
+@pytest.mark.parametrize("shape", [(3, 8, 16, 16), (2, 5, 7, 9), (4, 64, 32, 32), (2, 3, 1, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_channel_scale_and_dot_kernels(cuda, shape, dtype):
+    """fm_channel_scale / fm_channel_dot (vector and scalar paths) against the torch broadcast forms."""
+    from fm3d import ops
+    g = torch.Generator(device=cuda).manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g, device=cuda).to(dtype)
+    y = torch.randn(*shape, generator=g, device=cuda).to(dtype)
+    s = torch.randn(shape[0], shape[1], generator=g, device=cuda).to(dtype)
+    ref = (x.float() * s.float()[:, :, None, None]).to(dtype)
+    assert torch.equal(ops.channel_scale(x, s), ref)
+    dot = ops.channel_dot(x, y)
+    dref = (x.float() * y.float()).sum(dim=(2, 3))
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    torch.testing.assert_close(dot.float(), dref, rtol=tol, atol=tol * max(1.0, float(dref.abs().max())))
+
+
+def test_channel_scale_autograd_to_second_order(cuda):
+    """ChannelScale / ChannelDot (each the other's gradient) against autograd of the broadcast multiply: first-order
+    gradients and a double backward of the kind path-length regularisation takes through ModulatedConv2d."""
+    from fm3d import convgrad
+    g = torch.Generator(device=cuda).manual_seed(5)
+    B, C, H = 3, 12, 10
+    x0 = torch.randn(B, C, H, H, generator=g, device=cuda)
+    s0 = torch.randn(B, C, generator=g, device=cuda)
+    w = torch.randn(B, C, H, H, generator=g, device=cuda)
+    res = []
+    for native in (True, False):
+        x, s = x0.clone().requires_grad_(True), s0.clone().requires_grad_(True)
+        y = convgrad.channel_scale(x, s) if native else x * s.view(B, C, 1, 1)
+        loss = (y * w).sum() + y.pow(2).sum()
+        gx, gs = torch.autograd.grad(loss, [x, s], create_graph=True)
+        pen = gx.pow(2).sum() + gs.pow(2).sum()
+        ggx, ggs = torch.autograd.grad(pen, [x, s])
+        res.append((y.detach(), gx.detach(), gs.detach(), ggx, ggs))
+    for a, b in zip(*res):
+        assert _rel(a, b) < 1e-5
