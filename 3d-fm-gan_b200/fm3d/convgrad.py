@@ -293,6 +293,20 @@ class ChannelDot(Function):
         return ga, gb
 
 
+class BiasAdd(Function):
+    """y + bias[None, :, None, None] on the fused bias-act kernel in its linear mode (``y + bias.view(1, -1, 1, 1)`` runs on
+    ATen's non-vectorised broadcast kernel; the VGG16 convolutions of the LPIPS term add their biases to 256^2 x 64 maps).
+    The gradient is the identity and a sum: torch ops, differentiable again."""
+
+    @staticmethod
+    def forward(ctx, y, bias):
+        return ops.bias_act(y.detach(), bias.detach(), None, 1, 0, 0.0, 1.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g if ctx.needs_input_grad[0] else None), (g.sum(dim=(0, 2, 3)) if ctx.needs_input_grad[1] else None)
+
+
 def channel_scale(x, s):
     """x [B, C, H, W] * s [B, C] (any shape with B * C elements), differentiable to any order on the native kernels."""
     return ChannelScale.apply(x, s.reshape(x.shape[0], x.shape[1]))
@@ -313,7 +327,7 @@ def conv2d(x, w, bias=None, stride=1, padding=0):
         raise RuntimeError(f"conv2d: input has {x.shape[1]} channels, weight expects {w.shape[1]}")
     y = ConvFwd.apply(x.float(), w.float(), int(stride), int(padding))
     if bias is not None:
-        y = y + bias.view(1, -1, 1, 1)
+        y = BiasAdd.apply(y, bias.float())
     return y
 
 

@@ -176,3 +176,21 @@ def test_channel_scale_autograd_to_second_order(cuda):
         res.append((y.detach(), gx.detach(), gs.detach(), ggx, ggs))
     for a, b in zip(*res):
         assert _rel(a, b) < 1e-5
+
+
+def test_conv2d_bias_add_autograd(cuda):
+    """convgrad.conv2d with a bias (BiasAdd on the fused bias-act kernel): output, gradients w.r.t. input / weight / bias
+    and a double backward through the input gradient, against ATen."""
+    from fm3d import convgrad
+    x0, w0, g = _inputs(cuda, 2, 24, 40, 12, 3, 11)
+    b0 = torch.randn(40, generator=g, device=cuda)
+    res = []
+    for native in (True, False):
+        x, w, b = (t.clone().requires_grad_(True) for t in (x0, w0, b0))
+        xq, wq = (x, w) if native else (x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float())
+        y = convgrad.conv2d(xq, wq, b, 1, 1) if native else F.conv2d(xq, wq, b, 1, 1)
+        gx, gw, gb = torch.autograd.grad(y.pow(2).sum(), [x, w, b], create_graph=True)
+        ggb, = torch.autograd.grad(gx.pow(2).sum(), [b])
+        res.append((y.detach(), gx.detach(), gw.detach(), gb.detach(), ggb))
+    for a, r in zip(*res):
+        assert _rel(a, r) < 2e-2
