@@ -362,7 +362,80 @@ static int launch_channel_dot(float* out, const void* a, const void* b, int64_t 
   return FM_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// out[b, c, i] = x[b, c, i] + n[b * n_bstride + i]: a warp owns chunks of 128 consecutive 16-byte vectors as above; the plane
+// is read through L1 / L2 (it is reused by every channel).
+// ------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) plane_add_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ n,
+                                                        uint64_t total, uint64_t inner, uint64_t chan_inner, uint64_t n_bstride) {
+  constexpr int N = VEC ? Vec16<T>::N : 1;
+  constexpr int UNROLL = 4;
+  const uint64_t n_vec = total / N;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t v0 = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v0 < n_vec; v0 += stride * UNROLL) {
+    Pack<T, N> xv[UNROLL], nv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const uint64_t v = v0 + stride * u;
+      if (v < n_vec) {
+        const uint64_t e = v * N, b = e / chan_inner, i = e % inner;       // (sample, offset inside the plane)
+        if constexpr (VEC) { xv[u] = ld16<T>(x + e); nv[u] = ld16<T>(n + b * n_bstride + i); }
+        else { xv[u].v[0] = x[e]; nv[u].v[0] = __ldg(n + b * n_bstride + i); }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const uint64_t v = v0 + stride * u;
+      if (v < n_vec) {
+        Pack<T, N> o;
+#pragma unroll
+        for (int j = 0; j < N; ++j) o.v[j] = from_f32<T>(to_f32<T>(xv[u].v[j]) + to_f32<T>(nv[u].v[j]));
+        if constexpr (VEC) st16<T>(out + v * N, o); else out[v] = o.v[0];
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_plane_add(void* out, const void* x, const void* n, int64_t B, int64_t C, int64_t inner, int64_t n_bstride,
+                            cudaStream_t st) {
+  const uint64_t total = static_cast<uint64_t>(B) * C * inner;
+  if (total == 0) return FM_OK;
+  constexpr int N = Vec16<T>::N;
+  const bool vec = inner % N == 0 && n_bstride % N == 0 &&
+                   ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(n)) & 15) == 0;
+  const uint64_t n_vec = vec ? total / N : total;
+  const uint64_t want = (n_vec + 1023) / 1024;
+  const uint64_t cap = static_cast<uint64_t>(sm_count()) * 16;
+  const unsigned grid = static_cast<unsigned>(want < cap ? (want ? want : 1) : cap);
+  if (vec)
+    plane_add_kernel<T, true><<<grid, 256, 0, st>>>(static_cast<T*>(out), static_cast<const T*>(x), static_cast<const T*>(n), total,
+                                                    static_cast<uint64_t>(inner), static_cast<uint64_t>(C) * inner,
+                                                    static_cast<uint64_t>(n_bstride));
+  else
+    plane_add_kernel<T, false><<<grid, 256, 0, st>>>(static_cast<T*>(out), static_cast<const T*>(x), static_cast<const T*>(n), total,
+                                                     static_cast<uint64_t>(inner), static_cast<uint64_t>(C) * inner,
+                                                     static_cast<uint64_t>(n_bstride));
+  count_launch();
+  FM_LAUNCH_OK();
+  return FM_OK;
+}
+
 }  // namespace fm
+
+extern "C" int fm_plane_add(void* out, const void* x, const void* n, int64_t B, int64_t C, int64_t inner, int64_t n_bstride,
+                            int dtype, void* stream) {
+  FM_CHECK_ARG(B >= 0 && C >= 0 && inner >= 0 && (n_bstride == 0 || n_bstride == inner), "fm_plane_add: bad sizes");
+  FM_CHECK_ARG(out && x && n, "fm_plane_add: null tensor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case FM_F32: return fm::launch_plane_add<float>(out, x, n, B, C, inner, n_bstride, st);
+    case FM_F16: return fm::launch_plane_add<__half>(out, x, n, B, C, inner, n_bstride, st);
+    case FM_BF16: return fm::launch_plane_add<__nv_bfloat16>(out, x, n, B, C, inner, n_bstride, st);
+    default: fm::set_error("fm_plane_add: bad dtype %d", dtype); return FM_ERR_INVALID;
+  }
+}
 
 extern "C" int fm_channel_scale(void* out, const void* x, const void* s, int64_t rows, int64_t inner, int dtype, void* stream) {
   FM_CHECK_ARG(rows >= 0 && inner >= 0, "fm_channel_scale: negative size");

@@ -307,6 +307,29 @@ class BiasAdd(Function):
         return (g if ctx.needs_input_grad[0] else None), (g.sum(dim=(0, 2, 3)) if ctx.needs_input_grad[1] else None)
 
 
+class PlaneAdd(Function):
+    """image [B, C, H, W] + plane [B or 1, 1, H, W] (NoiseInjection, stylegan2.py:312): the gradient is the identity and a
+    sum over the channels (and the batch for a shared plane) -- torch ops, differentiable again."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.n_shape = n.shape
+        return ops.plane_add(x.detach(), n.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        gn = None
+        if ctx.needs_input_grad[1]:
+            gn = g.sum(dim=1, keepdim=True)
+            if ctx.n_shape[0] == 1 and g.shape[0] > 1:
+                gn = gn.sum(dim=0, keepdim=True)
+        return (g if ctx.needs_input_grad[0] else None), gn
+
+
+def plane_add(x, n):
+    return PlaneAdd.apply(x, n)
+
+
 def channel_scale(x, s):
     """x [B, C, H, W] * s [B, C] (any shape with B * C elements), differentiable to any order on the native kernels."""
     return ChannelScale.apply(x, s.reshape(x.shape[0], x.shape[1]))

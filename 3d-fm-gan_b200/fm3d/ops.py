@@ -177,6 +177,25 @@ def channel_scale(x, s):
     return out
 
 
+def plane_add(x, n):
+    """x [B, C, H, W] + n [B or 1, 1, H, W] broadcast over the channels (fm_plane_add)."""
+    _check_cuda(x, "input")
+    _check_cuda(n, "plane")
+    x = x.contiguous()
+    n = n.contiguous().to(x.dtype)
+    B, Cc = x.shape[0], x.shape[1]
+    inner = x.numel() // max(B * Cc, 1)
+    if n.numel() not in (inner, B * inner):
+        raise RuntimeError(f"plane_add: plane of {tuple(n.shape)} does not broadcast over the channels of {tuple(x.shape)}")
+    out = torch.empty_like(x)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            st = _lib.lib().fm_plane_add(_ptr(out), _ptr(x), _ptr(n), B, Cc, inner, inner if n.numel() == B * inner and B > 1 else 0,
+                                         _dtype_code(x), _stream())
+        _lib.check(st, "fm_plane_add")
+    return out
+
+
 def channel_dot(a, b):
     """sum over the trailing dims of a * b, [B, C, ...] x [B, C, ...] -> [B, C] (fm_channel_dot)."""
     _check_cuda(a, "a")

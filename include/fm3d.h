@@ -72,6 +72,11 @@ int fm_bias_act_grad_bias(void* grad_in, float* grad_bias_f32, const void* grad_
 int fm_channel_scale(void* out, const void* x, const void* s, int64_t rows, int64_t inner, int dtype, void* stream);
 int fm_channel_dot(float* out_f32, const void* a, const void* b, int64_t rows, int64_t inner, int dtype, void* stream);
 
+/* out[b, c, i] = x[b, c, i] + n[b * n_bstride + i]  (n_bstride = inner for a per-sample plane, 0 for one shared plane):
+ * NoiseInjection's broadcast add over the channels (stylegan2.py:312, image + weight * noise) under autograd. */
+int fm_plane_add(void* out, const void* x, const void* n, int64_t B, int64_t C, int64_t inner, int64_t n_bstride, int dtype,
+                 void* stream);
+
 /* ------------------------------------------------------------------------------------
  * upfirdn2d: zero-stuff x up, pad/crop, correlate with the flipped kernel, decimate.
  * Replaces: upfirdn2d(input[major,H,W,minor], kernel[kh,kw], up_x, up_y, down_x, down_y,

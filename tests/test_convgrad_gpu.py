@@ -194,3 +194,29 @@ def test_conv2d_bias_add_autograd(cuda):
         res.append((y.detach(), gx.detach(), gw.detach(), gb.detach(), ggb))
     for a, r in zip(*res):
         assert _rel(a, r) < 2e-2
+
+
+@pytest.mark.parametrize("shape,shared", [((3, 8, 16, 16), False), ((3, 8, 16, 16), True), ((2, 5, 7, 9), False), ((1, 4, 32, 32), False),
+                                          ((2, 3, 5, 5), True)])
+def test_plane_add_and_noise_injection(cuda, shape, shared):
+    """fm_plane_add (vector and scalar paths, per-sample and shared planes) and NoiseInjection on it: output, gradients
+    w.r.t. the image and the noise weight, and a double backward, against the broadcast form."""
+    import stylegan2
+    from fm3d import ops
+    g = torch.Generator(device=cuda).manual_seed(sum(shape))
+    B, C, H, W = shape
+    x0 = torch.randn(*shape, generator=g, device=cuda)
+    n = torch.randn(1 if shared else B, 1, H, W, generator=g, device=cuda)
+    assert torch.equal(ops.plane_add(x0, n), x0 + n)
+    inj = stylegan2.NoiseInjection().to(cuda)
+    with torch.no_grad():
+        inj.weight.fill_(0.37)
+    res = []
+    for native in (True, False):
+        x = x0.clone().requires_grad_(True)
+        y = inj(x, noise=n) if native else x + inj.weight * n
+        gx, gw = torch.autograd.grad(y.pow(3).sum(), [x, inj.weight], create_graph=True)
+        ggx, ggw = torch.autograd.grad(gx.pow(2).sum() + gw.pow(2).sum(), [x, inj.weight])
+        res.append((y.detach(), gx.detach(), gw.detach(), ggx, ggw))
+    for a, r in zip(*res):
+        assert _rel(a, r) < 1e-5
